@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py -- channel-samples/s of the fused G.711 decode -> meter -> mix -> encode
+path on N B200s (BASELINE.json metric), with its HBM roofline, the end-to-end
+number through the C ABI with host buffers, and the CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the fused kernel over one resident batch of
+BASELINE config 3: 4096 channels (1024 bridges x 4 legs) x 1640 frames of
+20 ms (1.07 GB of G.711 codes per GPU, >> the 126 MB L2).  N > 1: one rank per
+GPU (torchrun), every rank owns its own 1024 bridges (weak scaling, no
+collective on the data path); the per-channel event summaries are gathered to
+rank 0 over NCCL once, outside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "channel-samples/s G.711 dec+meter+mix+enc"
+UNIT = "channel-samples/s"
+B, G, F = 1024, 4, 1640                 # bridges, legs per bridge, frames per step (per GPU)
+C = B * G
+FRAME = 160
+# algorithmic bytes per bridge-frame (G=4, 16 B meter record per leg)
+BYTES_PER_BF = G * FRAME + 2 * FRAME + FRAME + G * 16      # 1184
+WORKLOAD = (f"cfg3: {C} channels ({B} bridges x {G} legs, A-law/u-law alternating) x {F} frames of 20 ms, "
+            "noise+tone, gates 2-of-4 open at gain 2.0")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "fused_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def oracle_lib():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_py as O   # bench.py's cpu_baseline / --impl reference legs: the oracle is timed, never shipped
+    return O
+
+
+def cpu_sample(seconds_target=12.0):
+    """Times the CPU oracle (reference-faithful scalar port, -O2) with all host threads on a
+    bounded sample of the same workload.  Returns (channel-samples/s, cores, description)."""
+    import numpy as np
+    from igate4xsoftphonedsp_b200 import synth
+    O = oracle_lib()
+    cores = os.cpu_count() or 1
+    rng = np.random.default_rng(0)
+    law, out_law = synth.laws(C), synth.out_laws(B)
+
+    def run(nf):
+        codes = rng.integers(0, 256, (nf, C, FRAME), dtype=np.uint8)
+        gain = synth.gains(nf, B, G)
+        t0 = time.perf_counter()
+        O.process_batch(codes, law, gain, out_law, G, threads=cores)
+        return time.perf_counter() - t0
+
+    t = run(8)                                   # calibration (also warms the thread pool / pages)
+    nf = int(max(8, min(F, 8 * seconds_target / max(t, 1e-6))))
+    dt = run(nf)
+    return C * nf * FRAME / dt, cores, f"{C} channels x {nf} frames, {cores} threads, {dt:.1f} s"
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference cannot be
+    built here (Qt/PJSIP/Boost absent) so this is the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    desc, cores = "", 1
+    for i in range(args.warmup + args.steps):
+        v, cores, desc = cpu_sample(seconds_target=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(v)
+    value = sum(vals) / len(vals)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import igate4xsoftphonedsp_b200 as ig
+    from igate4xsoftphonedsp_b200 import sharding, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    vp = ig.VoicePath(local)                    # raises if libigate_dsp.so / an sm_100 GPU is missing
+    vp.use_torch_stream()
+    # ---- resident inputs: this rank's bridges [rank*B, (rank+1)*B) of a world*B-bridge system
+    ch0 = rank * C
+    law = torch.from_numpy(synth.laws(C, ch0)).to(dev)
+    out_law = torch.from_numpy(synth.out_laws(B, rank * B)).to(dev)
+    gain_np = synth.gains(F, B, G)
+    gain = torch.from_numpy(gain_np.view(np.int16)).to(dev)
+    pcm = synth.pcm_noise_tone_torch(F, C, dev, ch0=ch0)
+    codes = vp.g711_encode(pcm, law)            # inputs are G.711 codes, produced by the GPU encoder
+    del pcm
+    out = vp.alloc_outputs(F, B, G)
+    torch.cuda.synchronize()
+
+    def step():
+        vp.process_batch(codes, law, gain, out_law, G, out=out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = vp.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    launches = vp.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps))
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    samples_per_step = world * C * F * FRAME
+    value = samples_per_step * args.steps / (total_ms_max * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel: algorithmic bytes / avg launch duration
+    peak, peak_src = peaks()
+    avg_launch_s = (total_ms / args.steps) * 1e-3
+    achieved = BYTES_PER_BF * B * F / avg_launch_s / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "kernel": "k_fused<4,32>", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": BYTES_PER_BF * B * F,
+                "launch_ms": {"avg": total_ms / args.steps, "min": per_launch_ms[0], "max": per_launch_ms[-1]}}
+
+    # ---- parity spot check on the timed outputs (oracle as checker, outside the timed region)
+    parity = None
+    if rank == 0:
+        O = oracle_lib()
+        fs = [0, 25, F - 1]
+        sel = torch.tensor(fs, device=dev)
+        want = O.process_batch(codes[sel].cpu().numpy(), law.cpu().numpy(), gain_np[fs], out_law.cpu().numpy(), G,
+                               threads=os.cpu_count() or 1)
+        parity = bool(np.array_equal(out["mix"][sel].cpu().numpy(), want[0]) and
+                      np.array_equal(out["enc"][sel].cpu().numpy(), want[1]) and
+                      np.array_equal(out["meter"][sel].cpu().numpy()[..., :2].reshape(len(fs), C, 2),
+                                     want[2].view(np.uint32).reshape(len(fs), C, 4)[..., :2]))
+
+    # ---- per-channel summaries gathered to rank 0 (the only collective; outside the timed region)
+    summ, _ = vp.event_summary(out["meter"], gain, want_db=False)
+    torch.cuda.synchronize()
+    gathered = sharding.gather_records(summ, world * B, G) if world > 1 else summ
+    n_summaries = int(gathered.shape[0]) if rank == 0 else None
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + kernel + D2H every step
+    e2e = None
+    if not args.no_e2e:
+        h_codes = torch.empty((F, C, FRAME), dtype=torch.uint8, pin_memory=True)
+        h_codes.copy_(codes)
+        h_in = {"codes": h_codes.numpy(), "law": law.cpu().numpy(), "gain": gain_np, "out_law": out_law.cpu().numpy()}
+        h_out_t = {"mix": torch.empty((F, B, FRAME), dtype=torch.int16, pin_memory=True),
+                   "enc": torch.empty((F, B, FRAME), dtype=torch.uint8, pin_memory=True),
+                   "meter": torch.empty((F, C, 4), dtype=torch.int32, pin_memory=True),
+                   "bmeter": torch.empty((F, B), dtype=torch.int32, pin_memory=True)}
+        h_out = {"mix": h_out_t["mix"].numpy(), "enc": h_out_t["enc"].numpy(),
+                 "meter": h_out_t["meter"].numpy().view(ig.METER_DT).reshape(F, C),
+                 "bmeter": h_out_t["bmeter"].numpy().view(ig.BRIDGE_DT).reshape(F, B)}
+        esteps = max(2, min(args.steps, 5))
+        for _ in range(2):
+            vp.process_batch(h_in["codes"], h_in["law"], h_in["gain"], h_in["out_law"], G, out=h_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            vp.process_batch(h_in["codes"], h_in["law"], h_in["gain"], h_in["out_law"], G, out=h_out)
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = h_in["codes"].nbytes + h_in["gain"].nbytes + h_in["law"].nbytes + h_in["out_law"].nbytes
+        d2h = sum(v.nbytes for v in h_out.values())
+        e2e_ok = bool(torch.equal(h_out_t["mix"], out["mix"].cpu()) and torch.equal(h_out_t["enc"], out["enc"].cpu()))
+        e2e = {"value": samples_per_step * esteps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": esteps, "matches_device_path": e2e_ok}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, desc = cpu_sample()
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_codes_bytes": C * F * FRAME, "l2": "inputs larger than L2",
+                       "parallelism": f"bridges sharded over {world} GPU(s), no data-path collective",
+                       "summaries_gathered_to_rank0": n_summaries},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "parity_vs_oracle_on_timed_output": parity,
+        }))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    vp.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,597 @@
+// igd_capi.cu -- the extern "C" surface declared in include/igate_dsp.h.
+//
+// Host pointers (IGD_MEM_HOST) are staged through grow-only device scratch
+// buffers owned by the context; device pointers (IGD_MEM_DEVICE) are used in
+// place.  Every arithmetic entry point launches a CUDA kernel -- there is no
+// CPU implementation behind this API.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "igd_kernels.cuh"
+
+namespace {
+constexpr int kSlots = 12;
+}
+
+struct igd_ctx {
+    int device;
+    cudaStream_t own_stream, stream;
+    cudaStream_t copy_streams[2];
+    cudaEvent_t ev[8];
+    cudaDeviceProp prop;
+    void *scratch[kSlots];
+    size_t scratch_cap[kSlots];
+    uint64_t launches;
+    char err[256];
+};
+
+namespace {
+
+int fail(igd_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    if (c) {
+        if (e != cudaSuccess)
+            snprintf(c->err, sizeof(c->err), "%s: %s", what, cudaGetErrorString(e));
+        else
+            snprintf(c->err, sizeof(c->err), "%s", what);
+    }
+    return code;
+}
+
+#define IGD_CUDA(c, call)                                                 \
+    do {                                                                  \
+        cudaError_t e_ = (call);                                          \
+        if (e_ != cudaSuccess) return fail((c), IGD_ECUDA, #call, e_);    \
+    } while (0)
+
+struct Bind {
+    igd_ctx *c;
+    explicit Bind(igd_ctx *ctx) : c(ctx) { cudaSetDevice(ctx->device); }
+};
+
+igd_launch_cfg cfg_of(igd_ctx *c)
+{
+    igd_launch_cfg k;
+    k.sm_count = c->prop.multiProcessorCount;
+    k.stream = c->stream;
+    return k;
+}
+
+// grow-only device scratch
+int scratch(igd_ctx *c, int slot, size_t bytes, void **out)
+{
+    if (bytes == 0) bytes = 16;
+    if (c->scratch_cap[slot] < bytes) {
+        if (c->scratch[slot]) {
+            cudaStreamSynchronize(c->stream);
+            cudaFree(c->scratch[slot]);
+            c->scratch[slot] = nullptr;
+            c->scratch_cap[slot] = 0;
+        }
+        size_t cap = bytes + bytes / 8;
+        cap = (cap + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&c->scratch[slot], cap);
+        if (e != cudaSuccess) return fail(c, IGD_ENOMEM, "cudaMalloc(scratch)", e);
+        c->scratch_cap[slot] = cap;
+    }
+    *out = c->scratch[slot];
+    return IGD_OK;
+}
+
+// resolves an input: device pointer as is, host pointer copied into `slot`
+template <class T>
+int in_arg(igd_ctx *c, int mem, int slot, const T *p, size_t count, const T **out)
+{
+    if (mem == IGD_MEM_DEVICE) { *out = p; return IGD_OK; }
+    void *d = nullptr;
+    int rc = scratch(c, slot, count * sizeof(T), &d);
+    if (rc) return rc;
+    if (count) IGD_CUDA(c, cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    *out = static_cast<const T *>(d);
+    return IGD_OK;
+}
+template <class T>
+int out_arg(igd_ctx *c, int mem, int slot, T *p, size_t count, T **out)
+{
+    if (mem == IGD_MEM_DEVICE) { *out = p; return IGD_OK; }
+    void *d = nullptr;
+    int rc = scratch(c, slot, count * sizeof(T), &d);
+    if (rc) return rc;
+    *out = static_cast<T *>(d);
+    return IGD_OK;
+}
+template <class T>
+int out_done(igd_ctx *c, int mem, T *host, const T *dev, size_t count)
+{
+    if (mem == IGD_MEM_DEVICE || count == 0) return IGD_OK;
+    IGD_CUDA(c, cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, c->stream));
+    return IGD_OK;
+}
+int finish(igd_ctx *c, int mem)
+{
+    if (mem == IGD_MEM_HOST) IGD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return IGD_OK;
+}
+bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int igd_abi_version(void) { return IGD_ABI_VERSION; }
+
+int igd_init(int device, igd_ctx **out)
+{
+    if (!out) return IGD_EINVAL;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return IGD_ENODEV;
+    igd_ctx *c = new (std::nothrow) igd_ctx();
+    if (!c) return IGD_ENOMEM;
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&c->prop, device) != cudaSuccess) {
+        delete c;
+        return IGD_ENODEV;
+    }
+    if (c->prop.major < 10) {   // kernels are built for sm_100a only
+        delete c;
+        return IGD_ENODEV;
+    }
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return IGD_ECUDA;
+    }
+    c->stream = c->own_stream;
+    for (auto &s : c->copy_streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    for (auto &e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    *out = c;
+    return IGD_OK;
+}
+
+int igd_shutdown(igd_ctx *c)
+{
+    if (!c) return IGD_EINVAL;
+    Bind b(c);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < kSlots; i++)
+        if (c->scratch[i]) cudaFree(c->scratch[i]);
+    for (auto &e : c->ev) cudaEventDestroy(e);
+    for (auto &s : c->copy_streams) cudaStreamDestroy(s);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return IGD_OK;
+}
+
+int igd_set_stream(igd_ctx *c, void *s)
+{
+    if (!c) return IGD_EINVAL;
+    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    return IGD_OK;
+}
+
+int igd_sync(igd_ctx *c)
+{
+    if (!c) return IGD_EINVAL;
+    Bind b(c);
+    IGD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return IGD_OK;
+}
+
+const char *igd_last_error(igd_ctx *c) { return c ? c->err : "null context"; }
+
+int igd_device_info(igd_ctx *c, igd_devinfo *o)
+{
+    if (!c || !o) return IGD_EINVAL;
+    o->device = c->device;
+    o->sm_count = c->prop.multiProcessorCount;
+    o->cc_major = c->prop.major;
+    o->cc_minor = c->prop.minor;
+    o->total_mem = c->prop.totalGlobalMem;
+    strncpy(o->name, c->prop.name, sizeof(o->name) - 1);
+    o->name[sizeof(o->name) - 1] = 0;
+    return IGD_OK;
+}
+
+uint64_t igd_launch_count(igd_ctx *c) { return c ? c->launches : 0; }
+
+void *igd_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr;
+}
+void igd_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+void *igd_dev_alloc(igd_ctx *c, size_t bytes)
+{
+    if (!c) return nullptr;
+    Bind b(c);
+    void *p = nullptr;
+    return cudaMalloc(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr;
+}
+void igd_dev_free(igd_ctx *c, void *p)
+{
+    if (!c || !p) return;
+    Bind b(c);
+    cudaFree(p);
+}
+int igd_copy_to_device(igd_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (!c) return IGD_EINVAL;
+    Bind b(c);
+    IGD_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    IGD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return IGD_OK;
+}
+int igd_copy_to_host(igd_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (!c) return IGD_EINVAL;
+    Bind b(c);
+    IGD_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    IGD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return IGD_OK;
+}
+
+// ---------------------------------------------------------------- G.711
+static int g711_decode_impl(igd_ctx *c, const uint8_t *codes, const uint8_t *law_ch, int law,
+                            int16_t *pcm, size_t n, size_t nch, int mem)
+{
+    if (!c || (n && (!codes || !pcm)) || (law != IGD_LAW_ALAW && law != IGD_LAW_ULAW))
+        return fail(c, IGD_EINVAL, "igd_g711_decode: bad argument");
+    if (n == 0) return IGD_OK;
+    if (mem == IGD_MEM_DEVICE && (!aligned(codes, 16) || !aligned(pcm, 32)))
+        return fail(c, IGD_EINVAL, "igd_g711_decode: device pointers must be 16/32-byte aligned");
+    Bind b(c);
+    const uint8_t *dc; const uint8_t *dl = nullptr; int16_t *dp;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, codes, n, &dc))) return rc;
+    if (law_ch && (rc = in_arg(c, mem, 1, law_ch, nch, &dl))) return rc;
+    if ((rc = out_arg(c, mem, 2, pcm, n, &dp))) return rc;
+    IGD_CUDA(c, igd_k_g711_decode(cfg_of(c), dc, dl, law, dp, n, nch));
+    c->launches++;
+    if ((rc = out_done(c, mem, pcm, dp, n))) return rc;
+    return finish(c, mem);
+}
+
+int igd_g711_decode(igd_ctx *c, const uint8_t *codes, int16_t *pcm, size_t n, int law, int mem)
+{
+    return g711_decode_impl(c, codes, nullptr, law, pcm, n, 1, mem);
+}
+int igd_g711_decode_ch(igd_ctx *c, const uint8_t *codes, const uint8_t *law, int16_t *pcm,
+                       size_t nframes, size_t nch, int mem)
+{
+    if (!law || nch == 0) return fail(c, IGD_EINVAL, "igd_g711_decode_ch: bad argument");
+    return g711_decode_impl(c, codes, law, 0, pcm, nframes * nch * IGD_FRAME, nch, mem);
+}
+
+static int g711_encode_impl(igd_ctx *c, const int16_t *pcm, const uint8_t *law_ch, int law,
+                            uint8_t *codes, size_t n, size_t nch, int mem)
+{
+    if (!c || (n && (!codes || !pcm)) || (law != IGD_LAW_ALAW && law != IGD_LAW_ULAW))
+        return fail(c, IGD_EINVAL, "igd_g711_encode: bad argument");
+    if (n == 0) return IGD_OK;
+    if (mem == IGD_MEM_DEVICE && (!aligned(codes, 16) || !aligned(pcm, 32)))
+        return fail(c, IGD_EINVAL, "igd_g711_encode: device pointers must be 16/32-byte aligned");
+    Bind b(c);
+    const int16_t *dp; const uint8_t *dl = nullptr; uint8_t *dc;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, pcm, n, &dp))) return rc;
+    if (law_ch && (rc = in_arg(c, mem, 1, law_ch, nch, &dl))) return rc;
+    if ((rc = out_arg(c, mem, 2, codes, n, &dc))) return rc;
+    IGD_CUDA(c, igd_k_g711_encode(cfg_of(c), dp, dl, law, dc, n, nch));
+    c->launches++;
+    if ((rc = out_done(c, mem, codes, dc, n))) return rc;
+    return finish(c, mem);
+}
+
+int igd_g711_encode(igd_ctx *c, const int16_t *pcm, uint8_t *codes, size_t n, int law, int mem)
+{
+    return g711_encode_impl(c, pcm, nullptr, law, codes, n, 1, mem);
+}
+int igd_g711_encode_ch(igd_ctx *c, const int16_t *pcm, const uint8_t *law, uint8_t *codes,
+                       size_t nframes, size_t nch, int mem)
+{
+    if (!law || nch == 0) return fail(c, IGD_EINVAL, "igd_g711_encode_ch: bad argument");
+    return g711_encode_impl(c, pcm, law, 0, codes, nframes * nch * IGD_FRAME, nch, mem);
+}
+
+// ---------------------------------------------------------------- meters
+int igd_frame_meter(igd_ctx *c, const int16_t *pcm, size_t nframes, igd_meter_rec *out, int mem)
+{
+    if (!c || (nframes && (!pcm || !out))) return fail(c, IGD_EINVAL, "igd_frame_meter: bad argument");
+    if (nframes == 0) return IGD_OK;
+    if (mem == IGD_MEM_DEVICE && (!aligned(pcm, 32) || !aligned(out, 16)))
+        return fail(c, IGD_EINVAL, "igd_frame_meter: device pointers must be 32/16-byte aligned");
+    Bind b(c);
+    const int16_t *dp; igd_meter_rec *dout;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, pcm, nframes * IGD_FRAME, &dp))) return rc;
+    if ((rc = out_arg(c, mem, 2, out, nframes, &dout))) return rc;
+    IGD_CUDA(c, igd_k_frame_meter(cfg_of(c), dp, nframes, dout));
+    c->launches++;
+    if ((rc = out_done(c, mem, out, dout, nframes))) return rc;
+    return finish(c, mem);
+}
+
+int igd_bytemean(igd_ctx *c, const uint8_t *payloads, size_t n, size_t len, size_t stride,
+                 unsigned flags, uint8_t *out, int mem)
+{
+    if (!c || (n && (!payloads || !out)) || stride < len) return fail(c, IGD_EINVAL, "igd_bytemean: bad argument");
+    if (n == 0) return IGD_OK;
+    Bind b(c);
+    const uint8_t *dp; uint8_t *dout;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, payloads, (n - 1) * stride + len, &dp))) return rc;
+    if ((rc = out_arg(c, mem, 2, out, n, &dout))) return rc;
+    IGD_CUDA(c, igd_k_bytemean(cfg_of(c), dp, n, len, stride, flags, dout));
+    c->launches++;
+    if ((rc = out_done(c, mem, out, dout, n))) return rc;
+    return finish(c, mem);
+}
+
+int igd_level_percent(igd_ctx *c, const int32_t *v, size_t n, int32_t *out, int mem)
+{
+    if (!c || (n && (!v || !out))) return fail(c, IGD_EINVAL, "igd_level_percent: bad argument");
+    if (n == 0) return IGD_OK;
+    Bind b(c);
+    const int32_t *dv; int32_t *dout;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, v, n, &dv))) return rc;
+    if ((rc = out_arg(c, mem, 2, out, n, &dout))) return rc;
+    IGD_CUDA(c, igd_k_level_percent(cfg_of(c), dv, n, dout));
+    c->launches++;
+    if ((rc = out_done(c, mem, out, dout, n))) return rc;
+    return finish(c, mem);
+}
+
+// ---------------------------------------------------------------- gain / mix
+int igd_gain_q7(float level)
+{
+    // pjsua_conf_adjust_rx_level(slot, level) as called at roip_ed137.cpp:5221
+    return (int)((level - 1.0f) * 128) + 128;
+}
+
+int igd_mix(igd_ctx *c, const int16_t *pcm, const uint16_t *gain, size_t F, size_t B, int G,
+            int16_t *mix, int mem)
+{
+    if (!c || G < 1 || G > IGD_MAX_LEGS || (F && B && (!pcm || !gain || !mix)))
+        return fail(c, IGD_EINVAL, "igd_mix: bad argument");
+    if (F == 0 || B == 0) return IGD_OK;
+    if (mem == IGD_MEM_DEVICE && (!aligned(pcm, 16) || !aligned(mix, 16)))
+        return fail(c, IGD_EINVAL, "igd_mix: device pointers must be 16-byte aligned");
+    Bind b(c);
+    const int16_t *dp; const uint16_t *dg; int16_t *dm;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, pcm, F * B * G * IGD_FRAME, &dp))) return rc;
+    if ((rc = in_arg(c, mem, 1, gain, F * B * G, &dg))) return rc;
+    if ((rc = out_arg(c, mem, 2, mix, F * B * IGD_FRAME, &dm))) return rc;
+    IGD_CUDA(c, igd_k_mix(cfg_of(c), dp, dg, F, B, G, dm));
+    c->launches++;
+    if ((rc = out_done(c, mem, mix, dm, F * B * IGD_FRAME))) return rc;
+    return finish(c, mem);
+}
+
+// ---------------------------------------------------------------- fused path
+int igd_process_batch(igd_ctx *c, const igd_batch_desc *d)
+{
+    if (!c || !d || d->struct_size != sizeof(igd_batch_desc))
+        return fail(c, IGD_EINVAL, "igd_process_batch: bad descriptor");
+    if (d->F < 0 || d->B < 0 || d->G < 1 || d->G > IGD_MAX_LEGS)
+        return fail(c, IGD_EINVAL, "igd_process_batch: bad shape");
+    if (d->F == 0 || d->B == 0) return IGD_OK;
+    if (!d->codes || !d->law || !d->gain_q7 || !d->out_law || !d->mix || !d->enc || !d->meter || !d->bmeter)
+        return fail(c, IGD_EINVAL, "igd_process_batch: null buffer");
+    const size_t F = d->F, B = d->B, G = d->G, C = B * G;
+    Bind b(c);
+    if (d->mem == IGD_MEM_DEVICE) {
+        if (!aligned(d->codes, 16) || !aligned(d->mix, 32) || !aligned(d->enc, 16) || !aligned(d->meter, 16) ||
+            !aligned(d->gain_q7, 2) || !aligned(d->bmeter, 4))
+            return fail(c, IGD_EINVAL, "igd_process_batch: misaligned device pointer");
+        IGD_CUDA(c, igd_k_fused(cfg_of(c), *d));
+        c->launches++;
+        return IGD_OK;
+    }
+    // Host buffers: stage through the GPU in frame chunks so that the H2D copy of
+    // chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap.
+    igd_batch_desc k = *d;
+    k.mem = IGD_MEM_DEVICE;
+    int rc;
+    const uint8_t *dlaw, *dol;
+    if ((rc = in_arg(c, IGD_MEM_HOST, 0, d->law, C, &dlaw))) return rc;
+    if ((rc = in_arg(c, IGD_MEM_HOST, 1, d->out_law, B, &dol))) return rc;
+    k.law = dlaw; k.out_law = dol;
+    // chunk size: ~32 MiB of codes per chunk, at least 1 frame
+    size_t fc = (32u << 20) / (C * IGD_FRAME);
+    if (fc < 1) fc = 1;
+    if (fc > F) fc = F;
+    const size_t nchunks = (F + fc - 1) / fc;
+    const int nbuf = nchunks > 1 ? 2 : 1;
+    void *dcodes, *dgain, *dmix, *denc, *dmeter, *dbm;
+    if ((rc = scratch(c, 2, nbuf * fc * C * IGD_FRAME, &dcodes))) return rc;
+    if ((rc = scratch(c, 3, nbuf * fc * C * sizeof(uint16_t), &dgain))) return rc;
+    if ((rc = scratch(c, 4, nbuf * fc * B * IGD_FRAME * sizeof(int16_t), &dmix))) return rc;
+    if ((rc = scratch(c, 5, nbuf * fc * B * IGD_FRAME, &denc))) return rc;
+    if ((rc = scratch(c, 6, nbuf * fc * C * sizeof(igd_meter_rec), &dmeter))) return rc;
+    if ((rc = scratch(c, 7, nbuf * fc * B * sizeof(igd_bridge_rec), &dbm))) return rc;
+    // law tables were queued on c->stream; copies below run on the copy streams
+    IGD_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
+    cudaStream_t sin = c->copy_streams[0], sout = c->copy_streams[1];
+    // ev[0..1]: input of buffer i ready; ev[2..3]: kernel on buffer i done; ev[4..5]: output drained
+    bool out_pending[2] = {false, false};
+    for (size_t ch = 0; ch < nchunks; ch++) {
+        const int i = (int)(ch % nbuf);
+        const size_t f0 = ch * fc, nf = (f0 + fc <= F) ? fc : F - f0;
+        uint8_t *bc = static_cast<uint8_t *>(dcodes) + (size_t)i * fc * C * IGD_FRAME;
+        uint16_t *bg = static_cast<uint16_t *>(dgain) + (size_t)i * fc * C;
+        int16_t *bm = static_cast<int16_t *>(dmix) + (size_t)i * fc * B * IGD_FRAME;
+        uint8_t *be = static_cast<uint8_t *>(denc) + (size_t)i * fc * B * IGD_FRAME;
+        igd_meter_rec *bmt = static_cast<igd_meter_rec *>(dmeter) + (size_t)i * fc * C;
+        igd_bridge_rec *bbr = static_cast<igd_bridge_rec *>(dbm) + (size_t)i * fc * B;
+        // the input buffer may only be overwritten once the kernel that read it is done
+        if (ch >= (size_t)nbuf) IGD_CUDA(c, cudaStreamWaitEvent(sin, c->ev[2 + i], 0));
+        IGD_CUDA(c, cudaMemcpyAsync(bc, d->codes + f0 * C * IGD_FRAME, nf * C * IGD_FRAME,
+                                    cudaMemcpyHostToDevice, sin));
+        IGD_CUDA(c, cudaMemcpyAsync(bg, d->gain_q7 + f0 * C, nf * C * sizeof(uint16_t),
+                                    cudaMemcpyHostToDevice, sin));
+        IGD_CUDA(c, cudaEventRecord(c->ev[i], sin));
+        IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[i], 0));
+        // the output buffer may only be overwritten once its previous D2H is done
+        if (out_pending[i]) IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[4 + i], 0));
+        k.F = (int32_t)nf;
+        k.codes = bc; k.gain_q7 = bg; k.mix = bm; k.enc = be; k.meter = bmt; k.bmeter = bbr;
+        IGD_CUDA(c, igd_k_fused(cfg_of(c), k));
+        c->launches++;
+        IGD_CUDA(c, cudaEventRecord(c->ev[2 + i], c->stream));
+        IGD_CUDA(c, cudaStreamWaitEvent(sout, c->ev[2 + i], 0));
+        IGD_CUDA(c, cudaMemcpyAsync(d->mix + f0 * B * IGD_FRAME, bm, nf * B * IGD_FRAME * sizeof(int16_t),
+                                    cudaMemcpyDeviceToHost, sout));
+        IGD_CUDA(c, cudaMemcpyAsync(d->enc + f0 * B * IGD_FRAME, be, nf * B * IGD_FRAME,
+                                    cudaMemcpyDeviceToHost, sout));
+        IGD_CUDA(c, cudaMemcpyAsync(d->meter + f0 * C, bmt, nf * C * sizeof(igd_meter_rec),
+                                    cudaMemcpyDeviceToHost, sout));
+        IGD_CUDA(c, cudaMemcpyAsync(d->bmeter + f0 * B, bbr, nf * B * sizeof(igd_bridge_rec),
+                                    cudaMemcpyDeviceToHost, sout));
+        IGD_CUDA(c, cudaEventRecord(c->ev[4 + i], sout));
+        out_pending[i] = true;
+    }
+    IGD_CUDA(c, cudaStreamSynchronize(sout));
+    IGD_CUDA(c, cudaStreamSynchronize(c->stream));
+    return IGD_OK;
+}
+
+// ---------------------------------------------------------------- summary
+int igd_event_summary(igd_ctx *c, const igd_meter_rec *meter, const uint16_t *gain, size_t F, size_t C,
+                      igd_summary_rec *out, igd_summary_db *db, int mem)
+{
+    if (!c || (C && (!out || (F && (!meter || !gain))))) return fail(c, IGD_EINVAL, "igd_event_summary: bad argument");
+    if (C == 0) return IGD_OK;
+    Bind b(c);
+    const igd_meter_rec *dm; const uint16_t *dg; igd_summary_rec *dout; igd_summary_db *ddb = nullptr;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, meter, F * C, &dm))) return rc;
+    if ((rc = in_arg(c, mem, 1, gain, F * C, &dg))) return rc;
+    if ((rc = out_arg(c, mem, 2, out, C, &dout))) return rc;
+    if (db && (rc = out_arg(c, mem, 3, db, C, &ddb))) return rc;
+    IGD_CUDA(c, igd_k_event_summary(cfg_of(c), dm, dg, F, C, dout, ddb));
+    c->launches++;
+    if ((rc = out_done(c, mem, out, dout, C))) return rc;
+    if (db && (rc = out_done(c, mem, db, ddb, C))) return rc;
+    return finish(c, mem);
+}
+
+// ---------------------------------------------------------------- ED-137
+unsigned igd_calltype_flags(const char *ct)
+{
+    // QString(calltype).contains(...) / == "Rx"  (TransportAdapter.cpp:675,801,821,826,830)
+    unsigned f = 0;
+    if (!ct) return 0;
+    if (strstr(ct, "Idle")) f |= IGD_CT_IDLE;
+    if (strstr(ct, "Rxonly") || strcmp(ct, "Rx") == 0) f |= IGD_CT_RXONLY;
+    if (strstr(ct, "Tx") || strstr(ct, "TRx")) f |= IGD_CT_TXISH;
+    return f;
+}
+
+void igd_ed137_state_init(igd_ed137_state *s, int radiocall, int callIn, const char *calltype,
+                          int keepAlivePeroid, int64_t now_ms)
+{
+    // pjmedia_custom_tp_adapter_create, TransportAdapter.cpp:97-128
+    memset(s, 0, sizeof(*s));
+    s->radiostatus = radiocall != 0;
+    s->callIn = callIn != 0;
+    s->calltype_flags = (uint8_t)igd_calltype_flags(calltype);
+    s->keepAlivePeroid = keepAlivePeroid;
+    s->r2sSendtime = now_ms;
+    s->firstR2SPacket = 1;
+}
+
+int igd_ed137_parse(igd_ctx *c, const uint8_t *pkts, const uint32_t *sizes, size_t npkts, size_t stride,
+                    igd_ed137_fields *fields, uint8_t *payload_out, int mem)
+{
+    if (!c || (npkts && (!pkts || !fields)) || stride < IGD_PKT_HDR || (stride & 3))
+        return fail(c, IGD_EINVAL, "igd_ed137_parse: bad argument (stride must be >= 20 and a multiple of 4)");
+    if (npkts == 0) return IGD_OK;
+    if (mem == IGD_MEM_DEVICE && (!aligned(pkts, 4) || !aligned(fields, 16) || (payload_out && !aligned(payload_out, 4))))
+        return fail(c, IGD_EINVAL, "igd_ed137_parse: misaligned device pointer");
+    Bind b(c);
+    const uint8_t *dp; const uint32_t *ds = nullptr; igd_ed137_fields *df; uint8_t *dpo = nullptr;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, pkts, npkts * stride, &dp))) return rc;
+    if (sizes && (rc = in_arg(c, mem, 1, sizes, npkts, &ds))) return rc;
+    if ((rc = out_arg(c, mem, 2, fields, npkts, &df))) return rc;
+    if (payload_out && (rc = out_arg(c, mem, 3, payload_out, npkts * IGD_FRAME, &dpo))) return rc;
+    IGD_CUDA(c, igd_k_ed137_parse(cfg_of(c), dp, ds, npkts, stride, df, dpo));
+    c->launches++;
+    if ((rc = out_done(c, mem, fields, df, npkts))) return rc;
+    if (payload_out && (rc = out_done(c, mem, payload_out, dpo, npkts * IGD_FRAME))) return rc;
+    return finish(c, mem);
+}
+
+int igd_ed137_pack(igd_ctx *c, const igd_ed137_pack_desc *d)
+{
+    if (!c || !d || d->struct_size != sizeof(igd_ed137_pack_desc))
+        return fail(c, IGD_EINVAL, "igd_ed137_pack: bad descriptor");
+    if (d->F < 0 || d->C < 0 || d->payload_len > IGD_FRAME || (d->payload_len & 3) ||
+        d->out_stride < IGD_PKT_HDR + d->payload_len || (d->out_stride & 3))
+        return fail(c, IGD_EINVAL, "igd_ed137_pack: bad shape (payload_len and out_stride must be multiples of 4)");
+    if (d->F == 0 || d->C == 0) return IGD_OK;
+    if (!d->rtp12 || !d->payload || !d->state || !d->pkts || !d->sizes || !d->bytemean_out)
+        return fail(c, IGD_EINVAL, "igd_ed137_pack: null buffer");
+    Bind b(c);
+    const size_t n = (size_t)d->F * d->C;
+    const int mem = d->mem;
+    igd_ed137_pack_desc k = *d;
+    int rc;
+    const uint8_t *drtp, *dpay; const igd_ed137_ctl *dctl = nullptr;
+    igd_ed137_state *dst; uint8_t *dpk; uint32_t *dsz; uint8_t *dbm; void *dplan;
+    if ((rc = in_arg(c, mem, 0, d->rtp12, n * 12, &drtp))) return rc;
+    if ((rc = in_arg(c, mem, 1, d->payload, n * IGD_FRAME, &dpay))) return rc;
+    if (d->ctl && (rc = in_arg(c, mem, 2, d->ctl, n, &dctl))) return rc;
+    {
+        const igd_ed137_state *tmp = nullptr;
+        if ((rc = in_arg(c, mem, 3, d->state, (size_t)d->C, &tmp))) return rc;
+        dst = const_cast<igd_ed137_state *>(tmp);
+    }
+    if ((rc = out_arg(c, mem, 4, d->pkts, n * d->out_stride, &dpk))) return rc;
+    if ((rc = out_arg(c, mem, 5, d->sizes, n, &dsz))) return rc;
+    if ((rc = out_arg(c, mem, 6, d->bytemean_out, n, &dbm))) return rc;
+    if ((rc = scratch(c, 8, n * sizeof(igd_tx_plan_rec), &dplan))) return rc;
+    if (mem == IGD_MEM_HOST) IGD_CUDA(c, cudaMemsetAsync(dpk, 0, n * d->out_stride, c->stream));
+    k.rtp12 = drtp; k.payload = dpay; k.ctl = dctl; k.state = dst; k.pkts = dpk; k.sizes = dsz; k.bytemean_out = dbm;
+    IGD_CUDA(c, igd_k_ed137_pack(cfg_of(c), k, static_cast<igd_tx_plan_rec *>(dplan)));
+    c->launches += igd_k_launches_ed137_pack();
+    if ((rc = out_done(c, mem, d->pkts, dpk, n * d->out_stride))) return rc;
+    if ((rc = out_done(c, mem, d->sizes, dsz, n))) return rc;
+    if ((rc = out_done(c, mem, d->bytemean_out, dbm, n))) return rc;
+    if ((rc = out_done(c, mem, d->state, dst, (size_t)d->C))) return rc;
+    return finish(c, mem);
+}
+
+// ---------------------------------------------------------------- recorder
+size_t igd_wav_size(size_t payload_bytes, int ref_quirks)
+{
+    return 44 + (ref_quirks ? 2 * payload_bytes : payload_bytes);
+}
+
+int igd_wav_image(igd_ctx *c, const uint8_t *payload, size_t n, int rate, int law, int ref_quirks,
+                  uint8_t *out, size_t *out_len, int mem)
+{
+    if (!c || !out || (n && !payload)) return fail(c, IGD_EINVAL, "igd_wav_image: bad argument");
+    if (mem == IGD_MEM_DEVICE && !aligned(out, 4)) return fail(c, IGD_EINVAL, "igd_wav_image: misaligned output");
+    Bind b(c);
+    const size_t total = igd_wav_size(n, ref_quirks);
+    const uint8_t *dp; uint8_t *dout;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, payload, n, &dp))) return rc;
+    if ((rc = out_arg(c, mem, 2, out, total, &dout))) return rc;
+    IGD_CUDA(c, igd_k_wav_image(cfg_of(c), dp, n, rate, law, ref_quirks, dout));
+    c->launches++;
+    if ((rc = out_done(c, mem, out, dout, total))) return rc;
+    if (out_len) *out_len = total;
+    return finish(c, mem);
+}
+
+}  // extern "C"

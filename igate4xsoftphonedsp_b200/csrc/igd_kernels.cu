@@ -1,0 +1,926 @@
+// igd_kernels.cu -- hand-written sm_100a kernels of the iGate4x voice path.
+//
+// Everything here is streaming integer/byte work bounded by HBM3e bandwidth or,
+// for the fused kernel, by instruction issue (see DESIGN.md "Kernels").  No
+// tensor cores: nothing on this path is a contraction.
+//
+// Common design points
+//  * 128-bit (LDG.128) loads / 128- and 256-bit (STG.E.ENL2.256) stores with the
+//    evict-first hint: every input byte is read once and every output written
+//    once, so nothing should stay in L2.
+//  * G.711 expansion through a 64 KB shared-memory table laid out so that a
+//    lookup can never bank-conflict: entry (code, lane, law) lives at word
+//    code*64 + 2*lane + (law ^ (lane>>4)), i.e. every lane owns its own bank for
+//    either law, and the byte address is ONE PRMT: (code<<8) | lane_byte.
+//  * G.711 compression in ALU through the float-exponent trick of igd_math.cuh
+//    (no 64 KB encode table, no data-dependent bank conflicts).
+//  * Per-frame meters: exact integer partial sums per 16-sample chunk, combined
+//    through a padded shared-memory array (conflict-free LDS.64), dB via SFU lg2.
+//  * Persistent grids: a multiple of the SM count, each CTA strides over tiles.
+#include "igd_kernels.cuh"
+#include "igd_math.cuh"
+
+namespace {
+
+constexpr int kChunks = IGD_FRAME / 16;   // 16-byte chunks per frame = 10
+constexpr int kPst = kChunks + 1;         // padded partial stride (odd => conflict-free)
+constexpr int kLutBytes = 256 * 64 * 4;   // 64 KB decode table
+
+// ------------------------------------------------------------------ memory ops
+__device__ __forceinline__ uint4 ld16_stream(const void *p)
+{
+    return __ldcs(reinterpret_cast<const uint4 *>(p));
+}
+__device__ __forceinline__ void st16_stream(void *p, uint4 v)
+{
+    __stcs(reinterpret_cast<uint4 *>(p), v);
+}
+// one 256-bit store (sm_100+): 16 PCM samples of one thread
+__device__ __forceinline__ void st32_stream(void *p, const uint32_t (&v)[8])
+{
+    asm volatile("st.global.cs.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]),
+                 "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void ld32_stream(const void *p, uint32_t (&v)[8])
+{
+    asm volatile("ld.global.cs.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]),
+                   "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+// {hi, lo} -> two saturated int16 packed in one word (I2IP.S16.S32.SAT)
+__device__ __forceinline__ uint32_t pack_sat16(int hi, int lo)
+{
+    uint32_t r;
+    asm("cvt.pack.sat.s16.s32 %0, %1, %2;" : "=r"(r) : "r"(hi), "r"(lo));
+    return r;
+}
+__device__ __forceinline__ int clamp16(int v) { return min(max(v, -32768), 32767); }
+
+// ------------------------------------------------------------------ decode LUT
+__device__ __forceinline__ void build_decode_lut(uint32_t *lut, int tid, int nthreads)
+{
+    for (int i = tid; i < 256 * 64; i += nthreads) {
+        const uint32_t code = (uint32_t)i >> 6, slot = i & 63;
+        const uint32_t lane = slot >> 1;
+        const uint32_t law = (slot & 1) ^ (lane >> 4);
+        lut[i] = (uint32_t)(law ? igd_ulaw2lin(code) : igd_alaw2lin(code));
+    }
+}
+// byte offset of this lane's column for `law`
+__device__ __forceinline__ uint32_t lut_lane_byte(uint32_t lane, uint32_t law)
+{
+    return 4u * (2u * lane + ((law & 1u) ^ (lane >> 4)));
+}
+template <int K>
+__device__ __forceinline__ int lut_decode(const uint8_t *lut_bytes, uint32_t word, uint32_t lane_byte)
+{
+    // (code<<8) | lane_byte in one PRMT: byte0 = lane_byte, byte1 = word.byteK
+    const uint32_t a = __byte_perm(word, lane_byte, 0x7604 + (K << 4));
+    return *reinterpret_cast<const int *>(lut_bytes + a);
+}
+
+// ------------------------------------------------------------------ partials
+// 8-byte per-chunk meter partial: lo = sumsq[31:0];
+// hi = sumsq[34:32] | peak<<3 (16 bit) | bytesum<<19 (13-bit signed)
+__device__ __forceinline__ uint2 partial_pack(unsigned long long sq, uint32_t peak, int bsum)
+{
+    uint2 r;
+    r.x = (uint32_t)sq;
+    r.y = (uint32_t)(sq >> 32) | (peak << 3) | ((uint32_t)bsum << 19);
+    return r;
+}
+__device__ __forceinline__ void partial_add(uint2 v, unsigned long long &sq, uint32_t &peak, int &bsum)
+{
+    sq += (unsigned long long)v.x | ((unsigned long long)(v.y & 7u) << 32);
+    peak = max(peak, (v.y >> 3) & 0xFFFFu);
+    bsum += (int)v.y >> 19;
+}
+__device__ __forceinline__ igd_meter_rec meter_finish(unsigned long long sq, uint32_t peak, int bsum,
+                                                      bool have_bytes)
+{
+    igd_meter_rec r;
+    r.sumsq_lo = (uint32_t)sq;
+    const uint32_t bm = have_bytes ? igd_bytemean_from_sum(bsum, IGD_FRAME) : 0u;
+    r.hi = ((uint32_t)(sq >> 32) & 0xFFu) | (bm << 8) | (peak << 16);
+    r.rms_dbfs = igd_rms_dbfs(sq);
+    r.peak_dbfs = igd_peak_dbfs(peak);
+    return r;
+}
+
+__device__ __forceinline__ int bytesum4(uint32_t w, bool signed_char, int acc)
+{
+    return signed_char ? __dp4a((int)w, 0x01010101, acc) : (int)__dp4a(w, 0x01010101u, (uint32_t)acc);
+}
+
+// encode 16 clamped samples -> 16 code bytes
+__device__ __forceinline__ uint4 encode16(const int (&x)[16], const igd_enc_law &L)
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t c0 = igd_g711_enc1(x[4 * j + 0], L), c1 = igd_g711_enc1(x[4 * j + 1], L);
+        const uint32_t c2 = igd_g711_enc1(x[4 * j + 2], L), c3 = igd_g711_enc1(x[4 * j + 3], L);
+        w[j] = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ==================================================================== fused
+struct FusedParams {
+    const uint8_t *codes;
+    const uint8_t *law;
+    const uint16_t *gain;
+    const uint8_t *out_law;
+    int16_t *mix;
+    uint8_t *enc;
+    igd_meter_rec *meter;
+    igd_bridge_rec *bmeter;
+    long long total_bf;   // F*B bridge-frames
+    long long num_tiles;
+    int B, G;
+    unsigned flags;
+};
+
+// decode + meter one 16-sample chunk of one leg; x[] receives the PCM
+__device__ __forceinline__ uint2 leg_chunk(const uint8_t *lut_bytes, uint4 w, uint32_t lane_byte,
+                                           bool signed_char, int (&x)[16])
+{
+    const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+    unsigned long long sq = 0;
+    int mx = 0, mn = 0, bsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int x0 = lut_decode<0>(lut_bytes, wd[j], lane_byte);
+        const int x1 = lut_decode<1>(lut_bytes, wd[j], lane_byte);
+        const int x2 = lut_decode<2>(lut_bytes, wd[j], lane_byte);
+        const int x3 = lut_decode<3>(lut_bytes, wd[j], lane_byte);
+        x[4 * j + 0] = x0; x[4 * j + 1] = x1; x[4 * j + 2] = x2; x[4 * j + 3] = x3;
+        // |G.711 sample| <= 32256, so four squares fit in 32 bits
+        const uint32_t s = (uint32_t)(x0 * x0) + (uint32_t)(x1 * x1) + (uint32_t)(x2 * x2) +
+                           (uint32_t)(x3 * x3);
+        sq += s;
+        mx = max(max(mx, x0), x1); mx = max(max(mx, x2), x3);
+        mn = min(min(mn, x0), x1); mn = min(min(mn, x2), x3);
+        bsum = bytesum4(wd[j], signed_char, bsum);
+    }
+    return partial_pack(sq, (uint32_t)max(mx, -mn), bsum);
+}
+
+template <int G, int BFPC>
+__global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused(const FusedParams q)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes);       // [2][BFPC*G][kPst]
+    uint2 *bpart = part + 2 * BFPC * G * kPst;                       // [2][BFPC][kPst]
+    const uint8_t *lut_bytes = smem;
+
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31;
+    build_decode_lut(lut, t, BFPC * kChunks);
+    __syncthreads();
+
+    const int bfl = t / kChunks, p = t - bfl * kChunks;
+    const bool signed_char = (q.flags & IGD_F_SIGNED_CHAR) != 0;
+    int buf = 0;
+    for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, buf ^= 1) {
+        const long long bf = tile * BFPC + bfl;
+        uint2 *mypart = part + (size_t)buf * BFPC * G * kPst + (size_t)bfl * G * kPst + p;
+        if (bf < q.total_bf) {
+            const int b = (int)(bf % q.B);
+            // ---- issue all loads of this bridge-frame chunk first
+            uint4 w[G];
+            const uint8_t *cb = q.codes + (size_t)bf * G * IGD_FRAME + p * 16;
+#pragma unroll
+            for (int g = 0; g < G; g++) w[g] = ld16_stream(cb + g * IGD_FRAME);
+            uint32_t adj[G], laws[G];
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                adj[g] = q.gain[(size_t)bf * G + g];
+                laws[g] = q.law[(size_t)b * G + g];
+            }
+            const igd_enc_law L = igd_enc_law_make(q.out_law[b]);
+
+            int acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = 0;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                int x[16];
+                mypart[g * kPst] = leg_chunk(lut_bytes, w[g], lut_lane_byte(lane, laws[g]),
+                                             signed_char, x);
+                const int a = (int)adj[g];
+                if (a != 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) acc[i] += clamp16((x[i] * a) >> 7);
+                }
+            }
+            // ---- bridge output: saturate, store PCM, compress, store codes
+            uint32_t pk[8];
+            int mpeak = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                acc[i] = clamp16(acc[i]);
+                mpeak = max(mpeak, abs(acc[i]));
+            }
+            st32_stream(q.mix + (size_t)bf * IGD_FRAME + p * 16, pk);
+            const uint4 e = encode16(acc, L);
+            st16_stream(q.enc + (size_t)bf * IGD_FRAME + p * 16, e);
+            int esum = 0;
+            esum = bytesum4(e.x, signed_char, esum); esum = bytesum4(e.y, signed_char, esum);
+            esum = bytesum4(e.z, signed_char, esum); esum = bytesum4(e.w, signed_char, esum);
+            bpart[(size_t)buf * BFPC * kPst + bfl * kPst + p] = make_uint2((uint32_t)esum, (uint32_t)mpeak);
+        }
+        __syncthreads();
+        // ---- per-frame meter records: one thread per leg-frame / bridge-frame
+        if (t < BFPC * G) {
+            const long long lf = tile * BFPC * G + t;
+            if (lf < q.total_bf * G) {
+                const uint2 *src = part + (size_t)buf * BFPC * G * kPst + (size_t)t * kPst;
+                unsigned long long sq = 0; uint32_t peak = 0; int bsum = 0;
+#pragma unroll
+                for (int i = 0; i < kChunks; i++) partial_add(src[i], sq, peak, bsum);
+                const igd_meter_rec r = meter_finish(sq, peak, bsum, true);
+                st16_stream(q.meter + lf, *reinterpret_cast<const uint4 *>(&r));
+            }
+        } else if (t >= BFPC * kChunks - BFPC) {
+            const int k = t - (BFPC * kChunks - BFPC);
+            const long long bf2 = tile * BFPC + k;
+            if (bf2 < q.total_bf) {
+                const uint2 *src = bpart + (size_t)buf * BFPC * kPst + k * kPst;
+                int esum = 0, mpeak = 0;
+#pragma unroll
+                for (int i = 0; i < kChunks; i++) { esum += (int)src[i].x; mpeak = max(mpeak, (int)src[i].y); }
+                int n_open = 0;
+#pragma unroll
+                for (int g = 0; g < G; g++) n_open += q.gain[(size_t)bf2 * G + g] != 0;
+                igd_bridge_rec r;
+                r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
+                r.n_open = (uint8_t)n_open;
+                r.mix_peak = (uint16_t)mpeak;
+                q.bmeter[bf2] = r;
+            }
+        }
+    }
+}
+
+// Any number of legs per bridge (1..IGD_MAX_LEGS): same algorithm, legs walked
+// in a loop with the partials reduced per leg through shared memory.
+template <int BFPC>
+__global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedParams q)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes);       // [BFPC][kPst]
+    uint2 *bpart = part + BFPC * kPst;                               // [BFPC][kPst]
+    const uint8_t *lut_bytes = smem;
+    const int t = threadIdx.x, G = q.G;
+    const uint32_t lane = t & 31;
+    build_decode_lut(lut, t, BFPC * kChunks);
+    __syncthreads();
+    const int bfl = t / kChunks, p = t - bfl * kChunks;
+    const bool signed_char = (q.flags & IGD_F_SIGNED_CHAR) != 0;
+    for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x) {
+        const long long bf = tile * BFPC + bfl;
+        const bool valid = bf < q.total_bf;
+        const int b = valid ? (int)(bf % q.B) : 0;
+        int acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = 0;
+        for (int g = 0; g < G; g++) {
+            if (valid) {
+                const uint4 w = ld16_stream(q.codes + ((size_t)bf * G + g) * IGD_FRAME + p * 16);
+                int x[16];
+                part[bfl * kPst + p] = leg_chunk(lut_bytes, w, lut_lane_byte(lane, q.law[(size_t)b * G + g]),
+                                                 signed_char, x);
+                const int a = q.gain[(size_t)bf * G + g];
+                if (a != 0) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) acc[i] += clamp16((x[i] * a) >> 7);
+                }
+            }
+            __syncthreads();
+            if (t < BFPC) {
+                const long long bf2 = tile * BFPC + t;
+                if (bf2 < q.total_bf) {
+                    unsigned long long sq = 0; uint32_t peak = 0; int bsum = 0;
+#pragma unroll
+                    for (int i = 0; i < kChunks; i++) partial_add(part[t * kPst + i], sq, peak, bsum);
+                    const igd_meter_rec r = meter_finish(sq, peak, bsum, true);
+                    st16_stream(q.meter + bf2 * G + g, *reinterpret_cast<const uint4 *>(&r));
+                }
+            }
+            __syncthreads();
+        }
+        if (valid) {
+            const igd_enc_law L = igd_enc_law_make(q.out_law[b]);
+            uint32_t pk[8];
+            int mpeak = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
+#pragma unroll
+            for (int i = 0; i < 16; i++) { acc[i] = clamp16(acc[i]); mpeak = max(mpeak, abs(acc[i])); }
+            st32_stream(q.mix + (size_t)bf * IGD_FRAME + p * 16, pk);
+            const uint4 e = encode16(acc, L);
+            st16_stream(q.enc + (size_t)bf * IGD_FRAME + p * 16, e);
+            int esum = 0;
+            esum = bytesum4(e.x, signed_char, esum); esum = bytesum4(e.y, signed_char, esum);
+            esum = bytesum4(e.z, signed_char, esum); esum = bytesum4(e.w, signed_char, esum);
+            bpart[bfl * kPst + p] = make_uint2((uint32_t)esum, (uint32_t)mpeak);
+        }
+        __syncthreads();
+        if (t < BFPC) {
+            const long long bf2 = tile * BFPC + t;
+            if (bf2 < q.total_bf) {
+                int esum = 0, mpeak = 0;
+#pragma unroll
+                for (int i = 0; i < kChunks; i++) { esum += (int)bpart[t * kPst + i].x; mpeak = max(mpeak, (int)bpart[t * kPst + i].y); }
+                int n_open = 0;
+                for (int g = 0; g < G; g++) n_open += q.gain[(size_t)bf2 * G + g] != 0;
+                igd_bridge_rec r;
+                r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
+                r.n_open = (uint8_t)n_open;
+                r.mix_peak = (uint16_t)mpeak;
+                q.bmeter[bf2] = r;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ============================================================ stand-alone G.711
+// codes -> PCM.  One thread per 16 codes.  law_ch != nullptr: law of chunk i is
+// law_ch[(i / 10) % nch] (frames of 160 samples laid out [frame][channel]).
+__global__ void __launch_bounds__(512) k_g711_decode(const uint8_t *__restrict__ codes,
+                                                     const uint8_t *__restrict__ law_ch, int law,
+                                                     int16_t *__restrict__ pcm, size_t n, size_t nch)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    build_decode_lut(reinterpret_cast<uint32_t *>(smem), threadIdx.x, blockDim.x);
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t nchunk = n / 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunk;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t lw = law_ch ? law_ch[(i / kChunks) % nch] : (uint32_t)law;
+        const uint32_t lb = lut_lane_byte(lane, lw);
+        const uint4 w = ld16_stream(codes + i * 16);
+        const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int x0 = lut_decode<0>(smem, wd[j], lb), x1 = lut_decode<1>(smem, wd[j], lb);
+            const int x2 = lut_decode<2>(smem, wd[j], lb), x3 = lut_decode<3>(smem, wd[j], lb);
+            pk[2 * j] = __byte_perm((uint32_t)x0, (uint32_t)x1, 0x5410);
+            pk[2 * j + 1] = __byte_perm((uint32_t)x2, (uint32_t)x3, 0x5410);
+        }
+        st32_stream(pcm + i * 16, pk);
+    }
+    // ragged tail (< 16 codes): straight formula, one thread
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t i = nchunk * 16; i < n; i++) {
+            const uint32_t lw = law_ch ? law_ch[(i / IGD_FRAME) % nch] : (uint32_t)law;
+            pcm[i] = (int16_t)(lw ? igd_ulaw2lin(codes[i]) : igd_alaw2lin(codes[i]));
+        }
+    }
+}
+
+// PCM -> codes.  One thread per 16 samples (256-bit load, 128-bit store).
+__global__ void __launch_bounds__(256) k_g711_encode(const int16_t *__restrict__ pcm,
+                                                     const uint8_t *__restrict__ law_ch, int law,
+                                                     uint8_t *__restrict__ codes, size_t n, size_t nch)
+{
+    const size_t nchunk = n / 16;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunk;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const int lw = law_ch ? law_ch[(i / kChunks) % nch] : law;
+        const igd_enc_law L = igd_enc_law_make(lw);
+        uint32_t pk[8];
+        ld32_stream(pcm + i * 16, pk);
+        int x[16];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            x[2 * j] = (int)(short)(pk[j] & 0xFFFFu);
+            x[2 * j + 1] = (int)pk[j] >> 16;
+        }
+        st16_stream(codes + i * 16, encode16(x, L));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (size_t i = nchunk * 16; i < n; i++) {
+            const int lw = law_ch ? law_ch[(i / IGD_FRAME) % nch] : law;
+            codes[i] = (uint8_t)igd_g711_enc1(pcm[i], igd_enc_law_make(lw));
+        }
+    }
+}
+
+// ============================================================ stand-alone meter
+// PCM frames -> records.  10 threads per frame, 16 samples (32 B) each.
+template <int FPC>
+__global__ void __launch_bounds__(FPC * kChunks) k_frame_meter(const int16_t *__restrict__ pcm,
+                                                               long long nframes, long long num_tiles,
+                                                               igd_meter_rec *__restrict__ out)
+{
+    __shared__ uint4 part[FPC * kPst];   // {sq_lo, sq_hi, peak, -}: general int16 needs 40 bits
+    const int t = threadIdx.x, fl = t / kChunks, p = t - fl * kChunks;
+    for (long long tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const long long f = tile * FPC + fl;
+        if (f < nframes) {
+            uint32_t pk[8];
+            ld32_stream(pcm + (size_t)f * IGD_FRAME + p * 16, pk);
+            unsigned long long sq = 0;
+            int peak = 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const int a = (int)(short)(pk[j] & 0xFFFFu), b = (int)pk[j] >> 16;
+                sq += (unsigned long long)(uint32_t)(a * a) + (unsigned long long)(uint32_t)(b * b);
+                peak = max(peak, max(abs(a), abs(b)));
+            }
+            part[fl * kPst + p] = make_uint4((uint32_t)sq, (uint32_t)(sq >> 32), (uint32_t)peak, 0u);
+        }
+        __syncthreads();
+        if (t < FPC) {
+            const long long f2 = tile * FPC + t;
+            if (f2 < nframes) {
+                unsigned long long sq = 0; uint32_t peak = 0;
+#pragma unroll
+                for (int i = 0; i < kChunks; i++) {
+                    const uint4 v = part[t * kPst + i];
+                    sq += (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+                    peak = max(peak, v.z);
+                }
+                const igd_meter_rec r = meter_finish(sq, peak, 0, false);
+                st16_stream(out + f2, *reinterpret_cast<const uint4 *>(&r));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// reference per-packet level over arbitrary (stride, len): one warp per payload
+__global__ void __launch_bounds__(256) k_bytemean(const uint8_t *__restrict__ base, size_t n, size_t len,
+                                                  size_t stride, unsigned flags, uint8_t *__restrict__ out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const bool sc = (flags & IGD_F_SIGNED_CHAR) != 0;
+    for (size_t i = warp; i < n; i += nwarps) {
+        const uint8_t *p = base + i * stride;
+        int s = 0;
+        for (size_t k = lane; k < len; k += 32) s += sc ? (int)(signed char)p[k] : (int)p[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) out[i] = (uint8_t)igd_bytemean_from_sum(s, (int)len);
+    }
+}
+
+// audiometer.cpp:30-31: int(float(v*100.0/30000.0))
+__global__ void k_level_percent(const int32_t *__restrict__ v, size_t n, int32_t *__restrict__ out)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (int)((float)(((double)v[i] * 100.0) / 30000.0));
+}
+
+// ============================================================ stand-alone mix
+// PCM legs -> saturating mix.  One thread per 8 samples of one bridge-frame.
+__global__ void __launch_bounds__(256) k_mix(const int16_t *__restrict__ pcm, const uint16_t *__restrict__ gain,
+                                             long long total_bf, int G, int16_t *__restrict__ mix)
+{
+    constexpr int kPer = IGD_FRAME / 8;   // 20 threads per bridge-frame
+    const long long nthreads_total = total_bf * kPer;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads_total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long bf = i / kPer;
+        const int p = (int)(i - bf * kPer);
+        int acc[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = 0;
+        for (int g = 0; g < G; g++) {
+            const int a = gain[bf * G + g];
+            if (a == 0) continue;
+            const uint4 w = ld16_stream(pcm + ((size_t)bf * G + g) * IGD_FRAME + p * 8);
+            const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int lo = (int)(short)(wd[j] & 0xFFFFu), hi = (int)wd[j] >> 16;
+                acc[2 * j] += clamp16((lo * a) >> 7);
+                acc[2 * j + 1] += clamp16((hi * a) >> 7);
+            }
+        }
+        uint4 o;
+        o.x = pack_sat16(acc[1], acc[0]); o.y = pack_sat16(acc[3], acc[2]);
+        o.z = pack_sat16(acc[5], acc[4]); o.w = pack_sat16(acc[7], acc[6]);
+        st16_stream(mix + (size_t)bf * IGD_FRAME + p * 8, o);
+    }
+}
+
+// ============================================================ event summary
+// Functions.cpp:2126-2145 over the frames whose gate is open; one warp per 32
+// channels x frame slice, slices combined through shared memory.
+constexpr int kSumSlices = 8;
+__global__ void __launch_bounds__(32 * kSumSlices) k_event_summary(const igd_meter_rec *__restrict__ meter,
+                                                                   const uint16_t *__restrict__ gain,
+                                                                   long long F, long long C,
+                                                                   igd_summary_rec *__restrict__ out,
+                                                                   igd_summary_db *__restrict__ db)
+{
+    __shared__ igd_summary_rec sh[kSumSlices][32];
+    const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+    const long long c = (long long)blockIdx.x * 32 + lane;
+    igd_summary_rec r;
+    r.count = 0; r.bm_sum = 0; r.bm_max = 0; r.bm_min = 255;          // Functions.cpp:2159-2167
+    r.sum_s = 0; r.max_s = 0; r.min_s = 255ull * IGD_FRAME;
+    if (c < C) {
+        for (long long f = slice; f < F; f += kSumSlices) {
+            const size_t i = (size_t)f * C + c;
+            if (gain[i] == 0) continue;
+            const uint4 m = *reinterpret_cast<const uint4 *>(meter + i);
+            const uint64_t s = (uint64_t)m.x | ((uint64_t)(m.y & 0xFFu) << 32);
+            const uint32_t bm = (m.y >> 8) & 0xFFu;
+            r.count += 1;
+            r.sum_s += s;
+            r.bm_sum = (uint16_t)(r.bm_sum + bm);
+            r.max_s = s > r.max_s ? s : r.max_s;
+            r.min_s = s < r.min_s ? s : r.min_s;
+            r.bm_max = (uint8_t)max((uint32_t)r.bm_max, bm);
+            r.bm_min = (uint8_t)min((uint32_t)r.bm_min, bm);
+        }
+    }
+    sh[slice][lane] = r;
+    __syncthreads();
+    if (slice == 0 && c < C) {
+        for (int k = 1; k < kSumSlices; k++) {
+            const igd_summary_rec o = sh[k][lane];
+            r.count += o.count;
+            r.sum_s += o.sum_s;
+            r.bm_sum = (uint16_t)(r.bm_sum + o.bm_sum);
+            r.max_s = o.max_s > r.max_s ? o.max_s : r.max_s;
+            r.min_s = o.min_s < r.min_s ? o.min_s : r.min_s;
+            r.bm_max = o.bm_max > r.bm_max ? o.bm_max : r.bm_max;
+            r.bm_min = o.bm_min < r.bm_min ? o.bm_min : r.bm_min;
+        }
+        out[c] = r;
+        if (db) {
+            igd_summary_db d;                                             // Functions.cpp:2196-2200
+            d.level_av_db = (float)(10.0 * log10(((double)r.sum_s / IGD_FRAME) / (double)r.count));
+            d.level_max_db = (float)(10.0 * log10((double)r.max_s / IGD_FRAME));
+            d.level_min_db = (float)(10.0 * log10((double)r.min_s / IGD_FRAME));
+            d.bm_av = r.count ? (uint32_t)(uint8_t)(r.bm_sum / r.count) : 0u;
+            db[c] = d;
+        }
+    }
+}
+
+// ============================================================ ED-137 parse
+// transport_rtp_cb (TransportAdapter.cpp:240-316) + field getters
+// (Functions.cpp:1001-1179).  One warp per packet: lanes 0..4 fetch the five
+// header words, every lane copies payload words.
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+__global__ void __launch_bounds__(256) k_ed137_parse(const uint8_t *__restrict__ pkts,
+                                                     const uint32_t *__restrict__ sizes, size_t npkts,
+                                                     size_t stride, igd_ed137_fields *__restrict__ fields,
+                                                     uint8_t *__restrict__ payload_out)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t i = warp; i < npkts; i += nwarps) {
+        const uint32_t *pw = reinterpret_cast<const uint32_t *>(pkts + i * stride);
+        const uint32_t size = sizes ? sizes[i] : (uint32_t)stride;
+        const uint32_t navail = min(size, (uint32_t)stride) / 4;
+        const uint32_t hw = (lane < 5 && lane < navail) ? __ldcs(pw + lane) : 0u;
+        const uint32_t w0 = __shfl_sync(0xffffffffu, hw, 0);
+        const uint32_t w3 = __shfl_sync(0xffffffffu, hw, 3);
+        const uint32_t w4 = __shfl_sync(0xffffffffu, hw, 4);
+        const uint32_t pt = (w0 >> 8) & 0x7Fu;                           // byte 1, low 7 bits
+        const bool too_short = size < IGD_PKT_HDR;
+        const uint32_t plen_raw = size - IGD_PKT_HDR;                     // unsigned wrap (:279)
+        const bool dropped = too_short || plen_raw >= 1024u;              // :286-291
+        const bool accepted = !too_short && (pt == 8 || pt == 0 || pt == 18 || pt == 123);   // :252
+        const uint32_t plen = dropped ? 0u : min(plen_raw, (uint32_t)IGD_FRAME);
+        if (lane == 0) {
+            igd_ed137_fields f;
+            const uint32_t word = accepted ? bswap32(w4) : 0u;            // ntohl (:342)
+            const igd_edf e = igd_ed137_fields_of(word);
+            f.word = word;
+            f.length_raw = accepted ? (uint16_t)(w3 >> 16) : (uint16_t)0; // bytes 14..15 as stored
+            f.payload_len = (uint16_t)plen;
+            f.pt = (uint8_t)pt;
+            f.accepted = accepted;
+            f.keepalive = (!too_short && pt == 123);
+            f.ptt_type = (uint8_t)e.ptt_type;
+            f.ptt_id = (uint8_t)e.ptt_id;
+            f.squelch = (uint8_t)e.squelch;
+            f.bss = (uint8_t)e.bss;
+            f.flags = (uint8_t)(e.flags | (dropped ? IGD_EDF_DROPPED : 0u));
+            *reinterpret_cast<uint4 *>(fields + i) = *reinterpret_cast<const uint4 *>(&f);
+        }
+        if (payload_out) {
+            uint32_t *dst = reinterpret_cast<uint32_t *>(payload_out + i * IGD_FRAME);
+            for (uint32_t k = lane; k < IGD_FRAME / 4; k += 32) {
+                uint32_t v = 0;
+                if (k * 4 < plen) {
+                    v = __ldcs(pw + 5 + k);
+                    const uint32_t rem = plen - k * 4;
+                    if (rem < 4) v &= (1u << (8 * rem)) - 1u;
+                }
+                dst[k] = v;
+            }
+        }
+    }
+}
+
+// ============================================================ ED-137 pack
+// Phase 1: one thread per channel walks its frames through the sender state
+// machine (transport_send_rtp, TransportAdapter.cpp:635-874) and writes a plan
+// record per packet.  The state is tiny and strictly sequential per channel.
+__global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d, igd_tx_plan_rec *__restrict__ plan)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    igd_ed137_state s = d.state[c];
+    int32_t src = -1;
+    for (int f = 0; f < d.F; f++) {
+        const size_t i = (size_t)f * d.C + c;
+        if (d.ctl) {                                                     // the setters, :135-213
+            const igd_ed137_ctl k = d.ctl[i];
+            s.pttstatus = k.pttstatus; s.pttpriority = k.pttpriority; s.callRecorder = k.callRecorder;
+            s.sqlstatus = k.sqlstatus; s.ed137_bssi = k.ed137_bssi; s.pttid = k.pttid;
+        }
+        if (s.radiostatus && 12u + d.payload_len > 60u) {                // stuck-audio detector :657-673
+            const uint8_t *pl = d.payload + i * IGD_FRAME;
+            const uint8_t a40 = pl[40 - 12], a50 = pl[50 - 12], a60 = pl[60 - 12];
+            if (a40 == a50 && a40 == a60 && a40 == 0xd5) s.rtpFalse += 1; else s.rtpFalse = 0;
+        }
+        const igd_tx_plan t = igd_ed137_tx_step(s, d.payload_len, d.now_ms0 + (long long)f * d.tick_ms);
+        if (t.copy_payload) src = f;
+        igd_tx_plan_rec r;
+        r.word = t.word;
+        r.size = (uint16_t)t.size;
+        r.flags = (uint8_t)(t.pt123 | (t.marker << 1) | (t.copy_payload << 2));
+        r.reserved = 0;
+        r.src_frame = (d.flags & IGD_F_REF_QUIRKS) ? src : f;            // quirk Q2
+        plan[i] = r;
+    }
+    d.state[c] = s;
+}
+
+// Phase 2: one warp per packet assembles header + payload (4-byte words; the
+// payload sits at byte 20 of a 180-byte packet, so 16-byte accesses do not apply)
+__global__ void __launch_bounds__(256) k_ed137_assemble(const igd_ed137_pack_desc d,
+                                                        const igd_tx_plan_rec *__restrict__ plan)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    const size_t npkts = (size_t)d.F * d.C;
+    const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0, quirks = (d.flags & IGD_F_REF_QUIRKS) != 0;
+    const uint32_t nwords = d.payload_len / 4;
+    for (size_t i = warp; i < npkts; i += nwarps) {
+        const igd_tx_plan_rec r = plan[i];
+        uint32_t *out = reinterpret_cast<uint32_t *>(d.pkts + i * d.out_stride);
+        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(d.rtp12 + i * 12);
+        const size_t c = i % (size_t)d.C;
+        if (lane == 0) d.sizes[i] = r.size;
+        int bsum = 0;
+        if (r.size == 0) {
+            if (lane == 0) d.bytemean_out[i] = 0;
+            continue;
+        }
+        if (lane < 5) {
+            uint32_t v;
+            if (lane < 3) {
+                v = hdr[lane];
+                if (lane == 0) {
+                    v |= 0x10u;                                            // x = 1 (:725)
+                    v = (v & ~0x8000u) | ((r.flags & 2u) ? 0x8000u : 0u);  // m (:715-723)
+                    if (r.flags & 1u) v = (v & ~0x7F00u) | (123u << 8);    // pt = 123
+                }
+            } else if (lane == 3) {
+                v = 0x01006701u;                                           // 0x0167, 0x0001 big-endian
+            } else {
+                v = bswap32(r.word);                                       // htonl (:800)
+            }
+            out[lane] = v;
+        }
+        const bool audio = !(r.flags & 1u);
+        if (r.size > IGD_PKT_HDR) {
+            const uint32_t *src = r.src_frame >= 0
+                ? reinterpret_cast<const uint32_t *>(d.payload + ((size_t)r.src_frame * d.C + c) * IGD_FRAME)
+                : nullptr;
+            for (uint32_t k = lane; k < nwords; k += 32) out[5 + k] = src ? src[k] : 0u;
+        }
+        if (audio) {
+            // setOutgoingRTP (roip_ed137.cpp:6500-6536).  Clean: mean of the payload
+            // bytes.  Quirk Q3: mean of the first payload_len bytes of the ORIGINAL
+            // packet (12 header bytes + payload[0 .. len-12)), TransportAdapter.cpp:654.
+            const uint32_t *cur = reinterpret_cast<const uint32_t *>(d.payload + i * IGD_FRAME);
+            if (!quirks) {
+                for (uint32_t k = lane; k < nwords; k += 32) bsum = bytesum4(cur[k], sc, bsum);
+            } else {
+                for (uint32_t k = lane; k < nwords; k += 32) {
+                    const uint32_t v = k < 3 ? hdr[k] : cur[k - 3];
+                    bsum = bytesum4(v, sc, bsum);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+        }
+        if (lane == 0) d.bytemean_out[i] = audio ? (uint8_t)igd_bytemean_from_sum(bsum, (int)d.payload_len) : 0;
+    }
+}
+
+// ============================================================ recorder sink
+__global__ void k_wav_image(const uint8_t *__restrict__ payload, size_t n, int rate, int law, int ref_quirks,
+                            uint8_t *__restrict__ out)
+{
+    const size_t body = ref_quirks ? 2 * n : n, total = 44 + body;
+    if (blockIdx.x == 0 && threadIdx.x < 11) {
+        const uint32_t channels = ref_quirks ? 2 : 1, bits = ref_quirks ? 16 : 8;
+        const uint32_t fmt = ref_quirks ? 7u : (law == IGD_LAW_ALAW ? 6u : 7u);
+        const uint32_t align = bits / 8 * channels;
+        uint32_t h[11];
+        h[0] = 0x46464952u;                      // "RIFF"
+        h[1] = (uint32_t)(total - 8);
+        h[2] = 0x45564157u;                      // "WAVE"
+        h[3] = 0x20746d66u;                      // "fmt "
+        h[4] = 16u;
+        h[5] = fmt | (channels << 16);
+        h[6] = (uint32_t)rate;
+        h[7] = (uint32_t)rate * align;
+        h[8] = align | (bits << 16);
+        h[9] = 0x61746164u;                      // "data"
+        h[10] = (uint32_t)body;
+        reinterpret_cast<uint32_t *>(out)[threadIdx.x] = h[threadIdx.x];
+    }
+    uint8_t *dst = out + 44;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        if (ref_quirks) reinterpret_cast<uint16_t *>(dst)[i] = payload[i];   // {b, 0x00}
+        else dst[i] = payload[i];
+    }
+}
+
+inline int grid_for(const igd_launch_cfg &c, size_t work_items, int threads, int per_sm)
+{
+    size_t blocks = (work_items + threads - 1) / threads;
+    size_t cap = (size_t)c.sm_count * per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+// ============================================================ launchers
+cudaError_t igd_k_g711_decode(const igd_launch_cfg &c, const uint8_t *codes, const uint8_t *law_ch,
+                              int law, int16_t *pcm, size_t n, size_t nch)
+{
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_g711_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutBytes);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int threads = 512;
+    k_g711_decode<<<grid_for(c, n / 16 + 1, threads, 3), threads, kLutBytes, c.stream>>>(codes, law_ch, law, pcm, n,
+                                                                                  nch ? nch : 1);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_g711_encode(const igd_launch_cfg &c, const int16_t *pcm, const uint8_t *law_ch,
+                              int law, uint8_t *codes, size_t n, size_t nch)
+{
+    const int threads = 256;
+    k_g711_encode<<<grid_for(c, n / 16 + 1, threads, 8), threads, 0, c.stream>>>(pcm, law_ch, law, codes, n,
+                                                                          nch ? nch : 1);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_frame_meter(const igd_launch_cfg &c, const int16_t *pcm, size_t nframes,
+                              igd_meter_rec *out)
+{
+    constexpr int FPC = 32;
+    const long long tiles = ((long long)nframes + FPC - 1) / FPC;
+    k_frame_meter<FPC><<<grid_for(c, (size_t)tiles, 1, 6), FPC * kChunks, 0, c.stream>>>(pcm, (long long)nframes,
+                                                                                  tiles, out);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_bytemean(const igd_launch_cfg &c, const uint8_t *payloads, size_t n, size_t len,
+                           size_t stride, unsigned flags, uint8_t *out)
+{
+    k_bytemean<<<grid_for(c, n * 32, 256, 8), 256, 0, c.stream>>>(payloads, n, len, stride, flags, out);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_level_percent(const igd_launch_cfg &c, const int32_t *v, size_t n, int32_t *out)
+{
+    k_level_percent<<<grid_for(c, n, 256, 8), 256, 0, c.stream>>>(v, n, out);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_mix(const igd_launch_cfg &c, const int16_t *pcm, const uint16_t *gain,
+                      size_t nframes, size_t nbridges, int legs, int16_t *mix)
+{
+    const long long total_bf = (long long)nframes * (long long)nbridges;
+    k_mix<<<grid_for(c, (size_t)total_bf * 20, 256, 8), 256, 0, c.stream>>>(pcm, gain, total_bf, legs, mix);
+    return cudaGetLastError();
+}
+
+namespace {
+template <int G, int BFPC>
+cudaError_t launch_fused(const igd_launch_cfg &c, const FusedParams &q)
+{
+    const size_t smem = kLutBytes + (size_t)2 * BFPC * G * kPst * 8 + (size_t)2 * BFPC * kPst * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_fused<G, BFPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<G, BFPC>, BFPC * kChunks, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    FusedParams p = q;
+    p.num_tiles = (q.total_bf + BFPC - 1) / BFPC;
+    long long grid = (long long)c.sm_count * per_sm;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    k_fused<G, BFPC><<<(int)grid, BFPC * kChunks, smem, c.stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int BFPC>
+cudaError_t launch_fused_anyg(const igd_launch_cfg &c, const FusedParams &q)
+{
+    const size_t smem = kLutBytes + (size_t)2 * BFPC * kPst * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_fused_anyg<BFPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_anyg<BFPC>, BFPC * kChunks, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    FusedParams p = q;
+    p.num_tiles = (q.total_bf + BFPC - 1) / BFPC;
+    long long grid = (long long)c.sm_count * per_sm;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    k_fused_anyg<BFPC><<<(int)grid, BFPC * kChunks, smem, c.stream>>>(p);
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
+{
+    FusedParams q;
+    q.codes = d.codes; q.law = d.law; q.gain = d.gain_q7; q.out_law = d.out_law;
+    q.mix = d.mix; q.enc = d.enc; q.meter = d.meter; q.bmeter = d.bmeter;
+    q.total_bf = (long long)d.F * d.B;
+    q.num_tiles = 0;
+    q.B = d.B; q.G = d.G; q.flags = d.flags;
+    switch (d.G) {
+    case 1: return launch_fused<1, 32>(c, q);
+    case 2: return launch_fused<2, 32>(c, q);
+    case 4: return launch_fused<4, 32>(c, q);
+    default: return launch_fused_anyg<32>(c, q);
+    }
+}
+
+cudaError_t igd_k_event_summary(const igd_launch_cfg &c, const igd_meter_rec *meter,
+                                const uint16_t *gain, size_t F, size_t C, igd_summary_rec *out,
+                                igd_summary_db *db)
+{
+    const int blocks = (int)((C + 31) / 32);
+    k_event_summary<<<blocks, 32 * kSumSlices, 0, c.stream>>>(meter, gain, (long long)F, (long long)C, out, db);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, const uint32_t *sizes,
+                              size_t npkts, size_t stride, igd_ed137_fields *fields,
+                              uint8_t *payload_out)
+{
+    k_ed137_parse<<<grid_for(c, npkts * 32, 256, 8), 256, 0, c.stream>>>(pkts, sizes, npkts, stride, fields,
+                                                                  payload_out);
+    return cudaGetLastError();
+}
+
+int igd_k_launches_ed137_pack() { return 2; }
+
+cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc &d,
+                             igd_tx_plan_rec *plan)
+{
+    k_ed137_plan<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d, plan);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    k_ed137_assemble<<<grid_for(c, (size_t)d.F * d.C * 32, 256, 8), 256, 0, c.stream>>>(d, plan);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_wav_image(const igd_launch_cfg &c, const uint8_t *payload, size_t n, int rate,
+                            int law, int ref_quirks, uint8_t *out)
+{
+    k_wav_image<<<grid_for(c, n + 1, 256, 8), 256, 0, c.stream>>>(payload, n, rate, law, ref_quirks, out);
+    return cudaGetLastError();
+}

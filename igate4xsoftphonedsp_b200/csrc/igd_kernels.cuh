@@ -1,0 +1,48 @@
+// igd_kernels.cuh -- launch interface between the C ABI (igd_capi.cu) and the
+// sm_100a kernels (igd_kernels.cu).  All pointers are device pointers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/igate_dsp.h"
+
+struct igd_launch_cfg {
+    int sm_count;
+    cudaStream_t stream;
+};
+
+// Plan of one outgoing packet, produced by the per-channel sender walk and
+// consumed by the packet assembly kernel.
+struct igd_tx_plan_rec {
+    uint32_t word;        // host-order ED-137 word
+    uint16_t size;        // 0 = suppressed
+    uint8_t flags;        // bit0 pt123, bit1 marker, bit2 copy_payload
+    uint8_t reserved;
+    int32_t src_frame;    // frame whose payload the packet carries (-1: none yet)
+};
+
+cudaError_t igd_k_g711_decode(const igd_launch_cfg &c, const uint8_t *codes, const uint8_t *law_ch,
+                              int law, int16_t *pcm, size_t n, size_t nch);
+cudaError_t igd_k_g711_encode(const igd_launch_cfg &c, const int16_t *pcm, const uint8_t *law_ch,
+                              int law, uint8_t *codes, size_t n, size_t nch);
+cudaError_t igd_k_frame_meter(const igd_launch_cfg &c, const int16_t *pcm, size_t nframes,
+                              igd_meter_rec *out);
+cudaError_t igd_k_bytemean(const igd_launch_cfg &c, const uint8_t *payloads, size_t n, size_t len,
+                           size_t stride, unsigned flags, uint8_t *out);
+cudaError_t igd_k_level_percent(const igd_launch_cfg &c, const int32_t *v, size_t n, int32_t *out);
+cudaError_t igd_k_mix(const igd_launch_cfg &c, const int16_t *pcm, const uint16_t *gain,
+                      size_t nframes, size_t nbridges, int legs, int16_t *mix);
+cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d);
+cudaError_t igd_k_event_summary(const igd_launch_cfg &c, const igd_meter_rec *meter,
+                                const uint16_t *gain, size_t F, size_t C, igd_summary_rec *out,
+                                igd_summary_db *db);
+cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, const uint32_t *sizes,
+                              size_t npkts, size_t stride, igd_ed137_fields *fields,
+                              uint8_t *payload_out);
+cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc &d,
+                             igd_tx_plan_rec *plan);
+cudaError_t igd_k_wav_image(const igd_launch_cfg &c, const uint8_t *payload, size_t n, int rate,
+                            int law, int ref_quirks, uint8_t *out);
+
+// number of kernel launches each wrapper above performs (for gpu_launches)
+int igd_k_launches_ed137_pack();

@@ -1,0 +1,369 @@
+"""Host-side mirror of the reference's voice-path interface over the C ABI.
+
+`VoicePath` is what a user of the reference switches to for the hot path:
+G.711 (PJSIP PCMA/PCMU, roip_ed137.cpp:3546-3574), the per-packet level meter
+(RoIP_ED137::setIncomingRTP/setOutgoingRTP, roip_ed137.cpp:6500-6587), the
+conference-bridge gain + mix (roip_ed137.cpp:4907-4920, 5221), the ED-137 RTP
+header extension (TransportAdapter.cpp:240-316, 635-874; Functions.cpp:
+1001-1179), the PTT event summary (Functions.cpp:2126-2230) and the WavWriter
+sink (WavWriter.cpp:63-156) -- batched over channels x 20 ms frames.
+
+Arguments are numpy arrays (host memory: the library stages them through the
+GPU) or torch CUDA tensors (used in place; results are torch CUDA tensors).
+Either way all arithmetic happens in the CUDA kernels of libigate_dsp.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+try:  # torch is plumbing only (device memory + streams)
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+class IgdError(RuntimeError):
+    pass
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def gain_q7(level):
+    """pjsua_conf_adjust_rx_level(level) -> Q7 multiplier (2.0->256, 0.1->13)."""
+    return N.load().igd_gain_q7(float(level))
+
+
+def calltype_flags(calltype):
+    return N.load().igd_calltype_flags(calltype.encode())
+
+
+def make_state(n, radiocall=True, callIn=False, calltype="TRx", keepAlivePeroid=200, now_ms=0):
+    """n sender states initialised like pjmedia_custom_tp_adapter_create."""
+    lib = N.load()
+    st = np.zeros(n, dtype=N.STATE_DT)
+    one = np.zeros(1, dtype=N.STATE_DT)
+    lib.igd_ed137_state_init(one.ctypes.data, int(radiocall), int(callIn), calltype.encode(),
+                             int(keepAlivePeroid), int(now_ms))
+    st[:] = one[0]
+    return st
+
+
+class VoicePath:
+    def __init__(self, device=0):
+        self._lib = N.load()
+        h = C.c_void_p()
+        rc = self._lib.igd_init(int(device), C.byref(h))
+        if rc != 0:
+            raise IgdError(f"igd_init(device={device}) failed: {N.ERRORS.get(rc, rc)} "
+                           "(an sm_100 CUDA device is required; there is no CPU fallback)")
+        self._h = h
+        self.device = int(device)
+
+    # ------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.igd_shutdown(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _chk(self, rc):
+        if rc != 0:
+            msg = self._lib.igd_last_error(self._h)
+            raise IgdError(f"{N.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def use_torch_stream(self, stream=None):
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        self._chk(self._lib.igd_set_stream(self._h, C.c_void_p(s.cuda_stream)))
+
+    def sync(self):
+        self._chk(self._lib.igd_sync(self._h))
+
+    def launch_count(self):
+        return int(self._lib.igd_launch_count(self._h))
+
+    def device_info(self):
+        d = N.DevInfo()
+        self._chk(self._lib.igd_device_info(self._h, C.byref(d)))
+        return {"device": d.device, "sm_count": d.sm_count, "cc": (d.cc_major, d.cc_minor),
+                "total_mem": d.total_mem, "name": d.name.decode()}
+
+    @staticmethod
+    def _ptr(x):
+        if x is None:
+            return None
+        if _is_torch(x):
+            return C.c_void_p(x.data_ptr())
+        return C.c_void_p(x.ctypes.data)
+
+    def _mode(self, *arrays):
+        kinds = {_is_torch(a) for a in arrays if a is not None}
+        if len(kinds) != 1:
+            raise IgdError("all buffers of one call must be numpy arrays or all torch CUDA tensors")
+        dev = kinds.pop()
+        if dev:
+            for a in arrays:
+                if a is not None and (not a.is_cuda or not a.is_contiguous()):
+                    raise IgdError("torch arguments must be contiguous CUDA tensors")
+        return N.MEM_DEVICE if dev else N.MEM_HOST
+
+    def _empty(self, like_torch, shape, np_dtype):
+        """uninitialised output: torch byte tensor viewed as records, or numpy."""
+        if like_torch:
+            nbytes = int(np.prod(shape)) * np.dtype(np_dtype).itemsize
+            return torch.empty(max(nbytes, 1), dtype=torch.uint8, device=f"cuda:{self.device}")
+        return np.empty(shape, dtype=np_dtype)
+
+    @staticmethod
+    def _tview(t, tdtype, shape):
+        return t.view(tdtype).reshape(shape)
+
+    # ------------------------------------------------------------ G.711
+    def g711_decode(self, codes, law):
+        """codes u8 [...] -> PCM int16 [...]. `law`: LAW_* or a [nch] array for
+        codes laid out [frames][nch][160]."""
+        per_ch = not np.isscalar(law)
+        mem = self._mode(codes, law if per_ch else None)
+        if mem == N.MEM_DEVICE:
+            out = torch.empty(codes.shape, dtype=torch.int16, device=codes.device)
+            n = codes.numel()
+        else:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            out = np.empty(codes.shape, dtype=np.int16)
+            n = codes.size
+            if per_ch:
+                law = np.ascontiguousarray(law, dtype=np.uint8)
+        if per_ch:
+            nch = law.numel() if _is_torch(law) else law.size
+            if codes.shape[-1] != N.FRAME or n % (nch * N.FRAME):
+                raise IgdError("per-channel law needs codes shaped [frames][nch][160]")
+            self._chk(self._lib.igd_g711_decode_ch(self._h, self._ptr(codes), self._ptr(law), self._ptr(out),
+                                                   n // (nch * N.FRAME), nch, mem))
+        else:
+            self._chk(self._lib.igd_g711_decode(self._h, self._ptr(codes), self._ptr(out), n, int(law), mem))
+        return out
+
+    def g711_encode(self, pcm, law):
+        per_ch = not np.isscalar(law)
+        mem = self._mode(pcm, law if per_ch else None)
+        if mem == N.MEM_DEVICE:
+            out = torch.empty(pcm.shape, dtype=torch.uint8, device=pcm.device)
+            n = pcm.numel()
+        else:
+            pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+            out = np.empty(pcm.shape, dtype=np.uint8)
+            n = pcm.size
+            if per_ch:
+                law = np.ascontiguousarray(law, dtype=np.uint8)
+        if per_ch:
+            nch = law.numel() if _is_torch(law) else law.size
+            if pcm.shape[-1] != N.FRAME or n % (nch * N.FRAME):
+                raise IgdError("per-channel law needs pcm shaped [frames][nch][160]")
+            self._chk(self._lib.igd_g711_encode_ch(self._h, self._ptr(pcm), self._ptr(law), self._ptr(out),
+                                                   n // (nch * N.FRAME), nch, mem))
+        else:
+            self._chk(self._lib.igd_g711_encode(self._h, self._ptr(pcm), self._ptr(out), n, int(law), mem))
+        return out
+
+    # ------------------------------------------------------------ meters
+    def frame_meter(self, pcm):
+        """pcm int16 [..., 160] -> igd_meter_rec per frame (numpy structured /
+        torch int32 [..., 4] raw words)."""
+        mem = self._mode(pcm)
+        if pcm.shape[-1] != N.FRAME:
+            raise IgdError("pcm must be shaped [..., 160]")
+        lead = tuple(pcm.shape[:-1])
+        nfr = int(np.prod(lead)) if lead else 1
+        if mem == N.MEM_DEVICE:
+            raw = self._empty(True, (nfr,), N.METER_DT)
+            self._chk(self._lib.igd_frame_meter(self._h, self._ptr(pcm), nfr, self._ptr(raw), mem))
+            return self._tview(raw[: nfr * 16], torch.int32, lead + (4,))
+        pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+        out = np.empty(lead, dtype=N.METER_DT)
+        self._chk(self._lib.igd_frame_meter(self._h, self._ptr(pcm), nfr, self._ptr(out), mem))
+        return out
+
+    def bytemean(self, payloads, length=None, flags=0):
+        """payloads u8 [n][stride] -> reference per-packet level u8 [n]."""
+        mem = self._mode(payloads)
+        n, stride = payloads.shape
+        length = stride if length is None else int(length)
+        if mem == N.MEM_DEVICE:
+            out = torch.empty(n, dtype=torch.uint8, device=payloads.device)
+        else:
+            payloads = np.ascontiguousarray(payloads, dtype=np.uint8)
+            out = np.empty(n, dtype=np.uint8)
+        self._chk(self._lib.igd_bytemean(self._h, self._ptr(payloads), n, length, stride, flags,
+                                         self._ptr(out), mem))
+        return out
+
+    def level_percent(self, v):
+        """AudioMeter scale: int(float(v*100.0/30000.0)) (audiometer.cpp:30-31)."""
+        mem = self._mode(v)
+        if mem == N.MEM_DEVICE:
+            out = torch.empty_like(v)
+            n = v.numel()
+        else:
+            v = np.ascontiguousarray(v, dtype=np.int32)
+            out = np.empty(v.shape, dtype=np.int32)
+            n = v.size
+        self._chk(self._lib.igd_level_percent(self._h, self._ptr(v), n, self._ptr(out), mem))
+        return out
+
+    # ------------------------------------------------------------ mix
+    def mix(self, pcm, gain, legs):
+        """pcm int16 [F][B*legs][160], gain u16 [F][B*legs] -> mix int16 [F][B][160]."""
+        mem = self._mode(pcm, gain)
+        F, Cn, n = pcm.shape
+        if n != N.FRAME or Cn % legs:
+            raise IgdError("pcm must be [F][B*legs][160]")
+        B = Cn // legs
+        if mem == N.MEM_DEVICE:
+            out = torch.empty((F, B, N.FRAME), dtype=torch.int16, device=pcm.device)
+        else:
+            pcm = np.ascontiguousarray(pcm, dtype=np.int16)
+            gain = np.ascontiguousarray(gain, dtype=np.uint16)
+            out = np.empty((F, B, N.FRAME), dtype=np.int16)
+        self._chk(self._lib.igd_mix(self._h, self._ptr(pcm), self._ptr(gain), F, B, legs, self._ptr(out), mem))
+        return out
+
+    # ------------------------------------------------------------ fused path
+    def alloc_outputs(self, F, B, G):
+        """Device output buffers for process_batch (torch)."""
+        dev = f"cuda:{self.device}"
+        return {
+            "mix": torch.empty((F, B, N.FRAME), dtype=torch.int16, device=dev),
+            "enc": torch.empty((F, B, N.FRAME), dtype=torch.uint8, device=dev),
+            "meter": torch.empty((F, B * G, 4), dtype=torch.int32, device=dev),
+            "bmeter": torch.empty((F, B), dtype=torch.int32, device=dev),
+        }
+
+    def process_batch(self, codes, law, gain_q7, out_law, legs, flags=0, out=None):
+        """decode -> meter -> gate/gain -> mix -> encode in one pass.
+
+        codes u8 [F][B*legs][160]; law u8 [B*legs]; gain_q7 u16 [F][B*legs]
+        (0 = gate shut); out_law u8 [B].  Returns dict(mix, enc, meter, bmeter).
+        """
+        mem = self._mode(codes, law, gain_q7, out_law)
+        F, Cn, n = codes.shape
+        if n != N.FRAME or Cn % legs:
+            raise IgdError("codes must be [F][B*legs][160]")
+        B = Cn // legs
+        if mem == N.MEM_DEVICE:
+            if codes.dtype != torch.uint8 or law.dtype != torch.uint8 or out_law.dtype != torch.uint8:
+                raise IgdError("codes/law/out_law must be uint8")
+            if gain_q7.dtype not in (torch.int16, torch.uint16):
+                raise IgdError("gain_q7 must be a 16-bit tensor")
+            o = out if out is not None else self.alloc_outputs(F, B, legs)
+        else:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            law = np.ascontiguousarray(law, dtype=np.uint8)
+            gain_q7 = np.ascontiguousarray(gain_q7, dtype=np.uint16)
+            out_law = np.ascontiguousarray(out_law, dtype=np.uint8)
+            o = out if out is not None else {
+                "mix": np.empty((F, B, N.FRAME), dtype=np.int16),
+                "enc": np.empty((F, B, N.FRAME), dtype=np.uint8),
+                "meter": np.empty((F, Cn), dtype=N.METER_DT),
+                "bmeter": np.empty((F, B), dtype=N.BRIDGE_DT),
+            }
+        if law.shape[0] != Cn or out_law.shape[0] != B or tuple(gain_q7.shape) != (F, Cn):
+            raise IgdError("law / out_law / gain_q7 shapes do not match codes")
+        d = N.BatchDesc(C.sizeof(N.BatchDesc), mem, F, B, legs, flags,
+                        self._ptr(codes), self._ptr(law), self._ptr(gain_q7), self._ptr(out_law),
+                        self._ptr(o["mix"]), self._ptr(o["enc"]), self._ptr(o["meter"]), self._ptr(o["bmeter"]))
+        self._chk(self._lib.igd_process_batch(self._h, C.byref(d)))
+        return o
+
+    # ------------------------------------------------------------ summary
+    def event_summary(self, meter, gain_q7, want_db=True):
+        """meter [F][C] records, gain_q7 [F][C] -> (summary [C], db [C])."""
+        mem = self._mode(meter, gain_q7)
+        if mem == N.MEM_DEVICE:
+            F, Cn = gain_q7.shape
+            out = torch.empty((Cn, 8), dtype=torch.int32, device=gain_q7.device)
+            db = torch.empty((Cn, 4), dtype=torch.int32, device=gain_q7.device) if want_db else None
+        else:
+            meter = np.ascontiguousarray(meter, dtype=N.METER_DT)
+            gain_q7 = np.ascontiguousarray(gain_q7, dtype=np.uint16)
+            F, Cn = gain_q7.shape
+            out = np.empty(Cn, dtype=N.SUMMARY_DT)
+            db = np.empty(Cn, dtype=N.SUMMARY_DB_DT) if want_db else None
+        self._chk(self._lib.igd_event_summary(self._h, self._ptr(meter), self._ptr(gain_q7), F, Cn,
+                                              self._ptr(out), self._ptr(db), mem))
+        return out, db
+
+    # ------------------------------------------------------------ ED-137
+    def ed137_parse(self, pkts, sizes=None, want_payload=True):
+        """pkts u8 [n][stride] (+ sizes u32 [n]) -> (fields [n], payload u8 [n][160])."""
+        mem = self._mode(pkts, sizes)
+        n, stride = pkts.shape
+        if mem == N.MEM_DEVICE:
+            fields = torch.empty((n, 4), dtype=torch.int32, device=pkts.device)
+            pay = torch.empty((n, N.FRAME), dtype=torch.uint8, device=pkts.device) if want_payload else None
+        else:
+            pkts = np.ascontiguousarray(pkts, dtype=np.uint8)
+            if sizes is not None:
+                sizes = np.ascontiguousarray(sizes, dtype=np.uint32)
+            fields = np.empty(n, dtype=N.FIELDS_DT)
+            pay = np.empty((n, N.FRAME), dtype=np.uint8) if want_payload else None
+        self._chk(self._lib.igd_ed137_parse(self._h, self._ptr(pkts), self._ptr(sizes), n, stride,
+                                            self._ptr(fields), self._ptr(pay), mem))
+        return fields, pay
+
+    def ed137_pack(self, rtp12, payload, state, ctl=None, now_ms0=0, tick_ms=20, payload_len=N.FRAME,
+                   out_stride=N.PKT_MAX, flags=0):
+        """Batched transport_send_rtp.  rtp12 u8 [F][C][12], payload u8 [F][C][160],
+        state [C] (updated in place), ctl [F][C] or None.
+        Returns (pkts u8 [F][C][out_stride], sizes u32 [F][C], bytemean_out u8 [F][C])."""
+        mem = self._mode(rtp12, payload, state, ctl)
+        F, Cn = rtp12.shape[0], rtp12.shape[1]
+        if mem == N.MEM_DEVICE:
+            dev = rtp12.device
+            pkts = torch.zeros((F, Cn, out_stride), dtype=torch.uint8, device=dev)
+            sizes = torch.empty((F, Cn), dtype=torch.int32, device=dev)
+            bm = torch.empty((F, Cn), dtype=torch.uint8, device=dev)
+        else:
+            rtp12 = np.ascontiguousarray(rtp12, dtype=np.uint8)
+            payload = np.ascontiguousarray(payload, dtype=np.uint8)
+            if state.dtype != N.STATE_DT or not state.flags.c_contiguous:
+                raise IgdError("state must be a contiguous STATE_DT array (updated in place)")
+            if ctl is not None:
+                ctl = np.ascontiguousarray(ctl, dtype=N.CTL_DT)
+            pkts = np.zeros((F, Cn, out_stride), dtype=np.uint8)
+            sizes = np.empty((F, Cn), dtype=np.uint32)
+            bm = np.empty((F, Cn), dtype=np.uint8)
+        d = N.PackDesc(C.sizeof(N.PackDesc), mem, F, Cn, flags, payload_len, out_stride, tick_ms, now_ms0,
+                       self._ptr(rtp12), self._ptr(payload), self._ptr(ctl), self._ptr(state),
+                       self._ptr(pkts), self._ptr(sizes), self._ptr(bm))
+        self._chk(self._lib.igd_ed137_pack(self._h, C.byref(d)))
+        return pkts, sizes, bm
+
+    # ------------------------------------------------------------ recorder
+    def wav_image(self, payload, rate=8000, law=N.LAW_ULAW, ref_quirks=False):
+        """WavWriter file image (header + body) built on the GPU."""
+        mem = self._mode(payload)
+        n = payload.numel() if mem == N.MEM_DEVICE else payload.size
+        total = self._lib.igd_wav_size(n, int(ref_quirks))
+        if mem == N.MEM_DEVICE:
+            out = torch.empty(total, dtype=torch.uint8, device=payload.device)
+        else:
+            payload = np.ascontiguousarray(payload, dtype=np.uint8)
+            out = np.empty(total, dtype=np.uint8)
+        ln = C.c_size_t()
+        self._chk(self._lib.igd_wav_image(self._h, self._ptr(payload), n, rate, law, int(ref_quirks),
+                                          self._ptr(out), C.byref(ln), mem))
+        return out

@@ -1,0 +1,154 @@
+"""GPU parity of the fused decode -> meter -> mix -> encode path against the
+oracle (BASELINE configs 1-3) plus size-independent properties at full size."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+import igate4xsoftphonedsp_b200 as ig
+from igate4xsoftphonedsp_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DB_TOL = 1e-4
+
+
+def check(got, want):
+    mix, enc, meter, bmeter = want
+    assert np.array_equal(got["mix"], mix), "mixed PCM differs"
+    assert np.array_equal(got["enc"], enc), "encoded mix differs"
+    g, w = got["meter"], meter
+    assert np.array_equal(g["sumsq_lo"], w["sumsq_lo"]) and np.array_equal(g["hi"], w["hi"]), "integer meters differ"
+    for k in ("rms_dbfs", "peak_dbfs"):
+        inf = np.isinf(w[k])
+        assert np.array_equal(np.isinf(g[k]), inf)
+        if (~inf).any():
+            assert np.abs(g[k][~inf].astype(np.float64) - w[k][~inf].astype(np.float64)).max() < DB_TOL
+    assert got["bmeter"].tobytes() == bmeter.tobytes(), "bridge records differ"
+
+
+def make(F, B, G, ch0=0, random_codes=False, seed=0):
+    Cn = B * G
+    law = synth.laws(Cn, ch0)
+    if random_codes:
+        codes = np.random.default_rng(seed).integers(0, 256, (F, Cn, 160), dtype=np.uint8)
+    else:
+        pcm = synth.pcm_noise_tone(F, Cn, ch0=ch0)
+        codes = np.stack([O.g711_encode(pcm[:, c], int(law[c])) for c in range(Cn)], axis=1)
+    return codes, law, synth.gains(F, B, G), synth.out_laws(B)
+
+
+def test_cfg1_one_channel_tone_alaw(vp):
+    pcm = synth.tone_1k(60 * 8000).reshape(3000, 1, 160)
+    codes = O.g711_encode(pcm, 0)
+    law, out_law = np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    gain = np.full((3000, 1), 128, np.uint16)           # unity: the mix is the decoded leg
+    got = vp.process_batch(codes, law, gain, out_law, 1)
+    check(got, O.process_batch(codes, law, gain, out_law, 1))
+    assert np.array_equal(got["enc"], codes)            # decode -> encode is idempotent on codes
+    assert abs(float(got["meter"]["rms_dbfs"][0, 0]) - (-9.03)) < 0.05   # A-law quantised tone
+    assert abs(float(got["meter"]["peak_dbfs"][0, 0]) - (-6.02)) < 0.3
+
+
+def test_cfg2_igate4x_golden(vp, golden_dir):
+    g = np.load(os.path.join(golden_dir, "fused_cfg2.npz"))
+    got = vp.process_batch(g["codes"], g["law"], g["gain"], g["out_law"], 4)
+    assert np.array_equal(got["mix"], g["mix"]) and np.array_equal(got["enc"], g["enc"])
+    m = got["meter"].view(np.uint32).reshape(g["meter"].shape)
+    assert np.array_equal(m[..., :2], g["meter"][..., :2])
+    assert got["bmeter"].view(np.uint32).reshape(g["bmeter"].shape).tolist() == g["bmeter"].tolist()
+
+
+def test_cfg2_igate4x_3000_frames(vp):
+    codes, law, gain, out_law = make(3000, 1, 4, ch0=64)
+    check(vp.process_batch(codes, law, gain, out_law, 4), O.process_batch(codes, law, gain, out_law, 4))
+
+
+@pytest.mark.parametrize("G,B,F", [(4, 37, 9), (4, 32, 1), (4, 1, 1), (2, 45, 7), (1, 100, 3), (3, 21, 5),
+                                   (8, 13, 4), (5, 7, 6), (32, 3, 2)])
+def test_random_codes_all_leg_counts(vp, G, B, F):
+    """every code value, ragged tile tails (F*B not a multiple of 32), templated and generic G."""
+    codes, law, _, out_law = make(F, B, G, random_codes=True, seed=G * 100 + B)
+    rng = np.random.default_rng(7)
+    gain = rng.choice(np.array([0, 0, 13, 64, 128, 256, 300], np.uint16), (F, B * G))
+    law = rng.integers(0, 2, B * G).astype(np.uint8)
+    check(vp.process_batch(codes, law, gain, out_law, G), O.process_batch(codes, law, gain, out_law, G))
+
+
+def test_all_gates_shut_and_all_silence(vp):
+    F, B, G = 3, 5, 4
+    law = synth.laws(B * G)
+    codes = np.where(law.reshape(1, -1, 1) == 0, 0xD5, 0xFF).astype(np.uint8) * np.ones((F, 1, 160), np.uint8)
+    gain = np.zeros((F, B * G), np.uint16)
+    got = vp.process_batch(codes, law, gain, synth.out_laws(B), G)
+    check(got, O.process_batch(codes, law, gain, synth.out_laws(B), G))
+    assert (got["mix"] == 0).all() and (got["bmeter"]["n_open"] == 0).all()
+    ul = got["meter"]["rms_dbfs"][:, 1::2]               # u-law 0xFF decodes to 0 -> -inf
+    assert np.isinf(ul).all() and (ul < 0).all()
+
+
+def test_signed_char_quirk(vp):
+    codes, law, gain, out_law = make(4, 6, 4, random_codes=True, seed=3)
+    got = vp.process_batch(codes, law, gain, out_law, 4, flags=ig.F_SIGNED_CHAR)
+    check(got, O.process_batch(codes, law, gain, out_law, 4, signed_char=1))
+
+
+def test_empty_batch(vp):
+    got = vp.process_batch(np.zeros((0, 8, 160), np.uint8), synth.laws(8), np.zeros((0, 8), np.uint16),
+                           synth.out_laws(2), 4)
+    assert got["mix"].shape == (0, 2, 160)
+
+
+def test_host_path_chunked_pipeline(vp):
+    """host buffers larger than one staging chunk (32 MiB of codes): double-buffered H2D/kernel/D2H."""
+    F, B, G = 60, 1024, 4
+    codes, law, gain, out_law = make(F, B, G, random_codes=True, seed=11)
+    assert codes.nbytes > (32 << 20)
+    check(vp.process_batch(codes, law, gain, out_law, G),
+          O.process_batch(codes, law, gain, out_law, G, threads=os.cpu_count() or 1))
+
+
+def test_cfg3_full_size_properties(vp):
+    """BASELINE config 3 shape (4096 channels x 1640 frames, > 1 GiB of codes) on device buffers:
+    sampled frames against the oracle + size-independent properties."""
+    import torch
+    F, B, G = 1640, 1024, 4
+    Cn = B * G
+    dev = "cuda:0"
+    pcm = synth.pcm_noise_tone_torch(F, Cn, dev)
+    law = torch.from_numpy(synth.laws(Cn)).to(dev)
+    vp.use_torch_stream()
+    codes = vp.g711_encode(pcm, law)
+    del pcm
+    gain = torch.from_numpy(synth.gains(F, B, G).view(np.int16)).to(dev)
+    out_law = torch.from_numpy(synth.out_laws(B)).to(dev)
+    got = vp.process_batch(codes, law, gain, out_law, G)
+    torch.cuda.synchronize()
+    # (1) sampled frames, every bridge, against the oracle
+    fs = [0, 1, 24, 25, 777, 1639]
+    sel = torch.tensor(fs, device=dev)
+    c_np = codes[sel].cpu().numpy()
+    g_np = gain[sel].cpu().numpy().view(np.uint16)
+    want = O.process_batch(c_np, law.cpu().numpy(), g_np, out_law.cpu().numpy(), G, threads=os.cpu_count() or 1)
+    sub = {"mix": got["mix"][sel].cpu().numpy(), "enc": got["enc"][sel].cpu().numpy(),
+           "meter": got["meter"][sel].cpu().numpy().view(ig.METER_DT).reshape(len(fs), Cn),
+           "bmeter": got["bmeter"][sel].cpu().numpy().view(ig.BRIDGE_DT).reshape(len(fs), B)}
+    check(sub, want)
+    # (2) enc == encode(mix) through the independent stand-alone encoder, whole batch
+    enc2 = vp.g711_encode(got["mix"], out_law.repeat_interleave(1))
+    torch.cuda.synchronize()
+    assert torch.equal(enc2, got["enc"])
+    # (3) closed gates contribute nothing: zeroing a shut leg's codes leaves mix/enc unchanged
+    codes2 = codes.clone()
+    shut = (gain == 0).unsqueeze(-1)
+    codes2.masked_fill_(shut, 0x55)
+    got2 = vp.process_batch(codes2, law, gain, out_law, G)
+    torch.cuda.synchronize()
+    assert torch.equal(got2["mix"], got["mix"]) and torch.equal(got2["enc"], got["enc"])
+    # (4) the integer meter of a leg equals the stand-alone meter of its decoded PCM (checksum of checksums)
+    dec = vp.g711_decode(codes[:64], law)
+    m2 = vp.frame_meter(dec)
+    torch.cuda.synchronize()
+    a = got["meter"][:64].reshape(-1, 4)
+    b = m2.reshape(-1, 4)
+    assert torch.equal(a[:, 0], b[:, 0]) and torch.equal(a[:, 1] & ~0xFF00, b[:, 1])
