@@ -253,7 +253,7 @@ def main():
                                threads=os.cpu_count() or 1)
         parity = bool(np.array_equal(out["mix"][sel].cpu().numpy(), want[0]) and
                       np.array_equal(out["enc"][sel].cpu().numpy(), want[1]) and
-                      np.array_equal(out["meter"][sel].cpu().numpy()[..., :2].reshape(len(fs), C, 2),
+                      np.array_equal(out["meter"][sel].cpu().numpy().view(np.uint32)[..., :2].reshape(len(fs), C, 2),
                                      want[2].view(np.uint32).reshape(len(fs), C, 4)[..., :2]))
 
     # ---- per-channel summaries gathered to rank 0 (the only collective; outside the timed region)

@@ -74,6 +74,7 @@ SYMBOLS = {
     "igd_init": (_i, [_i, C.POINTER(_vp)]),
     "igd_shutdown": (_i, [_vp]),
     "igd_set_stream": (_i, [_vp, _vp]),
+    "igd_use_own_stream": (_i, [_vp]),
     "igd_sync": (_i, [_vp]),
     "igd_last_error": (C.c_char_p, [_vp]),
     "igd_device_info": (_i, [_vp, C.POINTER(DevInfo)]),

@@ -170,7 +170,14 @@ int igd_shutdown(igd_ctx *c)
 int igd_set_stream(igd_ctx *c, void *s)
 {
     if (!c) return IGD_EINVAL;
-    c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream;
+    c->stream = static_cast<cudaStream_t>(s);
+    return IGD_OK;
+}
+
+int igd_use_own_stream(igd_ctx *c)
+{
+    if (!c) return IGD_EINVAL;
+    c->stream = c->own_stream;
     return IGD_OK;
 }
 

@@ -59,13 +59,19 @@ __device__ __forceinline__ uint32_t pack_sat16(int hi, int lo)
 __device__ __forceinline__ int clamp16(int v) { return min(max(v, -32768), 32767); }
 
 // ------------------------------------------------------------------ decode LUT
+// Entry = two int16: low half x = decoded sample, high half clamp16(2x) = the
+// sample after the reference's open-gate gain 2.0 (SLOT_VOLUME, Functions.cpp:
+// 1682) with pjmedia's per-port clip.  One IDP.2A then selects x (gain 1.0),
+// clamp16(2x) (gain 2.0) or nothing (gate shut) AND accumulates it into the mix.
 __device__ __forceinline__ void build_decode_lut(uint32_t *lut, int tid, int nthreads)
 {
     for (int i = tid; i < 256 * 64; i += nthreads) {
         const uint32_t code = (uint32_t)i >> 6, slot = i & 63;
         const uint32_t lane = slot >> 1;
         const uint32_t law = (slot & 1) ^ (lane >> 4);
-        lut[i] = (uint32_t)(law ? igd_ulaw2lin(code) : igd_alaw2lin(code));
+        const int x = law ? igd_ulaw2lin(code) : igd_alaw2lin(code);
+        const int y2 = min(max(2 * x, -32768), 32767);
+        lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)x & 0xFFFFu);
     }
 }
 // byte offset of this lane's column for `law`
@@ -74,11 +80,51 @@ __device__ __forceinline__ uint32_t lut_lane_byte(uint32_t lane, uint32_t law)
     return 4u * (2u * lane + ((law & 1u) ^ (lane >> 4)));
 }
 template <int K>
-__device__ __forceinline__ int lut_decode(const uint8_t *lut_bytes, uint32_t word, uint32_t lane_byte)
+__device__ __forceinline__ uint32_t lut_lookup(const uint8_t *lut_bytes, uint32_t word, uint32_t lane_byte)
 {
     // (code<<8) | lane_byte in one PRMT: byte0 = lane_byte, byte1 = word.byteK
     const uint32_t a = __byte_perm(word, lane_byte, 0x7604 + (K << 4));
-    return *reinterpret_cast<const int *>(lut_bytes + a);
+    return *reinterpret_cast<const uint32_t *>(lut_bytes + a);
+}
+template <int K>
+__device__ __forceinline__ int lut_decode(const uint8_t *lut_bytes, uint32_t word, uint32_t lane_byte)
+{
+    return (int)(short)(lut_lookup<K>(lut_bytes, word, lane_byte) & 0xFFFFu);
+}
+// d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1   (IDP.2A.LO.S16.U8, FMA pipe)
+__device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// packed 2 x 16-bit ALU ops (VIMNMX[3].S16x2 / .U16x2, VIADD.16x2, VIADDMNMX.S16x2)
+__device__ __forceinline__ uint32_t max_s16x2(uint32_t a, uint32_t b)
+{
+    uint32_t r; asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t min_s16x2(uint32_t a, uint32_t b)
+{
+    uint32_t r; asm("min.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b)
+{
+    uint32_t r; asm("max.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+__device__ __forceinline__ uint32_t min_u16x2(uint32_t a, uint32_t b)
+{
+    uint32_t r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
+}
+// PRMT with the full 4-bit selectors (bit 3 = replicate the byte's sign); the
+// __byte_perm intrinsic masks that bit away.
+template <uint32_t kSel>
+__device__ __forceinline__ uint32_t prmt_full(uint32_t a, uint32_t b)
+{
+    uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "n"(kSel)); return r;
+}
+__device__ __forceinline__ uint32_t add_16x2(uint32_t a, uint32_t b)
+{
+    uint32_t r; asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
 }
 
 // ------------------------------------------------------------------ partials
@@ -114,7 +160,7 @@ __device__ __forceinline__ int bytesum4(uint32_t w, bool signed_char, int acc)
     return signed_char ? __dp4a((int)w, 0x01010101, acc) : (int)__dp4a(w, 0x01010101u, (uint32_t)acc);
 }
 
-// encode 16 clamped samples -> 16 code bytes
+// encode 16 clamped samples -> 16 code bytes (scalar form; stand-alone encoder)
 __device__ __forceinline__ uint4 encode16(const int (&x)[16], const igd_enc_law &L)
 {
     uint32_t w[4];
@@ -123,6 +169,56 @@ __device__ __forceinline__ uint4 encode16(const int (&x)[16], const igd_enc_law 
         const uint32_t c0 = igd_g711_enc1(x[4 * j + 0], L), c1 = igd_g711_enc1(x[4 * j + 1], L);
         const uint32_t c2 = igd_g711_enc1(x[4 * j + 2], L), c3 = igd_g711_enc1(x[4 * j + 3], L);
         w[j] = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// The same compressor (igd_math.cuh) on PACKED pairs of int16: the pre-bias, clip
+// and segment normalisation run two samples per instruction on the 16x2 ALU ops,
+// only the exponent extraction (one PRMT + FFMA + shift) is per sample.
+struct enc_pk {
+    uint32_t bias_pos, bias_x;   // packed pre-bias for x>=0, and pos^neg
+    uint32_t hi_pos, hi_x;       // packed upper clip of t so that t+bias <= 0x7FFF
+    uint32_t thr;                // packed 256 (A-law) / 0 (u-law)
+    uint32_t mask4;              // output XOR mask for x>=0, replicated per byte
+};
+__device__ __forceinline__ enc_pk enc_pk_make(int law)
+{
+    const igd_enc_law L = igd_enc_law_make(law);
+    enc_pk e;
+    const uint32_t bp = (uint32_t)L.bpos & 0xFFFFu, bn = (uint32_t)L.bneg & 0xFFFFu;
+    const uint32_t hp = (uint32_t)(0x7FFF - max(L.bpos, 0)), hn = (uint32_t)(0x7FFF - max(L.bneg, 0));
+    e.bias_pos = bp * 0x10001u; e.bias_x = (bp ^ bn) * 0x10001u;
+    e.hi_pos = hp * 0x10001u;   e.hi_x = (hp ^ hn) * 0x10001u;
+    e.thr = (uint32_t)L.thr * 0x10001u;
+    e.mask4 = L.mpos * 0x01010101u;
+    return e;
+}
+// two packed samples -> two codes, each left in byte 3 of c0 / c1; sgn = 0xFFFF per negative half
+__device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t &c0, uint32_t &c1, uint32_t &sgn)
+{
+    sgn = prmt_full<0xBB99>(pk, 0u);                                    // sign of each half, replicated
+    uint32_t t = pk ^ sgn;                                          // |x| or |x|-1
+    t = min_u16x2(t, E.hi_pos ^ (sgn & E.hi_x));                    // u-law clip
+    const uint32_t p = max_s16x2(add_16x2(t, E.bias_pos ^ (sgn & E.bias_x)), 0u);
+    const uint32_t P = add_16x2(p, max_u16x2(p, E.thr));            // leading one -> segment
+    const float g0 = fmaf(__uint_as_float(__byte_perm(P, 0x4B000000u, 0x7410)), 0.0078125f, -65536.0f);
+    const float g1 = fmaf(__uint_as_float(__byte_perm(P, 0x4B000000u, 0x7432)), 0.0078125f, -65536.0f);
+    c0 = __float_as_uint(g0) << 5;                                  // bits[26:19] -> byte 3
+    c1 = __float_as_uint(g1) << 5;
+}
+// 8 packed words (16 samples) -> 16 code bytes
+__device__ __forceinline__ uint4 encode16_packed(const uint32_t (&pk)[8], const enc_pk &E)
+{
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t c0, c1, c2, c3, s01, s23;
+        enc_pair(pk[2 * j], E, c0, c1, s01);
+        enc_pair(pk[2 * j + 1], E, c2, c3, s23);
+        const uint32_t codes = __byte_perm(__byte_perm(c0, c1, 0x0073), __byte_perm(c2, c3, 0x0073), 0x5410);
+        const uint32_t sg = __byte_perm(s01, s23, 0x6420);          // one sign byte per sample
+        w[j] = codes ^ ((sg & 0x80808080u) ^ E.mask4);
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
@@ -143,32 +239,82 @@ struct FusedParams {
     unsigned flags;
 };
 
-// decode + meter one 16-sample chunk of one leg; x[] receives the PCM
+constexpr uint32_t kSelGeneral = 0xFFFFFFFFu;
+// gain_q7 -> IDP.2A selector: 0 -> nothing, 128 -> x, 256 -> clamp16(2x); anything else
+// takes the general multiply / shift / clip path.
+__device__ __forceinline__ uint32_t gain_selector(uint32_t adj)
+{
+    return adj == 0u ? 0u : adj == 128u ? 0x0001u : adj == 256u ? 0x0100u : kSelGeneral;
+}
+
+// decode + meter + gain/accumulate one 16-sample chunk of one leg
+template <bool kSigned>
 __device__ __forceinline__ uint2 leg_chunk(const uint8_t *lut_bytes, uint4 w, uint32_t lane_byte,
-                                           bool signed_char, int (&x)[16])
+                                           uint32_t sel, int adj, int (&acc)[16])
 {
     const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
     unsigned long long sq = 0;
-    int mx = 0, mn = 0, bsum = 0;
+    uint32_t mx = 0, mn = 0;       // packed running max / min of (x, clamp16(2x))
+    int bsum = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int x0 = lut_decode<0>(lut_bytes, wd[j], lane_byte);
-        const int x1 = lut_decode<1>(lut_bytes, wd[j], lane_byte);
-        const int x2 = lut_decode<2>(lut_bytes, wd[j], lane_byte);
-        const int x3 = lut_decode<3>(lut_bytes, wd[j], lane_byte);
-        x[4 * j + 0] = x0; x[4 * j + 1] = x1; x[4 * j + 2] = x2; x[4 * j + 3] = x3;
+        const uint32_t e0 = lut_lookup<0>(lut_bytes, wd[j], lane_byte);
+        const uint32_t e1 = lut_lookup<1>(lut_bytes, wd[j], lane_byte);
+        const uint32_t e2 = lut_lookup<2>(lut_bytes, wd[j], lane_byte);
+        const uint32_t e3 = lut_lookup<3>(lut_bytes, wd[j], lane_byte);
+        const int x0 = dp2a_lo(e0, 1u, 0), x1 = dp2a_lo(e1, 1u, 0);
+        const int x2 = dp2a_lo(e2, 1u, 0), x3 = dp2a_lo(e3, 1u, 0);
         // |G.711 sample| <= 32256, so four squares fit in 32 bits
-        const uint32_t s = (uint32_t)(x0 * x0) + (uint32_t)(x1 * x1) + (uint32_t)(x2 * x2) +
-                           (uint32_t)(x3 * x3);
-        sq += s;
-        mx = max(max(mx, x0), x1); mx = max(max(mx, x2), x3);
-        mn = min(min(mn, x0), x1); mn = min(min(mn, x2), x3);
-        bsum = bytesum4(wd[j], signed_char, bsum);
+        sq += (uint32_t)(x0 * x0) + (uint32_t)(x1 * x1) + (uint32_t)(x2 * x2) + (uint32_t)(x3 * x3);
+        mx = max_s16x2(max_s16x2(mx, e0), e1); mx = max_s16x2(max_s16x2(mx, e2), e3);
+        mn = min_s16x2(min_s16x2(mn, e0), e1); mn = min_s16x2(min_s16x2(mn, e2), e3);
+        bsum = kSigned ? __dp4a((int)wd[j], 0x01010101, bsum) : (int)__dp4a(wd[j], 0x01010101u, (uint32_t)bsum);
+        if (sel != kSelGeneral) {
+            acc[4 * j + 0] = dp2a_lo(e0, sel, acc[4 * j + 0]);
+            acc[4 * j + 1] = dp2a_lo(e1, sel, acc[4 * j + 1]);
+            acc[4 * j + 2] = dp2a_lo(e2, sel, acc[4 * j + 2]);
+            acc[4 * j + 3] = dp2a_lo(e3, sel, acc[4 * j + 3]);
+        } else {
+            acc[4 * j + 0] += clamp16((x0 * adj) >> 7);
+            acc[4 * j + 1] += clamp16((x1 * adj) >> 7);
+            acc[4 * j + 2] += clamp16((x2 * adj) >> 7);
+            acc[4 * j + 3] += clamp16((x3 * adj) >> 7);
+        }
     }
-    return partial_pack(sq, (uint32_t)max(mx, -mn), bsum);
+    const int pmax = (int)(short)(mx & 0xFFFFu), pmin = (int)(short)(mn & 0xFFFFu);
+    return partial_pack(sq, (uint32_t)max(pmax, -pmin), bsum);
 }
 
-template <int G, int BFPC>
+// bridge output of one 16-sample chunk: saturate, store PCM, compress, store codes
+template <bool kSigned>
+__device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_pk &E, int16_t *mix_dst,
+                                               uint8_t *enc_dst)
+{
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
+    st32_stream(mix_dst, pk);
+    uint32_t mx = max_s16x2(max_s16x2(pk[0], pk[1]), pk[2]), mn = min_s16x2(min_s16x2(pk[0], pk[1]), pk[2]);
+    mx = max_s16x2(max_s16x2(mx, pk[3]), pk[4]); mn = min_s16x2(min_s16x2(mn, pk[3]), pk[4]);
+    mx = max_s16x2(max_s16x2(mx, pk[5]), pk[6]); mn = min_s16x2(min_s16x2(mn, pk[5]), pk[6]);
+    mx = max_s16x2(mx, pk[7]); mn = min_s16x2(mn, pk[7]);
+    const int hi = max((int)(short)(mx & 0xFFFFu), (int)mx >> 16);
+    const int lo = min((int)(short)(mn & 0xFFFFu), (int)mn >> 16);
+    const uint4 e = encode16_packed(pk, E);
+    st16_stream(enc_dst, e);
+    int esum = 0;
+    if (kSigned) {
+        esum = __dp4a((int)e.x, 0x01010101, esum); esum = __dp4a((int)e.y, 0x01010101, esum);
+        esum = __dp4a((int)e.z, 0x01010101, esum); esum = __dp4a((int)e.w, 0x01010101, esum);
+    } else {
+        uint32_t u = __dp4a(e.x, 0x01010101u, 0u); u = __dp4a(e.y, 0x01010101u, u);
+        u = __dp4a(e.z, 0x01010101u, u); u = __dp4a(e.w, 0x01010101u, u);
+        esum = (int)u;
+    }
+    return make_uint2((uint32_t)esum, (uint32_t)max(hi, -lo));
+}
+
+template <int G, int BFPC, bool kSigned>
 __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused(const FusedParams q)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -183,58 +329,49 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused(const FusedParams q
     __syncthreads();
 
     const int bfl = t / kChunks, p = t - bfl * kChunks;
-    const bool signed_char = (q.flags & IGD_F_SIGNED_CHAR) != 0;
+    // bridge index of this thread's bridge-frame, advanced incrementally (no per-tile division)
+    const long long bf_step = (long long)gridDim.x * BFPC;
+    const int b_step = (int)(bf_step % q.B);
+    long long bf = (long long)blockIdx.x * BFPC + bfl;
+    int b = (int)(bf % q.B);
     int buf = 0;
-    for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, buf ^= 1) {
-        const long long bf = tile * BFPC + bfl;
+    for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, buf ^= 1, bf += bf_step) {
         uint2 *mypart = part + (size_t)buf * BFPC * G * kPst + (size_t)bfl * G * kPst + p;
         if (bf < q.total_bf) {
-            const int b = (int)(bf % q.B);
             // ---- issue all loads of this bridge-frame chunk first
             uint4 w[G];
             const uint8_t *cb = q.codes + (size_t)bf * G * IGD_FRAME + p * 16;
 #pragma unroll
             for (int g = 0; g < G; g++) w[g] = ld16_stream(cb + g * IGD_FRAME);
             uint32_t adj[G], laws[G];
+            if (G == 4) {
+                const uint2 gq = *reinterpret_cast<const uint2 *>(q.gain + (size_t)bf * 4);
+                const uint32_t lw = *reinterpret_cast<const uint32_t *>(q.law + (size_t)b * 4);
+                adj[0] = gq.x & 0xFFFFu; adj[1 % G] = gq.x >> 16; adj[2 % G] = gq.y & 0xFFFFu; adj[3 % G] = gq.y >> 16;
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                adj[g] = q.gain[(size_t)bf * G + g];
-                laws[g] = q.law[(size_t)b * G + g];
+                for (int g = 0; g < G; g++) laws[g] = (lw >> (8 * g)) & 1u;
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    adj[g] = q.gain[(size_t)bf * G + g];
+                    laws[g] = q.law[(size_t)b * G + g];
+                }
             }
-            const igd_enc_law L = igd_enc_law_make(q.out_law[b]);
+            const enc_pk E = enc_pk_make(q.out_law[b]);
 
             int acc[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) acc[i] = 0;
 #pragma unroll
-            for (int g = 0; g < G; g++) {
-                int x[16];
-                mypart[g * kPst] = leg_chunk(lut_bytes, w[g], lut_lane_byte(lane, laws[g]),
-                                             signed_char, x);
-                const int a = (int)adj[g];
-                if (a != 0) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) acc[i] += clamp16((x[i] * a) >> 7);
-                }
-            }
-            // ---- bridge output: saturate, store PCM, compress, store codes
-            uint32_t pk[8];
-            int mpeak = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                acc[i] = clamp16(acc[i]);
-                mpeak = max(mpeak, abs(acc[i]));
-            }
-            st32_stream(q.mix + (size_t)bf * IGD_FRAME + p * 16, pk);
-            const uint4 e = encode16(acc, L);
-            st16_stream(q.enc + (size_t)bf * IGD_FRAME + p * 16, e);
-            int esum = 0;
-            esum = bytesum4(e.x, signed_char, esum); esum = bytesum4(e.y, signed_char, esum);
-            esum = bytesum4(e.z, signed_char, esum); esum = bytesum4(e.w, signed_char, esum);
-            bpart[(size_t)buf * BFPC * kPst + bfl * kPst + p] = make_uint2((uint32_t)esum, (uint32_t)mpeak);
+            for (int g = 0; g < G; g++)
+                mypart[g * kPst] = leg_chunk<kSigned>(lut_bytes, w[g], lut_lane_byte(lane, laws[g]),
+                                                      gain_selector(adj[g]), (int)adj[g], acc);
+            bpart[(size_t)buf * BFPC * kPst + bfl * kPst + p] =
+                mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)bf * IGD_FRAME + p * 16,
+                                       q.enc + (size_t)bf * IGD_FRAME + p * 16);
         }
+        b += b_step;
+        if (b >= q.B) b -= q.B;
         __syncthreads();
         // ---- per-frame meter records: one thread per leg-frame / bridge-frame
         if (t < BFPC * G) {
@@ -270,7 +407,7 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused(const FusedParams q
 
 // Any number of legs per bridge (1..IGD_MAX_LEGS): same algorithm, legs walked
 // in a loop with the partials reduced per leg through shared memory.
-template <int BFPC>
+template <int BFPC, bool kSigned>
 __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedParams q)
 {
     extern __shared__ __align__(16) uint8_t smem[];
@@ -283,7 +420,6 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
     build_decode_lut(lut, t, BFPC * kChunks);
     __syncthreads();
     const int bfl = t / kChunks, p = t - bfl * kChunks;
-    const bool signed_char = (q.flags & IGD_F_SIGNED_CHAR) != 0;
     for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x) {
         const long long bf = tile * BFPC + bfl;
         const bool valid = bf < q.total_bf;
@@ -294,14 +430,9 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
         for (int g = 0; g < G; g++) {
             if (valid) {
                 const uint4 w = ld16_stream(q.codes + ((size_t)bf * G + g) * IGD_FRAME + p * 16);
-                int x[16];
-                part[bfl * kPst + p] = leg_chunk(lut_bytes, w, lut_lane_byte(lane, q.law[(size_t)b * G + g]),
-                                                 signed_char, x);
-                const int a = q.gain[(size_t)bf * G + g];
-                if (a != 0) {
-#pragma unroll
-                    for (int i = 0; i < 16; i++) acc[i] += clamp16((x[i] * a) >> 7);
-                }
+                const uint32_t a = q.gain[(size_t)bf * G + g];
+                part[bfl * kPst + p] = leg_chunk<kSigned>(lut_bytes, w, lut_lane_byte(lane, q.law[(size_t)b * G + g]),
+                                                          gain_selector(a), (int)a, acc);
             }
             __syncthreads();
             if (t < BFPC) {
@@ -316,22 +447,10 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
             }
             __syncthreads();
         }
-        if (valid) {
-            const igd_enc_law L = igd_enc_law_make(q.out_law[b]);
-            uint32_t pk[8];
-            int mpeak = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
-#pragma unroll
-            for (int i = 0; i < 16; i++) { acc[i] = clamp16(acc[i]); mpeak = max(mpeak, abs(acc[i])); }
-            st32_stream(q.mix + (size_t)bf * IGD_FRAME + p * 16, pk);
-            const uint4 e = encode16(acc, L);
-            st16_stream(q.enc + (size_t)bf * IGD_FRAME + p * 16, e);
-            int esum = 0;
-            esum = bytesum4(e.x, signed_char, esum); esum = bytesum4(e.y, signed_char, esum);
-            esum = bytesum4(e.z, signed_char, esum); esum = bytesum4(e.w, signed_char, esum);
-            bpart[bfl * kPst + p] = make_uint2((uint32_t)esum, (uint32_t)mpeak);
-        }
+        if (valid)
+            bpart[bfl * kPst + p] = mix_out_chunk<kSigned>(acc, enc_pk_make(q.out_law[b]),
+                                                           q.mix + (size_t)bf * IGD_FRAME + p * 16,
+                                                           q.enc + (size_t)bf * IGD_FRAME + p * 16);
         __syncthreads();
         if (t < BFPC) {
             const long long bf2 = tile * BFPC + t;
@@ -398,16 +517,9 @@ __global__ void __launch_bounds__(256) k_g711_encode(const int16_t *__restrict__
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunk;
          i += (size_t)gridDim.x * blockDim.x) {
         const int lw = law_ch ? law_ch[(i / kChunks) % nch] : law;
-        const igd_enc_law L = igd_enc_law_make(lw);
         uint32_t pk[8];
         ld32_stream(pcm + i * 16, pk);
-        int x[16];
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            x[2 * j] = (int)(short)(pk[j] & 0xFFFFu);
-            x[2 * j + 1] = (int)pk[j] >> 16;
-        }
-        st16_stream(codes + i * 16, encode16(x, L));
+        st16_stream(codes + i * 16, encode16_packed(pk, enc_pk_make(lw)));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (size_t i = nchunk * 16; i < n; i++) {
@@ -835,39 +947,39 @@ cudaError_t igd_k_mix(const igd_launch_cfg &c, const int16_t *pcm, const uint16_
 }
 
 namespace {
-template <int G, int BFPC>
+template <int G, int BFPC, bool kSigned>
 cudaError_t launch_fused(const igd_launch_cfg &c, const FusedParams &q)
 {
     const size_t smem = kLutBytes + (size_t)2 * BFPC * G * kPst * 8 + (size_t)2 * BFPC * kPst * 8;
-    cudaError_t e = cudaFuncSetAttribute(k_fused<G, BFPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_fused<G, BFPC, kSigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<G, BFPC>, BFPC * kChunks, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<G, BFPC, kSigned>, BFPC * kChunks, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     FusedParams p = q;
     p.num_tiles = (q.total_bf + BFPC - 1) / BFPC;
     long long grid = (long long)c.sm_count * per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    k_fused<G, BFPC><<<(int)grid, BFPC * kChunks, smem, c.stream>>>(p);
+    k_fused<G, BFPC, kSigned><<<(int)grid, BFPC * kChunks, smem, c.stream>>>(p);
     return cudaGetLastError();
 }
 
-template <int BFPC>
+template <int BFPC, bool kSigned>
 cudaError_t launch_fused_anyg(const igd_launch_cfg &c, const FusedParams &q)
 {
     const size_t smem = kLutBytes + (size_t)2 * BFPC * kPst * 8;
-    cudaError_t e = cudaFuncSetAttribute(k_fused_anyg<BFPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_fused_anyg<BFPC, kSigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_anyg<BFPC>, BFPC * kChunks, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_anyg<BFPC, kSigned>, BFPC * kChunks, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     FusedParams p = q;
     p.num_tiles = (q.total_bf + BFPC - 1) / BFPC;
     long long grid = (long long)c.sm_count * per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    k_fused_anyg<BFPC><<<(int)grid, BFPC * kChunks, smem, c.stream>>>(p);
+    k_fused_anyg<BFPC, kSigned><<<(int)grid, BFPC * kChunks, smem, c.stream>>>(p);
     return cudaGetLastError();
 }
 }  // namespace
@@ -880,11 +992,12 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     q.total_bf = (long long)d.F * d.B;
     q.num_tiles = 0;
     q.B = d.B; q.G = d.G; q.flags = d.flags;
+    const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
     switch (d.G) {
-    case 1: return launch_fused<1, 32>(c, q);
-    case 2: return launch_fused<2, 32>(c, q);
-    case 4: return launch_fused<4, 32>(c, q);
-    default: return launch_fused_anyg<32>(c, q);
+    case 1: return sc ? launch_fused<1, 32, true>(c, q) : launch_fused<1, 32, false>(c, q);
+    case 2: return sc ? launch_fused<2, 32, true>(c, q) : launch_fused<2, 32, false>(c, q);
+    case 4: return sc ? launch_fused<4, 32, true>(c, q) : launch_fused<4, 32, false>(c, q);
+    default: return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
     }
 }
 

@@ -87,8 +87,12 @@ class VoicePath:
             raise IgdError(f"{N.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
 
     def use_torch_stream(self, stream=None):
+        """Launch on a torch stream (default: torch's current stream on this device)."""
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         self._chk(self._lib.igd_set_stream(self._h, C.c_void_p(s.cuda_stream)))
+
+    def use_own_stream(self):
+        self._chk(self._lib.igd_use_own_stream(self._h))
 
     def sync(self):
         self._chk(self._lib.igd_sync(self._h))
@@ -119,6 +123,7 @@ class VoicePath:
             for a in arrays:
                 if a is not None and (not a.is_cuda or not a.is_contiguous()):
                     raise IgdError("torch arguments must be contiguous CUDA tensors")
+            self.use_torch_stream()      # device buffers are ordered on torch's current stream
         return N.MEM_DEVICE if dev else N.MEM_HOST
 
     def _empty(self, like_torch, shape, np_dtype):

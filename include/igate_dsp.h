@@ -66,8 +66,11 @@ int igd_abi_version(void);
 /* Creates a context on CUDA device `device` with its own stream.              */
 int igd_init(int device, igd_ctx **ctx);
 int igd_shutdown(igd_ctx *ctx);
-/* Use an existing CUDA stream (cudaStream_t cast to void*; NULL = ctx's own).  */
+/* Run on an existing CUDA stream: cudaStream_t cast to void*; NULL is CUDA's
+ * legacy default stream (what torch.cuda.current_stream() is by default).     */
 int igd_set_stream(igd_ctx *ctx, void *cuda_stream);
+/* Back to the context's own (non-blocking) stream.                            */
+int igd_use_own_stream(igd_ctx *ctx);
 int igd_sync(igd_ctx *ctx);
 const char *igd_last_error(igd_ctx *ctx);
 typedef struct {

@@ -12,7 +12,7 @@
 __global__ void __launch_bounds__(1024) k_##name(unsigned *out, unsigned seed, long long *cyc) { \
     unsigned a[NCH]; unsigned b = seed | 1u, c = seed * 3u + 7u;                   \
     __shared__ unsigned sh[1024];                                                  \
-    sh[threadIdx.x] = threadIdx.x * 4;                                             \
+    sh[threadIdx.x] = (threadIdx.x * 4 + seed) & 0xFFCu;                                             \
     for (int i = 0; i < NCH; i++) a[i] = seed + threadIdx.x * 17u + i * 101u;      \
     INIT;                                                                          \
     __syncthreads();                                                               \
@@ -43,7 +43,8 @@ BENCH_KERNEL(idp2a,   , asm volatile("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(a[
 BENCH_KERNEL(ffma,    , asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)))
 BENCH_KERNEL(iabs,    , asm volatile("abs.s32 %0, %0;" : "+r"(a[i])); asm volatile("sub.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(b)))
 BENCH_KERNEL(flo,     , asm volatile("clz.b32 %0, %0;" : "+r"(a[i])); asm volatile("add.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(b)))
-BENCH_KERNEL(lds,     , { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"((a[i] & 0xFFCu))); a[i] = v; })
+BENCH_KERNEL(lds,     , a[i] = ((volatile unsigned *)sh)[(a[i] >> 2) & 1023u])
+BENCH_KERNEL(lds_prmt_imad, , { unsigned ad = __byte_perm(a[i], b, 0x7614) & 0xFFCu; unsigned v = ((volatile unsigned *)sh)[ad >> 2]; a[i] = v * v + a[i]; })
 BENCH_KERNEL(vimnmx16x2, , asm volatile("max.s16x2 %0, %0, %1;" : "+r"(a[i]) : "r"(b)))
 BENCH_KERNEL(mix_imad_alu, , asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(a[i]) : "r"(b), "r"(c)); asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[i]) : "r"(b), "r"(c)))
 
@@ -87,6 +88,7 @@ int main()
         run("iabs+sub", k_iabs, 2, threads);
         run("flo+add", k_flo, 2, threads);
         run("lds", k_lds, 1, threads);
+        run("lds+prmt+imad", k_lds_prmt_imad, 3, threads);
         run("vimnmx.s16x2", k_vimnmx16x2, 1, threads);
         run("imad+lop3", k_mix_imad_alu, 2, threads);
     }

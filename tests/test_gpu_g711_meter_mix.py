@@ -44,6 +44,10 @@ def test_encode_exhaustive(vp, law):
     pcm = np.arange(-32768, 32768, dtype=np.int32).astype(np.int16)
     got = vp.g711_encode(pcm, law)
     assert np.array_equal(got, O.encode_table(law))
+    # the encoder works on packed pairs: every value next to partners of either sign
+    for seed in range(3):
+        shuf = np.random.default_rng(seed).permutation(pcm)
+        assert np.array_equal(vp.g711_encode(shuf, law), O.g711_encode(shuf, law))
 
 
 @pytest.mark.parametrize("n", [0, 1, 15, 16, 17, 159, 161, 4099])
