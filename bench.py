@@ -166,9 +166,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=F, help="frames per step (default: the config-3 value)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
     args = ap.parse_args()
+    if args.frames != F:
+        globals()["F"] = args.frames
+        globals()["WORKLOAD"] = WORKLOAD.replace("x 1640 frames", f"x {args.frames} frames (non-default)")
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)

@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG_DIR, "libigate_dsp.so")
+# IGD_LIB_PATH: developer knob to load an experimental build of the same library
+LIB_PATH = os.environ.get("IGD_LIB_PATH") or os.path.join(PKG_DIR, "libigate_dsp.so")
 
 FRAME = 160
 PKT_HDR = 20

@@ -17,6 +17,8 @@
 //  * Per-frame meters: exact integer partial sums per 16-sample chunk, combined
 //    through a padded shared-memory array (conflict-free LDS.64), dB via SFU lg2.
 //  * Persistent grids: a multiple of the SM count, each CTA strides over tiles.
+#include <cstdlib>
+
 #include "igd_kernels.cuh"
 #include "igd_math.cuh"
 
@@ -59,43 +61,52 @@ __device__ __forceinline__ uint32_t pack_sat16(int hi, int lo)
 __device__ __forceinline__ int clamp16(int v) { return min(max(v, -32768), 32767); }
 
 // ------------------------------------------------------------------ decode LUT
-// Entry = two int16: low half x = decoded sample, high half clamp16(2x) = the
-// sample after the reference's open-gate gain 2.0 (SLOT_VOLUME, Functions.cpp:
-// 1682) with pjmedia's per-port clip.  One IDP.2A then selects x (gain 1.0),
+// 64 KB: one 32 KB table per law, row = code (128 B), column = lane (4 B), so a
+// lookup can never bank-conflict (every lane owns its bank) and its address is ONE
+// instruction on the FMA pipe: IDP.4A(word, 0x80 << 8k, lane_base) = code_k*128 +
+// lane_base -- the ALU pipe, which bounds this kernel, is not involved.
+// Entry = two int16: low half x/4 (every G.711 sample is a multiple of 4, so this is
+// exact and sum((x/4)^2) over a 16-sample chunk fits 32 bits), high half clamp16(2x) =
+// the sample after the reference's open-gate gain 2.0 (SLOT_VOLUME, Functions.cpp:
+// 1682) with pjmedia's per-port clip.  One IDP.2A then selects 4*(x/4) (gain 1.0),
 // clamp16(2x) (gain 2.0) or nothing (gate shut) AND accumulates it into the mix.
 __device__ __forceinline__ void build_decode_lut(uint32_t *lut, int tid, int nthreads)
 {
-    for (int i = tid; i < 256 * 64; i += nthreads) {
-        const uint32_t code = (uint32_t)i >> 6, slot = i & 63;
-        const uint32_t lane = slot >> 1;
-        const uint32_t law = (slot & 1) ^ (lane >> 4);
+    for (int i = tid; i < 2 * 256 * 32; i += nthreads) {
+        const uint32_t law = (uint32_t)i >> 13, code = ((uint32_t)i >> 5) & 255u;
         const int x = law ? igd_ulaw2lin(code) : igd_alaw2lin(code);
         const int y2 = min(max(2 * x, -32768), 32767);
-        lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)x & 0xFFFFu);
+        lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)(x >> 2) & 0xFFFFu);
     }
 }
-// byte offset of this lane's column for `law`
-__device__ __forceinline__ uint32_t lut_lane_byte(uint32_t lane, uint32_t law)
+// shared-window byte address of this lane's column in the table of `law`
+__device__ __forceinline__ uint32_t lut_lane_base(uint32_t lut_s, uint32_t lane, uint32_t law)
 {
-    return 4u * (2u * lane + ((law & 1u) ^ (lane >> 4)));
+    return lut_s + 4u * lane + ((law & 1u) << 15);
 }
 template <int K>
-__device__ __forceinline__ uint32_t lut_lookup(const uint8_t *lut_bytes, uint32_t word, uint32_t lane_byte)
+__device__ __forceinline__ uint32_t lut_lookup(uint32_t lane_base, uint32_t word)
 {
-    // (code<<8) | lane_byte in one PRMT: byte0 = lane_byte, byte1 = word.byteK
-    const uint32_t a = __byte_perm(word, lane_byte, 0x7604 + (K << 4));
-    return *reinterpret_cast<const uint32_t *>(lut_bytes + a);
+    const uint32_t a = __dp4a(word, 0x80u << (8 * K), lane_base);
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
 }
-template <int K>
-__device__ __forceinline__ int lut_decode(const uint8_t *lut_bytes, uint32_t word, uint32_t lane_byte)
+__device__ __forceinline__ uint32_t shared_addr(const void *p)
 {
-    return (int)(short)(lut_lookup<K>(lut_bytes, word, lane_byte) & 0xFFFFu);
+    return (uint32_t)__cvta_generic_to_shared(p);
 }
 // d = c + a.lo16 * b.byte0 + a.hi16 * b.byte1   (IDP.2A.LO.S16.U8, FMA pipe)
 __device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c)
 {
     int d;
     asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t dp2a_lo_u(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
 // packed 2 x 16-bit ALU ops (VIMNMX[3].S16x2 / .U16x2, VIADD.16x2, VIADDMNMX.S16x2)
@@ -128,20 +139,17 @@ __device__ __forceinline__ uint32_t add_16x2(uint32_t a, uint32_t b)
 }
 
 // ------------------------------------------------------------------ partials
-// 8-byte per-chunk meter partial: lo = sumsq[31:0];
-// hi = sumsq[34:32] | peak<<3 (16 bit) | bytesum<<19 (13-bit signed)
-__device__ __forceinline__ uint2 partial_pack(unsigned long long sq, uint32_t peak, int bsum)
+// 8-byte per-chunk meter partial: lo = sum((x/4)^2) over the 16 samples (< 2^31);
+// hi = max|x|/4 (16 bit) | bytesum<<16 (signed 16 bit)
+__device__ __forceinline__ uint2 partial_pack(uint32_t sq16, uint32_t peakq, int bsum)
 {
-    uint2 r;
-    r.x = (uint32_t)sq;
-    r.y = (uint32_t)(sq >> 32) | (peak << 3) | ((uint32_t)bsum << 19);
-    return r;
+    return make_uint2(sq16, (peakq & 0xFFFFu) | ((uint32_t)bsum << 16));
 }
-__device__ __forceinline__ void partial_add(uint2 v, unsigned long long &sq, uint32_t &peak, int &bsum)
+__device__ __forceinline__ void partial_add(uint2 v, unsigned long long &sq16, uint32_t &peakq, int &bsum)
 {
-    sq += (unsigned long long)v.x | ((unsigned long long)(v.y & 7u) << 32);
-    peak = max(peak, (v.y >> 3) & 0xFFFFu);
-    bsum += (int)v.y >> 19;
+    sq16 += v.x;
+    peakq = max(peakq, v.y & 0xFFFFu);
+    bsum += (int)v.y >> 16;
 }
 __device__ __forceinline__ igd_meter_rec meter_finish(unsigned long long sq, uint32_t peak, int bsum,
                                                       bool have_bytes)
@@ -202,8 +210,9 @@ __device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t 
     t = min_u16x2(t, E.hi_pos ^ (sgn & E.hi_x));                    // u-law clip
     const uint32_t p = max_s16x2(add_16x2(t, E.bias_pos ^ (sgn & E.bias_x)), 0u);
     const uint32_t P = add_16x2(p, max_u16x2(p, E.thr));            // leading one -> segment
-    const float g0 = fmaf(__uint_as_float(__byte_perm(P, 0x4B000000u, 0x7410)), 0.0078125f, -65536.0f);
-    const float g1 = fmaf(__uint_as_float(__byte_perm(P, 0x4B000000u, 0x7432)), 0.0078125f, -65536.0f);
+    // 8388608.0f + P per half, built on the FMA pipe (IDP.2A picks the half and adds the magic)
+    const float g0 = fmaf(__uint_as_float(dp2a_lo_u(P, 0x0001u, 0x4B000000u)), 0.0078125f, -65536.0f);
+    const float g1 = fmaf(__uint_as_float(dp2a_lo_u(P, 0x0100u, 0x4B000000u)), 0.0078125f, -65536.0f);
     c0 = __float_as_uint(g0) << 5;                                  // bits[26:19] -> byte 3
     c1 = __float_as_uint(g1) << 5;
 }
@@ -244,41 +253,43 @@ constexpr uint32_t kSelGeneral = 0xFFFFFFFFu;
 // takes the general multiply / shift / clip path.
 __device__ __forceinline__ uint32_t gain_selector(uint32_t adj)
 {
-    return adj == 0u ? 0u : adj == 128u ? 0x0001u : adj == 256u ? 0x0100u : kSelGeneral;
+    return adj == 0u ? 0u : adj == 128u ? 0x0004u : adj == 256u ? 0x0100u : kSelGeneral;
 }
 
 // decode + meter + gain/accumulate one 16-sample chunk of one leg
-template <bool kSigned>
-__device__ __forceinline__ uint2 leg_chunk(const uint8_t *lut_bytes, uint4 w, uint32_t lane_byte,
-                                           uint32_t sel, int adj, int (&acc)[16])
+// kMode: 0 = gate shut (meter only), 1 = gain 1.0 / 2.0 through the IDP.2A selector,
+//        2 = arbitrary Q7 gain (multiply, shift, clip)
+template <bool kSigned, int kMode>
+__device__ __forceinline__ uint2 leg_chunk(uint32_t lane_base, uint4 w, uint32_t sel, int adj, int (&acc)[16])
 {
     const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
-    unsigned long long sq = 0;
-    uint32_t mx = 0, mn = 0;       // packed running max / min of (x, clamp16(2x))
+    uint32_t sq = 0;               // sum of (x/4)^2: 16 * 8064^2 < 2^31
+    uint32_t mx = 0, mn = 0;       // packed running max / min of (x/4, clamp16(2x))
     int bsum = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const uint32_t e0 = lut_lookup<0>(lut_bytes, wd[j], lane_byte);
-        const uint32_t e1 = lut_lookup<1>(lut_bytes, wd[j], lane_byte);
-        const uint32_t e2 = lut_lookup<2>(lut_bytes, wd[j], lane_byte);
-        const uint32_t e3 = lut_lookup<3>(lut_bytes, wd[j], lane_byte);
-        const int x0 = dp2a_lo(e0, 1u, 0), x1 = dp2a_lo(e1, 1u, 0);
-        const int x2 = dp2a_lo(e2, 1u, 0), x3 = dp2a_lo(e3, 1u, 0);
-        // |G.711 sample| <= 32256, so four squares fit in 32 bits
+        const uint32_t e0 = lut_lookup<0>(lane_base, wd[j]);
+        const uint32_t e1 = lut_lookup<1>(lane_base, wd[j]);
+        const uint32_t e2 = lut_lookup<2>(lane_base, wd[j]);
+        const uint32_t e3 = lut_lookup<3>(lane_base, wd[j]);
+        // x/4 sign-extended from the low half: PRMT (ALU pipe) -- the rest of this loop body
+        // is IDP/IMAD on the FMA pipe, so this keeps the two pipes evenly loaded
+        const int x0 = (int)prmt_full<0x9910>(e0, 0u), x1 = (int)prmt_full<0x9910>(e1, 0u);
+        const int x2 = (int)prmt_full<0x9910>(e2, 0u), x3 = (int)prmt_full<0x9910>(e3, 0u);
         sq += (uint32_t)(x0 * x0) + (uint32_t)(x1 * x1) + (uint32_t)(x2 * x2) + (uint32_t)(x3 * x3);
         mx = max_s16x2(max_s16x2(mx, e0), e1); mx = max_s16x2(max_s16x2(mx, e2), e3);
         mn = min_s16x2(min_s16x2(mn, e0), e1); mn = min_s16x2(min_s16x2(mn, e2), e3);
         bsum = kSigned ? __dp4a((int)wd[j], 0x01010101, bsum) : (int)__dp4a(wd[j], 0x01010101u, (uint32_t)bsum);
-        if (sel != kSelGeneral) {
+        if (kMode == 1) {
             acc[4 * j + 0] = dp2a_lo(e0, sel, acc[4 * j + 0]);
             acc[4 * j + 1] = dp2a_lo(e1, sel, acc[4 * j + 1]);
             acc[4 * j + 2] = dp2a_lo(e2, sel, acc[4 * j + 2]);
             acc[4 * j + 3] = dp2a_lo(e3, sel, acc[4 * j + 3]);
-        } else {
-            acc[4 * j + 0] += clamp16((x0 * adj) >> 7);
-            acc[4 * j + 1] += clamp16((x1 * adj) >> 7);
-            acc[4 * j + 2] += clamp16((x2 * adj) >> 7);
-            acc[4 * j + 3] += clamp16((x3 * adj) >> 7);
+        } else if (kMode == 2) {
+            acc[4 * j + 0] += clamp16((4 * x0 * adj) >> 7);
+            acc[4 * j + 1] += clamp16((4 * x1 * adj) >> 7);
+            acc[4 * j + 2] += clamp16((4 * x2 * adj) >> 7);
+            acc[4 * j + 3] += clamp16((4 * x3 * adj) >> 7);
         }
     }
     const int pmax = (int)(short)(mx & 0xFFFFu), pmin = (int)(short)(mn & 0xFFFFu);
@@ -314,94 +325,257 @@ __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_p
     return make_uint2((uint32_t)esum, (uint32_t)max(hi, -lo));
 }
 
-template <int G, int BFPC, bool kSigned>
-__global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused(const FusedParams q)
+// ---------------------------------------------------------------- mbarrier / TMA
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(shared_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(shared_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(shared_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra WAIT_%=;\n\t}"
+        ::"r"(shared_addr(bar)), "r"(parity) : "memory");
+}
+// same, for the helper warps: let the hardware park the warp (suspend-time hint)
+// so that waiting does not take issue slots from the producer warps
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITB_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@!p bra WAITB_%=;\n\t}"
+        ::"r"(shared_addr(bar)), "r"(parity), "r"(0x20000u) : "memory");
+}
+// TMA bulk copy global -> shared (UBLKCP): no registers, no LSU issue slots; the
+// bytes land asynchronously and complete_tx on `bar`.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_s), "l"(src), "r"(bytes), "r"(shared_addr(bar)) : "memory");
+}
+
+#ifndef IGD_METER_WARPS
+#define IGD_METER_WARPS 1
+#endif
+constexpr int kMeterThreads = 32 * IGD_METER_WARPS;
+constexpr int kHelperThreads = kMeterThreads + 32;     // meter warps + the TMA issue warp
+
+// raw gain bits of one bridge-frame (G u16 values) in two registers
+template <int G>
+__device__ __forceinline__ uint2 load_gains(const uint16_t *g)
+{
+    if (G == 4) return *reinterpret_cast<const uint2 *>(g);
+    if (G == 2) return make_uint2(*reinterpret_cast<const uint32_t *>(g), 0u);
+    return make_uint2(*g, 0u);
+}
+
+// Fused decode -> meter -> gate/gain -> mix -> encode (G in {1,2,4} legs per bridge).
+//   One CTA owns tiles of BFPC consecutive bridge-frames (contiguous in every array).
+//   * BFPC*10 producer threads: thread = one 16-sample chunk of one bridge-frame, all
+//     G legs.  The tile's codes (BFPC*G*160 contiguous bytes) are staged into shared
+//     memory by ONE bulk async copy (TMA, cp.async.bulk + mbarrier complete_tx) issued
+//     a tile ahead, so no warp ever waits on HBM latency; gains ride in two prefetched
+//     registers.
+//   * IGD_METER_WARPS meter warps turn the per-chunk partials (double-buffered in
+//     shared memory, mbarrier full/empty handshake) into the 16-byte records.
+//   * one more warp only issues the bulk copies (a single lane), a tile ahead.
+template <int G, int BFPC, bool kSigned, int kStages, int kCtasPerSm>
+__global__ void __launch_bounds__(BFPC * kChunks + kHelperThreads, kCtasPerSm) k_fused(const FusedParams q)
+{
+    constexpr int kProducers = BFPC * kChunks, kThreads = kProducers + kHelperThreads;
+    constexpr int kProducerWarps = (kProducers + 31) / 32;
+    constexpr int kStageBytes = BFPC * G * IGD_FRAME;
+    __shared__ uint64_t part_full[2], part_empty[2], stage_full[kStages], stage_empty[kStages];
+    __shared__ __align__(16) uint32_t enc_tab[2][8];
+    extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
-    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes);       // [2][BFPC*G][kPst]
+    uint8_t *stage = smem + kLutBytes;                               // [kStages][BFPC][G][160] codes
+    uint2 *part = reinterpret_cast<uint2 *>(stage + kStages * kStageBytes);   // [2][BFPC*G][kPst]
     uint2 *bpart = part + 2 * BFPC * G * kPst;                       // [2][BFPC][kPst]
-    const uint8_t *lut_bytes = smem;
+    const uint32_t lut_bytes = shared_addr(smem);
 
     const int t = threadIdx.x;
     const uint32_t lane = t & 31;
-    build_decode_lut(lut, t, BFPC * kChunks);
+    build_decode_lut(lut, t, kThreads);
+    if (t < 2) {
+        const enc_pk e = enc_pk_make(t);
+        enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
+        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4;
+    }
+    if (t == 0) {
+        mbar_init(&part_full[0], kProducerWarps); mbar_init(&part_full[1], kProducerWarps);
+        mbar_init(&part_empty[0], IGD_METER_WARPS); mbar_init(&part_empty[1], IGD_METER_WARPS);
+        for (int i = 0; i < kStages; i++) { mbar_init(&stage_full[i], 1); mbar_init(&stage_empty[i], kProducerWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
+    auto tile_bytes = [&](long long tile) -> uint32_t {
+        const long long left = q.total_bf - tile * BFPC;
+        return (uint32_t)(left < BFPC ? left : BFPC) * (uint32_t)(G * IGD_FRAME);
+    };
+
+    if (t >= kProducers + kMeterThreads) {
+        // ================= TMA issue warp: one lane stages tile i+1 while tile i is processed
+        if (lane == 0) {
+            int it = 0;
+            for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, it++) {
+                const int st = it % kStages;
+                // the slot's previous tenant (tile it-kStages) has been read by every producer warp
+                if (it >= kStages) mbar_wait_backoff(&stage_empty[st], (it / kStages - 1) & 1);
+                mbar_expect_tx(&stage_full[st], tile_bytes(tile));
+                bulk_g2s(shared_addr(stage) + st * kStageBytes, q.codes + (size_t)tile * kStageBytes,
+                         tile_bytes(tile), &stage_full[st]);
+            }
+        }
+        return;
+    }
+    if (t >= kProducers) {
+        // ================= meter warps
+        const int mt = t - kProducers;
+        int buf = 0, it = 0;
+        for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, buf ^= 1, it++) {
+            mbar_wait_backoff(&part_full[buf], (it >> 1) & 1);
+            const uint2 *pb = part + (size_t)buf * BFPC * G * kPst;
+            for (int k = mt; k < BFPC * G; k += kMeterThreads) {
+                const long long lf = tile * BFPC * G + k;
+                if (lf < q.total_bf * G) {
+                    const uint2 *src = pb + (size_t)k * kPst;
+                    unsigned long long sq = 0; uint32_t peak = 0; int bsum = 0;
+#pragma unroll
+                    for (int i = 0; i < kChunks; i++) partial_add(src[i], sq, peak, bsum);
+                    const igd_meter_rec r = meter_finish(sq << 4, peak << 2, bsum, true);
+                    st16_stream(q.meter + lf, *reinterpret_cast<const uint4 *>(&r));
+                }
+            }
+            for (int k = kMeterThreads - 1 - mt; k < BFPC; k += kMeterThreads) {
+                const long long bf2 = tile * BFPC + k;
+                if (bf2 < q.total_bf) {
+                    const uint2 *src = bpart + (size_t)buf * BFPC * kPst + k * kPst;
+                    int esum = 0, mpeak = 0;
+#pragma unroll
+                    for (int i = 0; i < kChunks; i++) { esum += (int)src[i].x; mpeak = max(mpeak, (int)src[i].y); }
+                    int n_open = 0;
+#pragma unroll
+                    for (int g = 0; g < G; g++) n_open += q.gain[(size_t)bf2 * G + g] != 0;
+                    igd_bridge_rec r;
+                    r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
+                    r.n_open = (uint8_t)n_open;
+                    r.mix_peak = (uint16_t)mpeak;
+                    q.bmeter[bf2] = r;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&part_empty[buf]);            // buffer may be refilled
+        }
+        return;
+    }
+
+    // ================= producer warps
     const int bfl = t / kChunks, p = t - bfl * kChunks;
+    const uint32_t my_stage = shared_addr(stage) + (uint32_t)(bfl * G * IGD_FRAME + p * 16);
     // bridge index of this thread's bridge-frame, advanced incrementally (no per-tile division)
     const long long bf_step = (long long)gridDim.x * BFPC;
     const int b_step = (int)(bf_step % q.B);
     long long bf = (long long)blockIdx.x * BFPC + bfl;
     int b = (int)(bf % q.B);
-    int buf = 0;
-    for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, buf ^= 1, bf += bf_step) {
+    uint2 gq = bf < q.total_bf ? load_gains<G>(q.gain + (size_t)bf * G) : make_uint2(0u, 0u);
+    auto load_laws = [&](int bb) -> uint32_t {      // the G leg laws (1 bit each) and the output law (bit 8)
+        uint32_t r = 0;
+        if (G == 4) {
+            const uint32_t lw = *reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4);
+            r = (lw & 1u) | ((lw >> 7) & 2u) | ((lw >> 14) & 4u) | ((lw >> 21) & 8u);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; g++) r |= (uint32_t)(q.law[(size_t)bb * G + g] & 1u) << g;
+        }
+        return r | ((uint32_t)(q.out_law[bb] & 1u) << 8);
+    };
+    uint32_t lwq = bf < q.total_bf ? load_laws(b) : 0u;
+    int buf = 0, it = 0;
+    for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, buf ^= 1, bf += bf_step, it++) {
         uint2 *mypart = part + (size_t)buf * BFPC * G * kPst + (size_t)bfl * G * kPst + p;
-        if (bf < q.total_bf) {
-            // ---- issue all loads of this bridge-frame chunk first
-            uint4 w[G];
-            const uint8_t *cb = q.codes + (size_t)bf * G * IGD_FRAME + p * 16;
+        // ---- this tile's codes from the staging ring, then hand the slot back
+        const int st = it % kStages;
+        mbar_wait(&stage_full[st], (it / kStages) & 1);
+        uint4 w[G];
 #pragma unroll
-            for (int g = 0; g < G; g++) w[g] = ld16_stream(cb + g * IGD_FRAME);
-            uint32_t adj[G], laws[G];
-            if (G == 4) {
-                const uint2 gq = *reinterpret_cast<const uint2 *>(q.gain + (size_t)bf * 4);
-                const uint32_t lw = *reinterpret_cast<const uint32_t *>(q.law + (size_t)b * 4);
-                adj[0] = gq.x & 0xFFFFu; adj[1 % G] = gq.x >> 16; adj[2 % G] = gq.y & 0xFFFFu; adj[3 % G] = gq.y >> 16;
-#pragma unroll
-                for (int g = 0; g < G; g++) laws[g] = (lw >> (8 * g)) & 1u;
-            } else {
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                    adj[g] = q.gain[(size_t)bf * G + g];
-                    laws[g] = q.law[(size_t)b * G + g];
-                }
+        for (int g = 0; g < G; g++)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(w[g].x), "=r"(w[g].y), "=r"(w[g].z), "=r"(w[g].w)
+                         : "r"(my_stage + st * kStageBytes + g * IGD_FRAME));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stage_empty[st]);
+        const uint2 gcur = gq;
+        const uint32_t lcur = lwq;
+        {
+            int bn = b + b_step;
+            if (bn >= q.B) bn -= q.B;
+            if (bf + bf_step < q.total_bf) {          // next tile's gains and laws ride in three registers
+                gq = load_gains<G>(q.gain + (size_t)(bf + bf_step) * G);
+                lwq = load_laws(bn);
             }
-            const enc_pk E = enc_pk_make(q.out_law[b]);
-
+        }
+        if (it >= 2) mbar_wait(&part_empty[buf], ((it >> 1) - 1) & 1); // meter warps are done with this buffer
+        if (bf < q.total_bf) {
+            uint32_t laws[G], sel[G], adj[G];
+            bool general;
+#pragma unroll
+            for (int g = 0; g < G; g++) laws[g] = (lcur >> g) & 1u;
+            {   // gain_q7 -> IDP.2A selectors, two legs per word: 0 -> 0, 128 -> 0x0004, 256 -> 0x0100
+                const uint32_t s01 = ((gcur.x >> 5) & 0x00040004u) | (gcur.x & 0x01000100u);
+                const uint32_t s23 = ((gcur.y >> 5) & 0x00040004u) | (gcur.y & 0x01000100u);
+                const uint32_t bad = ((gcur.x | gcur.y) & 0xFE7FFE7Fu) | (((gcur.x << 1) & gcur.x) & 0x01000100u) |
+                                     (((gcur.y << 1) & gcur.y) & 0x01000100u);
+                general = bad != 0u;
+                sel[0] = s01 & 0xFFFFu; adj[0] = gcur.x & 0xFFFFu;
+                if (G > 1) { sel[1 % G] = s01 >> 16; adj[1 % G] = gcur.x >> 16; }
+                if (G > 2) { sel[2 % G] = s23 & 0xFFFFu; adj[2 % G] = gcur.y & 0xFFFFu; sel[3 % G] = s23 >> 16; adj[3 % G] = gcur.y >> 16; }
+            }
+            enc_pk E;
+            {
+                const uint32_t *et = enc_tab[(lcur >> 8) & 1u];
+                const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
+                const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
+                E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
+            }
             int acc[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) acc[i] = 0;
+            if (!general) {        // gains in {0, 1.0, 2.0}: one IDP.2A per sample of an open leg
 #pragma unroll
-            for (int g = 0; g < G; g++)
-                mypart[g * kPst] = leg_chunk<kSigned>(lut_bytes, w[g], lut_lane_byte(lane, laws[g]),
-                                                      gain_selector(adj[g]), (int)adj[g], acc);
+                for (int g = 0; g < G; g++) {
+                    const uint32_t lb = lut_lane_base(lut_bytes, lane, laws[g]);
+                    mypart[g * kPst] = sel[g] ? leg_chunk<kSigned, 1>(lb, w[g], sel[g], 0, acc)
+                                              : leg_chunk<kSigned, 0>(lb, w[g], 0u, 0, acc);
+                }
+            } else {               // arbitrary Q7 gains: multiply, shift, clip
+#pragma unroll
+                for (int g = 0; g < G; g++)
+                    mypart[g * kPst] = leg_chunk<kSigned, 2>(lut_lane_base(lut_bytes, lane, laws[g]), w[g],
+                                                             0u, (int)adj[g], acc);
+            }
             bpart[(size_t)buf * BFPC * kPst + bfl * kPst + p] =
                 mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)bf * IGD_FRAME + p * 16,
                                        q.enc + (size_t)bf * IGD_FRAME + p * 16);
         }
         b += b_step;
         if (b >= q.B) b -= q.B;
-        __syncthreads();
-        // ---- per-frame meter records: one thread per leg-frame / bridge-frame
-        if (t < BFPC * G) {
-            const long long lf = tile * BFPC * G + t;
-            if (lf < q.total_bf * G) {
-                const uint2 *src = part + (size_t)buf * BFPC * G * kPst + (size_t)t * kPst;
-                unsigned long long sq = 0; uint32_t peak = 0; int bsum = 0;
-#pragma unroll
-                for (int i = 0; i < kChunks; i++) partial_add(src[i], sq, peak, bsum);
-                const igd_meter_rec r = meter_finish(sq, peak, bsum, true);
-                st16_stream(q.meter + lf, *reinterpret_cast<const uint4 *>(&r));
-            }
-        } else if (t >= BFPC * kChunks - BFPC) {
-            const int k = t - (BFPC * kChunks - BFPC);
-            const long long bf2 = tile * BFPC + k;
-            if (bf2 < q.total_bf) {
-                const uint2 *src = bpart + (size_t)buf * BFPC * kPst + k * kPst;
-                int esum = 0, mpeak = 0;
-#pragma unroll
-                for (int i = 0; i < kChunks; i++) { esum += (int)src[i].x; mpeak = max(mpeak, (int)src[i].y); }
-                int n_open = 0;
-#pragma unroll
-                for (int g = 0; g < G; g++) n_open += q.gain[(size_t)bf2 * G + g] != 0;
-                igd_bridge_rec r;
-                r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
-                r.n_open = (uint8_t)n_open;
-                r.mix_peak = (uint16_t)mpeak;
-                q.bmeter[bf2] = r;
-            }
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&part_full[buf]);                  // this warp's partials are published
     }
 }
 
@@ -414,7 +588,7 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
     uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes);       // [BFPC][kPst]
     uint2 *bpart = part + BFPC * kPst;                               // [BFPC][kPst]
-    const uint8_t *lut_bytes = smem;
+    const uint32_t lut_bytes = shared_addr(smem);
     const int t = threadIdx.x, G = q.G;
     const uint32_t lane = t & 31;
     build_decode_lut(lut, t, BFPC * kChunks);
@@ -431,8 +605,10 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
             if (valid) {
                 const uint4 w = ld16_stream(q.codes + ((size_t)bf * G + g) * IGD_FRAME + p * 16);
                 const uint32_t a = q.gain[(size_t)bf * G + g];
-                part[bfl * kPst + p] = leg_chunk<kSigned>(lut_bytes, w, lut_lane_byte(lane, q.law[(size_t)b * G + g]),
-                                                          gain_selector(a), (int)a, acc);
+                const uint32_t sl = gain_selector(a), lb = lut_lane_base(lut_bytes, lane, q.law[(size_t)b * G + g]);
+                part[bfl * kPst + p] = sl == kSelGeneral ? leg_chunk<kSigned, 2>(lb, w, 0u, (int)a, acc)
+                                       : sl             ? leg_chunk<kSigned, 1>(lb, w, sl, 0, acc)
+                                                        : leg_chunk<kSigned, 0>(lb, w, 0u, 0, acc);
             }
             __syncthreads();
             if (t < BFPC) {
@@ -441,7 +617,7 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
                     unsigned long long sq = 0; uint32_t peak = 0; int bsum = 0;
 #pragma unroll
                     for (int i = 0; i < kChunks; i++) partial_add(part[t * kPst + i], sq, peak, bsum);
-                    const igd_meter_rec r = meter_finish(sq, peak, bsum, true);
+                    const igd_meter_rec r = meter_finish(sq << 4, peak << 2, bsum, true);
                     st16_stream(q.meter + bf2 * G + g, *reinterpret_cast<const uint4 *>(&r));
                 }
             }
@@ -482,20 +658,21 @@ __global__ void __launch_bounds__(512) k_g711_decode(const uint8_t *__restrict__
     build_decode_lut(reinterpret_cast<uint32_t *>(smem), threadIdx.x, blockDim.x);
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lut_s = shared_addr(smem);
     const size_t nchunk = n / 16;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunk;
          i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t lw = law_ch ? law_ch[(i / kChunks) % nch] : (uint32_t)law;
-        const uint32_t lb = lut_lane_byte(lane, lw);
+        const uint32_t lb = lut_lane_base(lut_s, lane, lw);
         const uint4 w = ld16_stream(codes + i * 16);
         const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
         uint32_t pk[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int x0 = lut_decode<0>(smem, wd[j], lb), x1 = lut_decode<1>(smem, wd[j], lb);
-            const int x2 = lut_decode<2>(smem, wd[j], lb), x3 = lut_decode<3>(smem, wd[j], lb);
-            pk[2 * j] = __byte_perm((uint32_t)x0, (uint32_t)x1, 0x5410);
-            pk[2 * j + 1] = __byte_perm((uint32_t)x2, (uint32_t)x3, 0x5410);
+        for (int j = 0; j < 4; j++) {      // low halves of the table entries are the samples / 4
+            const uint32_t e0 = lut_lookup<0>(lb, wd[j]), e1 = lut_lookup<1>(lb, wd[j]);
+            const uint32_t e2 = lut_lookup<2>(lb, wd[j]), e3 = lut_lookup<3>(lb, wd[j]);
+            pk[2 * j] = (__byte_perm(e0, e1, 0x5410) << 2) & 0xFFFCFFFCu;
+            pk[2 * j + 1] = (__byte_perm(e2, e3, 0x5410) << 2) & 0xFFFCFFFCu;
         }
         st32_stream(pcm + i * 16, pk);
     }
@@ -947,21 +1124,23 @@ cudaError_t igd_k_mix(const igd_launch_cfg &c, const int16_t *pcm, const uint16_
 }
 
 namespace {
-template <int G, int BFPC, bool kSigned>
+template <int G, int BFPC, bool kSigned, int kStages, int kCtasPerSm>
 cudaError_t launch_fused(const igd_launch_cfg &c, const FusedParams &q)
 {
-    const size_t smem = kLutBytes + (size_t)2 * BFPC * G * kPst * 8 + (size_t)2 * BFPC * kPst * 8;
-    cudaError_t e = cudaFuncSetAttribute(k_fused<G, BFPC, kSigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = k_fused<G, BFPC, kSigned, kStages, kCtasPerSm>;
+    const size_t smem = kLutBytes + (size_t)kStages * BFPC * G * IGD_FRAME + (size_t)2 * BFPC * G * kPst * 8 +
+                        (size_t)2 * BFPC * kPst * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused<G, BFPC, kSigned>, BFPC * kChunks, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BFPC * kChunks + kHelperThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     FusedParams p = q;
     p.num_tiles = (q.total_bf + BFPC - 1) / BFPC;
     long long grid = (long long)c.sm_count * per_sm;
     if (grid > p.num_tiles) grid = p.num_tiles;
-    k_fused<G, BFPC, kSigned><<<(int)grid, BFPC * kChunks, smem, c.stream>>>(p);
+    kern<<<(int)grid, BFPC * kChunks + kHelperThreads, smem, c.stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -994,9 +1173,13 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     q.B = d.B; q.G = d.G; q.flags = d.flags;
     const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
     switch (d.G) {
-    case 1: return sc ? launch_fused<1, 32, true>(c, q) : launch_fused<1, 32, false>(c, q);
-    case 2: return sc ? launch_fused<2, 32, true>(c, q) : launch_fused<2, 32, false>(c, q);
-    case 4: return sc ? launch_fused<4, 32, true>(c, q) : launch_fused<4, 32, false>(c, q);
+    case 1: return sc ? launch_fused<1, 32, true, 1, 2>(c, q) : launch_fused<1, 32, false, 1, 2>(c, q);
+    case 2: return sc ? launch_fused<2, 32, true, 1, 2>(c, q) : launch_fused<2, 32, false, 1, 2>(c, q);
+    case 4: {
+        static const int big = getenv("IGD_FUSED_BIGCTA") ? atoi(getenv("IGD_FUSED_BIGCTA")) : 0;   // tuning knob
+        if (big) return sc ? launch_fused<4, 64, true, 2, 1>(c, q) : launch_fused<4, 64, false, 2, 1>(c, q);
+        return sc ? launch_fused<4, 32, true, 1, 2>(c, q) : launch_fused<4, 32, false, 1, 2>(c, q);
+    }
     default: return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
     }
 }
