@@ -168,19 +168,6 @@ __device__ __forceinline__ int bytesum4(uint32_t w, bool signed_char, int acc)
     return signed_char ? __dp4a((int)w, 0x01010101, acc) : (int)__dp4a(w, 0x01010101u, (uint32_t)acc);
 }
 
-// encode 16 clamped samples -> 16 code bytes (scalar form; stand-alone encoder)
-__device__ __forceinline__ uint4 encode16(const int (&x)[16], const igd_enc_law &L)
-{
-    uint32_t w[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        const uint32_t c0 = igd_g711_enc1(x[4 * j + 0], L), c1 = igd_g711_enc1(x[4 * j + 1], L);
-        const uint32_t c2 = igd_g711_enc1(x[4 * j + 2], L), c3 = igd_g711_enc1(x[4 * j + 3], L);
-        w[j] = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-
 // The same compressor (igd_math.cuh) on PACKED pairs of int16: the pre-bias, clip
 // and segment normalisation run two samples per instruction on the 16x2 ALU ops,
 // only the exponent extraction (one PRMT + FFMA + shift) is per sample.
@@ -367,11 +354,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void *src, uint32
                  ::"r"(dst_s), "l"(src), "r"(bytes), "r"(shared_addr(bar)) : "memory");
 }
 
-#ifndef IGD_METER_WARPS
-#define IGD_METER_WARPS 1
-#endif
-constexpr int kMeterThreads = 32 * IGD_METER_WARPS;
-constexpr int kHelperThreads = kMeterThreads + 32;     // meter warps + the TMA issue warp
 
 // raw gain bits of one bridge-frame (G u16 values) in two registers
 template <int G>
@@ -389,12 +371,15 @@ __device__ __forceinline__ uint2 load_gains(const uint16_t *g)
 //     memory by ONE bulk async copy (TMA, cp.async.bulk + mbarrier complete_tx) issued
 //     a tile ahead, so no warp ever waits on HBM latency; gains ride in two prefetched
 //     registers.
-//   * IGD_METER_WARPS meter warps turn the per-chunk partials (double-buffered in
-//     shared memory, mbarrier full/empty handshake) into the 16-byte records.
-//   * one more warp only issues the bulk copies (a single lane), a tile ahead.
-template <int G, int BFPC, bool kSigned, int kStages, int kCtasPerSm>
-__global__ void __launch_bounds__(BFPC * kChunks + kHelperThreads, kCtasPerSm) k_fused(const FusedParams q)
+//   * kMeterWarps meter warps turn the per-chunk partials (double-buffered in shared
+//     memory, mbarrier full/empty handshake) into the 16-byte records.
+//   * one more warp only issues the bulk copies (a single lane), kStages-1 tiles ahead.
+// Shipped shapes: G=4 -> one 64-bridge-frame CTA per SM (20 producer + 3 meter + 1 TMA
+// warps, 2-stage ring); G=1,2 -> two 32-bridge-frame CTAs per SM, single stage.
+template <int G, int BFPC, bool kSigned, int kStages, int kCtasPerSm, int kMeterWarps>
+__global__ void __launch_bounds__(BFPC * kChunks + 32 * kMeterWarps + 32, kCtasPerSm) k_fused(const FusedParams q)
 {
+    constexpr int kMeterThreads = 32 * kMeterWarps, kHelperThreads = kMeterThreads + 32;
     constexpr int kProducers = BFPC * kChunks, kThreads = kProducers + kHelperThreads;
     constexpr int kProducerWarps = (kProducers + 31) / 32;
     constexpr int kStageBytes = BFPC * G * IGD_FRAME;
@@ -417,7 +402,7 @@ __global__ void __launch_bounds__(BFPC * kChunks + kHelperThreads, kCtasPerSm) k
     }
     if (t == 0) {
         mbar_init(&part_full[0], kProducerWarps); mbar_init(&part_full[1], kProducerWarps);
-        mbar_init(&part_empty[0], IGD_METER_WARPS); mbar_init(&part_empty[1], IGD_METER_WARPS);
+        mbar_init(&part_empty[0], kMeterWarps); mbar_init(&part_empty[1], kMeterWarps);
         for (int i = 0; i < kStages; i++) { mbar_init(&stage_full[i], 1); mbar_init(&stage_empty[i], kProducerWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -584,7 +569,7 @@ __global__ void __launch_bounds__(BFPC * kChunks + kHelperThreads, kCtasPerSm) k
 template <int BFPC, bool kSigned>
 __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedParams q)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
     uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes);       // [BFPC][kPst]
     uint2 *bpart = part + BFPC * kPst;                               // [BFPC][kPst]
@@ -654,7 +639,7 @@ __global__ void __launch_bounds__(512) k_g711_decode(const uint8_t *__restrict__
                                                      const uint8_t *__restrict__ law_ch, int law,
                                                      int16_t *__restrict__ pcm, size_t n, size_t nch)
 {
-    extern __shared__ __align__(16) uint8_t smem[];
+    extern __shared__ __align__(128) uint8_t smem[];
     build_decode_lut(reinterpret_cast<uint32_t *>(smem), threadIdx.x, blockDim.x);
     __syncthreads();
     const uint32_t lane = threadIdx.x & 31;
@@ -1124,10 +1109,11 @@ cudaError_t igd_k_mix(const igd_launch_cfg &c, const int16_t *pcm, const uint16_
 }
 
 namespace {
-template <int G, int BFPC, bool kSigned, int kStages, int kCtasPerSm>
+template <int G, int BFPC, bool kSigned, int kStages, int kCtasPerSm, int kMeterWarps>
 cudaError_t launch_fused(const igd_launch_cfg &c, const FusedParams &q)
 {
-    auto kern = k_fused<G, BFPC, kSigned, kStages, kCtasPerSm>;
+    auto kern = k_fused<G, BFPC, kSigned, kStages, kCtasPerSm, kMeterWarps>;
+    constexpr int kHelperThreads = 32 * kMeterWarps + 32;
     const size_t smem = kLutBytes + (size_t)kStages * BFPC * G * IGD_FRAME + (size_t)2 * BFPC * G * kPst * 8 +
                         (size_t)2 * BFPC * kPst * 8;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1173,13 +1159,9 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     q.B = d.B; q.G = d.G; q.flags = d.flags;
     const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
     switch (d.G) {
-    case 1: return sc ? launch_fused<1, 32, true, 1, 2>(c, q) : launch_fused<1, 32, false, 1, 2>(c, q);
-    case 2: return sc ? launch_fused<2, 32, true, 1, 2>(c, q) : launch_fused<2, 32, false, 1, 2>(c, q);
-    case 4: {
-        static const int big = getenv("IGD_FUSED_BIGCTA") ? atoi(getenv("IGD_FUSED_BIGCTA")) : 0;   // tuning knob
-        if (big) return sc ? launch_fused<4, 64, true, 2, 1>(c, q) : launch_fused<4, 64, false, 2, 1>(c, q);
-        return sc ? launch_fused<4, 32, true, 1, 2>(c, q) : launch_fused<4, 32, false, 1, 2>(c, q);
-    }
+    case 1: return sc ? launch_fused<1, 32, true, 1, 2, 1>(c, q) : launch_fused<1, 32, false, 1, 2, 1>(c, q);
+    case 2: return sc ? launch_fused<2, 32, true, 1, 2, 1>(c, q) : launch_fused<2, 32, false, 1, 2, 1>(c, q);
+    case 4: return sc ? launch_fused<4, 64, true, 2, 1, 3>(c, q) : launch_fused<4, 64, false, 2, 1, 3>(c, q);
     default: return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
     }
 }
