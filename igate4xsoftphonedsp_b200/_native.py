@@ -65,7 +65,8 @@ class PackDesc(C.Structure):
                 ("flags", C.c_uint32), ("payload_len", C.c_uint32), ("out_stride", C.c_uint32),
                 ("tick_ms", C.c_int32), ("now_ms0", C.c_int64),
                 ("rtp12", C.c_void_p), ("payload", C.c_void_p), ("ctl", C.c_void_p), ("state", C.c_void_p),
-                ("pkts", C.c_void_p), ("sizes", C.c_void_p), ("bytemean_out", C.c_void_p)]
+                ("pkts", C.c_void_p), ("sizes", C.c_void_p), ("bytemean_out", C.c_void_p),
+                ("stale_payload", C.c_void_p)]
 
 
 # every symbol include/igate_dsp.h declares: name -> (restype, argtypes)

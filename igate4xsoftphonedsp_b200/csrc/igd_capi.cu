@@ -566,10 +566,21 @@ int igd_ed137_pack(igd_ctx *c, const igd_ed137_pack_desc *d)
     if ((rc = out_arg(c, mem, 5, d->sizes, n, &dsz))) return rc;
     if ((rc = out_arg(c, mem, 6, d->bytemean_out, n, &dbm))) return rc;
     if ((rc = scratch(c, 8, n * sizeof(igd_tx_plan_rec), &dplan))) return rc;
+    void *dlast;
+    if ((rc = scratch(c, 9, (size_t)d->C * sizeof(int32_t), &dlast))) return rc;
+    uint8_t *dstale = nullptr;
+    if (d->stale_payload) {
+        const uint8_t *tmp2 = nullptr;
+        if ((rc = in_arg(c, mem, 10, static_cast<const uint8_t *>(d->stale_payload), (size_t)d->C * IGD_FRAME, &tmp2)))
+            return rc;
+        dstale = const_cast<uint8_t *>(tmp2);
+    }
     if (mem == IGD_MEM_HOST) IGD_CUDA(c, cudaMemsetAsync(dpk, 0, n * d->out_stride, c->stream));
     k.rtp12 = drtp; k.payload = dpay; k.ctl = dctl; k.state = dst; k.pkts = dpk; k.sizes = dsz; k.bytemean_out = dbm;
-    IGD_CUDA(c, igd_k_ed137_pack(cfg_of(c), k, static_cast<igd_tx_plan_rec *>(dplan)));
-    c->launches += igd_k_launches_ed137_pack();
+    k.stale_payload = dstale;
+    IGD_CUDA(c, igd_k_ed137_pack(cfg_of(c), k, static_cast<igd_tx_plan_rec *>(dplan), static_cast<int32_t *>(dlast)));
+    c->launches += dstale ? 3 : 2;
+    if (dstale && (rc = out_done(c, mem, d->stale_payload, dstale, (size_t)d->C * IGD_FRAME))) return rc;
     if ((rc = out_done(c, mem, d->pkts, dpk, n * d->out_stride))) return rc;
     if ((rc = out_done(c, mem, d->sizes, dsz, n))) return rc;
     if ((rc = out_done(c, mem, d->bytemean_out, dbm, n))) return rc;

@@ -914,7 +914,8 @@ __global__ void __launch_bounds__(256) k_ed137_parse(const uint8_t *__restrict__
 // Phase 1: one thread per channel walks its frames through the sender state
 // machine (transport_send_rtp, TransportAdapter.cpp:635-874) and writes a plan
 // record per packet.  The state is tiny and strictly sequential per channel.
-__global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d, igd_tx_plan_rec *__restrict__ plan)
+__global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d, igd_tx_plan_rec *__restrict__ plan,
+                                                    int32_t *__restrict__ last_src)
 {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
@@ -943,6 +944,23 @@ __global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d,
         plan[i] = r;
     }
     d.state[c] = s;
+    last_src[c] = src;
+}
+
+// after the packets are assembled: remember the payload each adapter's send buffer ends up holding
+__global__ void __launch_bounds__(256) k_ed137_stale_update(const igd_ed137_pack_desc d,
+                                                            const int32_t *__restrict__ last_src)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t c = warp; c < (size_t)d.C; c += nwarps) {
+        const int32_t f = last_src[c];
+        if (f < 0) continue;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(d.payload + ((size_t)f * d.C + c) * IGD_FRAME);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(d.stale_payload + c * IGD_FRAME);
+        for (uint32_t k = lane; k < IGD_FRAME / 4; k += 32) dst[k] = src[k];
+    }
 }
 
 // Phase 2: one warp per packet assembles header + payload (4-byte words; the
@@ -987,7 +1005,7 @@ __global__ void __launch_bounds__(256) k_ed137_assemble(const igd_ed137_pack_des
         if (r.size > IGD_PKT_HDR) {
             const uint32_t *src = r.src_frame >= 0
                 ? reinterpret_cast<const uint32_t *>(d.payload + ((size_t)r.src_frame * d.C + c) * IGD_FRAME)
-                : nullptr;
+                : (d.stale_payload ? reinterpret_cast<const uint32_t *>(d.stale_payload + c * IGD_FRAME) : nullptr);
             for (uint32_t k = lane; k < nwords; k += 32) out[5 + k] = src ? src[k] : 0u;
         }
         if (audio) {
@@ -1184,15 +1202,18 @@ cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, cons
     return cudaGetLastError();
 }
 
-int igd_k_launches_ed137_pack() { return 2; }
+int igd_k_launches_ed137_pack() { return 3; }
 
 cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc &d,
-                             igd_tx_plan_rec *plan)
+                             igd_tx_plan_rec *plan, int32_t *last_src)
 {
-    k_ed137_plan<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d, plan);
+    k_ed137_plan<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d, plan, last_src);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     k_ed137_assemble<<<grid_for(c, (size_t)d.F * d.C * 32, 256, 8), 256, 0, c.stream>>>(d, plan);
+    e = cudaGetLastError();
+    if (e != cudaSuccess || !d.stale_payload) return e;
+    k_ed137_stale_update<<<grid_for(c, (size_t)d.C * 32, 256, 8), 256, 0, c.stream>>>(d, last_src);
     return cudaGetLastError();
 }
 

@@ -40,7 +40,7 @@ cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, cons
                               size_t npkts, size_t stride, igd_ed137_fields *fields,
                               uint8_t *payload_out);
 cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc &d,
-                             igd_tx_plan_rec *plan);
+                             igd_tx_plan_rec *plan, int32_t *last_src);
 cudaError_t igd_k_wav_image(const igd_launch_cfg &c, const uint8_t *payload, size_t n, int rate,
                             int law, int ref_quirks, uint8_t *out);
 

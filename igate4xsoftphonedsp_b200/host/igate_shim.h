@@ -1,0 +1,123 @@
+// igate_shim.h -- thin host shim that keeps the reference's call signatures
+// (TransportAdapter.h:18-38, RoIP_ED137 getters Functions.cpp:1001-1179,
+// WavWriter.h:44-53, audiometer.cpp:30-31) and routes the per-packet work of a
+// whole 20 ms tick through ONE batched call of libigate_dsp.so (include/igate_dsp.h).
+//
+// The reference does the ED-137 work inside PJSIP callbacks, one packet at a
+// time per call (transport_rtp_cb / transport_send_rtp).  Here every adapter is
+// a slot of an igd_bank: the callbacks only STAGE their packet, and the owner
+// of the tick clock (PJSIP's conference clock thread in the reference,
+// roip_ed137.cpp:3031-3036) calls igd_bank_flush_tx / igd_bank_flush_rx once
+// per tick.  All arithmetic runs on the GPU; this file holds no codec, meter or
+// header math.
+//
+// Built against pjproject the PJ types come from <pjsua.h>; without it (this
+// repo's tests) minimal stand-ins are declared below.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/igate_dsp.h"
+
+#ifndef __PJ_TYPES_H__
+typedef int pj_status_t;
+typedef int pj_bool_t;
+typedef uint8_t pj_uint8_t;
+typedef uint16_t pj_uint16_t;
+typedef uint32_t pj_uint32_t;
+typedef size_t pj_size_t;
+typedef long pj_ssize_t;
+typedef int pjsua_call_id;
+#define PJ_SUCCESS 0
+struct pjmedia_transport;   // opaque handle, as handed around by the reference
+struct pjmedia_endpt;
+#endif
+
+// wire image of the reference's struct custom_rtp_hdr (ed137_rtp.h:22-47)
+#pragma pack(push, 1)
+struct custom_rtp_hdr {
+    uint8_t vpxcc;          // V:2 P:1 X:1 CC:4
+    uint8_t mpt;            // M:1 PT:7
+    uint16_t seq;           // network order
+    uint32_t ts;            // network order
+    uint32_t ssrc;          // network order
+    uint16_t profile_data;  // network order (0x0167)
+    uint16_t length;        // network order (1)
+    uint32_t ed137;         // network order
+};
+#pragma pack(pop)
+static_assert(sizeof(custom_rtp_hdr) == 20, "ed137_rtp.h:22-47");
+
+struct igd_bank;
+
+// ---- bank = all adapters of one process + the GPU context
+igd_bank *igd_bank_open(int device, int max_channels);
+void igd_bank_close(igd_bank *bank);
+void igd_bank_set_default(igd_bank *bank);    // the bank pjmedia_custom_tp_adapter_create allocates from
+igd_ctx *igd_bank_ctx(igd_bank *bank);
+
+// ---- reference signatures (TransportAdapter.h:18-38), same names and argument meaning
+pj_status_t pjmedia_custom_tp_adapter_create(pjmedia_endpt *endpt, const char *name, pjmedia_transport *transport,
+                                             pj_bool_t del_base, pj_bool_t radiocall, pj_bool_t callIn,
+                                             const char *calltype, pjsua_call_id callId, pjmedia_transport **p_tp,
+                                             const char *callIndex, const char *trxmode, int keepAlivePeroid,
+                                             pj_bool_t connToRadio, pj_bool_t pttWithPayload);
+pj_status_t decodeRtp(void *pkt, custom_rtp_hdr **hdr);
+pj_uint32_t get_ed137_value(pjmedia_transport *tp);
+pj_status_t setAdapterPtt(pjmedia_transport *tp, bool pttval, int priority, int userRec);
+pj_status_t setTxRxSlaveEnable(pjmedia_transport *tp, pj_bool_t rx, pj_bool_t tx);
+pj_status_t setAdapterRadioModeAndType(pjmedia_transport *tp, char const *type, char const *txrxmode);
+pj_status_t setAdapterQslOn(pjmedia_transport *tp, bool sqlval, int priority, pj_uint32_t bssi);
+pj_status_t setAdapterPttId(pjmedia_transport *tp, int pttid);
+pj_status_t setcallRecorder(pjmedia_transport *tp, bool val);
+pj_status_t setCallType(pjmedia_transport *tp, char const *calltype);
+long long getR2SStatus(pjmedia_transport *tp);
+
+// ---- RoIP_ED137 field getters (Functions.cpp:1001-1179), per adapter instead of per call id
+int get_IPRadioBss(pjmedia_transport *tp);
+int get_IPRadioPttStatus(pjmedia_transport *tp);
+int get_IPRadioPttId(pjmedia_transport *tp);
+int get_IPRadioSquelch(pjmedia_transport *tp);
+bool get_IPRadioStatus(pjmedia_transport *tp);
+uint8_t get_IncomingRTP(pjmedia_transport *tp);   // trx->IncomingRTP, roip_ed137.cpp:6541-6587
+uint8_t get_OutgoingRTP(pjmedia_transport *tp);   // trx->OutgoingRTP, roip_ed137.cpp:6500-6536
+
+// ---- per-tick staging (what the PJSIP callbacks become)
+// transport_send_rtp(tp, pkt, size): pkt = 12-byte RTP header + G.711 payload
+pj_status_t igd_submit_tx(pjmedia_transport *tp, const void *pkt, pj_size_t size);
+// transport_rtp_cb(user_data, pkt, size): a received packet (20-byte header + payload)
+pj_status_t igd_submit_rx(pjmedia_transport *tp, const void *pkt, pj_ssize_t size);
+typedef void (*igd_send_fn)(void *user, pjmedia_transport *tp, const void *pkt, pj_size_t size);
+// runs the staged TX packets of this tick through igd_ed137_pack and hands every packet that the
+// reference would have given to pjmedia_transport_send_rtp() to `send`; returns packets sent or <0
+int igd_bank_flush_tx(igd_bank *bank, long long now_ms, unsigned flags, igd_send_fn send, void *user);
+// runs the staged RX packets through igd_ed137_parse (+ the byte-mean meter); afterwards the getters
+// above return the new values; `stream_cb` (may be NULL) receives the audio packets (PT != 123) like
+// stream_rtp_cb does in the reference.  Returns packets parsed or <0
+int igd_bank_flush_rx(igd_bank *bank, long long now_ms, igd_send_fn stream_cb, void *user);
+
+// ---- WavWriter (WavWriter.h:44-53), same public methods; the file image is built on the GPU at stop()
+class WavWriter {
+public:
+    WavWriter();
+    ~WavWriter();
+    void writeRTPWav(const char *pktbuf, const char *payloadbuf, unsigned int pktlen, unsigned int payloadlen);
+    void start(std::string prefix, int rate);
+    void stop();
+    void wav_write(unsigned char *buf, unsigned int len);
+    bool isRunning();
+    // additions: which bank/GPU builds the image, the reference's byte-exact header quirks on/off
+    void attach(igd_bank *bank, bool ref_quirks, int law);
+    const std::string &fileName() const { return m_file; }
+
+private:
+    igd_bank *m_bank;
+    bool m_running, m_quirks;
+    int m_rate, m_law;
+    std::string m_file, m_data;
+};
+
+// ---- AudioMeter scale (audiometer.cpp:30-31) for a batch of raw levels
+int igd_audio_level_percent(igd_bank *bank, const int32_t *raw, size_t n, int32_t *percent);

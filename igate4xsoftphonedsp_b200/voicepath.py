@@ -330,11 +330,11 @@ class VoicePath:
         return fields, pay
 
     def ed137_pack(self, rtp12, payload, state, ctl=None, now_ms0=0, tick_ms=20, payload_len=N.FRAME,
-                   out_stride=N.PKT_MAX, flags=0):
+                   out_stride=N.PKT_MAX, flags=0, stale_payload=None):
         """Batched transport_send_rtp.  rtp12 u8 [F][C][12], payload u8 [F][C][160],
         state [C] (updated in place), ctl [F][C] or None.
         Returns (pkts u8 [F][C][out_stride], sizes u32 [F][C], bytemean_out u8 [F][C])."""
-        mem = self._mode(rtp12, payload, state, ctl)
+        mem = self._mode(rtp12, payload, state, ctl, stale_payload)
         F, Cn = rtp12.shape[0], rtp12.shape[1]
         if mem == N.MEM_DEVICE:
             dev = rtp12.device
@@ -353,7 +353,7 @@ class VoicePath:
             bm = np.empty((F, Cn), dtype=np.uint8)
         d = N.PackDesc(C.sizeof(N.PackDesc), mem, F, Cn, flags, payload_len, out_stride, tick_ms, now_ms0,
                        self._ptr(rtp12), self._ptr(payload), self._ptr(ctl), self._ptr(state),
-                       self._ptr(pkts), self._ptr(sizes), self._ptr(bm))
+                       self._ptr(pkts), self._ptr(sizes), self._ptr(bm), self._ptr(stale_payload))
         self._chk(self._lib.igd_ed137_pack(self._h, C.byref(d)))
         return pkts, sizes, bm
 

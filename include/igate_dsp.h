@@ -291,6 +291,11 @@ typedef struct {
     uint8_t *pkts;
     uint32_t *sizes;
     uint8_t *bytemean_out;
+    uint8_t *stale_payload;      /* optional [C][160], in/out: the payload bytes last copied
+                                    into each adapter's send buffer (send_pkt_buff+20,
+                                    TransportAdapter.cpp:683).  Only used with
+                                    IGD_F_REF_QUIRKS: carries quirk Q2 across calls.
+                                    NULL = zero-filled at the start of every call.  */
 } igd_ed137_pack_desc;
 int igd_ed137_pack(igd_ctx *ctx, const igd_ed137_pack_desc *d);
 

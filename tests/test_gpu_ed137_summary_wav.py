@@ -53,6 +53,27 @@ def test_pack_state_carries_across_batches(vp):
     assert np.array_equal(hdr[sent], want_pk[..., :20][sent])
 
 
+@pytest.mark.parametrize("name", ["trx_out_gated", "fuzz64"])
+def test_pack_quirk_q2_stale_payload_across_batches(vp, name):
+    """one tick per call (what the host shim does): the adapters' stale send buffers travel in stale_payload"""
+    s = [x for x in T.SCENARIOS if x["name"] == name][0]
+    want_pk, want_sz, want_bm, _ = T.run_oracle(s)
+    st = T.gpu_inputs(s)
+    Cn = len(s["legs"])
+    stale = np.zeros((Cn, 160), np.uint8)
+    step = 7
+    for f0 in range(0, s["F"], step):
+        sl = slice(f0, f0 + step)
+        pk, sz, bm = vp.ed137_pack(s["rtp12"][sl], s["payload"][sl], st, ctl=s["ctl"][sl],
+                                   now_ms0=s["now0"] + f0 * s["tick_ms"], tick_ms=s["tick_ms"],
+                                   flags=ig.F_REF_QUIRKS, stale_payload=stale)
+        assert np.array_equal(sz, want_sz[sl]) and np.array_equal(bm, want_bm[sl])
+        for f in range(sz.shape[0]):
+            for c in range(Cn):
+                n = int(sz[f, c])
+                assert pk[f, c, :n].tobytes() == want_pk[f0 + f, c, :n].tobytes(), (name, f0 + f, c)
+
+
 def test_parse_golden_reference_headers(vp, golden_dir):
     g = json.load(open(os.path.join(golden_dir, "ed137_ref_headers.json")))
     n = len(g["cases"])
