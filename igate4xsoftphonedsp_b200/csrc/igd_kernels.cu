@@ -22,6 +22,10 @@
 #include "igd_kernels.cuh"
 #include "igd_math.cuh"
 
+#ifndef IGD_X_EXTRACT
+#define IGD_X_EXTRACT 1   // 0: PRMT (ALU pipe), 1: IDP.2A (FMA pipe; measured best), 2: alternate
+#endif
+
 namespace {
 
 constexpr int kChunks = IGD_FRAME / 16;   // 16-byte chunks per frame = 10
@@ -261,8 +265,16 @@ __device__ __forceinline__ uint2 leg_chunk(uint32_t lane_base, uint4 w, uint32_t
         const uint32_t e3 = lut_lookup<3>(lane_base, wd[j]);
         // x/4 sign-extended from the low half: PRMT (ALU pipe) -- the rest of this loop body
         // is IDP/IMAD on the FMA pipe, so this keeps the two pipes evenly loaded
+#if IGD_X_EXTRACT == 0
         const int x0 = (int)prmt_full<0x9910>(e0, 0u), x1 = (int)prmt_full<0x9910>(e1, 0u);
         const int x2 = (int)prmt_full<0x9910>(e2, 0u), x3 = (int)prmt_full<0x9910>(e3, 0u);
+#elif IGD_X_EXTRACT == 1
+        const int x0 = dp2a_lo(e0, 1u, 0), x1 = dp2a_lo(e1, 1u, 0);
+        const int x2 = dp2a_lo(e2, 1u, 0), x3 = dp2a_lo(e3, 1u, 0);
+#else
+        const int x0 = (int)prmt_full<0x9910>(e0, 0u), x1 = dp2a_lo(e1, 1u, 0);
+        const int x2 = (int)prmt_full<0x9910>(e2, 0u), x3 = dp2a_lo(e3, 1u, 0);
+#endif
         sq += (uint32_t)(x0 * x0) + (uint32_t)(x1 * x1) + (uint32_t)(x2 * x2) + (uint32_t)(x3 * x3);
         mx = max_s16x2(max_s16x2(mx, e0), e1); mx = max_s16x2(max_s16x2(mx, e2), e3);
         mn = min_s16x2(min_s16x2(mn, e0), e1); mn = min_s16x2(min_s16x2(mn, e2), e3);
@@ -286,12 +298,12 @@ __device__ __forceinline__ uint2 leg_chunk(uint32_t lane_base, uint4 w, uint32_t
 // bridge output of one 16-sample chunk: saturate, store PCM, compress, store codes
 template <bool kSigned>
 __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_pk &E, int16_t *mix_dst,
-                                               uint8_t *enc_dst)
+                                               uint8_t *enc_dst, bool do_store = true)
 {
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
-    st32_stream(mix_dst, pk);
+    if (do_store) st32_stream(mix_dst, pk);
     uint32_t mx = max_s16x2(max_s16x2(pk[0], pk[1]), pk[2]), mn = min_s16x2(min_s16x2(pk[0], pk[1]), pk[2]);
     mx = max_s16x2(max_s16x2(mx, pk[3]), pk[4]); mn = min_s16x2(min_s16x2(mn, pk[3]), pk[4]);
     mx = max_s16x2(max_s16x2(mx, pk[5]), pk[6]); mn = min_s16x2(min_s16x2(mn, pk[5]), pk[6]);
@@ -299,7 +311,7 @@ __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_p
     const int hi = max((int)(short)(mx & 0xFFFFu), (int)mx >> 16);
     const int lo = min((int)(short)(mn & 0xFFFFu), (int)mn >> 16);
     const uint4 e = encode16_packed(pk, E);
-    st16_stream(enc_dst, e);
+    if (do_store) st16_stream(enc_dst, e);
     int esum = 0;
     if (kSigned) {
         esum = __dp4a((int)e.x, 0x01010101, esum); esum = __dp4a((int)e.y, 0x01010101, esum);
@@ -561,6 +573,283 @@ __global__ void __launch_bounds__(BFPC * kChunks + 32 * kMeterWarps + 32, kCtasP
         if (b >= q.B) b -= q.B;
         __syncwarp();
         if (lane == 0) mbar_arrive(&part_full[buf]);                  // this warp's partials are published
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Warp-autonomous fused kernel (G in {1,2,4}): no cross-warp handshake at all.
+// A warp owns "items" of kBfPerItem = 6 consecutive bridge-frames (6*G*160 contiguous
+// code bytes) and strides over them on its own:
+//   * the item's codes are fetched by the warp's OWN bulk async copies (TMA, one per
+//     bridge-frame into a padded, bank-conflict-free slot), completion on the warp's
+//     private mbarrier; the copies of item i+1 are issued as soon as every lane holds
+//     the last codes of item i, so HBM latency hides behind half an item (~1.5 us) and
+//     ~77 KB per SM are in flight;
+//   * lane = two 16-sample chunks (c and c+5) of one bridge-frame, all G legs (5 lanes
+//     per bridge-frame, 30 of 32 lanes busy): per-bridge-frame setup (gains, laws,
+//     selectors, addresses) is paid once per 32 samples;
+//   * the per-chunk meter partials meet in the warp's private shared scratch after a
+//     __syncwarp; lanes 0..6G-1 finish one leg record each, the next 6 lanes one bridge
+//     record each.
+// Warps drift freely: nobody spins on a peer (the CTA-cooperative kernel above spends
+// ~16 % of its issue slots in mbarrier spin loops).
+//
+// Decode table of this kernel: low half |x|/4 (unsigned -> the frame peak is ONE packed
+// max per two samples, no min), high half clamp16(2x).  The one-instruction accumulate
+// covers the reference's gains 0.0 and 2.0; every other gain (sidetone 0.1, 0.5, 1.0)
+// takes the multiply/shift/clip path with the sign recovered from the high half.
+constexpr int kBfPerItem = 6;
+constexpr int kC32 = IGD_FRAME / 32;      // lanes per bridge-frame = 5
+// shared-memory stride of one bridge-frame inside a slot: G*160 code bytes + a pad that makes
+// the stride == 5 (mod 8) in 16-byte units, so that lane l's LDS.128 of chunk c (+5 for the
+// second half) lands in bank group (l + 5h) mod 8: conflict-free for every quarter-warp.
+template <int G> struct slot_geom {
+    static constexpr int kBfBytes = G * IGD_FRAME;
+    static constexpr int kStride = kBfBytes + ((5 - (kBfBytes / 16) % 8 + 8) % 8) * 16;
+    static constexpr int kSlotBytes = kBfPerItem * kStride;
+};
+
+__device__ __forceinline__ void build_decode_lut_abs(uint32_t *lut, int tid, int nthreads)
+{
+    for (int i = tid; i < 2 * 256 * 32; i += nthreads) {
+        const uint32_t law = (uint32_t)i >> 13, code = ((uint32_t)i >> 5) & 255u;
+        const int x = law ? igd_ulaw2lin(code) : igd_alaw2lin(code);
+        const int y2 = min(max(2 * x, -32768), 32767);
+        lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)(abs(x) >> 2) & 0xFFFFu);
+    }
+}
+
+// decode + meter + gain/accumulate one 16-sample chunk of one leg (|x|/4 table)
+// kMode: 0 = gate shut for the whole warp (meter only), 1 = gain 2.0 or shut through the
+//        IDP.2A selector (0x0100 / 0), 2 = arbitrary Q7 gain (multiply, shift, clip)
+template <bool kSigned, int kMode>
+__device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32_t sel, int adj, int (&acc)[16])
+{
+    const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+    uint32_t sq = 0;               // sum of (x/4)^2: 16 * 8064^2 < 2^31
+    uint32_t mx = 0;               // packed running max of (|x|/4, junk)
+    int bsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t e0 = lut_lookup<0>(lane_base, wd[j]);
+        const uint32_t e1 = lut_lookup<1>(lane_base, wd[j]);
+        const uint32_t e2 = lut_lookup<2>(lane_base, wd[j]);
+        const uint32_t e3 = lut_lookup<3>(lane_base, wd[j]);
+        // |x|/4 out of the low half: two on the FMA pipe (IDP.2A), two on the ALU pipe (LOP3)
+        const uint32_t x0 = dp2a_lo_u(e0, 1u, 0u), x1 = e1 & 0xFFFFu;
+        const uint32_t x2 = dp2a_lo_u(e2, 1u, 0u), x3 = e3 & 0xFFFFu;
+        sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+        mx = max_u16x2(max_u16x2(mx, e0), e1); mx = max_u16x2(max_u16x2(mx, e2), e3);
+        bsum = kSigned ? __dp4a((int)wd[j], 0x01010101, bsum) : (int)__dp4a(wd[j], 0x01010101u, (uint32_t)bsum);
+        if (kMode == 1) {
+            acc[4 * j + 0] = dp2a_lo(e0, sel, acc[4 * j + 0]);
+            acc[4 * j + 1] = dp2a_lo(e1, sel, acc[4 * j + 1]);
+            acc[4 * j + 2] = dp2a_lo(e2, sel, acc[4 * j + 2]);
+            acc[4 * j + 3] = dp2a_lo(e3, sel, acc[4 * j + 3]);
+        } else if (kMode == 2) {
+            const int s0 = (int)e0 < 0 ? -(int)x0 : (int)x0, s1 = (int)e1 < 0 ? -(int)x1 : (int)x1;
+            const int s2 = (int)e2 < 0 ? -(int)x2 : (int)x2, s3 = (int)e3 < 0 ? -(int)x3 : (int)x3;
+            acc[4 * j + 0] += clamp16((4 * s0 * adj) >> 7);
+            acc[4 * j + 1] += clamp16((4 * s1 * adj) >> 7);
+            acc[4 * j + 2] += clamp16((4 * s2 * adj) >> 7);
+            acc[4 * j + 3] += clamp16((4 * s3 * adj) >> 7);
+        }
+    }
+    return make_uint2(sq, __byte_perm(mx, (uint32_t)bsum, 0x5410));   // {sq, peak/4 | bsum << 16}
+}
+
+template <int G, bool kSigned, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
+{
+    static_assert(kBfPerItem * G + kBfPerItem <= 32, "finish needs one lane per record");
+    using geom = slot_geom<G>;
+    constexpr int kLegParts = kBfPerItem * G * kPst, kBrParts = kBfPerItem * kPst;
+    __shared__ uint64_t bars[kWarps];
+    __shared__ __align__(16) uint32_t enc_tab[2][8];
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t lut_bytes = shared_addr(smem);
+
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, (uint32_t)t >> 5, 0);   // warp-uniform for the compiler too
+    const uint32_t slot_s = shared_addr(smem + kLutBytes) + warp * geom::kSlotBytes;
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes + (size_t)kWarps * geom::kSlotBytes) +
+                  (size_t)warp * (kLegParts + kBrParts);
+    uint2 *bpart = part + kLegParts;
+    const uint32_t bar_s = shared_addr(bars) + warp * 8;
+
+    build_decode_lut_abs(lut, t, kWarps * 32);
+    if (t < 2) {
+        const enc_pk e = enc_pk_make(t);
+        enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
+        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4;
+    }
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // bridge-frame and item indices fit 32 bits (the launcher checks total_bf < 2^31 - slack)
+    const uint32_t total_bf = (uint32_t)q.total_bf;
+    const uint32_t items = (total_bf + kBfPerItem - 1) / kBfPerItem;
+    const uint32_t nw = gridDim.x * kWarps;
+    uint32_t item = warp * gridDim.x + blockIdx.x;      // neighbouring items on different SMs
+    // one elected lane posts the byte count and issues one bulk async copy per bridge-frame of the
+    // item into the padded slot; every operand is warp-uniform (uniform datapath, no R2UR shuffles)
+    auto fetch = [&](uint32_t it_idx) {
+        const uint32_t bf0 = it_idx * kBfPerItem;
+        const uint32_t left = total_bf - bf0;
+        const uint32_t nbf = left < (uint32_t)kBfPerItem ? left : (uint32_t)kBfPerItem;
+        if (lane == 0) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(nbf * geom::kBfBytes)
+                         : "memory");
+            const uint8_t *g = q.codes + (size_t)bf0 * geom::kBfBytes;
+#pragma unroll
+            for (int k = 0; k < kBfPerItem; k++)
+                if ((uint32_t)k < nbf)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(slot_s + k * geom::kStride), "l"(g + k * geom::kBfBytes), "r"(geom::kBfBytes), "r"(bar_s)
+                                 : "memory");
+        }
+    };
+    if (item < items) fetch(item);
+
+    const bool worker = lane < kBfPerItem * kC32;
+    const uint32_t bfl = worker ? lane / kC32 : 0u, c = worker ? lane - bfl * kC32 : 0u;
+    const uint32_t src = slot_s + bfl * geom::kStride + c * 16;
+    const uint32_t lane4 = lut_bytes + 4u * lane;
+    const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kBfPerItem) % (uint32_t)q.B);
+    uint32_t b = (item * kBfPerItem + bfl) % (uint32_t)q.B;
+    auto load_laws = [&](uint32_t bb) -> uint32_t {      // the G leg laws (1 bit each) and the output law (bit 8)
+        uint32_t r = 0;
+        if (G == 4) {
+            const uint32_t lw = __ldg(reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4));
+            r = (lw & 1u) | ((lw >> 7) & 2u) | ((lw >> 14) & 4u) | ((lw >> 21) & 8u);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; g++) r |= (uint32_t)(__ldg(q.law + (size_t)bb * G + g) & 1u) << g;
+        }
+        return r | ((uint32_t)(__ldg(q.out_law + bb) & 1u) << 8);
+    };
+    uint2 gq = make_uint2(0u, 0u);
+    uint32_t lwq = 0u;
+    if (worker && item < items && item * kBfPerItem + bfl < total_bf) {
+        gq = load_gains<G>(q.gain + (size_t)(item * kBfPerItem + bfl) * G);
+        lwq = load_laws(b);
+    }
+
+    for (uint32_t it = 0; item < items; item += nw, it++) {
+        const uint32_t bf = item * kBfPerItem + bfl;
+        const uint32_t next = item + nw;
+        {   // this item's codes have landed
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "WAITW_%=:\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                "@!p bra WAITW_%=;\n\t}" ::"r"(bar_s), "r"(it & 1u) : "memory");
+        }
+        const uint2 gcur = gq;
+        const uint32_t lcur = lwq;
+        const bool valid = worker && bf < total_bf;
+        {
+            b += b_step;
+            if (b >= (uint32_t)q.B) b -= (uint32_t)q.B;
+            const uint32_t bfn = bf + nw * kBfPerItem;
+            if (worker && next < items && bfn < total_bf) {      // next item's gains and laws ride in three registers
+                gq = load_gains<G>(q.gain + (size_t)bfn * G);
+                lwq = load_laws(b);
+            }
+        }
+        // every lane runs the same instruction stream (idle / tail lanes on stale bytes with all
+        // gates shut); only the stores are predicated, and the mode branches are warp-uniform
+        auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
+        // gains other than 0 / 256 anywhere in the warp -> general path
+        const bool general = __any_sync(0xFFFFFFFFu, ((gcur.x | gcur.y) & 0xFEFFFEFFu) != 0u);
+        uint32_t open_mask = 0;       // bit g: some lane of the warp has leg g open
+#pragma unroll
+        for (int g = 0; g < G; g++) open_mask |= __any_sync(0xFFFFFFFFu, adj_of(g) != 0u) ? (1u << g) : 0u;
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            uint4 wh[G];
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
+                             : "r"(src + g * IGD_FRAME + h * (kC32 * 16)));
+            if (h == 1) {        // every lane holds the rest of its codes: refill the slot
+                __syncwarp();
+                if (next < items) fetch(next);
+            }
+            uint2 *mypart = part + bfl * (G * kPst) + c + kC32 * h;
+            int acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = 0;
+            if (!general) {        // gains in {0, 2.0}: one IDP.2A per sample of an open leg
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
+                    const uint2 ph = (open_mask >> g) & 1u ? leg_chunk_u<kSigned, 1>(lb, wh[g], adj_of(g), 0, acc)
+                                                           : leg_chunk_u<kSigned, 0>(lb, wh[g], 0u, 0, acc);
+                    if (valid) mypart[g * kPst] = ph;
+                }
+            } else {               // arbitrary Q7 gains: multiply, shift, clip
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
+                    const uint2 ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
+                    if (valid) mypart[g * kPst] = ph;
+                }
+            }
+            enc_pk E;
+            {
+                const uint32_t *et = enc_tab[(lcur >> 8) & 1u];
+                const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
+                const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
+                E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
+            }
+            const uint32_t o16 = bf * (IGD_FRAME / 16) + c + kC32 * h;     // 16-sample chunk index of the outputs
+            const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)o16 * 16, q.enc + (size_t)o16 * 16, valid);
+            if (valid) bpart[bfl * kPst + c + kC32 * h] = mo;
+        }
+        __syncwarp();
+        // ---- finish: one lane per record
+        {
+            const uint32_t bf0 = item * kBfPerItem;
+            if (lane < kBfPerItem * G) {
+                if (bf0 + lane / G < total_bf) {
+                    const uint2 *src_p = part + lane * kPst;
+                    unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
+#pragma unroll
+                    for (int i = 0; i < kChunks; i++) {
+                        const uint2 v = src_p[i];
+                        sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
+                    }
+                    const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
+                    st16_stream(q.meter + ((size_t)bf0 * G + lane), *reinterpret_cast<const uint4 *>(&r));
+                }
+            } else if (lane < kBfPerItem * G + kBfPerItem) {
+                const uint32_t j = lane - kBfPerItem * G;
+                if (bf0 + j < total_bf) {
+                    const uint2 *src_p = bpart + j * kPst;
+                    int esum = 0; uint32_t mpeak = 0;
+#pragma unroll
+                    for (int i = 0; i < kChunks; i++) { esum += (int)src_p[i].x; mpeak = max(mpeak, src_p[i].y); }
+                    const uint2 gj = load_gains<G>(q.gain + (size_t)(bf0 + j) * G);
+                    int n_open = 0;
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        n_open += ((g < 2 ? gj.x : gj.y) >> (16 * (g & 1)) & 0xFFFFu) != 0u;
+                    igd_bridge_rec r;
+                    r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
+                    r.n_open = (uint8_t)n_open;
+                    r.mix_peak = (uint16_t)mpeak;
+                    q.bmeter[bf0 + j] = r;
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -1148,6 +1437,21 @@ cudaError_t launch_fused(const igd_launch_cfg &c, const FusedParams &q)
     return cudaGetLastError();
 }
 
+template <int G, bool kSigned, int kWarps>
+cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
+{
+    auto kern = k_fused_w<G, kSigned, kWarps>;
+    const size_t smem = kLutBytes + (size_t)kWarps * slot_geom<G>::kSlotBytes +
+                        (size_t)kWarps * (kBfPerItem * G * kPst + kBfPerItem * kPst) * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (q.total_bf + kBfPerItem - 1) / kBfPerItem;
+    long long grid = c.sm_count;
+    if (grid > items) grid = items;      // small ticks: one item per SM before a second warp gets one
+    kern<<<(int)grid, kWarps * 32, smem, c.stream>>>(q);
+    return cudaGetLastError();
+}
+
 template <int BFPC, bool kSigned>
 cudaError_t launch_fused_anyg(const igd_launch_cfg &c, const FusedParams &q)
 {
@@ -1179,7 +1483,15 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     switch (d.G) {
     case 1: return sc ? launch_fused<1, 32, true, 1, 2, 1>(c, q) : launch_fused<1, 32, false, 1, 2, 1>(c, q);
     case 2: return sc ? launch_fused<2, 32, true, 1, 2, 1>(c, q) : launch_fused<2, 32, false, 1, 2, 1>(c, q);
-    case 4: return sc ? launch_fused<4, 64, true, 2, 1, 3>(c, q) : launch_fused<4, 64, false, 2, 1, 3>(c, q);
+    case 4: {
+        static const int variant = getenv("IGD_FUSED_VARIANT") ? atoi(getenv("IGD_FUSED_VARIANT")) : 1;
+        if (q.total_bf < (1ll << 31) - (1ll << 24)) {
+            if (variant == 1) return sc ? launch_fused_w<4, true, 20>(c, q) : launch_fused_w<4, false, 20>(c, q);
+            if (variant == 2) return launch_fused_w<4, false, 16>(c, q);
+            if (variant == 3) return launch_fused_w<4, false, 12>(c, q);
+        }
+        return sc ? launch_fused<4, 64, true, 2, 1, 3>(c, q) : launch_fused<4, 64, false, 2, 1, 3>(c, q);
+    }
     default: return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
     }
 }
