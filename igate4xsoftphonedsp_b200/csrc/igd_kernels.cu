@@ -193,19 +193,17 @@ __device__ __forceinline__ enc_pk enc_pk_make(int law)
     e.mask4 = L.mpos * 0x01010101u;
     return e;
 }
-// two packed samples -> two codes, each left in byte 3 of c0 / c1; sgn = 0xFFFF per negative half
-__device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t &c0, uint32_t &c1, uint32_t &sgn)
+// two packed samples -> the float whose bits [26:19] are seg<<4|mant, per sample
+__device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t &g0, uint32_t &g1)
 {
-    sgn = prmt_full<0xBB99>(pk, 0u);                                    // sign of each half, replicated
+    const uint32_t sgn = prmt_full<0xBB99>(pk, 0u);                 // sign of each half, replicated
     uint32_t t = pk ^ sgn;                                          // |x| or |x|-1
     t = min_u16x2(t, E.hi_pos ^ (sgn & E.hi_x));                    // u-law clip
     const uint32_t p = max_s16x2(add_16x2(t, E.bias_pos ^ (sgn & E.bias_x)), 0u);
     const uint32_t P = add_16x2(p, max_u16x2(p, E.thr));            // leading one -> segment
     // 8388608.0f + P per half, built on the FMA pipe (IDP.2A picks the half and adds the magic)
-    const float g0 = fmaf(__uint_as_float(dp2a_lo_u(P, 0x0001u, 0x4B000000u)), 0.0078125f, -65536.0f);
-    const float g1 = fmaf(__uint_as_float(dp2a_lo_u(P, 0x0100u, 0x4B000000u)), 0.0078125f, -65536.0f);
-    c0 = __float_as_uint(g0) << 5;                                  // bits[26:19] -> byte 3
-    c1 = __float_as_uint(g1) << 5;
+    g0 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, 0x0001u, 0x4B000000u)), 0.0078125f, -65536.0f));
+    g1 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, 0x0100u, 0x4B000000u)), 0.0078125f, -65536.0f));
 }
 // 8 packed words (16 samples) -> 16 code bytes
 __device__ __forceinline__ uint4 encode16_packed(const uint32_t (&pk)[8], const enc_pk &E)
@@ -213,11 +211,14 @@ __device__ __forceinline__ uint4 encode16_packed(const uint32_t (&pk)[8], const 
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        uint32_t c0, c1, c2, c3, s01, s23;
-        enc_pair(pk[2 * j], E, c0, c1, s01);
-        enc_pair(pk[2 * j + 1], E, c2, c3, s23);
-        const uint32_t codes = __byte_perm(__byte_perm(c0, c1, 0x0073), __byte_perm(c2, c3, 0x0073), 0x5410);
-        const uint32_t sg = __byte_perm(s01, s23, 0x6420);          // one sign byte per sample
+        uint32_t g0, g1, g2, g3;
+        enc_pair(pk[2 * j], E, g0, g1);
+        enc_pair(pk[2 * j + 1], E, g2, g3);
+        // upper halves of the floats hold the code at bits [10:3]: pack two per word, one shift
+        // moves both into bytes 1 and 3, one PRMT gathers the four codes
+        const uint32_t h01 = __byte_perm(g0, g1, 0x7632) << 5, h23 = __byte_perm(g2, g3, 0x7632) << 5;
+        const uint32_t codes = __byte_perm(h01, h23, 0x7531);
+        const uint32_t sg = __byte_perm(pk[2 * j], pk[2 * j + 1], 0x7531);   // sign bit of each sample in bit 7
         w[j] = codes ^ ((sg & 0x80808080u) ^ E.mask4);
     }
     return make_uint4(w[0], w[1], w[2], w[3]);
@@ -600,14 +601,15 @@ __global__ void __launch_bounds__(BFPC * kChunks + 32 * kMeterWarps + 32, kCtasP
 // takes the multiply/shift/clip path with the sign recovered from the high half.
 constexpr int kBfPerItem = 6;
 constexpr int kC32 = IGD_FRAME / 32;      // lanes per bridge-frame = 5
-// shared-memory stride of one bridge-frame inside a slot: G*160 code bytes + a pad that makes
-// the stride == 5 (mod 8) in 16-byte units, so that lane l's LDS.128 of chunk c (+5 for the
-// second half) lands in bank group (l + 5h) mod 8: conflict-free for every quarter-warp.
+// A slot is the item's 6*G*160 code bytes as they lie in HBM (ONE bulk copy).  Lane (bfl, c)
+// works on the 16-sample chunks (c + rot(bfl)) % 10 and that + 5; the per-bridge-frame rotation
+// (0,5,0,7,3,0) is the brute-forced minimum of LDS.128 bank conflicts for this layout (12
+// wavefronts instead of 8 per leg; padding the slot instead would cost six copies per item).
 template <int G> struct slot_geom {
     static constexpr int kBfBytes = G * IGD_FRAME;
-    static constexpr int kStride = kBfBytes + ((5 - (kBfBytes / 16) % 8 + 8) % 8) * 16;
-    static constexpr int kSlotBytes = kBfPerItem * kStride;
+    static constexpr int kSlotBytes = kBfPerItem * kBfBytes;
 };
+__device__ __forceinline__ uint32_t chunk_rotation(uint32_t bfl) { return (0x037050u >> (4 * bfl)) & 0xFu; }
 
 __device__ __forceinline__ void build_decode_lut_abs(uint32_t *lut, int tid, int nthreads)
 {
@@ -696,29 +698,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
     const uint32_t items = (total_bf + kBfPerItem - 1) / kBfPerItem;
     const uint32_t nw = gridDim.x * kWarps;
     uint32_t item = warp * gridDim.x + blockIdx.x;      // neighbouring items on different SMs
-    // one elected lane posts the byte count and issues one bulk async copy per bridge-frame of the
-    // item into the padded slot; every operand is warp-uniform (uniform datapath, no R2UR shuffles)
+    // one elected lane posts the byte count and issues the item's bulk async copy; every operand is
+    // warp-uniform (uniform datapath, no R2UR shuffles)
     auto fetch = [&](uint32_t it_idx) {
         const uint32_t bf0 = it_idx * kBfPerItem;
         const uint32_t left = total_bf - bf0;
-        const uint32_t nbf = left < (uint32_t)kBfPerItem ? left : (uint32_t)kBfPerItem;
+        const uint32_t bytes = (left < (uint32_t)kBfPerItem ? left : (uint32_t)kBfPerItem) * geom::kBfBytes;
         if (lane == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(nbf * geom::kBfBytes)
-                         : "memory");
-            const uint8_t *g = q.codes + (size_t)bf0 * geom::kBfBytes;
-#pragma unroll
-            for (int k = 0; k < kBfPerItem; k++)
-                if ((uint32_t)k < nbf)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(slot_s + k * geom::kStride), "l"(g + k * geom::kBfBytes), "r"(geom::kBfBytes), "r"(bar_s)
-                                 : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(slot_s), "l"(q.codes + (size_t)bf0 * geom::kBfBytes), "r"(bytes), "r"(bar_s) : "memory");
         }
     };
     if (item < items) fetch(item);
 
     const bool worker = lane < kBfPerItem * kC32;
-    const uint32_t bfl = worker ? lane / kC32 : 0u, c = worker ? lane - bfl * kC32 : 0u;
-    const uint32_t src = slot_s + bfl * geom::kStride + c * 16;
+    const uint32_t bfl = worker ? lane / kC32 : 0u;
+    const uint32_t c0 = worker ? (lane - bfl * kC32 + chunk_rotation(bfl)) % kChunks : 0u;   // first chunk; second = +-5
+    const uint32_t src = slot_s + bfl * geom::kBfBytes;
     const uint32_t lane4 = lut_bytes + 4u * lane;
     const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kBfPerItem) % (uint32_t)q.B);
     uint32_t b = (item * kBfPerItem + bfl) % (uint32_t)q.B;
@@ -765,24 +762,26 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         // every lane runs the same instruction stream (idle / tail lanes on stale bytes with all
         // gates shut); only the stores are predicated, and the mode branches are warp-uniform
         auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
-        // gains other than 0 / 256 anywhere in the warp -> general path
-        const bool general = __any_sync(0xFFFFFFFFu, ((gcur.x | gcur.y) & 0xFEFFFEFFu) != 0u);
-        uint32_t open_mask = 0;       // bit g: some lane of the warp has leg g open
-#pragma unroll
-        for (int g = 0; g < G; g++) open_mask |= __any_sync(0xFFFFFFFFu, adj_of(g) != 0u) ? (1u << g) : 0u;
+        // warp-wide OR of the gains (REDUX): anything but 0 / 256 anywhere in the warp -> general
+        // path; bit g of open_mask: some lane of the warp has leg g open
+        const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
+        const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
+        const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
+                                   ((ory >> 16) ? 8u : 0u);
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
+            const uint32_t ch = h == 0 ? c0 : (c0 >= (uint32_t)kC32 ? c0 - kC32 : c0 + kC32);   // this pass's chunk
             uint4 wh[G];
 #pragma unroll
             for (int g = 0; g < G; g++)
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
-                             : "r"(src + g * IGD_FRAME + h * (kC32 * 16)));
+                             : "r"(src + g * IGD_FRAME + ch * 16));
             if (h == 1) {        // every lane holds the rest of its codes: refill the slot
                 __syncwarp();
                 if (next < items) fetch(next);
             }
-            uint2 *mypart = part + bfl * (G * kPst) + c + kC32 * h;
+            uint2 *mypart = part + bfl * (G * kPst) + ch;
             int acc[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) acc[i] = 0;
@@ -809,42 +808,41 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                 const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
                 E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
             }
-            const uint32_t o16 = bf * (IGD_FRAME / 16) + c + kC32 * h;     // 16-sample chunk index of the outputs
+            const uint32_t o16 = bf * kChunks + ch;     // 16-sample chunk index of the outputs
             const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)o16 * 16, q.enc + (size_t)o16 * 16, valid);
-            if (valid) bpart[bfl * kPst + c + kC32 * h] = mo;
+            if (valid) bpart[bfl * kPst + ch] = mo;
         }
         __syncwarp();
-        // ---- finish: one lane per record
+        // ---- finish: one lane per record (leg records, then bridge records: bpart follows part,
+        // and both kinds of partial are {sum, max | sum << 16}, so the ten-partial walk is shared)
         {
             const uint32_t bf0 = item * kBfPerItem;
+            const uint2 *src_p = part + lane * kPst;
+            unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
+            if (lane < kBfPerItem * G + kBfPerItem) {
+#pragma unroll
+                for (int i = 0; i < kChunks; i++) {
+                    const uint2 v = src_p[i];
+                    sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
+                }
+            }
             if (lane < kBfPerItem * G) {
                 if (bf0 + lane / G < total_bf) {
-                    const uint2 *src_p = part + lane * kPst;
-                    unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
-#pragma unroll
-                    for (int i = 0; i < kChunks; i++) {
-                        const uint2 v = src_p[i];
-                        sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
-                    }
                     const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
                     st16_stream(q.meter + ((size_t)bf0 * G + lane), *reinterpret_cast<const uint4 *>(&r));
                 }
             } else if (lane < kBfPerItem * G + kBfPerItem) {
                 const uint32_t j = lane - kBfPerItem * G;
                 if (bf0 + j < total_bf) {
-                    const uint2 *src_p = bpart + j * kPst;
-                    int esum = 0; uint32_t mpeak = 0;
-#pragma unroll
-                    for (int i = 0; i < kChunks; i++) { esum += (int)src_p[i].x; mpeak = max(mpeak, src_p[i].y); }
                     const uint2 gj = load_gains<G>(q.gain + (size_t)(bf0 + j) * G);
                     int n_open = 0;
 #pragma unroll
                     for (int g = 0; g < G; g++)
                         n_open += ((g < 2 ? gj.x : gj.y) >> (16 * (g & 1)) & 0xFFFFu) != 0u;
                     igd_bridge_rec r;
-                    r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
+                    r.bytemean_out = (uint8_t)igd_bytemean_from_sum((int)(uint32_t)sq, IGD_FRAME);
                     r.n_open = (uint8_t)n_open;
-                    r.mix_peak = (uint16_t)mpeak;
+                    r.mix_peak = (uint16_t)(pk & 0xFFFFu);
                     q.bmeter[bf0 + j] = r;
                 }
             }
@@ -1484,11 +1482,11 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     case 1: return sc ? launch_fused<1, 32, true, 1, 2, 1>(c, q) : launch_fused<1, 32, false, 1, 2, 1>(c, q);
     case 2: return sc ? launch_fused<2, 32, true, 1, 2, 1>(c, q) : launch_fused<2, 32, false, 1, 2, 1>(c, q);
     case 4: {
-        static const int variant = getenv("IGD_FUSED_VARIANT") ? atoi(getenv("IGD_FUSED_VARIANT")) : 1;
+        static const int variant = getenv("IGD_FUSED_VARIANT") ? atoi(getenv("IGD_FUSED_VARIANT")) : 3;   // dev knob
         if (q.total_bf < (1ll << 31) - (1ll << 24)) {
             if (variant == 1) return sc ? launch_fused_w<4, true, 20>(c, q) : launch_fused_w<4, false, 20>(c, q);
             if (variant == 2) return launch_fused_w<4, false, 16>(c, q);
-            if (variant == 3) return launch_fused_w<4, false, 12>(c, q);
+            if (variant == 3) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
         }
         return sc ? launch_fused<4, 64, true, 2, 1, 3>(c, q) : launch_fused<4, 64, false, 2, 1, 3>(c, q);
     }
