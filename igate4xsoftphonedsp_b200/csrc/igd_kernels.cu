@@ -8,23 +8,19 @@
 //  * 128-bit (LDG.128) loads / 128- and 256-bit (STG.E.ENL2.256) stores with the
 //    evict-first hint: every input byte is read once and every output written
 //    once, so nothing should stay in L2.
-//  * G.711 expansion through a 64 KB shared-memory table laid out so that a
-//    lookup can never bank-conflict: entry (code, lane, law) lives at word
-//    code*64 + 2*lane + (law ^ (lane>>4)), i.e. every lane owns its own bank for
-//    either law, and the byte address is ONE PRMT: (code<<8) | lane_byte.
+//  * G.711 expansion through a 64 KB shared-memory table: one 32 KB table per law,
+//    row = code (128 B), column = lane, so a lookup can never bank-conflict and its
+//    byte address is ONE FMA-pipe instruction: IDP.4A(word, 0x80 << 8k, lane_base).
 //  * G.711 compression in ALU through the float-exponent trick of igd_math.cuh
 //    (no 64 KB encode table, no data-dependent bank conflicts).
 //  * Per-frame meters: exact integer partial sums per 16-sample chunk, combined
-//    through a padded shared-memory array (conflict-free LDS.64), dB via SFU lg2.
-//  * Persistent grids: a multiple of the SM count, each CTA strides over tiles.
+//    through a padded shared-memory scratch (conflict-free LDS.64), dB via SFU lg2.
+//  * Persistent grids: a multiple of the SM count; the fused kernel runs one CTA of
+//    24 autonomous warps per SM, every warp with its own TMA slot and mbarrier.
 #include <cstdlib>
 
 #include "igd_kernels.cuh"
 #include "igd_math.cuh"
-
-#ifndef IGD_X_EXTRACT
-#define IGD_X_EXTRACT 1   // 0: PRMT (ALU pipe), 1: IDP.2A (FMA pipe; measured best), 2: alternate
-#endif
 
 namespace {
 
@@ -264,18 +260,9 @@ __device__ __forceinline__ uint2 leg_chunk(uint32_t lane_base, uint4 w, uint32_t
         const uint32_t e1 = lut_lookup<1>(lane_base, wd[j]);
         const uint32_t e2 = lut_lookup<2>(lane_base, wd[j]);
         const uint32_t e3 = lut_lookup<3>(lane_base, wd[j]);
-        // x/4 sign-extended from the low half: PRMT (ALU pipe) -- the rest of this loop body
-        // is IDP/IMAD on the FMA pipe, so this keeps the two pipes evenly loaded
-#if IGD_X_EXTRACT == 0
-        const int x0 = (int)prmt_full<0x9910>(e0, 0u), x1 = (int)prmt_full<0x9910>(e1, 0u);
-        const int x2 = (int)prmt_full<0x9910>(e2, 0u), x3 = (int)prmt_full<0x9910>(e3, 0u);
-#elif IGD_X_EXTRACT == 1
+        // x/4 sign-extended from the low half (IDP.2A with a unit selector)
         const int x0 = dp2a_lo(e0, 1u, 0), x1 = dp2a_lo(e1, 1u, 0);
         const int x2 = dp2a_lo(e2, 1u, 0), x3 = dp2a_lo(e3, 1u, 0);
-#else
-        const int x0 = (int)prmt_full<0x9910>(e0, 0u), x1 = dp2a_lo(e1, 1u, 0);
-        const int x2 = (int)prmt_full<0x9910>(e2, 0u), x3 = dp2a_lo(e3, 1u, 0);
-#endif
         sq += (uint32_t)(x0 * x0) + (uint32_t)(x1 * x1) + (uint32_t)(x2 * x2) + (uint32_t)(x3 * x3);
         mx = max_s16x2(max_s16x2(mx, e0), e1); mx = max_s16x2(max_s16x2(mx, e2), e3);
         mn = min_s16x2(min_s16x2(mn, e0), e1); mn = min_s16x2(min_s16x2(mn, e2), e3);
@@ -326,45 +313,30 @@ __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_p
 }
 
 // ---------------------------------------------------------------- mbarrier / TMA
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+// (all on shared-window byte addresses, so that warp-uniform operands stay in uniform registers)
+__device__ __forceinline__ void mbar_init(uint32_t bar_s, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(shared_addr(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_s, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(shared_addr(bar)) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(shared_addr(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity)
 {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
         "@!p bra WAIT_%=;\n\t}"
-        ::"r"(shared_addr(bar)), "r"(parity) : "memory");
-}
-// same, for the helper warps: let the hardware park the warp (suspend-time hint)
-// so that waiting does not take issue slots from the producer warps
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAITB_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
-        "@!p bra WAITB_%=;\n\t}"
-        ::"r"(shared_addr(bar)), "r"(parity), "r"(0x20000u) : "memory");
+        ::"r"(bar_s), "r"(parity) : "memory");
 }
 // TMA bulk copy global -> shared (UBLKCP): no registers, no LSU issue slots; the
-// bytes land asynchronously and complete_tx on `bar`.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void *src, uint32_t bytes, uint64_t *bar)
+// bytes land asynchronously and complete_tx on the mbarrier.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void *src, uint32_t bytes, uint32_t bar_s)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_s), "l"(src), "r"(bytes), "r"(shared_addr(bar)) : "memory");
+                 ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
 }
 
 
@@ -375,206 +347,6 @@ __device__ __forceinline__ uint2 load_gains(const uint16_t *g)
     if (G == 4) return *reinterpret_cast<const uint2 *>(g);
     if (G == 2) return make_uint2(*reinterpret_cast<const uint32_t *>(g), 0u);
     return make_uint2(*g, 0u);
-}
-
-// Fused decode -> meter -> gate/gain -> mix -> encode (G in {1,2,4} legs per bridge).
-//   One CTA owns tiles of BFPC consecutive bridge-frames (contiguous in every array).
-//   * BFPC*10 producer threads: thread = one 16-sample chunk of one bridge-frame, all
-//     G legs.  The tile's codes (BFPC*G*160 contiguous bytes) are staged into shared
-//     memory by ONE bulk async copy (TMA, cp.async.bulk + mbarrier complete_tx) issued
-//     a tile ahead, so no warp ever waits on HBM latency; gains ride in two prefetched
-//     registers.
-//   * kMeterWarps meter warps turn the per-chunk partials (double-buffered in shared
-//     memory, mbarrier full/empty handshake) into the 16-byte records.
-//   * one more warp only issues the bulk copies (a single lane), kStages-1 tiles ahead.
-// Shipped shapes: G=4 -> one 64-bridge-frame CTA per SM (20 producer + 3 meter + 1 TMA
-// warps, 2-stage ring); G=1,2 -> two 32-bridge-frame CTAs per SM, single stage.
-template <int G, int BFPC, bool kSigned, int kStages, int kCtasPerSm, int kMeterWarps>
-__global__ void __launch_bounds__(BFPC * kChunks + 32 * kMeterWarps + 32, kCtasPerSm) k_fused(const FusedParams q)
-{
-    constexpr int kMeterThreads = 32 * kMeterWarps, kHelperThreads = kMeterThreads + 32;
-    constexpr int kProducers = BFPC * kChunks, kThreads = kProducers + kHelperThreads;
-    constexpr int kProducerWarps = (kProducers + 31) / 32;
-    constexpr int kStageBytes = BFPC * G * IGD_FRAME;
-    __shared__ uint64_t part_full[2], part_empty[2], stage_full[kStages], stage_empty[kStages];
-    __shared__ __align__(16) uint32_t enc_tab[2][8];
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
-    uint8_t *stage = smem + kLutBytes;                               // [kStages][BFPC][G][160] codes
-    uint2 *part = reinterpret_cast<uint2 *>(stage + kStages * kStageBytes);   // [2][BFPC*G][kPst]
-    uint2 *bpart = part + 2 * BFPC * G * kPst;                       // [2][BFPC][kPst]
-    const uint32_t lut_bytes = shared_addr(smem);
-
-    const int t = threadIdx.x;
-    const uint32_t lane = t & 31;
-    build_decode_lut(lut, t, kThreads);
-    if (t < 2) {
-        const enc_pk e = enc_pk_make(t);
-        enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
-        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4;
-    }
-    if (t == 0) {
-        mbar_init(&part_full[0], kProducerWarps); mbar_init(&part_full[1], kProducerWarps);
-        mbar_init(&part_empty[0], kMeterWarps); mbar_init(&part_empty[1], kMeterWarps);
-        for (int i = 0; i < kStages; i++) { mbar_init(&stage_full[i], 1); mbar_init(&stage_empty[i], kProducerWarps); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto tile_bytes = [&](long long tile) -> uint32_t {
-        const long long left = q.total_bf - tile * BFPC;
-        return (uint32_t)(left < BFPC ? left : BFPC) * (uint32_t)(G * IGD_FRAME);
-    };
-
-    if (t >= kProducers + kMeterThreads) {
-        // ================= TMA issue warp: one lane stages tile i+1 while tile i is processed
-        if (lane == 0) {
-            int it = 0;
-            for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, it++) {
-                const int st = it % kStages;
-                // the slot's previous tenant (tile it-kStages) has been read by every producer warp
-                if (it >= kStages) mbar_wait_backoff(&stage_empty[st], (it / kStages - 1) & 1);
-                mbar_expect_tx(&stage_full[st], tile_bytes(tile));
-                bulk_g2s(shared_addr(stage) + st * kStageBytes, q.codes + (size_t)tile * kStageBytes,
-                         tile_bytes(tile), &stage_full[st]);
-            }
-        }
-        return;
-    }
-    if (t >= kProducers) {
-        // ================= meter warps
-        const int mt = t - kProducers;
-        int buf = 0, it = 0;
-        for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, buf ^= 1, it++) {
-            mbar_wait_backoff(&part_full[buf], (it >> 1) & 1);
-            const uint2 *pb = part + (size_t)buf * BFPC * G * kPst;
-            for (int k = mt; k < BFPC * G; k += kMeterThreads) {
-                const long long lf = tile * BFPC * G + k;
-                if (lf < q.total_bf * G) {
-                    const uint2 *src = pb + (size_t)k * kPst;
-                    unsigned long long sq = 0; uint32_t peak = 0; int bsum = 0;
-#pragma unroll
-                    for (int i = 0; i < kChunks; i++) partial_add(src[i], sq, peak, bsum);
-                    const igd_meter_rec r = meter_finish(sq << 4, peak << 2, bsum, true);
-                    st16_stream(q.meter + lf, *reinterpret_cast<const uint4 *>(&r));
-                }
-            }
-            for (int k = kMeterThreads - 1 - mt; k < BFPC; k += kMeterThreads) {
-                const long long bf2 = tile * BFPC + k;
-                if (bf2 < q.total_bf) {
-                    const uint2 *src = bpart + (size_t)buf * BFPC * kPst + k * kPst;
-                    int esum = 0, mpeak = 0;
-#pragma unroll
-                    for (int i = 0; i < kChunks; i++) { esum += (int)src[i].x; mpeak = max(mpeak, (int)src[i].y); }
-                    int n_open = 0;
-#pragma unroll
-                    for (int g = 0; g < G; g++) n_open += q.gain[(size_t)bf2 * G + g] != 0;
-                    igd_bridge_rec r;
-                    r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
-                    r.n_open = (uint8_t)n_open;
-                    r.mix_peak = (uint16_t)mpeak;
-                    q.bmeter[bf2] = r;
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&part_empty[buf]);            // buffer may be refilled
-        }
-        return;
-    }
-
-    // ================= producer warps
-    const int bfl = t / kChunks, p = t - bfl * kChunks;
-    const uint32_t my_stage = shared_addr(stage) + (uint32_t)(bfl * G * IGD_FRAME + p * 16);
-    // bridge index of this thread's bridge-frame, advanced incrementally (no per-tile division)
-    const long long bf_step = (long long)gridDim.x * BFPC;
-    const int b_step = (int)(bf_step % q.B);
-    long long bf = (long long)blockIdx.x * BFPC + bfl;
-    int b = (int)(bf % q.B);
-    uint2 gq = bf < q.total_bf ? load_gains<G>(q.gain + (size_t)bf * G) : make_uint2(0u, 0u);
-    auto load_laws = [&](int bb) -> uint32_t {      // the G leg laws (1 bit each) and the output law (bit 8)
-        uint32_t r = 0;
-        if (G == 4) {
-            const uint32_t lw = *reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4);
-            r = (lw & 1u) | ((lw >> 7) & 2u) | ((lw >> 14) & 4u) | ((lw >> 21) & 8u);
-        } else {
-#pragma unroll
-            for (int g = 0; g < G; g++) r |= (uint32_t)(q.law[(size_t)bb * G + g] & 1u) << g;
-        }
-        return r | ((uint32_t)(q.out_law[bb] & 1u) << 8);
-    };
-    uint32_t lwq = bf < q.total_bf ? load_laws(b) : 0u;
-    int buf = 0, it = 0;
-    for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, buf ^= 1, bf += bf_step, it++) {
-        uint2 *mypart = part + (size_t)buf * BFPC * G * kPst + (size_t)bfl * G * kPst + p;
-        // ---- this tile's codes from the staging ring, then hand the slot back
-        const int st = it % kStages;
-        mbar_wait(&stage_full[st], (it / kStages) & 1);
-        uint4 w[G];
-#pragma unroll
-        for (int g = 0; g < G; g++)
-            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(w[g].x), "=r"(w[g].y), "=r"(w[g].z), "=r"(w[g].w)
-                         : "r"(my_stage + st * kStageBytes + g * IGD_FRAME));
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&stage_empty[st]);
-        const uint2 gcur = gq;
-        const uint32_t lcur = lwq;
-        {
-            int bn = b + b_step;
-            if (bn >= q.B) bn -= q.B;
-            if (bf + bf_step < q.total_bf) {          // next tile's gains and laws ride in three registers
-                gq = load_gains<G>(q.gain + (size_t)(bf + bf_step) * G);
-                lwq = load_laws(bn);
-            }
-        }
-        if (it >= 2) mbar_wait(&part_empty[buf], ((it >> 1) - 1) & 1); // meter warps are done with this buffer
-        if (bf < q.total_bf) {
-            uint32_t laws[G], sel[G], adj[G];
-            bool general;
-#pragma unroll
-            for (int g = 0; g < G; g++) laws[g] = (lcur >> g) & 1u;
-            {   // gain_q7 -> IDP.2A selectors, two legs per word: 0 -> 0, 128 -> 0x0004, 256 -> 0x0100
-                const uint32_t s01 = ((gcur.x >> 5) & 0x00040004u) | (gcur.x & 0x01000100u);
-                const uint32_t s23 = ((gcur.y >> 5) & 0x00040004u) | (gcur.y & 0x01000100u);
-                const uint32_t bad = ((gcur.x | gcur.y) & 0xFE7FFE7Fu) | (((gcur.x << 1) & gcur.x) & 0x01000100u) |
-                                     (((gcur.y << 1) & gcur.y) & 0x01000100u);
-                general = bad != 0u;
-                sel[0] = s01 & 0xFFFFu; adj[0] = gcur.x & 0xFFFFu;
-                if (G > 1) { sel[1 % G] = s01 >> 16; adj[1 % G] = gcur.x >> 16; }
-                if (G > 2) { sel[2 % G] = s23 & 0xFFFFu; adj[2 % G] = gcur.y & 0xFFFFu; sel[3 % G] = s23 >> 16; adj[3 % G] = gcur.y >> 16; }
-            }
-            enc_pk E;
-            {
-                const uint32_t *et = enc_tab[(lcur >> 8) & 1u];
-                const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
-                const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
-                E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
-            }
-            int acc[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) acc[i] = 0;
-            if (!general) {        // gains in {0, 1.0, 2.0}: one IDP.2A per sample of an open leg
-#pragma unroll
-                for (int g = 0; g < G; g++) {
-                    const uint32_t lb = lut_lane_base(lut_bytes, lane, laws[g]);
-                    mypart[g * kPst] = sel[g] ? leg_chunk<kSigned, 1>(lb, w[g], sel[g], 0, acc)
-                                              : leg_chunk<kSigned, 0>(lb, w[g], 0u, 0, acc);
-                }
-            } else {               // arbitrary Q7 gains: multiply, shift, clip
-#pragma unroll
-                for (int g = 0; g < G; g++)
-                    mypart[g * kPst] = leg_chunk<kSigned, 2>(lut_lane_base(lut_bytes, lane, laws[g]), w[g],
-                                                             0u, (int)adj[g], acc);
-            }
-            bpart[(size_t)buf * BFPC * kPst + bfl * kPst + p] =
-                mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)bf * IGD_FRAME + p * 16,
-                                       q.enc + (size_t)bf * IGD_FRAME + p * 16);
-        }
-        b += b_step;
-        if (b >= q.B) b -= q.B;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&part_full[buf]);                  // this warp's partials are published
-    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -619,6 +391,12 @@ __device__ __forceinline__ void build_decode_lut_abs(uint32_t *lut, int tid, int
         const int y2 = min(max(2 * x, -32768), 32767);
         lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)(abs(x) >> 2) & 0xFFFFu);
     }
+}
+
+// bit 15 / 31 set for every non-zero 16-bit half of x
+__device__ __forceinline__ uint32_t nonzero_halves(uint32_t x)
+{
+    return (((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) & 0x80008000u;
 }
 
 // decode + meter + gain/accumulate one 16-sample chunk of one leg (|x|/4 table)
@@ -688,7 +466,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4;
     }
     if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_s), "r"(1) : "memory");
+        mbar_init(bar_s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -705,9 +483,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         const uint32_t left = total_bf - bf0;
         const uint32_t bytes = (left < (uint32_t)kBfPerItem ? left : (uint32_t)kBfPerItem) * geom::kBfBytes;
         if (lane == 0) {
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(slot_s), "l"(q.codes + (size_t)bf0 * geom::kBfBytes), "r"(bytes), "r"(bar_s) : "memory");
+            mbar_expect_tx(bar_s, bytes);
+            bulk_g2s(slot_s, q.codes + (size_t)bf0 * geom::kBfBytes, bytes, bar_s);
         }
     };
     if (item < items) fetch(item);
@@ -740,13 +517,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
     for (uint32_t it = 0; item < items; item += nw, it++) {
         const uint32_t bf = item * kBfPerItem + bfl;
         const uint32_t next = item + nw;
-        {   // this item's codes have landed
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "WAITW_%=:\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-                "@!p bra WAITW_%=;\n\t}" ::"r"(bar_s), "r"(it & 1u) : "memory");
-        }
+        mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
         const uint2 gcur = gq;
         const uint32_t lcur = lwq;
         const bool valid = worker && bf < total_bf;
@@ -768,6 +539,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
         const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
                                    ((ory >> 16) ? 8u : 0u);
+        // open legs of this lane's bridge-frame, pre-shifted into the high half of the bridge partial
+        // (every one of the ten partials carries it; the finish divides the sum by ten)
+        const uint32_t n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y))) << 16;
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const uint32_t ch = h == 0 ? c0 : (c0 >= (uint32_t)kC32 ? c0 - kC32 : c0 + kC32);   // this pass's chunk
@@ -810,7 +584,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             }
             const uint32_t o16 = bf * kChunks + ch;     // 16-sample chunk index of the outputs
             const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)o16 * 16, q.enc + (size_t)o16 * 16, valid);
-            if (valid) bpart[bfl * kPst + ch] = mo;
+            if (valid) bpart[bfl * kPst + ch] = make_uint2(mo.x, mo.y | n_open16);
         }
         __syncwarp();
         // ---- finish: one lane per record (leg records, then bridge records: bpart follows part,
@@ -834,14 +608,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             } else if (lane < kBfPerItem * G + kBfPerItem) {
                 const uint32_t j = lane - kBfPerItem * G;
                 if (bf0 + j < total_bf) {
-                    const uint2 gj = load_gains<G>(q.gain + (size_t)(bf0 + j) * G);
-                    int n_open = 0;
-#pragma unroll
-                    for (int g = 0; g < G; g++)
-                        n_open += ((g < 2 ? gj.x : gj.y) >> (16 * (g & 1)) & 0xFFFFu) != 0u;
                     igd_bridge_rec r;
                     r.bytemean_out = (uint8_t)igd_bytemean_from_sum((int)(uint32_t)sq, IGD_FRAME);
-                    r.n_open = (uint8_t)n_open;
+                    r.n_open = (uint8_t)((uint32_t)bsum / kChunks);
                     r.mix_peak = (uint16_t)(pk & 0xFFFFu);
                     q.bmeter[bf0 + j] = r;
                 }
@@ -1414,27 +1183,6 @@ cudaError_t igd_k_mix(const igd_launch_cfg &c, const int16_t *pcm, const uint16_
 }
 
 namespace {
-template <int G, int BFPC, bool kSigned, int kStages, int kCtasPerSm, int kMeterWarps>
-cudaError_t launch_fused(const igd_launch_cfg &c, const FusedParams &q)
-{
-    auto kern = k_fused<G, BFPC, kSigned, kStages, kCtasPerSm, kMeterWarps>;
-    constexpr int kHelperThreads = 32 * kMeterWarps + 32;
-    const size_t smem = kLutBytes + (size_t)kStages * BFPC * G * IGD_FRAME + (size_t)2 * BFPC * G * kPst * 8 +
-                        (size_t)2 * BFPC * kPst * 8;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BFPC * kChunks + kHelperThreads, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) per_sm = 1;
-    FusedParams p = q;
-    p.num_tiles = (q.total_bf + BFPC - 1) / BFPC;
-    long long grid = (long long)c.sm_count * per_sm;
-    if (grid > p.num_tiles) grid = p.num_tiles;
-    kern<<<(int)grid, BFPC * kChunks + kHelperThreads, smem, c.stream>>>(p);
-    return cudaGetLastError();
-}
-
 template <int G, bool kSigned, int kWarps>
 cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
 {
@@ -1478,20 +1226,13 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     q.num_tiles = 0;
     q.B = d.B; q.G = d.G; q.flags = d.flags;
     const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
-    switch (d.G) {
-    case 1: return sc ? launch_fused<1, 32, true, 1, 2, 1>(c, q) : launch_fused<1, 32, false, 1, 2, 1>(c, q);
-    case 2: return sc ? launch_fused<2, 32, true, 1, 2, 1>(c, q) : launch_fused<2, 32, false, 1, 2, 1>(c, q);
-    case 4: {
-        static const int variant = getenv("IGD_FUSED_VARIANT") ? atoi(getenv("IGD_FUSED_VARIANT")) : 3;   // dev knob
-        if (q.total_bf < (1ll << 31) - (1ll << 24)) {
-            if (variant == 1) return sc ? launch_fused_w<4, true, 20>(c, q) : launch_fused_w<4, false, 20>(c, q);
-            if (variant == 2) return launch_fused_w<4, false, 16>(c, q);
-            if (variant == 3) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
-        }
-        return sc ? launch_fused<4, 64, true, 2, 1, 3>(c, q) : launch_fused<4, 64, false, 2, 1, 3>(c, q);
-    }
-    default: return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
-    }
+    // the warp-autonomous kernel indexes bridge-frames in 32 bits; anything larger (> 1.3 TB of
+    // codes at G = 1) cannot be resident on one GPU anyway and takes the generic kernel
+    const bool fits32 = q.total_bf < (1ll << 31) - (1ll << 24);
+    if (fits32 && d.G == 4) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
+    if (fits32 && d.G == 2) return sc ? launch_fused_w<2, true, 24>(c, q) : launch_fused_w<2, false, 24>(c, q);
+    if (fits32 && d.G == 1) return sc ? launch_fused_w<1, true, 24>(c, q) : launch_fused_w<1, false, 24>(c, q);
+    return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
 }
 
 cudaError_t igd_k_event_summary(const igd_launch_cfg &c, const igd_meter_rec *meter,

@@ -20,7 +20,14 @@ static inline int igd_min(int a, int b) { return a < b ? a : b; }
 #define IGD_HD __device__ __forceinline__
 __device__ __forceinline__ int igd_f2i(float f) { return __float_as_int(f); }
 __device__ __forceinline__ float igd_i2f(int i) { return __int_as_float(i); }
-__device__ __forceinline__ float igd_log2(float x) { return __log2f(x); }
+// arguments are integers converted to float (0 or >= 1): never denormal, so the bare SFU op
+// (no denormal pre-scaling) is exact enough; lg2(0) = -inf
+__device__ __forceinline__ float igd_log2(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ int igd_max(int a, int b) { return max(a, b); }
 __device__ __forceinline__ int igd_min(int a, int b) { return min(a, b); }
 #endif
