@@ -197,7 +197,8 @@ __device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t 
     t = min_u16x2(t, E.hi_pos ^ (sgn & E.hi_x));                    // u-law clip
     const uint32_t p = max_s16x2(add_16x2(t, E.bias_pos ^ (sgn & E.bias_x)), 0u);
     const uint32_t P = add_16x2(p, max_u16x2(p, E.thr));            // leading one -> segment
-    // 8388608.0f + P per half, built on the FMA pipe (IDP.2A picks the half and adds the magic)
+    // 8388608.0f + P per half, built on the FMA pipe (IDP.2A picks the half and adds the magic;
+    // the compressor is ALU-bound, a PRMT here measured 4 % slower)
     g0 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, 0x0001u, 0x4B000000u)), 0.0078125f, -65536.0f));
     g1 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, 0x0100u, 0x4B000000u)), 0.0078125f, -65536.0f));
 }
@@ -415,9 +416,9 @@ __device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32
         const uint32_t e1 = lut_lookup<1>(lane_base, wd[j]);
         const uint32_t e2 = lut_lookup<2>(lane_base, wd[j]);
         const uint32_t e3 = lut_lookup<3>(lane_base, wd[j]);
-        // |x|/4 out of the low half: two on the FMA pipe (IDP.2A), two on the ALU pipe (LOP3)
-        const uint32_t x0 = dp2a_lo_u(e0, 1u, 0u), x1 = e1 & 0xFFFFu;
-        const uint32_t x2 = dp2a_lo_u(e2, 1u, 0u), x3 = e3 & 0xFFFFu;
+        // |x|/4 out of the low half on the ALU pipe (LOP3): everything else in this loop body is
+        // IDP/IMAD on the FMA pipe, which bounds this phase (measured: any IDP.2A here is slower)
+        const uint32_t x0 = e0 & 0xFFFFu, x1 = e1 & 0xFFFFu, x2 = e2 & 0xFFFFu, x3 = e3 & 0xFFFFu;
         sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
         mx = max_u16x2(max_u16x2(mx, e0), e1); mx = max_u16x2(max_u16x2(mx, e2), e3);
         bsum = kSigned ? __dp4a((int)wd[j], 0x01010101, bsum) : (int)__dp4a(wd[j], 0x01010101u, (uint32_t)bsum);
