@@ -45,7 +45,17 @@ CTL_DT = np.dtype([("pttstatus", "u1"), ("sqlstatus", "u1"), ("pttpriority", "u1
                    ("pttid", "u1"), ("callRecorder", "u1"), ("reserved", "u1", (2,))])
 assert METER_DT.itemsize == 16 and BRIDGE_DT.itemsize == 4 and SUMMARY_DT.itemsize == 32
 assert SUMMARY_DB_DT.itemsize == 16 and FIELDS_DT.itemsize == 16 and STATE_DT.itemsize == 40
-assert CTL_DT.itemsize == 8
+RX_STATE_DT = np.dtype([("r2sPacket", "<i8"), ("ed137_value", "<u4"), ("payloadsize", "<u2"), ("rtpAudio", "u1"),
+                        ("r2sCount", "u1")])
+RX_EVENT_DT = np.dtype([("word", "<u4"), ("flags", "u1"), ("r2sCount", "u1"), ("reserved", "<u2")])
+ARB_LEG_DT = np.dtype([("last", "u1"), ("msec", "u1"), ("on", "u1"), ("rssi", "i1"), ("gain_q7", "<u2"),
+                       ("reserved", "<u2")])
+ARB_BRIDGE_DT = np.dtype([("ptt_level", "<i4"), ("sqlStatusCount", "<i4"), ("sqlStatusOn", "u1"),
+                          ("reserved", "u1", (7,))])
+RXE_PACKET, RXE_AUDIO, RXE_EDGE, RXE_DROPPED, RXE_LATE, RXE_HANGUP = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+ARB_CLIENT_PTT, ARB_SERVER_BEST = 0, 1
+assert CTL_DT.itemsize == 8 and RX_STATE_DT.itemsize == 16 and RX_EVENT_DT.itemsize == 8
+assert ARB_LEG_DT.itemsize == 8 and ARB_BRIDGE_DT.itemsize == 16
 
 
 class DevInfo(C.Structure):
@@ -67,6 +77,20 @@ class PackDesc(C.Structure):
                 ("rtp12", C.c_void_p), ("payload", C.c_void_p), ("ctl", C.c_void_p), ("state", C.c_void_p),
                 ("pkts", C.c_void_p), ("sizes", C.c_void_p), ("bytemean_out", C.c_void_p),
                 ("stale_payload", C.c_void_p)]
+
+
+class RxTrackDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("F", C.c_int32), ("C", C.c_int32),
+                ("tick_ms", C.c_int32), ("r2s_period_ms", C.c_int32), ("wd_ticks", C.c_int32),
+                ("frame0", C.c_int32), ("now_ms0", C.c_int64),
+                ("fields", C.c_void_p), ("present", C.c_void_p), ("state", C.c_void_p), ("events", C.c_void_p)]
+
+
+class ArbDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("F", C.c_int32), ("B", C.c_int32),
+                ("G", C.c_int32), ("mode", C.c_int32), ("word_stride", C.c_uint32), ("reserved", C.c_uint32),
+                ("words", C.c_void_p), ("active", C.c_void_p), ("legs", C.c_void_p), ("bridges", C.c_void_p),
+                ("gain_q7", C.c_void_p)]
 
 
 # every symbol include/igate_dsp.h declares: name -> (restype, argtypes)
@@ -102,6 +126,8 @@ SYMBOLS = {
     "igd_calltype_flags": (C.c_uint, [C.c_char_p]),
     "igd_ed137_state_init": (None, [_vp, _i, _i, C.c_char_p, _i, C.c_int64]),
     "igd_ed137_pack": (_i, [_vp, C.POINTER(PackDesc)]),
+    "igd_rx_track": (_i, [_vp, C.POINTER(RxTrackDesc)]),
+    "igd_gate_arbitrate": (_i, [_vp, C.POINTER(ArbDesc)]),
     "igd_wav_size": (_sz, [_sz, _i]),
     "igd_wav_image": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, C.POINTER(_sz), _i]),
 }

@@ -588,6 +588,73 @@ int igd_ed137_pack(igd_ctx *c, const igd_ed137_pack_desc *d)
     return finish(c, mem);
 }
 
+// ---------------------------------------------------------------- RX liveness, gate arbitration
+int igd_rx_track(igd_ctx *c, const igd_rx_track_desc *d)
+{
+    if (!c || !d || d->struct_size != sizeof(igd_rx_track_desc)) return fail(c, IGD_EINVAL, "igd_rx_track: bad descriptor");
+    if (d->F < 0 || d->C < 0 || d->wd_ticks < 0) return fail(c, IGD_EINVAL, "igd_rx_track: bad shape");
+    if (d->F == 0 || d->C == 0) return IGD_OK;
+    if (!d->fields || !d->state || !d->events) return fail(c, IGD_EINVAL, "igd_rx_track: null buffer");
+    const int mem = d->mem;
+    if (mem == IGD_MEM_DEVICE && (!aligned(d->fields, 16) || !aligned(d->state, 16) || !aligned(d->events, 8)))
+        return fail(c, IGD_EINVAL, "igd_rx_track: misaligned device pointer");
+    Bind b(c);
+    const size_t n = (size_t)d->F * d->C;
+    igd_rx_track_desc k = *d;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, d->fields, n, &k.fields))) return rc;
+    if (d->present && (rc = in_arg(c, mem, 1, d->present, n, &k.present))) return rc;
+    {
+        const igd_rx_state *tmp = nullptr;
+        if ((rc = in_arg(c, mem, 2, d->state, (size_t)d->C, &tmp))) return rc;
+        k.state = const_cast<igd_rx_state *>(tmp);
+    }
+    if ((rc = out_arg(c, mem, 3, d->events, n, &k.events))) return rc;
+    IGD_CUDA(c, igd_k_rx_track(cfg_of(c), k));
+    c->launches++;
+    if ((rc = out_done(c, mem, d->state, k.state, (size_t)d->C))) return rc;
+    if ((rc = out_done(c, mem, d->events, k.events, n))) return rc;
+    return finish(c, mem);
+}
+
+int igd_gate_arbitrate(igd_ctx *c, const igd_arb_desc *d)
+{
+    if (!c || !d || d->struct_size != sizeof(igd_arb_desc)) return fail(c, IGD_EINVAL, "igd_gate_arbitrate: bad descriptor");
+    if (d->F < 0 || d->B < 0 || d->G < 1 || d->G > IGD_MAX_LEGS || (d->word_stride != 4 && d->word_stride != 8) ||
+        (d->mode != IGD_ARB_CLIENT_PTT && d->mode != IGD_ARB_SERVER_BEST))
+        return fail(c, IGD_EINVAL, "igd_gate_arbitrate: bad shape / mode / word_stride");
+    if (d->B == 0) return IGD_OK;
+    if (!d->legs || !d->bridges || (d->F && (!d->words || !d->gain_q7)))
+        return fail(c, IGD_EINVAL, "igd_gate_arbitrate: null buffer");
+    const int mem = d->mem;
+    if (mem == IGD_MEM_DEVICE && (!aligned(d->words, 4) || !aligned(d->legs, 8) || !aligned(d->bridges, 4)))
+        return fail(c, IGD_EINVAL, "igd_gate_arbitrate: misaligned device pointer");
+    Bind b(c);
+    const size_t Cn = (size_t)d->B * d->G, n = (size_t)d->F * Cn;
+    igd_arb_desc k = *d;
+    int rc;
+    {
+        const uint8_t *w = nullptr;
+        if ((rc = in_arg(c, mem, 0, static_cast<const uint8_t *>(d->words), n * d->word_stride, &w))) return rc;
+        k.words = w;
+    }
+    if (d->active && (rc = in_arg(c, mem, 1, d->active, Cn, &k.active))) return rc;
+    {
+        const igd_arb_leg *tl = nullptr; const igd_arb_bridge *tb = nullptr;
+        if ((rc = in_arg(c, mem, 2, d->legs, Cn, &tl))) return rc;
+        if ((rc = in_arg(c, mem, 3, d->bridges, (size_t)d->B, &tb))) return rc;
+        k.legs = const_cast<igd_arb_leg *>(tl);
+        k.bridges = const_cast<igd_arb_bridge *>(tb);
+    }
+    if ((rc = out_arg(c, mem, 4, d->gain_q7, n, &k.gain_q7))) return rc;
+    IGD_CUDA(c, igd_k_gate_arbitrate(cfg_of(c), k));
+    c->launches++;
+    if ((rc = out_done(c, mem, d->legs, k.legs, Cn))) return rc;
+    if ((rc = out_done(c, mem, d->bridges, k.bridges, (size_t)d->B))) return rc;
+    if ((rc = out_done(c, mem, d->gain_q7, k.gain_q7, n))) return rc;
+    return finish(c, mem);
+}
+
 // ---------------------------------------------------------------- recorder
 size_t igd_wav_size(size_t payload_bytes, int ref_quirks)
 {

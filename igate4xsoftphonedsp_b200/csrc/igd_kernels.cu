@@ -968,6 +968,70 @@ __global__ void __launch_bounds__(256) k_ed137_parse(const uint8_t *__restrict__
 }
 
 // ============================================================ ED-137 pack
+// ============================================================ RX liveness walk
+// One thread per channel walks its frames through the receive-side state of
+// transport_rtp_cb (TransportAdapter.cpp:240-316) and the R2S watchdog
+// (roip_ed137.cpp:1767-1780).  Consecutive threads read consecutive 16-byte field
+// records and write consecutive 8-byte events: coalesced, latency-bound.
+__global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
+{
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d.C) return;
+    igd_rx_state s = d.state[c];
+    for (int f = 0; f < d.F; f++) {
+        const size_t i = (size_t)f * d.C + c;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(d.fields + i));
+        const igd_ed137_fields fl = *reinterpret_cast<const igd_ed137_fields *>(&raw);
+        const bool present = d.present ? d.present[i] != 0 : true;
+        const bool wd = d.wd_ticks > 0 && ((d.frame0 + f) % d.wd_ticks) == d.wd_ticks - 1;
+        const uint32_t ev = igd_rx_step(s, fl, present, wd, d.now_ms0 + (long long)f * d.tick_ms, d.r2s_period_ms);
+        igd_rx_event e;
+        e.word = s.ed137_value;
+        e.flags = (uint8_t)ev;
+        e.r2sCount = s.r2sCount;
+        e.reserved = 0;
+        *reinterpret_cast<uint2 *>(d.events + i) = *reinterpret_cast<const uint2 *>(&e);
+    }
+    d.state[c] = s;
+}
+
+// ============================================================ gate arbitration
+// One thread per bridge walks its frames through checkEvents()'s gate decisions
+// (igd_math.cuh: igd_arb_client_tick / igd_arb_server_best_tick); the leg state of
+// the block's bridges lives in shared memory for the walk.
+constexpr int kArbThreads = 32;
+__global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_desc d)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    igd_arb_leg *legs_s = reinterpret_cast<igd_arb_leg *>(smem);       // [kArbThreads][G]
+    const int b = blockIdx.x * kArbThreads + threadIdx.x;
+    const int G = d.G;
+    const int nb = min(kArbThreads, d.B - blockIdx.x * kArbThreads);
+    // cooperative, coalesced load of the block's leg state
+    for (int k = threadIdx.x; k < nb * G; k += kArbThreads)
+        legs_s[k] = d.legs[(size_t)blockIdx.x * kArbThreads * G + k];
+    __syncthreads();
+    if (b < d.B) {
+        igd_arb_leg *legs = legs_s + threadIdx.x * G;
+        igd_arb_bridge br = d.bridges[b];
+        const uint8_t *act = d.active ? d.active + (size_t)b * G : nullptr;
+        const size_t Cn = (size_t)d.B * G;
+        for (int f = 0; f < d.F; f++) {
+            const uint8_t *wbase = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)f * Cn + (size_t)b * G) * d.word_stride;
+            auto word = [&](int g) { return *reinterpret_cast<const uint32_t *>(wbase + (size_t)g * d.word_stride); };
+            auto active = [&](int g) { return act ? act[g] != 0 : true; };
+            if (d.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, G, word, active);
+            else igd_arb_server_best_tick(br, legs, G, word, active);
+            uint16_t *gout = d.gain_q7 + (size_t)f * Cn + (size_t)b * G;
+            for (int g = 0; g < G; g++) gout[g] = legs[g].gain_q7;
+        }
+        d.bridges[b] = br;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb * G; k += kArbThreads)
+        d.legs[(size_t)blockIdx.x * kArbThreads * G + k] = legs_s[k];
+}
+
 // Phase 1: one thread per channel walks its frames through the sender state
 // machine (transport_send_rtp, TransportAdapter.cpp:635-874) and writes a plan
 // record per packet.  The state is tiny and strictly sequential per channel.
@@ -1251,6 +1315,19 @@ cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, cons
 {
     k_ed137_parse<<<grid_for(c, npkts * 32, 256, 8), 256, 0, c.stream>>>(pkts, sizes, npkts, stride, fields,
                                                                   payload_out);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d)
+{
+    k_rx_track<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d)
+{
+    const size_t smem = (size_t)kArbThreads * d.G * sizeof(igd_arb_leg);
+    k_gate_arbitrate<<<(d.B + kArbThreads - 1) / kArbThreads, kArbThreads, smem, c.stream>>>(d);
     return cudaGetLastError();
 }
 

@@ -204,3 +204,139 @@ IGD_HD igd_tx_plan igd_ed137_tx_step(S &a, uint32_t payload_len, long long now)
     else if (a.packetCnt >= 30) a.firstR2SPacket = 0;
     return r;
 }
+
+// ---------------------------------------------------------------- RX liveness
+// One tick of the receive side of one radio call: the state the reference keeps in
+// struct tp_adapter across transport_rtp_cb calls (TransportAdapter.cpp:240-316) plus the
+// R2S keep-alive watchdog of RoIP_ED137::detectR2SPacketAndReconn (roip_ed137.cpp:1767-1780).
+// `S` has the igd_rx_state field names, `FL` the igd_ed137_fields ones.  Returns IGD_RXE_* bits.
+template <class S, class FL>
+IGD_HD uint32_t igd_rx_step(S &a, const FL &f, bool present, bool run_watchdog, long long now, int r2s_period)
+{
+    uint32_t ev = 0;
+    if (present) {
+        ev |= 0x01u;                                                  // IGD_RXE_PACKET
+        if (f.accepted) {
+            a.ed137_value = f.word;                                   // :252-256 (kept in host order)
+            a.payloadsize = f.length_raw;
+        }
+        if (f.flags & 0x10u) {                                        // :286-291 oversized / truncated packet
+            a.r2sPacket = now;
+            ev |= 0x08u;                                              // IGD_RXE_DROPPED
+        } else if (f.pt != 123) {                                     // :298-307
+            a.r2sPacket = now;
+            ev |= 0x02u;                                              // IGD_RXE_AUDIO
+            if (!a.rtpAudio) ev |= 0x04u;                             // IGD_RXE_EDGE -> setIncomingED137Value
+            a.rtpAudio = 1;
+        } else {                                                      // :308-315
+            a.r2sPacket = now;
+            if (a.rtpAudio) ev |= 0x04u;
+            a.rtpAudio = 0;
+        }
+    }
+    if (run_watchdog) {                                               // roip_ed137.cpp:1767-1780
+        const long long secDiff = now - a.r2sPacket;
+        if (secDiff > (long long)r2s_period * 3) {
+            ev |= 0x10u;                                              // IGD_RXE_LATE
+            if (a.r2sCount == 5) ev |= 0x20u;                         // IGD_RXE_HANGUP (WG-67 cause 2001)
+            if (a.r2sCount < 255) a.r2sCount++;
+        } else {
+            a.r2sCount = 0;
+        }
+    }
+    return ev;
+}
+
+// ---------------------------------------------------------------- gate arbitration
+// One checkEvents() pass over the G legs of one bridge.  `L` has the igd_arb_leg field names,
+// `BR` the igd_arb_bridge ones; `word(g)` returns leg g's latched ED-137 word (host order),
+// `active(g)` whether the leg takes part (callState, and trxmode != RX for CLIENT / != TX for SERVER).
+// CLIENT mode: highest ptt_type wins, winner gets SLOT_VOLUME 2.0 (256), pressed losers 0
+// (roip_ed137.cpp:6124-6231); a released PTT is held for five more ticks (:6140-6153).
+template <class BR, class L, class W, class A>
+IGD_HD void igd_arb_client_tick(BR &b, L *legs, int G, W word, A active)
+{
+    for (int i = 0; i < G; i++) {
+        if (!active(i)) continue;
+        int ptt = (int)((word(i) & 0xe0000000u) >> 29);
+        if (ptt != legs[i].last) {
+            if (ptt == 0) {
+                legs[i].msec++;
+                if (legs[i].msec < 6) ptt = 1;
+            }
+        } else {
+            legs[i].msec = 0;
+        }
+        legs[i].last = (uint8_t)ptt;
+        if (ptt && ptt > b.ptt_level) {
+            b.ptt_level = ptt;
+            legs[i].gain_q7 = 256;
+            for (int j = 0; j < G; j++)
+                if (legs[j].on && j != i) legs[j].gain_q7 = 0;
+        }
+        if (ptt > 0 && !legs[i].on) {
+            legs[i].on = 1;
+        } else if (ptt == 0 && legs[i].on) {
+            legs[i].on = 0;
+            legs[i].gain_q7 = 0;
+            b.ptt_level = ptt;
+        }
+    }
+}
+
+// SERVER mode with rxBestSignalEnable: per-radio squelch bookkeeping (roip_ed137.cpp:5627-5719 and
+// its three twins), then after five consecutive ticks of squelch only the radio with the best BSS
+// quality index is unmuted (:5985-6121).
+template <class BR, class L, class W, class A>
+IGD_HD void igd_arb_server_best_tick(BR &b, L *legs, int G, W word, A active)
+{
+    for (int i = 0; i < G; i++) {
+        if (!active(i)) continue;
+        const uint32_t w = word(i);
+        int sqlon = (int)((w & 0x10000000u) >> 28);
+        legs[i].rssi = (int8_t)((w & 0xf8u) >> 3);
+        if (sqlon != legs[i].last) {
+            if (sqlon == 0) {
+                legs[i].msec++;
+                if (legs[i].msec < 1) sqlon = 1;
+            }
+        } else {
+            legs[i].msec = 0;
+        }
+        if (legs[i].last != sqlon) {
+            legs[i].last = (uint8_t)sqlon;
+            if (!sqlon) legs[i].gain_q7 = 0;
+        }
+    }
+    bool any = false;
+    for (int i = 0; i < G; i++) {
+        if (!active(i) || legs[i].last == 0) {
+            if (legs[i].on) { b.sqlStatusCount = 0; b.sqlStatusOn = 0; }
+            legs[i].on = 0;
+            legs[i].rssi = -1;
+        }
+        any = any || legs[i].last > 0;
+    }
+    if (any) {
+        b.sqlStatusCount++;
+        if (b.sqlStatusCount >= 5 && !b.sqlStatusOn) {
+            for (int i = 0; i < G; i++)
+                if (legs[i].last > 0) legs[i].gain_q7 = 0;
+            b.sqlStatusOn = 1;
+            for (int i = 0; i < G; i++) {
+                bool best = legs[i].last != 0;
+                for (int j = 0; j < G && best; j++)
+                    if (j != i && legs[i].rssi < legs[j].rssi) best = false;
+                if (best) {
+                    for (int j = 0; j < G; j++) legs[j].on = (uint8_t)(j == i);
+                    if (active(i)) legs[i].gain_q7 = 256;
+                    break;
+                }
+            }
+        }
+    } else {
+        b.sqlStatusCount = 0;
+        b.sqlStatusOn = 0;
+        for (int i = 0; i < G; i++) legs[i].on = 0;
+    }
+}

@@ -357,6 +357,48 @@ class VoicePath:
         self._chk(self._lib.igd_ed137_pack(self._h, C.byref(d)))
         return pkts, sizes, bm
 
+    # ------------------------------------------------------------ RX liveness, gate arbitration
+    def rx_track(self, fields, state, present=None, now_ms0=0, tick_ms=20, r2s_period_ms=200, wd_ticks=2,
+                 frame0=0):
+        """Batched receive-side state of transport_rtp_cb + the R2S watchdog.
+        fields [F][C] (from ed137_parse), state [C] (RX_STATE_DT, updated in place),
+        present u8 [F][C] or None.  Returns events [F][C] (RX_EVENT_DT)."""
+        mem = self._mode(fields, state, present)
+        F, Cn = fields.shape[0], fields.shape[1]
+        if mem == N.MEM_DEVICE:
+            events = torch.empty((F, Cn, 2), dtype=torch.int32, device=fields.device)
+        else:
+            fields = np.ascontiguousarray(fields, dtype=N.FIELDS_DT)
+            if present is not None:
+                present = np.ascontiguousarray(present, dtype=np.uint8)
+            events = np.empty((F, Cn), dtype=N.RX_EVENT_DT)
+        d = N.RxTrackDesc(C.sizeof(N.RxTrackDesc), mem, F, Cn, int(tick_ms), int(r2s_period_ms), int(wd_ticks),
+                          int(frame0), int(now_ms0), self._ptr(fields), self._ptr(present), self._ptr(state),
+                          self._ptr(events))
+        self._chk(self._lib.igd_rx_track(self._h, C.byref(d)))
+        return events
+
+    def gate_arbitrate(self, words, legs, bridges, G, mode=N.ARB_CLIENT_PTT, active=None):
+        """checkEvents() gate decisions.  words: u32 [F][B*G] or an RX_EVENT_DT array [F][B*G]
+        (its .word is read in place); legs [B*G] (ARB_LEG_DT) and bridges [B] (ARB_BRIDGE_DT)
+        are updated in place.  Returns gain_q7 u16 [F][B*G] for process_batch."""
+        mem = self._mode(words, legs, bridges, active)
+        F, Cn = words.shape[0], words.shape[1]
+        B = Cn // G
+        if mem == N.MEM_DEVICE:
+            stride = 8 if (words.dim() == 3 and words.shape[2] == 2) else 4
+            gain = torch.empty((F, Cn), dtype=torch.int16, device=words.device)
+        else:
+            stride = 8 if words.dtype == N.RX_EVENT_DT else 4
+            words = np.ascontiguousarray(words) if stride == 8 else np.ascontiguousarray(words, dtype=np.uint32)
+            if active is not None:
+                active = np.ascontiguousarray(active, dtype=np.uint8)
+            gain = np.empty((F, Cn), dtype=np.uint16)
+        d = N.ArbDesc(C.sizeof(N.ArbDesc), mem, F, B, int(G), int(mode), stride, 0, self._ptr(words),
+                      self._ptr(active), self._ptr(legs), self._ptr(bridges), self._ptr(gain))
+        self._chk(self._lib.igd_gate_arbitrate(self._h, C.byref(d)))
+        return gain
+
     # ------------------------------------------------------------ recorder
     def wav_image(self, payload, rate=8000, law=N.LAW_ULAW, ref_quirks=False):
         """WavWriter file image (header + body) built on the GPU."""

@@ -299,6 +299,94 @@ typedef struct {
 } igd_ed137_pack_desc;
 int igd_ed137_pack(igd_ctx *ctx, const igd_ed137_pack_desc *d);
 
+/* -------------------------------------------------- RX liveness / call events
+ * replaces: the receive-side state transport_rtp_cb keeps per call
+ * (TransportAdapter.cpp:240-316: ed137_value / payloadsize latch :252-256,
+ * r2sPacket stamp :289,302,311, rtpAudio edge -> setIncomingED137Value ->
+ * checkEvents() :304-306,312-314), getR2SStatus (:317-325) and the R2S
+ * keep-alive watchdog RoIP_ED137::detectR2SPacketAndReconn
+ * (roip_ed137.cpp:1756-1780: no packet for more than 3*r2sPeriod on five
+ * consecutive 40 ms timer ticks -> hang up with "WG-67 ;cause=2001").
+ * Together with igd_ed137_parse this is the batched RX front-end.             */
+typedef struct {
+    int64_t r2sPacket;           /* ms of the last packet (getR2SStatus)          */
+    uint32_t ed137_value;        /* latched word in HOST order (get_ed137_value)  */
+    uint16_t payloadsize;        /* hdr->length as stored                          */
+    uint8_t rtpAudio;            /* last packet carried audio (pt != 123)          */
+    uint8_t r2sCount;            /* watchdog strikes                               */
+} igd_rx_state;                  /* 16 bytes; zero-init + r2sPacket = call start   */
+typedef struct {
+    uint32_t word;               /* get_ed137_value() after this tick              */
+    uint8_t flags;               /* IGD_RXE_*                                      */
+    uint8_t r2sCount;
+    uint16_t reserved;
+} igd_rx_event;                  /* 8 bytes                                        */
+#define IGD_RXE_PACKET 0x01u     /* a packet arrived on this tick                  */
+#define IGD_RXE_AUDIO 0x02u      /* forwarded to the stream (pt != 123)            */
+#define IGD_RXE_EDGE 0x04u       /* audio <-> keep-alive edge: setIncomingED137Value(word) */
+#define IGD_RXE_DROPPED 0x08u    /* oversized / truncated packet (:286-291)        */
+#define IGD_RXE_LATE 0x10u       /* watchdog: now - r2sPacket > 3*r2s_period       */
+#define IGD_RXE_HANGUP 0x20u     /* watchdog: sixth late tick in a row, hang up    */
+typedef struct {
+    uint32_t struct_size;
+    int32_t mem;
+    int32_t F, C;
+    int32_t tick_ms;             /* 20: packet time of frame f = now_ms0 + f*tick_ms */
+    int32_t r2s_period_ms;       /* radio->r2sPeriod, default 200 (roip_ed137.h:685) */
+    int32_t wd_ticks;            /* the watchdog runs on every wd_ticks-th frame
+                                    (40 ms timer / 20 ms frames = 2); 0 = never    */
+    int32_t frame0;              /* index of this call's first frame (watchdog phase) */
+    int64_t now_ms0;
+    const igd_ed137_fields *fields;   /* [F][C] from igd_ed137_parse               */
+    const uint8_t *present;      /* [F][C] 0 = no packet on that tick; NULL = all  */
+    igd_rx_state *state;         /* [C], updated in place                          */
+    igd_rx_event *events;        /* [F][C] out                                     */
+} igd_rx_track_desc;
+int igd_rx_track(igd_ctx *ctx, const igd_rx_track_desc *d);
+
+/* ---------------------------------------------------------- gate arbitration
+ * replaces: the gate decisions of RoIP_ED137::checkEvents() that end in
+ * setSlotVolume (roip_ed137.cpp:5190-5234) -- the only inputs are the legs'
+ * latched ED-137 words, the output is the gain_q7 array igd_process_batch
+ * consumes:
+ *   IGD_ARB_CLIENT_PTT  highest ptt_type wins: winner SLOT_VOLUME 2.0, pressed
+ *                       losers 0.0, five-tick release hold (roip_ed137.cpp:6124-6231)
+ *   IGD_ARB_SERVER_BEST per-radio squelch gate (:5627-5719) + best-signal
+ *                       selection: after five ticks of squelch only the radio with
+ *                       the best BSS quality index is unmuted (:5985-6121)
+ * MUTE/UNMUTE are taken as gain 0 / 256 (Functions.cpp:1664-1705 with its
+ * sidetone / group-mute side conditions left to the host).                     */
+enum { IGD_ARB_CLIENT_PTT = 0, IGD_ARB_SERVER_BEST = 1 };
+typedef struct {
+    uint8_t last;                /* lastTx (CLIENT) / lastRx (SERVER)             */
+    uint8_t msec;                /* lastTxmsec / lastRxmsec                       */
+    uint8_t on;                  /* m_PttPressed (CLIENT) / audioSQLOn (SERVER)   */
+    int8_t rssi;                 /* radio->rssi, -1 while not receiving           */
+    uint16_t gain_q7;            /* the slot volume the leg currently has         */
+    uint16_t reserved;
+} igd_arb_leg;                   /* 8 bytes                                       */
+typedef struct {
+    int32_t ptt_level;           /* CLIENT                                        */
+    int32_t sqlStatusCount;      /* SERVER                                        */
+    uint8_t sqlStatusOn;         /* SERVER                                        */
+    uint8_t reserved[7];
+} igd_arb_bridge;                /* 16 bytes                                      */
+typedef struct {
+    uint32_t struct_size;
+    int32_t mem;
+    int32_t F, B, G;             /* G <= IGD_MAX_LEGS                             */
+    int32_t mode;                /* IGD_ARB_*                                     */
+    uint32_t word_stride;        /* bytes between consecutive words: 4 for a plain
+                                    u32 array, 8 to read igd_rx_event.word in place */
+    uint32_t reserved;
+    const void *words;           /* [F][B*G] latched ED-137 words, host order     */
+    const uint8_t *active;       /* [B*G] leg takes part (callState...); NULL = all */
+    igd_arb_leg *legs;           /* [B*G], updated in place                       */
+    igd_arb_bridge *bridges;     /* [B], updated in place                         */
+    uint16_t *gain_q7;           /* [F][B*G] out                                  */
+} igd_arb_desc;
+int igd_gate_arbitrate(igd_ctx *ctx, const igd_arb_desc *d);
+
 /* ------------------------------------------------------------ recorder sink
  * replaces: WavWriter::start/wav_write/stop (WavWriter.cpp:63-156).
  * Builds the complete file image on the GPU: 44-byte header + body.

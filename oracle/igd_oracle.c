@@ -714,3 +714,116 @@ size_t orc_wav_body(const uint8_t *buf, size_t len, uint8_t *out)
     }
     return 2 * len;
 }
+
+/* ------------------------------------------------------------------------- */
+/* R2S watchdog: RoIP_ED137::detectR2SPacketAndReconn, roip_ed137.cpp:1767-1780 */
+int orc_r2s_watchdog(long long now, long long r2sPacket, int r2sPeriod, int *r2sCount)
+{
+    int flags = 0;
+    long long secDiff = now - r2sPacket;                 /* :1767 */
+    if (secDiff > (long long)r2sPeriod * 3) {            /* :1768 */
+        flags |= 1;
+        if (*r2sCount == 5) flags |= 2;                  /* :1770-1774 trx_call_hangup(...2001...) */
+        (*r2sCount)++;                                   /* :1775 */
+    } else {
+        *r2sCount = 0;                                   /* :1778 */
+    }
+    return flags;
+}
+
+/* ------------------------------------------------------------------------- */
+/* CLIENT-mode gate arbitration, roip_ed137.cpp:6124-6231.  setSlotVolume with
+ * SLOT_VOLUME = 2.0f / 0.0f becomes gain_q7 = 256 / 0 (orc_gain_adj).          */
+void orc_arb_client_tick(orc_arb_bridge *b, orc_arb_leg *legs, const uint32_t *words,
+                         const uint8_t *active, int G)
+{
+    int checkPTT = 0;                                                    /* :6126 */
+    for (int i = 0; i < G; i++) {                                        /* :6127 */
+        if (active && !active[i]) continue;                              /* :6131-6134 */
+        int pttstatus = (int)((words[i] & 0xe0000000u) >> 29);           /* :6138, Functions.cpp:1136 */
+        if (pttstatus != legs[i].last) {                                 /* :6140 */
+            if (pttstatus == 0) {
+                legs[i].msec++;                                          /* :6143 */
+                if (legs[i].msec < 6) pttstatus = 1;                     /* :6144-6147 */
+            }
+        } else {
+            legs[i].msec = 0;                                            /* :6152 */
+        }
+        legs[i].last = (uint8_t)pttstatus;                               /* :6155 */
+        if (pttstatus) {                                                 /* :6158 */
+            if (pttstatus > b->ptt_level) {                              /* :6159 */
+                b->ptt_level = pttstatus;                                /* :6161 */
+                legs[i].gain_q7 = 256;                                   /* :6162-6163 SLOT_VOLUME = 2.0f */
+                for (int j = 0; j < G; j++)                              /* :6164-6174 */
+                    if (legs[j].on && j != i) legs[j].gain_q7 = 0;
+            }
+        }
+        if (pttstatus > 0 && !legs[i].on) {                              /* :6190 */
+            legs[i].on = 1;
+        } else if (pttstatus == 0 && legs[i].on) {                       /* :6197 */
+            legs[i].on = 0;
+            for (int j = 0; j < G; j++) if (legs[j].on) checkPTT++;      /* :6201-6205 */
+            legs[i].gain_q7 = 0;                                         /* :6217-6218 */
+            b->ptt_level = pttstatus;                                    /* :6221 */
+        }
+    }
+    (void)checkPTT;
+}
+
+/* SERVER mode with rxBestSignalEnable: roip_ed137.cpp:5627-5719 (x4 radios),
+ * then :5985-6121.  setvolume(MUTE) -> gain 0; setvolume(UNMUTE) -> gain 256
+ * (the SLOT_VOLUME = 2.0f branch of Functions.cpp:1664-1705; its trxStatus /
+ * sidetone side conditions belong to the control plane and are taken as met). */
+void orc_arb_server_best_tick(orc_arb_bridge *b, orc_arb_leg *legs, const uint32_t *words,
+                              const uint8_t *active, int G)
+{
+    for (int i = 0; i < G; i++) {
+        if (active && !active[i]) continue;                              /* :5614 */
+        int sqlon = (int)((words[i] & 0x10000000u) >> 28);               /* :5627, Functions.cpp:1160 */
+        legs[i].rssi = (int8_t)((words[i] & 0xf8u) >> 3);                /* :5657, Functions.cpp:1018 */
+        if (sqlon != legs[i].last) {                                     /* :5658 */
+            if (sqlon == 0) {
+                legs[i].msec++;                                          /* :5660 */
+                if (legs[i].msec < 1) sqlon = 1;                         /* :5661-5664 */
+            }
+        } else {
+            legs[i].msec = 0;                                            /* :5669 */
+        }
+        if (legs[i].last != sqlon) {                                     /* :5694 */
+            legs[i].last = (uint8_t)sqlon;                               /* :5713 */
+            if (!legs[i].last) legs[i].gain_q7 = 0;                      /* :5717-5718 */
+        }
+    }
+    int any = 0;
+    for (int i = 0; i < G; i++) {                                        /* :5987-6030 */
+        const int callState = !active || active[i];
+        if (!callState || legs[i].last == 0) {
+            if (legs[i].on) { b->sqlStatusCount = 0; b->sqlStatusOn = 0; }
+            legs[i].on = 0;
+            legs[i].rssi = -1;
+        }
+        if (legs[i].last > 0) any = 1;
+    }
+    if (any) {                                                           /* :6026 */
+        b->sqlStatusCount++;                                             /* :6028 */
+        if (b->sqlStatusCount >= 5 && !b->sqlStatusOn) {                 /* :6029 */
+            for (int i = 0; i < G; i++)                                  /* :6031-6038 */
+                if (legs[i].last > 0) legs[i].gain_q7 = 0;
+            b->sqlStatusOn = 1;                                          /* :6039 */
+            for (int i = 0; i < G; i++) {                                /* :6046-6109: first radio whose */
+                int best = legs[i].last != 0;                            /* rssi is >= every other one   */
+                for (int j = 0; j < G && best; j++)
+                    if (j != i && legs[i].rssi < legs[j].rssi) best = 0;
+                if (best) {
+                    for (int j = 0; j < G; j++) legs[j].on = (uint8_t)(j == i);
+                    if (!active || active[i]) legs[i].gain_q7 = 256;     /* :6056-6057 */
+                    break;
+                }
+            }
+        }
+    } else {                                                             /* :6112-6120 */
+        b->sqlStatusCount = 0;
+        b->sqlStatusOn = 0;
+        for (int i = 0; i < G; i++) legs[i].on = 0;
+    }
+}

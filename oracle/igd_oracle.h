@@ -202,6 +202,42 @@ void orc_hdr_write(uint8_t out[20], int v, int p, int x, int cc, int m, int pt,
                    uint16_t seq, uint32_t ts, uint32_t ssrc, uint16_t profile,
                    uint16_t length, uint32_t ed137_host);
 
+/* ---------------- R2S liveness watchdog (roip_ed137.cpp:1756-1777) --------- */
+/* One timer tick of RoIP_ED137::detectR2SPacketAndReconn for one connected radio:
+ *   secDiff = now - r2sPacket; if (secDiff > r2sPeriod*3) { if (r2sCount == 5) hang up
+ *   ("WG-67 ;cause=2001"); r2sCount++; } else r2sCount = 0;
+ * Returns bit0 = late, bit1 = hang-up requested on this tick.                 */
+int orc_r2s_watchdog(long long now, long long r2sPacket, int r2sPeriod, int *r2sCount);
+
+/* ---------------- gate arbitration (RoIP_ED137::checkEvents) --------------- */
+/* Per-leg and per-bridge state, names as in the reference's trx / radio
+ * structs (roip_ed137.h).  gain_q7 = the slot volume the leg was last given
+ * through setSlotVolume (roip_ed137.cpp:5190-5234): 0.0f -> 0, 2.0f -> 256.   */
+typedef struct {
+    uint8_t last;        /* lastTx (CLIENT) / lastRx (SERVER)                  */
+    uint8_t msec;        /* lastTxmsec / lastRxmsec                            */
+    uint8_t on;          /* m_PttPressed (CLIENT) / audioSQLOn (SERVER)        */
+    int8_t rssi;         /* radio->rssi, -1 when not receiving (SERVER)        */
+    uint16_t gain_q7;
+    uint16_t reserved;
+} orc_arb_leg;
+typedef struct {
+    int32_t ptt_level;        /* CLIENT: roip_ed137.cpp:6157                    */
+    int32_t sqlStatusCount;   /* SERVER: :6028                                  */
+    uint8_t sqlStatusOn;      /* SERVER: :6029                                  */
+    uint8_t reserved[7];
+} orc_arb_bridge;
+/* CLIENT mode, one checkEvents() pass over the G legs of one bridge
+ * (roip_ed137.cpp:6124-6231): highest ptt_type wins.  words[g] = the leg's
+ * latched ED-137 word (host order); active[g] = callState && trxmode != RX.   */
+void orc_arb_client_tick(orc_arb_bridge *b, orc_arb_leg *legs, const uint32_t *words,
+                         const uint8_t *active, int G);
+/* SERVER mode with rxBestSignalEnable, one checkEvents() pass: per-radio
+ * squelch bookkeeping (roip_ed137.cpp:5627-5719 and its three twins) followed
+ * by the best-signal selection with the 5-tick hold-off (:5985-6121).         */
+void orc_arb_server_best_tick(orc_arb_bridge *b, orc_arb_leg *legs, const uint32_t *words,
+                              const uint8_t *active, int G);
+
 /* ---------------- WavWriter sink (WavWriter.cpp:63-156, Appendix E) ------- */
 /* Writes the 44-byte header exactly as WavWriter::start() lays it out, with
  * the two size fields as WavWriter::stop() patches them for `payload_bytes`

@@ -29,4 +29,16 @@ void emul_tx_step(igd_ed137_state *s, unsigned payload_len, long long now, unsig
     igd_tx_plan p = igd_ed137_tx_step(*s, payload_len, now);
     o[0] = p.word; o[1] = p.size; o[2] = p.pt123; o[3] = p.marker; o[4] = p.copy_payload;
 }
+// one RX tick: fields record, state in/out; returns IGD_RXE_* bits
+unsigned emul_rx_step(igd_rx_state *s, const igd_ed137_fields *f, int present, int wd, long long now, int period)
+{
+    return igd_rx_step(*s, *f, present != 0, wd != 0, now, period);
+}
+void emul_arb_tick(int mode, igd_arb_bridge *b, igd_arb_leg *legs, const unsigned *words, const unsigned char *active, int G)
+{
+    auto word = [&](int g) { return words[g]; };
+    auto act = [&](int g) { return active ? active[g] != 0 : true; };
+    if (mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(*b, legs, G, word, act);
+    else igd_arb_server_best_tick(*b, legs, G, word, act);
+}
 }
