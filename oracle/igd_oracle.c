@@ -9,6 +9,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -826,4 +827,35 @@ void orc_arb_server_best_tick(orc_arb_bridge *b, orc_arb_leg *legs, const uint32
         b->sqlStatusOn = 0;
         for (int i = 0; i < G; i++) legs[i].on = 0;
     }
+}
+
+/* ------------------------------------------------------------------------- */
+/* createPTTEventDataLogger's message, Functions.cpp:2169-2181 and :2199-2211:
+ * QString("{" "\"menuID\"   :\"PTTEventDataLogger\", " ... "}").arg(...) x9.     */
+static void orc_qnum(char *b, size_t n, double v)
+{
+    if (isnan(v)) snprintf(b, n, "nan");
+    else if (isinf(v)) snprintf(b, n, v < 0 ? "-inf" : "inf");
+    else snprintf(b, n, "%g", v);                 /* QString::number(v, 'g', 6) */
+}
+size_t orc_ptt_event_json(char *out, size_t cap, int softPhoneID, const char *strEvent,
+                          double av, double mx, double mn, const char *url,
+                          int rtp_av, int rtp_max, int rtp_min)
+{
+    char a[64], b[64], c[64];
+    orc_qnum(a, sizeof a, av); orc_qnum(b, sizeof b, mx); orc_qnum(c, sizeof c, mn);
+    int n = snprintf(out, cap,
+        "{"
+        "\"menuID\"                       :\"PTTEventDataLogger\", "
+        "\"softPhoneID\"                  :%d, "
+        "\"Ptt\"                          :\"%s\", "
+        "\"level_in_av\"                  :%s, "
+        "\"level_in_max\"                 :%s, "
+        "\"level_in_min\"                 :%s, "
+        "\"radioUrl \"                    :\"%s\","
+        "\"OutgoingRTPAv\"                :%d, "
+        "\"OutgoingRTPmax\"               :%d, "
+        "\"OutgoingRTPmin\"               :%d "
+        "}", softPhoneID, strEvent, a, b, c, url, rtp_av, rtp_max, rtp_min);
+    return n < 0 ? 0 : (size_t)n;
 }

@@ -238,6 +238,14 @@ void orc_arb_client_tick(orc_arb_bridge *b, orc_arb_leg *legs, const uint32_t *w
 void orc_arb_server_best_tick(orc_arb_bridge *b, orc_arb_leg *legs, const uint32_t *words,
                               const uint8_t *active, int G);
 
+/* ---------------- PTT event logger message (Functions.cpp:2169-2211) ------- */
+/* The "PTTEventDataLogger" JSON exactly as createPTTEventDataLogger lays it out;
+ * doubles as QString::arg(double) prints them ('g', 6 digits), ints as arg(int).
+ * Returns the length written (without the NUL).                               */
+size_t orc_ptt_event_json(char *out, size_t cap, int softPhoneID, const char *strEvent,
+                          double level_in_av, double level_in_max, double level_in_min,
+                          const char *url, int rtp_av, int rtp_max, int rtp_min);
+
 /* ---------------- WavWriter sink (WavWriter.cpp:63-156, Appendix E) ------- */
 /* Writes the 44-byte header exactly as WavWriter::start() lays it out, with
  * the two size fields as WavWriter::stop() patches them for `payload_bytes`

@@ -125,6 +125,9 @@ def lib():
         L.orc_wav_header.argtypes = [C.c_void_p, C.c_int, C.c_size_t]
         L.orc_wav_body.restype = C.c_size_t
         L.orc_wav_body.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p]
+        L.orc_ptt_event_json.restype = C.c_size_t
+        L.orc_ptt_event_json.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_char_p, C.c_double, C.c_double, C.c_double,
+                                         C.c_char_p, C.c_int, C.c_int, C.c_int]
         L.orc_r2s_watchdog.restype = C.c_int
         L.orc_r2s_watchdog.argtypes = [C.c_longlong, C.c_longlong, C.c_int, C.POINTER(C.c_int)]
         L.orc_arb_client_tick.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
