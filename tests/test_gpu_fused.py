@@ -152,3 +152,48 @@ def test_cfg3_full_size_properties(vp):
     a = got["meter"][:64].reshape(-1, 4)
     b = m2.reshape(-1, 4)
     assert torch.equal(a[:, 0], b[:, 0]) and torch.equal(a[:, 1] & ~0xFF00, b[:, 1])
+
+
+def test_cfg5_65536_mixed_codec_channels_with_summary(vp):
+    """BASELINE config 5 shape: 65 536 channels (16 384 bridges), A-law/u-law mixed per leg and per
+    bridge output, a handful of frames; everything against the oracle, then the per-channel dBFS
+    summary (what rank 0 gathers) against the oracle's event summary."""
+    F, B, G = 6, 16384, 4
+    Cn = B * G
+    rng = np.random.default_rng(65536)
+    law = rng.integers(0, 2, Cn).astype(np.uint8)
+    out_law = rng.integers(0, 2, B).astype(np.uint8)
+    codes = rng.integers(0, 256, (F, Cn, 160), dtype=np.uint8)
+    gain = rng.choice(np.array([0, 0, 256, 256, 13, 64, 128], np.uint16), (F, Cn))
+    got = vp.process_batch(codes, law, gain, out_law, G)
+    want = O.process_batch(codes, law, gain, out_law, G, threads=os.cpu_count() or 1)
+    check(got, want)
+    rec, db = vp.event_summary(got["meter"], gain)
+    wrec = O.event_summary(want[2], gain)
+    assert rec.tobytes() == wrec.tobytes()
+    for c in (0, 1, 4097, Cn - 1):
+        av, mx, mn, bm = O.summary_db(wrec[c])
+        if wrec[c]["count"]:
+            assert abs(float(db["level_av_db"][c]) - av) < DB_TOL and int(db["bm_av"][c]) == bm
+
+
+def test_decode_encode_round_trip_is_identity_on_codes_at_full_size(vp):
+    """size-independent property at 1 GiB: one open leg per bridge at unity gain -> enc == that leg's codes
+    (G.711 encode(decode(c)) == c except the two codes that decode to -0 / duplicate values)."""
+    import torch
+    F, B, G = 1640, 1024, 4
+    dev = "cuda:0"
+    g = torch.Generator(device=dev).manual_seed(7)
+    codes = torch.randint(0, 256, (F, B * G, 160), dtype=torch.uint8, device=dev, generator=g)
+    law = torch.from_numpy(synth.laws(B * G)).to(dev)
+    out_law = law.reshape(B, G)[:, 1].contiguous()                 # encode with leg 1's own law
+    gain = torch.zeros((F, B, G), dtype=torch.int16, device=dev)
+    gain[:, :, 1] = 128
+    got = vp.process_batch(codes, law, gain.reshape(F, B * G), out_law, G)
+    torch.cuda.synchronize()
+    leg = codes.reshape(F, B, G, 160)[:, :, 1]
+    # u-law 0x7F (-0) re-encodes as 0xFF (+0): the only non-idempotent code (SURVEY 8c)
+    is_u = (out_law == 1).reshape(1, B, 1)
+    expect = torch.where(is_u & (leg == 0x7F), torch.full_like(leg, 0xFF), leg)
+    assert torch.equal(got["enc"], expect)
+    assert int(got["bmeter"].reshape(-1, 1).view(torch.uint8).reshape(F, B, 4)[..., 1].min()) == 1   # n_open
