@@ -913,6 +913,81 @@ __global__ void __launch_bounds__(32 * kSumSlices) k_event_summary(const igd_met
 // header words, every lane copies payload words.
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
+// Tile form of the receive parse for the wire stride (180 B): a CTA stages 64 packets
+// (11 520 contiguous bytes) in shared memory with 16-byte loads, 64 threads extract the fields,
+// all threads write the 64 x 160 payload bytes with 16-byte stores.  Same results as
+// k_ed137_parse below (which keeps serving other strides / unaligned buffers).
+constexpr int kPktTile = 64, kPktWords = IGD_PKT_MAX / 4;      // 45 words per packet
+__global__ void __launch_bounds__(256) k_ed137_parse_tile(const uint8_t *__restrict__ pkts,
+                                                          const uint32_t *__restrict__ sizes, size_t npkts,
+                                                          igd_ed137_fields *__restrict__ fields,
+                                                          uint8_t *__restrict__ payload_out)
+{
+    __shared__ __align__(16) uint32_t img[kPktTile * kPktWords];
+    __shared__ uint32_t plen_s[kPktTile];
+    const size_t first = (size_t)blockIdx.x * kPktTile;
+    const uint32_t np = (uint32_t)min((size_t)kPktTile, npkts - first);
+    const uint4 *src = reinterpret_cast<const uint4 *>(pkts + first * IGD_PKT_MAX);
+    const uint32_t nvec = (np * IGD_PKT_MAX + 15) / 16;      // the buffer holds whole packets: a partial
+    for (uint32_t j = threadIdx.x; j < nvec; j += blockDim.x) {   // last vector only exists when np*180 % 16 != 0
+        uint4 v;
+        if ((j + 1) * 16 <= np * IGD_PKT_MAX) v = __ldcs(src + j);
+        else {                                               // ragged tail of the whole buffer: word loads
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(src + j);
+            const uint32_t left = (np * IGD_PKT_MAX - j * 16) / 4;
+            v.x = left > 0 ? w[0] : 0u; v.y = left > 1 ? w[1] : 0u; v.z = left > 2 ? w[2] : 0u; v.w = 0u;
+        }
+        reinterpret_cast<uint4 *>(img)[j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < np) {
+        const uint32_t p = threadIdx.x;
+        const size_t i = first + p;
+        const uint32_t size = sizes ? sizes[i] : (uint32_t)IGD_PKT_MAX;
+        const uint32_t navail = min(size, (uint32_t)IGD_PKT_MAX) / 4;
+        const uint32_t *hw = img + p * kPktWords;
+        const uint32_t w0 = navail > 0 ? hw[0] : 0u, w3 = navail > 3 ? hw[3] : 0u, w4 = navail > 4 ? hw[4] : 0u;
+        const uint32_t pt = (w0 >> 8) & 0x7Fu;
+        const bool too_short = size < IGD_PKT_HDR;
+        const uint32_t plen_raw = size - IGD_PKT_HDR;
+        const bool dropped = too_short || plen_raw >= 1024u;
+        const bool accepted = !too_short && (pt == 8 || pt == 0 || pt == 18 || pt == 123);
+        const uint32_t plen = dropped ? 0u : min(plen_raw, (uint32_t)IGD_FRAME);
+        plen_s[p] = plen;
+        igd_ed137_fields f;
+        const uint32_t word = accepted ? bswap32(w4) : 0u;
+        const igd_edf e = igd_ed137_fields_of(word);
+        f.word = word;
+        f.length_raw = accepted ? (uint16_t)(w3 >> 16) : (uint16_t)0;
+        f.payload_len = (uint16_t)plen;
+        f.pt = (uint8_t)pt;
+        f.accepted = accepted;
+        f.keepalive = (!too_short && pt == 123);
+        f.ptt_type = (uint8_t)e.ptt_type;
+        f.ptt_id = (uint8_t)e.ptt_id;
+        f.squelch = (uint8_t)e.squelch;
+        f.bss = (uint8_t)e.bss;
+        f.flags = (uint8_t)(e.flags | (dropped ? IGD_EDF_DROPPED : 0u));
+        *reinterpret_cast<uint4 *>(fields + i) = *reinterpret_cast<const uint4 *>(&f);
+    }
+    if (!payload_out) return;
+    __syncthreads();
+    uint4 *dst = reinterpret_cast<uint4 *>(payload_out + first * IGD_FRAME);
+    for (uint32_t j = threadIdx.x; j < np * kChunks; j += blockDim.x) {
+        const uint32_t p = j / kChunks, ch = j - p * kChunks;
+        const uint32_t plen = plen_s[p], b0 = ch * 16;
+        const uint32_t *w = img + p * kPktWords + 5 + ch * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t b = b0 + 4 * k;
+            v[k] = b < plen ? w[k] : 0u;
+            if (b < plen && plen - b < 4) v[k] &= (1u << (8 * (plen - b))) - 1u;
+        }
+        __stcs(dst + j, make_uint4(v[0], v[1], v[2], v[3]));
+    }
+}
+
 __global__ void __launch_bounds__(256) k_ed137_parse(const uint8_t *__restrict__ pkts,
                                                      const uint32_t *__restrict__ sizes, size_t npkts,
                                                      size_t stride, igd_ed137_fields *__restrict__ fields,
@@ -978,19 +1053,34 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
     igd_rx_state s = d.state[c];
-    for (int f = 0; f < d.F; f++) {
-        const size_t i = (size_t)f * d.C + c;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(d.fields + i));
-        const igd_ed137_fields fl = *reinterpret_cast<const igd_ed137_fields *>(&raw);
-        const bool present = d.present ? d.present[i] != 0 : true;
-        const bool wd = d.wd_ticks > 0 && ((d.frame0 + f) % d.wd_ticks) == d.wd_ticks - 1;
-        const uint32_t ev = igd_rx_step(s, fl, present, wd, d.now_ms0 + (long long)f * d.tick_ms, d.r2s_period_ms);
-        igd_rx_event e;
-        e.word = s.ed137_value;
-        e.flags = (uint8_t)ev;
-        e.r2sCount = s.r2sCount;
-        e.reserved = 0;
-        *reinterpret_cast<uint2 *>(d.events + i) = *reinterpret_cast<const uint2 *>(&e);
+    constexpr int kAhead = 8;            // the walk is sequential, its inputs are not: fetch 8 frames ahead
+    for (int f0 = 0; f0 < d.F; f0 += kAhead) {
+        uint4 raw[kAhead];
+        uint8_t pres[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; u++) {
+            const int f = f0 + u;
+            if (f < d.F) {
+                const size_t i = (size_t)f * d.C + c;
+                raw[u] = __ldg(reinterpret_cast<const uint4 *>(d.fields + i));
+                pres[u] = d.present ? d.present[i] : (uint8_t)1;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kAhead; u++) {
+            const int f = f0 + u;
+            if (f >= d.F) break;
+            const size_t i = (size_t)f * d.C + c;
+            const igd_ed137_fields fl = *reinterpret_cast<const igd_ed137_fields *>(&raw[u]);
+            const bool wd = d.wd_ticks > 0 && ((d.frame0 + f) % d.wd_ticks) == d.wd_ticks - 1;
+            const uint32_t ev = igd_rx_step(s, fl, pres[u] != 0, wd, d.now_ms0 + (long long)f * d.tick_ms, d.r2s_period_ms);
+            igd_rx_event e;
+            e.word = s.ed137_value;
+            e.flags = (uint8_t)ev;
+            e.r2sCount = s.r2sCount;
+            e.reserved = 0;
+            *reinterpret_cast<uint2 *>(d.events + i) = *reinterpret_cast<const uint2 *>(&e);
+        }
     }
     d.state[c] = s;
 }
@@ -999,37 +1089,90 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
 // One thread per bridge walks its frames through checkEvents()'s gate decisions
 // (igd_math.cuh: igd_arb_client_tick / igd_arb_server_best_tick); the leg state of
 // the block's bridges lives in shared memory for the walk.
-constexpr int kArbThreads = 32;
+constexpr int kArbThreads = 64;
+constexpr int kArbStageWords = 4096;     // words (and gains) of a run of ticks staged per block
+template <int kG> struct arb_legs {      // compile-time leg count: the leg state lives in registers
+    igd_arb_leg v[kG > 0 ? kG : 1];
+};
+template <int kG>
 __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_desc d)
 {
     extern __shared__ __align__(128) uint8_t smem[];
-    igd_arb_leg *legs_s = reinterpret_cast<igd_arb_leg *>(smem);       // [kArbThreads][G]
-    const int b = blockIdx.x * kArbThreads + threadIdx.x;
-    const int G = d.G;
-    const int nb = min(kArbThreads, d.B - blockIdx.x * kArbThreads);
-    // cooperative, coalesced load of the block's leg state
-    for (int k = threadIdx.x; k < nb * G; k += kArbThreads)
-        legs_s[k] = d.legs[(size_t)blockIdx.x * kArbThreads * G + k];
-    __syncthreads();
-    if (b < d.B) {
-        igd_arb_leg *legs = legs_s + threadIdx.x * G;
-        igd_arb_bridge br = d.bridges[b];
-        const uint8_t *act = d.active ? d.active + (size_t)b * G : nullptr;
-        const size_t Cn = (size_t)d.B * G;
-        for (int f = 0; f < d.F; f++) {
-            const uint8_t *wbase = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)f * Cn + (size_t)b * G) * d.word_stride;
-            auto word = [&](int g) { return *reinterpret_cast<const uint32_t *>(wbase + (size_t)g * d.word_stride); };
-            auto active = [&](int g) { return act ? act[g] != 0 : true; };
-            if (d.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, G, word, active);
-            else igd_arb_server_best_tick(br, legs, G, word, active);
-            uint16_t *gout = d.gain_q7 + (size_t)f * Cn + (size_t)b * G;
-            for (int g = 0; g < G; g++) gout[g] = legs[g].gain_q7;
+    const int G = kG > 0 ? kG : d.G;
+    const int bpb = kArbThreads;                                        // bridges per block
+    uint32_t *words_s = reinterpret_cast<uint32_t *>(smem);             // [T][bpb*G]
+    uint16_t *gain_s = reinterpret_cast<uint16_t *>(words_s + kArbStageWords);   // [T][bpb*G]
+    igd_arb_leg *legs_s = reinterpret_cast<igd_arb_leg *>(gain_s + kArbStageWords);   // [bpb][G] (runtime G only)
+    const int b0 = blockIdx.x * bpb;
+    const int b = b0 + threadIdx.x;
+    const int nb = min(bpb, d.B - b0);
+    const int row = nb * G;                                             // words of this block per tick
+    const int T = max(1, kArbStageWords / (bpb * G));                   // ticks per staged run
+    const size_t Cn = (size_t)d.B * G;
+    arb_legs<kG> lr;
+    igd_arb_leg *legs;
+    if (kG > 0) {
+        legs = lr.v;
+        if (b < d.B) {
+#pragma unroll
+            for (int g = 0; g < (kG > 0 ? kG : 1); g++) lr.v[g] = d.legs[(size_t)b * G + g];
         }
-        d.bridges[b] = br;
+    } else {
+        for (int k = threadIdx.x; k < row; k += kArbThreads) legs_s[k] = d.legs[(size_t)b0 * G + k];
+        legs = legs_s + threadIdx.x * G;
+    }
+    igd_arb_bridge br;
+    if (b < d.B) br = d.bridges[b];
+    const uint8_t *act = d.active ? d.active + (size_t)b * G : nullptr;
+    uint32_t act_mask = 0xFFFFFFFFu;                                    // G <= 32 legs
+    if (act && b < d.B) {
+        act_mask = 0;
+        for (int g = 0; g < G; g++) act_mask |= (act[g] != 0 ? 1u : 0u) << g;
+    }
+    for (int f0 = 0; f0 < d.F; f0 += T) {
+        const int nt = min(T, d.F - f0);
+        __syncthreads();
+        for (int t = 0; t < nt; t++) {                                  // coalesced: a tick's words are contiguous
+            const uint8_t *wrow = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)(f0 + t) * Cn + (size_t)b0 * G) * d.word_stride;
+            for (int j = threadIdx.x; j < row; j += kArbThreads)
+                words_s[t * row + j] = *reinterpret_cast<const uint32_t *>(wrow + (size_t)j * d.word_stride);
+        }
+        __syncthreads();
+        if (b < d.B) {
+            for (int t = 0; t < nt; t++) {
+                const uint32_t *wt = words_s + t * row + threadIdx.x * G;
+                auto word = [&](int g) { return wt[g]; };
+                auto active = [&](int g) { return ((act_mask >> g) & 1u) != 0u; };
+                uint16_t *gt = gain_s + t * row + threadIdx.x * G;
+                if (kG > 0) {
+                    const igd_const_int<(kG > 0 ? kG : 1)> Gc;
+                    if (d.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, Gc, word, active);
+                    else igd_arb_server_best_tick(br, legs, Gc, word, active);
+#pragma unroll
+                    for (int g = 0; g < (kG > 0 ? kG : 1); g++) gt[g] = legs[g].gain_q7;
+                } else {
+                    if (d.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, G, word, active);
+                    else igd_arb_server_best_tick(br, legs, G, word, active);
+                    for (int g = 0; g < G; g++) gt[g] = legs[g].gain_q7;
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = 0; t < nt; t++) {
+            uint16_t *grow = d.gain_q7 + (size_t)(f0 + t) * Cn + (size_t)b0 * G;
+            for (int j = threadIdx.x; j < row; j += kArbThreads) grow[j] = gain_s[t * row + j];
+        }
     }
     __syncthreads();
-    for (int k = threadIdx.x; k < nb * G; k += kArbThreads)
-        d.legs[(size_t)blockIdx.x * kArbThreads * G + k] = legs_s[k];
+    if (b < d.B) d.bridges[b] = br;
+    if (kG > 0) {
+        if (b < d.B) {
+#pragma unroll
+            for (int g = 0; g < (kG > 0 ? kG : 1); g++) d.legs[(size_t)b * G + g] = lr.v[g];
+        }
+    } else {
+        for (int k = threadIdx.x; k < row; k += kArbThreads) d.legs[(size_t)b0 * G + k] = legs_s[k];
+    }
 }
 
 // Phase 1: one thread per channel walks its frames through the sender state
@@ -1042,27 +1185,46 @@ __global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d,
     if (c >= d.C) return;
     igd_ed137_state s = d.state[c];
     int32_t src = -1;
-    for (int f = 0; f < d.F; f++) {
-        const size_t i = (size_t)f * d.C + c;
-        if (d.ctl) {                                                     // the setters, :135-213
-            const igd_ed137_ctl k = d.ctl[i];
-            s.pttstatus = k.pttstatus; s.pttpriority = k.pttpriority; s.callRecorder = k.callRecorder;
-            s.sqlstatus = k.sqlstatus; s.ed137_bssi = k.ed137_bssi; s.pttid = k.pttid;
+    const bool stuck = 12u + d.payload_len > 60u;
+    constexpr int kAhead = 8;            // the walk is sequential, its inputs are not: fetch 8 frames ahead
+    for (int f0 = 0; f0 < d.F; f0 += kAhead) {
+        igd_ed137_ctl kk[kAhead];
+        uint32_t a40[kAhead], a50[kAhead], a60[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; u++) {
+            const int f = f0 + u;
+            if (f < d.F) {
+                const size_t i = (size_t)f * d.C + c;
+                if (d.ctl) kk[u] = d.ctl[i];
+                if (stuck) {
+                    const uint8_t *pl = d.payload + i * IGD_FRAME;
+                    a40[u] = pl[40 - 12]; a50[u] = pl[50 - 12]; a60[u] = pl[60 - 12];
+                }
+            }
         }
-        if (s.radiostatus && 12u + d.payload_len > 60u) {                // stuck-audio detector :657-673
-            const uint8_t *pl = d.payload + i * IGD_FRAME;
-            const uint8_t a40 = pl[40 - 12], a50 = pl[50 - 12], a60 = pl[60 - 12];
-            if (a40 == a50 && a40 == a60 && a40 == 0xd5) s.rtpFalse += 1; else s.rtpFalse = 0;
+#pragma unroll
+        for (int u = 0; u < kAhead; u++) {
+            const int f = f0 + u;
+            if (f >= d.F) break;
+            const size_t i = (size_t)f * d.C + c;
+            if (d.ctl) {                                                     // the setters, :135-213
+                const igd_ed137_ctl k = kk[u];
+                s.pttstatus = k.pttstatus; s.pttpriority = k.pttpriority; s.callRecorder = k.callRecorder;
+                s.sqlstatus = k.sqlstatus; s.ed137_bssi = k.ed137_bssi; s.pttid = k.pttid;
+            }
+            if (s.radiostatus && stuck) {                                    // stuck-audio detector :657-673
+                if (a40[u] == a50[u] && a40[u] == a60[u] && a40[u] == 0xd5) s.rtpFalse += 1; else s.rtpFalse = 0;
+            }
+            const igd_tx_plan t = igd_ed137_tx_step(s, d.payload_len, d.now_ms0 + (long long)f * d.tick_ms);
+            if (t.copy_payload) src = f;
+            igd_tx_plan_rec r;
+            r.word = t.word;
+            r.size = (uint16_t)t.size;
+            r.flags = (uint8_t)(t.pt123 | (t.marker << 1) | (t.copy_payload << 2));
+            r.reserved = 0;
+            r.src_frame = (d.flags & IGD_F_REF_QUIRKS) ? src : f;            // quirk Q2
+            plan[i] = r;
         }
-        const igd_tx_plan t = igd_ed137_tx_step(s, d.payload_len, d.now_ms0 + (long long)f * d.tick_ms);
-        if (t.copy_payload) src = f;
-        igd_tx_plan_rec r;
-        r.word = t.word;
-        r.size = (uint16_t)t.size;
-        r.flags = (uint8_t)(t.pt123 | (t.marker << 1) | (t.copy_payload << 2));
-        r.reserved = 0;
-        r.src_frame = (d.flags & IGD_F_REF_QUIRKS) ? src : f;            // quirk Q2
-        plan[i] = r;
     }
     d.state[c] = s;
     last_src[c] = src;
@@ -1146,6 +1308,93 @@ __global__ void __launch_bounds__(256) k_ed137_assemble(const igd_ed137_pack_des
             for (int o = 16; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
         }
         if (lane == 0) d.bytemean_out[i] = audio ? (uint8_t)igd_bytemean_from_sum(bsum, (int)d.payload_len) : 0;
+    }
+}
+
+// Tile form of the assembly for the wire shape (out_stride 180, 160-byte payloads): a CTA builds
+// 64 packets in shared memory (headers by 64 threads, payload chunks by all threads with 16-byte
+// loads) and writes the image out with coalesced word stores, only the bytes each packet's size
+// covers -- same bytes, sizes and levels as k_ed137_assemble above.
+__global__ void __launch_bounds__(256) k_ed137_assemble_tile(const igd_ed137_pack_desc d,
+                                                             const igd_tx_plan_rec *__restrict__ plan)
+{
+    __shared__ __align__(16) uint32_t img[kPktTile * kPktWords];
+    __shared__ uint32_t size_s[kPktTile];
+    __shared__ int32_t srcf_s[kPktTile];
+    __shared__ uint32_t flag_s[kPktTile];
+    __shared__ int bsum_s[kPktTile];
+    __shared__ uint32_t chan_s[kPktTile];
+    __shared__ int32_t frame_s[kPktTile];
+    const size_t npkts = (size_t)d.F * d.C;
+    const size_t first = (size_t)blockIdx.x * kPktTile;
+    const uint32_t np = (uint32_t)min((size_t)kPktTile, npkts - first);
+    const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0, quirks = (d.flags & IGD_F_REF_QUIRKS) != 0;
+    if (threadIdx.x < np) {
+        const uint32_t p = threadIdx.x;
+        const size_t i = first + p;
+        const igd_tx_plan_rec r = plan[i];
+        const uint32_t *hdr = reinterpret_cast<const uint32_t *>(d.rtp12 + i * 12);
+        const uint32_t h0 = hdr[0], h1 = hdr[1], h2 = hdr[2];
+        uint32_t v0 = h0 | 0x10u;                                              // x = 1 (:725)
+        v0 = (v0 & ~0x8000u) | ((r.flags & 2u) ? 0x8000u : 0u);                // m (:715-723)
+        if (r.flags & 1u) v0 = (v0 & ~0x7F00u) | (123u << 8);                  // pt = 123
+        uint32_t *o = img + p * kPktWords;
+        o[0] = v0; o[1] = h1; o[2] = h2; o[3] = 0x01006701u; o[4] = bswap32(r.word);
+        size_s[p] = r.size;
+        srcf_s[p] = r.src_frame;
+        flag_s[p] = r.flags;
+        frame_s[p] = (int32_t)(i / (size_t)d.C);
+        chan_s[p] = (uint32_t)(i - (size_t)frame_s[p] * d.C);
+        d.sizes[i] = r.size;
+        // quirk Q3: the level sums the first 160 bytes of the ORIGINAL packet = these 12 header bytes ...
+        int hs = 0;
+        if (quirks) { hs = bytesum4(h0, sc, hs); hs = bytesum4(h1, sc, hs); hs = bytesum4(h2, sc, hs); }
+        bsum_s[p] = hs;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < np * kChunks; j += blockDim.x) {
+        const uint32_t p = j / kChunks, ch = j - p * kChunks;
+        const size_t i = first + p;
+        const uint32_t size = size_s[p];
+        if (size == 0) continue;
+        const bool audio = !(flag_s[p] & 1u);
+        const size_t c = chan_s[p];
+        const int32_t f = frame_s[p], sf = srcf_s[p];
+        uint4 cur = make_uint4(0u, 0u, 0u, 0u);
+        const bool need_cur = audio || (size > IGD_PKT_HDR && sf == f);
+        if (need_cur) cur = __ldcs(reinterpret_cast<const uint4 *>(d.payload + i * IGD_FRAME) + ch);
+        if (size > IGD_PKT_HDR) {
+            uint4 v = cur;
+            if (sf != f) {
+                if (sf >= 0) v = __ldg(reinterpret_cast<const uint4 *>(d.payload + ((size_t)sf * d.C + c) * IGD_FRAME) + ch);
+                else if (d.stale_payload) v = __ldg(reinterpret_cast<const uint4 *>(d.stale_payload + c * IGD_FRAME) + ch);
+                else v = make_uint4(0u, 0u, 0u, 0u);
+            }
+            uint32_t *o = img + p * kPktWords + 5 + ch * 4;
+            o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+        }
+        if (audio) {        // setOutgoingRTP (roip_ed137.cpp:6500-6536): clean = the payload bytes;
+            int bs = 0;     // Q3 = ... + payload[0 .. 148) (TransportAdapter.cpp:654)
+            if (!quirks) {
+                bs = bytesum4(cur.x, sc, bs); bs = bytesum4(cur.y, sc, bs); bs = bytesum4(cur.z, sc, bs); bs = bytesum4(cur.w, sc, bs);
+            } else if (ch < 9) {
+                bs = bytesum4(cur.x, sc, bs); bs = bytesum4(cur.y, sc, bs); bs = bytesum4(cur.z, sc, bs); bs = bytesum4(cur.w, sc, bs);
+            } else {
+                bs = bytesum4(cur.x, sc, bs);                                  // bytes 144..147
+            }
+            atomicAdd(&bsum_s[p], bs);
+        }
+    }
+    __syncthreads();
+    uint32_t *out = reinterpret_cast<uint32_t *>(d.pkts + first * IGD_PKT_MAX);
+    for (uint32_t w = threadIdx.x; w < np * kPktWords; w += blockDim.x) {
+        const uint32_t p = w / kPktWords, k = w - p * kPktWords;
+        if (4 * k < size_s[p]) out[w] = img[w];
+    }
+    if (threadIdx.x < np) {
+        const uint32_t p = threadIdx.x;
+        const bool audio = size_s[p] != 0 && !(flag_s[p] & 1u);
+        d.bytemean_out[first + p] = audio ? (uint8_t)igd_bytemean_from_sum(bsum_s[p], IGD_FRAME) : (uint8_t)0;
     }
 }
 
@@ -1313,6 +1562,12 @@ cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, cons
                               size_t npkts, size_t stride, igd_ed137_fields *fields,
                               uint8_t *payload_out)
 {
+    const bool al16 = ((reinterpret_cast<uintptr_t>(pkts) | reinterpret_cast<uintptr_t>(payload_out)) & 15) == 0;
+    if (stride == IGD_PKT_MAX && al16 && npkts > 0) {
+        const size_t tiles = (npkts + kPktTile - 1) / kPktTile;
+        k_ed137_parse_tile<<<(unsigned)tiles, 256, 0, c.stream>>>(pkts, sizes, npkts, fields, payload_out);
+        return cudaGetLastError();
+    }
     k_ed137_parse<<<grid_for(c, npkts * 32, 256, 8), 256, 0, c.stream>>>(pkts, sizes, npkts, stride, fields,
                                                                   payload_out);
     return cudaGetLastError();
@@ -1326,8 +1581,15 @@ cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d)
 
 cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d)
 {
-    const size_t smem = (size_t)kArbThreads * d.G * sizeof(igd_arb_leg);
-    k_gate_arbitrate<<<(d.B + kArbThreads - 1) / kArbThreads, kArbThreads, smem, c.stream>>>(d);
+    const unsigned blocks = (unsigned)((d.B + kArbThreads - 1) / kArbThreads);
+    const size_t stage = (size_t)kArbStageWords * 6;
+    switch (d.G) {
+    case 1: k_gate_arbitrate<1><<<blocks, kArbThreads, stage, c.stream>>>(d); break;
+    case 2: k_gate_arbitrate<2><<<blocks, kArbThreads, stage, c.stream>>>(d); break;
+    case 4: k_gate_arbitrate<4><<<blocks, kArbThreads, stage, c.stream>>>(d); break;
+    default:   // runtime leg count: leg state in shared memory (<= 64 * 32 * 8 B = 16 KB, 40 KB in all)
+        k_gate_arbitrate<0><<<blocks, kArbThreads, stage + (size_t)kArbThreads * d.G * sizeof(igd_arb_leg), c.stream>>>(d);
+    }
     return cudaGetLastError();
 }
 
@@ -1339,7 +1601,14 @@ cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc 
     k_ed137_plan<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d, plan, last_src);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    k_ed137_assemble<<<grid_for(c, (size_t)d.F * d.C * 32, 256, 8), 256, 0, c.stream>>>(d, plan);
+    const bool al16 = ((reinterpret_cast<uintptr_t>(d.payload) | reinterpret_cast<uintptr_t>(d.stale_payload)) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(d.pkts) & 3) == 0;
+    if (d.out_stride == IGD_PKT_MAX && d.payload_len == IGD_FRAME && al16) {
+        const size_t tiles = ((size_t)d.F * d.C + kPktTile - 1) / kPktTile;
+        k_ed137_assemble_tile<<<(unsigned)tiles, 256, 0, c.stream>>>(d, plan);
+    } else {
+        k_ed137_assemble<<<grid_for(c, (size_t)d.F * d.C * 32, 256, 8), 256, 0, c.stream>>>(d, plan);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess || !d.stale_payload) return e;
     k_ed137_stale_update<<<grid_for(c, (size_t)d.C * 32, 256, 8), 256, 0, c.stream>>>(d, last_src);

@@ -8,6 +8,7 @@
 #include <stdint.h>
 
 #ifdef IGD_HOST_EMUL
+#define IGD_UNROLL
 #include <math.h>
 #include <string.h>
 #define IGD_HD inline
@@ -17,6 +18,7 @@ static inline float igd_log2(float x) { return log2f(x); }
 static inline int igd_max(int a, int b) { return a > b ? a : b; }
 static inline int igd_min(int a, int b) { return a < b ? a : b; }
 #else
+#define IGD_UNROLL _Pragma("unroll")
 #define IGD_HD __device__ __forceinline__
 __device__ __forceinline__ int igd_f2i(float f) { return __float_as_int(f); }
 __device__ __forceinline__ float igd_i2f(int i) { return __int_as_float(i); }
@@ -248,14 +250,23 @@ IGD_HD uint32_t igd_rx_step(S &a, const FL &f, bool present, bool run_watchdog, 
 }
 
 // ---------------------------------------------------------------- gate arbitration
+// a leg count known at compile time (loops unroll, leg state stays in registers)
+template <int N> struct igd_const_int {
+#ifdef IGD_HOST_EMUL
+    constexpr operator int() const { return N; }
+#else
+    __host__ __device__ constexpr operator int() const { return N; }
+#endif
+};
 // One checkEvents() pass over the G legs of one bridge.  `L` has the igd_arb_leg field names,
 // `BR` the igd_arb_bridge ones; `word(g)` returns leg g's latched ED-137 word (host order),
 // `active(g)` whether the leg takes part (callState, and trxmode != RX for CLIENT / != TX for SERVER).
 // CLIENT mode: highest ptt_type wins, winner gets SLOT_VOLUME 2.0 (256), pressed losers 0
 // (roip_ed137.cpp:6124-6231); a released PTT is held for five more ticks (:6140-6153).
-template <class BR, class L, class W, class A>
-IGD_HD void igd_arb_client_tick(BR &b, L *legs, int G, W word, A active)
+template <class BR, class L, class GI, class W, class A>
+IGD_HD void igd_arb_client_tick(BR &b, L *legs, GI G, W word, A active)
 {
+    IGD_UNROLL
     for (int i = 0; i < G; i++) {
         if (!active(i)) continue;
         int ptt = (int)((word(i) & 0xe0000000u) >> 29);
@@ -271,6 +282,7 @@ IGD_HD void igd_arb_client_tick(BR &b, L *legs, int G, W word, A active)
         if (ptt && ptt > b.ptt_level) {
             b.ptt_level = ptt;
             legs[i].gain_q7 = 256;
+            IGD_UNROLL
             for (int j = 0; j < G; j++)
                 if (legs[j].on && j != i) legs[j].gain_q7 = 0;
         }
@@ -287,9 +299,10 @@ IGD_HD void igd_arb_client_tick(BR &b, L *legs, int G, W word, A active)
 // SERVER mode with rxBestSignalEnable: per-radio squelch bookkeeping (roip_ed137.cpp:5627-5719 and
 // its three twins), then after five consecutive ticks of squelch only the radio with the best BSS
 // quality index is unmuted (:5985-6121).
-template <class BR, class L, class W, class A>
-IGD_HD void igd_arb_server_best_tick(BR &b, L *legs, int G, W word, A active)
+template <class BR, class L, class GI, class W, class A>
+IGD_HD void igd_arb_server_best_tick(BR &b, L *legs, GI G, W word, A active)
 {
+    IGD_UNROLL
     for (int i = 0; i < G; i++) {
         if (!active(i)) continue;
         const uint32_t w = word(i);
@@ -309,6 +322,7 @@ IGD_HD void igd_arb_server_best_tick(BR &b, L *legs, int G, W word, A active)
         }
     }
     bool any = false;
+    IGD_UNROLL
     for (int i = 0; i < G; i++) {
         if (!active(i) || legs[i].last == 0) {
             if (legs[i].on) { b.sqlStatusCount = 0; b.sqlStatusOn = 0; }
@@ -320,14 +334,18 @@ IGD_HD void igd_arb_server_best_tick(BR &b, L *legs, int G, W word, A active)
     if (any) {
         b.sqlStatusCount++;
         if (b.sqlStatusCount >= 5 && !b.sqlStatusOn) {
-            for (int i = 0; i < G; i++)
+            IGD_UNROLL
+    for (int i = 0; i < G; i++)
                 if (legs[i].last > 0) legs[i].gain_q7 = 0;
             b.sqlStatusOn = 1;
-            for (int i = 0; i < G; i++) {
+            IGD_UNROLL
+    for (int i = 0; i < G; i++) {
                 bool best = legs[i].last != 0;
-                for (int j = 0; j < G && best; j++)
-                    if (j != i && legs[i].rssi < legs[j].rssi) best = false;
+                IGD_UNROLL
+                for (int j = 0; j < G; j++)
+                    if (best && j != i && legs[i].rssi < legs[j].rssi) best = false;
                 if (best) {
+                    IGD_UNROLL
                     for (int j = 0; j < G; j++) legs[j].on = (uint8_t)(j == i);
                     if (active(i)) legs[i].gain_q7 = 256;
                     break;
@@ -337,6 +355,7 @@ IGD_HD void igd_arb_server_best_tick(BR &b, L *legs, int G, W word, A active)
     } else {
         b.sqlStatusCount = 0;
         b.sqlStatusOn = 0;
-        for (int i = 0; i < G; i++) legs[i].on = 0;
+        IGD_UNROLL
+    for (int i = 0; i < G; i++) legs[i].on = 0;
     }
 }
