@@ -853,7 +853,7 @@ __global__ void __launch_bounds__(256) k_mix(const int16_t *__restrict__ pcm, co
 // ============================================================ event summary
 // Functions.cpp:2126-2145 over the frames whose gate is open; one warp per 32
 // channels x frame slice, slices combined through shared memory.
-constexpr int kSumSlices = 8;
+constexpr int kSumSlices = 32;
 __global__ void __launch_bounds__(32 * kSumSlices) k_event_summary(const igd_meter_rec *__restrict__ meter,
                                                                    const uint16_t *__restrict__ gain,
                                                                    long long F, long long C,
@@ -867,19 +867,34 @@ __global__ void __launch_bounds__(32 * kSumSlices) k_event_summary(const igd_met
     r.count = 0; r.bm_sum = 0; r.bm_max = 0; r.bm_min = 255;          // Functions.cpp:2159-2167
     r.sum_s = 0; r.max_s = 0; r.min_s = 255ull * IGD_FRAME;
     if (c < C) {
-        for (long long f = slice; f < F; f += kSumSlices) {
-            const size_t i = (size_t)f * C + c;
-            if (gain[i] == 0) continue;
-            const uint4 m = *reinterpret_cast<const uint4 *>(meter + i);
-            const uint64_t s = (uint64_t)m.x | ((uint64_t)(m.y & 0xFFu) << 32);
-            const uint32_t bm = (m.y >> 8) & 0xFFu;
-            r.count += 1;
-            r.sum_s += s;
-            r.bm_sum = (uint16_t)(r.bm_sum + bm);
-            r.max_s = s > r.max_s ? s : r.max_s;
-            r.min_s = s < r.min_s ? s : r.min_s;
-            r.bm_max = (uint8_t)max((uint32_t)r.bm_max, bm);
-            r.bm_min = (uint8_t)min((uint32_t)r.bm_min, bm);
+        constexpr int kAhead = 4;                    // four frames of this slice in flight
+        for (long long f0 = slice; f0 < F; f0 += (long long)kSumSlices * kAhead) {
+            uint32_t g[kAhead];
+            uint4 mm[kAhead];
+#pragma unroll
+            for (int u = 0; u < kAhead; u++) {
+                const long long f = f0 + (long long)u * kSumSlices;
+                g[u] = f < F ? (uint32_t)gain[(size_t)f * C + c] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < kAhead; u++) {
+                const long long f = f0 + (long long)u * kSumSlices;
+                if (g[u]) mm[u] = __ldcs(reinterpret_cast<const uint4 *>(meter + (size_t)f * C + c));
+            }
+#pragma unroll
+            for (int u = 0; u < kAhead; u++) {
+                if (!g[u]) continue;
+                const uint4 m = mm[u];
+                const uint64_t s = (uint64_t)m.x | ((uint64_t)(m.y & 0xFFu) << 32);
+                const uint32_t bm = (m.y >> 8) & 0xFFu;
+                r.count += 1;
+                r.sum_s += s;
+                r.bm_sum = (uint16_t)(r.bm_sum + bm);
+                r.max_s = s > r.max_s ? s : r.max_s;
+                r.min_s = s < r.min_s ? s : r.min_s;
+                r.bm_max = (uint8_t)max((uint32_t)r.bm_max, bm);
+                r.bm_min = (uint8_t)min((uint32_t)r.bm_min, bm);
+            }
         }
     }
     sh[slice][lane] = r;
