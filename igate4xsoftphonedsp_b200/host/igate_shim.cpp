@@ -40,6 +40,11 @@ struct igd_bank {
     std::vector<uint32_t> rxsz;
     std::vector<igd_ed137_fields> rxf;
     std::vector<uint8_t> rxpay, rxbm;      // [cap][160], [cap]
+    std::vector<igd_rx_state> rxstate;     // [cap] receive-side state (igd_rx_track carries it on the GPU)
+    std::vector<igd_rx_event> rxev;        // [cap]
+    std::vector<uint8_t> rxpresent;        // [cap] a packet was staged this tick
+    igd_event_fn on_event;                 // setIncomingED137Value(word, callID) / hang-up request
+    void *on_event_user;
     std::vector<uint8_t> txmask;           // channel had a packet staged this tick
     std::vector<uint8_t> stale;            // [cap][160] what each adapter's send buffer still holds (quirk Q2)
 };
@@ -73,6 +78,11 @@ igd_bank *igd_bank_open(int device, int max_channels)
     b->rxf.resize(max_channels);
     b->rxpay.assign((size_t)max_channels * IGD_FRAME, 0);
     b->rxbm.assign(max_channels, 0);
+    b->rxstate.assign(max_channels, igd_rx_state());
+    b->rxev.assign(max_channels, igd_rx_event());
+    b->rxpresent.assign(max_channels, 0);
+    b->on_event = nullptr;
+    b->on_event_user = nullptr;
     b->txmask.assign(max_channels, 0);
     b->stale.assign((size_t)max_channels * IGD_FRAME, 0);
     if (!g_default_bank) g_default_bank = b;
@@ -110,6 +120,8 @@ pj_status_t pjmedia_custom_tp_adapter_create(pjmedia_endpt *, const char *, pjme
     strncpy(s->trxmode, trxmode ? trxmode : "", sizeof(s->trxmode) - 1);
     const long long now = now_ms_wall();
     s->r2sPacket = now;                                                    // TransportAdapter.cpp:122
+    memset(&b->rxstate[s->ch], 0, sizeof(igd_rx_state));
+    b->rxstate[s->ch].r2sPacket = now;
     igd_ed137_state_init(&b->state[s->ch], radiocall, callIn, s->calltype, keepAlivePeroid, now);
     memset(&b->ctl[s->ch], 0, sizeof(igd_ed137_ctl));
     b->slots.push_back(s);
@@ -182,6 +194,10 @@ void igd_test_set_sendtime(pjmedia_transport *tp, long long t)
     if (Slot *s = slot_of(tp)) { s->bank->state[s->ch].r2sSendtime = t; s->r2sPacket = t; }
 }
 pj_uint32_t get_ed137_value(pjmedia_transport *tp) { return tp ? slot_of(tp)->ed137_value : 0; }
+void igd_test_set_r2spacket(pjmedia_transport *tp, long long t)      // tests run on their own clock
+{
+    if (Slot *s = slot_of(tp)) { s->r2sPacket = t; s->bank->rxstate[s->ch].r2sPacket = t; }
+}
 long long getR2SStatus(pjmedia_transport *tp)
 {
     return tp ? slot_of(tp)->r2sPacket : now_ms_wall() - 3000;             // TransportAdapter.cpp:317-325
@@ -260,38 +276,86 @@ pj_status_t igd_submit_rx(pjmedia_transport *tp, const void *pkt, pj_ssize_t siz
     return PJ_SUCCESS;
 }
 
+void igd_bank_set_event_cb(igd_bank *b, igd_event_fn fn, void *user)
+{
+    if (b) { b->on_event = fn; b->on_event_user = user; }
+}
+
+// one igd_rx_track call over every adapter of the bank: F = 1 tick, `present` = who received a
+// packet, run_watchdog selects detectR2SPacketAndReconn's check (roip_ed137.cpp:1767-1780)
+static int rx_track_tick(igd_bank *b, long long now_ms, int r2s_period_ms, bool run_watchdog)
+{
+    igd_rx_track_desc d;
+    memset(&d, 0, sizeof(d));
+    d.struct_size = sizeof(d);
+    d.mem = IGD_MEM_HOST;
+    d.F = 1; d.C = b->n;
+    d.tick_ms = 20;
+    d.r2s_period_ms = r2s_period_ms;
+    d.wd_ticks = run_watchdog ? 1 : 0;
+    d.now_ms0 = now_ms;
+    d.fields = b->rxf.data();
+    d.present = b->rxpresent.data();
+    d.state = b->rxstate.data();
+    d.events = b->rxev.data();
+    return igd_rx_track(b->ctx, &d);
+}
+
 int igd_bank_flush_rx(igd_bank *b, long long now_ms, igd_send_fn stream_cb, void *user)
 {
     if (!b) return -1;
     const int n = b->n;
     if (n == 0) return 0;
-    for (int c = 0; c < n; c++) b->rxsz[c] = b->slots[c]->rx_staged ? b->slots[c]->rx_size : 0;   // 0: nothing arrived
+    for (int c = 0; c < n; c++) {
+        b->rxsz[c] = b->slots[c]->rx_staged ? b->slots[c]->rx_size : 0;   // 0: nothing arrived
+        b->rxpresent[c] = b->slots[c]->rx_staged ? 1 : 0;
+    }
     int rc = igd_ed137_parse(b->ctx, b->rxpk.data(), b->rxsz.data(), (size_t)n, IGD_PKT_MAX, b->rxf.data(),
                              b->rxpay.data(), IGD_MEM_HOST);
     if (rc == IGD_OK)   // setIncomingRTP: byte-mean of the payload (roip_ed137.cpp:6541-6587), on the GPU
         rc = igd_bytemean(b->ctx, b->rxpay.data(), (size_t)n, IGD_FRAME, IGD_FRAME, 0, b->rxbm.data(), IGD_MEM_HOST);
+    if (rc == IGD_OK)   // word latch, r2sPacket stamp, audio <-> keep-alive edge (TransportAdapter.cpp:252-315), on the GPU
+        rc = rx_track_tick(b, now_ms, 200, false);
     int parsed = 0;
     for (int c = 0; c < n; c++) {
         Slot *s = b->slots[c];
         if (rc == IGD_OK && s->rx_staged) {
             const igd_ed137_fields &f = b->rxf[c];
+            const igd_rx_event &e = b->rxev[c];
             parsed++;
-            s->r2sPacket = now_ms;                                           // :289,302,311
-            if (!(f.flags & IGD_EDF_DROPPED)) {
-                if (f.accepted) { s->last = f; s->ed137_value = f.word; }    // :252-256 latch
-                if (!f.keepalive) {                                          // :298-307
-                    if (f.payload_len == IGD_FRAME) s->IncomingRTP = b->rxbm[c];
-                    if (stream_cb)
-                        stream_cb(user, reinterpret_cast<pjmedia_transport *>(s), &b->rxpk[(size_t)c * IGD_PKT_MAX], s->rx_size);
-                    s->rtpAudio = true;
-                } else {
-                    s->rtpAudio = false;                                     // :308-315
-                }
+            s->r2sPacket = b->rxstate[c].r2sPacket;                          // :289,302,311
+            s->rtpAudio = b->rxstate[c].rtpAudio != 0;
+            s->ed137_value = e.word;                                         // :252-256 latch
+            if (f.accepted && !(f.flags & IGD_EDF_DROPPED)) s->last = f;
+            if (e.flags & IGD_RXE_AUDIO) {                                   // :298-307
+                if (f.payload_len == IGD_FRAME) s->IncomingRTP = b->rxbm[c];
+                if (stream_cb)
+                    stream_cb(user, reinterpret_cast<pjmedia_transport *>(s), &b->rxpk[(size_t)c * IGD_PKT_MAX], s->rx_size);
             }
+            if ((e.flags & IGD_RXE_EDGE) && b->on_event)                     // :304-306, :312-314
+                b->on_event(b->on_event_user, reinterpret_cast<pjmedia_transport *>(s), IGD_RXE_EDGE, e.word);
         }
         s->rx_staged = false;
     }
     return rc == IGD_OK ? parsed : rc;
+}
+
+int igd_bank_r2s_watchdog(igd_bank *b, long long now_ms, int r2s_period_ms)
+{
+    if (!b) return -1;
+    if (b->n == 0) return 0;
+    for (int c = 0; c < b->n; c++) b->rxpresent[c] = 0;
+    const int rc = rx_track_tick(b, now_ms, r2s_period_ms, true);
+    if (rc != IGD_OK) return rc;
+    int hangups = 0;
+    for (int c = 0; c < b->n; c++) {
+        if (b->rxev[c].flags & IGD_RXE_HANGUP) {
+            hangups++;
+            if (b->on_event)
+                b->on_event(b->on_event_user, reinterpret_cast<pjmedia_transport *>(b->slots[c]), IGD_RXE_HANGUP, b->rxev[c].word);
+        }
+    }
+    return hangups;
 }
 
 // ------------------------------------------------------------------ WavWriter

@@ -98,6 +98,17 @@ int igd_bank_flush_tx(igd_bank *bank, long long now_ms, unsigned flags, igd_send
 // stream_rtp_cb does in the reference.  Returns packets parsed or <0
 int igd_bank_flush_rx(igd_bank *bank, long long now_ms, igd_send_fn stream_cb, void *user);
 
+// events the receive side raises (what transport_rtp_cb / the 40 ms watchdog did inline):
+//   IGD_RXE_EDGE   -> RoIP_ED137::setIncomingED137Value(word, callID) -> checkEvents()
+//                     (TransportAdapter.cpp:304-306, 312-314)
+//   IGD_RXE_HANGUP -> trx_call_hangup(call_id, 500, "WG-67 ;cause=2001; text=\"missing R2S KeepAlive\"")
+//                     (roip_ed137.cpp:1770-1774)
+typedef void (*igd_event_fn)(void *user, pjmedia_transport *tp, unsigned rxe_flag, pj_uint32_t ed137_word);
+void igd_bank_set_event_cb(igd_bank *bank, igd_event_fn fn, void *user);
+// RoIP_ED137::detectR2SPacketAndReconn's liveness check for every adapter (one igd_rx_track call):
+// call it from the 40 ms timer (roip_ed137.cpp:482).  Returns the number of hang-up requests or <0.
+int igd_bank_r2s_watchdog(igd_bank *bank, long long now_ms, int r2s_period_ms);
+
 // ---- WavWriter (WavWriter.h:44-53), same public methods; the file image is built on the GPU at stop()
 class WavWriter {
 public:

@@ -26,6 +26,22 @@ static void on_send(void *user, pjmedia_transport *tp, const void *pkt, pj_size_
     o->sizes[(size_t)o->f * o->C + c] = (uint32_t)size;
 }
 
+struct Ev {
+    std::vector<uint8_t> edge;     // [F][C] setIncomingED137Value fired
+    std::vector<uint8_t> hang;     // [F][C] watchdog asked for a hang-up
+    int f, C;
+    std::vector<pjmedia_transport *> *tps;
+};
+
+static void on_event(void *user, pjmedia_transport *tp, unsigned flag, pj_uint32_t)
+{
+    Ev *e = static_cast<Ev *>(user);
+    int c = 0;
+    while ((*e->tps)[c] != tp) c++;
+    if (flag == IGD_RXE_EDGE) e->edge[(size_t)e->f * e->C + c] = 1;
+    if (flag == IGD_RXE_HANGUP) e->hang[(size_t)e->f * e->C + c] = 1;
+}
+
 int main(int argc, char **argv)
 {
     if (argc < 3) return 2;
@@ -65,8 +81,17 @@ int main(int argc, char **argv)
     o.tps = &tps;
     std::vector<uint8_t> out_level((size_t)F * C, 0), in_level((size_t)F * C, 0);
     std::vector<uint32_t> rx_word((size_t)F * C, 0);
+    Ev ev;
+    ev.edge.assign((size_t)F * C, 0);
+    ev.hang.assign((size_t)F * C, 0);
+    ev.C = C;
+    ev.tps = &tps;
+    igd_bank_set_event_cb(bank, on_event, &ev);
+    extern void igd_test_set_r2spacket(pjmedia_transport *, long long);
+    for (int c = 0; c < C; c++) igd_test_set_r2spacket(tps[c], now0);
     for (int f = 0; f < F; f++) {
         o.f = f;
+        ev.f = f;
         for (int c = 0; c < C; c++) {
             const igd_ed137_ctl &k = ctl[(size_t)f * C + c];
             setAdapterPtt(tps[c], k.pttstatus, k.pttpriority, k.callRecorder);      // what RoIP_ED137 does on PTT
@@ -89,6 +114,8 @@ int main(int argc, char **argv)
             rx_word[(size_t)f * C + c] = get_ed137_value(tps[c]);
             in_level[(size_t)f * C + c] = get_IncomingRTP(tps[c]);
         }
+        // the 40 ms timer of roip_ed137.cpp:482 -> detectR2SPacketAndReconn, every second 20 ms tick
+        if ((f & 1) == 1 && igd_bank_r2s_watchdog(bank, now0 + (long long)f * tick, 200) < 0) return 7;
     }
     FILE *out = fopen(argv[2], "wb");
     fwrite(o.sizes.data(), 4, o.sizes.size(), out);
@@ -96,6 +123,8 @@ int main(int argc, char **argv)
     fwrite(out_level.data(), 1, out_level.size(), out);
     fwrite(rx_word.data(), 4, rx_word.size(), out);
     fwrite(in_level.data(), 1, in_level.size(), out);
+    fwrite(ev.edge.data(), 1, ev.edge.size(), out);
+    fwrite(ev.hang.data(), 1, ev.hang.size(), out);
     fclose(out);
     // recorder sink: reference-exact file for the first channel's first 3 payloads
     WavWriter w;

@@ -66,7 +66,9 @@ def test_shim_matches_reference_send_path(tmp_path, name):
     pkts = np.frombuffer(raw, "u1", F * Cn * 180, o).reshape(F, Cn, 180); o += F * Cn * 180
     out_level = np.frombuffer(raw, "u1", F * Cn, o).reshape(F, Cn); o += F * Cn
     rx_word = np.frombuffer(raw, "<u4", F * Cn, o).reshape(F, Cn); o += 4 * F * Cn
-    in_level = np.frombuffer(raw, "u1", F * Cn, o).reshape(F, Cn)
+    in_level = np.frombuffer(raw, "u1", F * Cn, o).reshape(F, Cn); o += F * Cn
+    edge = np.frombuffer(raw, "u1", F * Cn, o).reshape(F, Cn); o += F * Cn
+    hang = np.frombuffer(raw, "u1", F * Cn, o).reshape(F, Cn)
     want_pk, want_sz, want_bm, _ = T.run_oracle(s)
     assert np.array_equal(sizes, want_sz)
     for f in range(F):
@@ -90,6 +92,29 @@ def test_shim_matches_reference_send_path(tmp_path, name):
                 p = np.ascontiguousarray(want_pk[f, c, 20:180])
                 lastin = L.orc_bytemean(p.ctypes.data, 160, 0)
             assert in_level[f, c] == lastin
+    # receive-side events: the emitted packets go through the oracle's transport_rtp_cb, the watchdog runs
+    # on every second tick (40 ms timer); edges = setIncomingED137Value calls, hang = cause-2001 requests
+    import ctypes as C
+    for c in range(Cn):
+        a = O.Adapter()
+        L.orc_adapter_init(C.byref(a), 1, 0, b"TRx", 200, 0)
+        a.r2sPacket = s["now0"]
+        cnt = C.c_int(0)
+        big = np.zeros(4096, np.uint8)
+        for f in range(F):
+            now = s["now0"] + f * s["tick_ms"]
+            n = int(sizes[f, c])
+            fired = 0
+            if n:
+                big[:180] = want_pk[f, c]
+                calls = a.checkEvents_calls
+                L.orc_transport_rtp_cb(C.byref(a), big.ctypes.data, n, now, 0, 0)
+                fired = int(a.checkEvents_calls != calls)
+            assert edge[f, c] == fired, (f, c)
+            h = 0
+            if f & 1:
+                h = (L.orc_r2s_watchdog(now, a.r2sPacket, 200, C.byref(cnt)) >> 1) & 1
+            assert hang[f, c] == h, (f, c)
     # WavWriter sink: reference-exact bytes
     rec = r.stdout.strip().splitlines()[-1]
     hdr = np.zeros(44, np.uint8)
