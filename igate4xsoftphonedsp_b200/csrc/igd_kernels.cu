@@ -1557,7 +1557,10 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
     // the warp-autonomous kernel indexes bridge-frames in 32 bits; anything larger (> 1.3 TB of
     // codes at G = 1) cannot be resident on one GPU anyway and takes the generic kernel
-    const bool fits32 = q.total_bf < (1ll << 31) - (1ll << 24);
+    // ... and reads a bridge-frame's G gains / a bridge's G laws as one 2G- / G-byte word
+    const bool fits32 = q.total_bf < (1ll << 31) - (1ll << 24) &&
+                        (reinterpret_cast<uintptr_t>(d.gain_q7) & (size_t)(2 * d.G - 1) & 7u) == 0 &&
+                        (d.G != 4 || (reinterpret_cast<uintptr_t>(d.law) & 3u) == 0);
     if (fits32 && d.G == 4) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
     if (fits32 && d.G == 2) return sc ? launch_fused_w<2, true, 24>(c, q) : launch_fused_w<2, false, 24>(c, q);
     if (fits32 && d.G == 1) return sc ? launch_fused_w<1, true, 24>(c, q) : launch_fused_w<1, false, 24>(c, q);

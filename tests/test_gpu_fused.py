@@ -197,3 +197,21 @@ def test_decode_encode_round_trip_is_identity_on_codes_at_full_size(vp):
     expect = torch.where(is_u & (leg == 0x7F), torch.full_like(leg, 0xFF), leg)
     assert torch.equal(got["enc"], expect)
     assert int(got["bmeter"].reshape(-1, 1).view(torch.uint8).reshape(F, B, 4)[..., 1].min()) == 1   # n_open
+
+
+def test_odd_gain_and_law_alignment_takes_the_generic_kernel(vp):
+    """device buffers whose gain / law arrays start at an odd element: same results (the warp kernel reads a
+    bridge-frame's four gains as one 8-byte word, so such buffers are routed to the generic kernel)."""
+    import torch
+    F, B, G = 5, 21, 4
+    codes, law, gain, out_law = make(F, B, G, random_codes=True, seed=3)
+    want = O.process_batch(codes, law, gain, out_law, G)
+    dev = "cuda:0"
+    gpad = torch.zeros(F * B * G + 1, dtype=torch.int16, device=dev)
+    gpad[1:] = torch.from_numpy(gain.view(np.int16).reshape(-1)).to(dev)
+    lpad = torch.zeros(B * G + 1, dtype=torch.uint8, device=dev)
+    lpad[1:] = torch.from_numpy(law).to(dev)
+    got = vp.process_batch(torch.from_numpy(codes).to(dev), lpad[1:], gpad[1:].reshape(F, B * G),
+                           torch.from_numpy(out_law).to(dev), G)
+    torch.cuda.synchronize()
+    assert np.array_equal(got["mix"].cpu().numpy(), want[0]) and np.array_equal(got["enc"].cpu().numpy(), want[1])
