@@ -108,6 +108,25 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def pin_to_gpu_numa_node(gpu_index):
+    """Binds this process to the CPUs NVML reports as local to the GPU, so that the pinned host
+    buffers of the e2e leg are allocated (first touch) on the GPU's own NUMA node.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus local to gpu {gpu_index}"
+    except Exception as e:                      # no NVML / not permitted: keep the default placement
+        return f"default ({type(e).__name__})"
+    return "default"
+
+
 def oracle_lib():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_py as O   # bench.py's cpu_baseline / --impl reference legs: the oracle is timed, never shipped
@@ -285,6 +304,8 @@ def main():
     # ---- end to end through the C ABI with HOST buffers (pinned), H2D + kernel + D2H every step
     e2e = None
     if not args.no_e2e:
+        affinity0 = os.sched_getaffinity(0)
+        numa = pin_to_gpu_numa_node(local)      # the pinned buffers are first-touched on the GPU's own NUMA node
         h_codes = torch.empty((F, C, FRAME), dtype=torch.uint8, pin_memory=True)
         h_codes.copy_(codes)
         h_in = {"codes": h_codes.numpy(), "law": law.cpu().numpy(), "gain": gain_np, "out_law": out_law.cpu().numpy()}
@@ -295,6 +316,9 @@ def main():
         h_out = {"mix": h_out_t["mix"].numpy(), "enc": h_out_t["enc"].numpy(),
                  "meter": h_out_t["meter"].numpy().view(ig.METER_DT).reshape(F, C),
                  "bmeter": h_out_t["bmeter"].numpy().view(ig.BRIDGE_DT).reshape(F, B)}
+        for t in h_out_t.values():
+            t.zero_()                           # first touch while bound
+        os.sched_setaffinity(0, affinity0)      # the CPU legs below use every host core again
         esteps = max(2, min(args.steps, 5))
         for _ in range(2):
             vp.process_batch(h_in["codes"], h_in["law"], h_in["gain"], h_in["out_law"], G, out=h_out)
@@ -310,7 +334,7 @@ def main():
         d2h = sum(v.nbytes for v in h_out.values())
         e2e_ok = bool(torch.equal(h_out_t["mix"], out["mix"].cpu()) and torch.equal(h_out_t["enc"], out["enc"].cpu()))
         e2e = {"value": samples_per_step * esteps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": esteps, "matches_device_path": e2e_ok}
+               "d2h_bytes_per_step": d2h, "steps": esteps, "matches_device_path": e2e_ok, "host_buffers": numa}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
