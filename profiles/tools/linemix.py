@@ -1,4 +1,4 @@
-"""per-source-line executed warp-instructions of one kernel: ncu report x nvdisasm -g line table.
+"""per-source-line executed warp-instructions of one kernel: ncu report x nvdisasm -g line table (run here, no GPU).
 usage: linemix.py report.ncu-rep libigate_dsp.so kernel_substr [nbf]"""
 import csv, io, re, subprocess, sys, collections, os, tempfile
 rep, so, ksub = sys.argv[1:4]
