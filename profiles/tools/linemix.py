@@ -24,7 +24,17 @@ for l in dis:
         ins.append((int(m.group(1), 16), cur, m.group(2).strip()))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hd = rows[1]; body = rows[2:]
+hd, body = None, []
+for r in rows:                       # first captured launch only
+    if r and r[0] == "Kernel Name":
+        if hd is not None:
+            break
+        continue
+    if r and r[0] == "Address":
+        hd = r
+        continue
+    if hd:
+        body.append(r)
 ia = hd.index("Instructions Executed"); isrc = hd.index("Source")
 assert len(body) == len(ins), (len(body), len(ins))
 per = collections.Counter(); ops = collections.defaultdict(collections.Counter)
