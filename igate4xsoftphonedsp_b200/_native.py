@@ -126,6 +126,7 @@ SYMBOLS = {
     "igd_calltype_flags": (C.c_uint, [C.c_char_p]),
     "igd_ed137_state_init": (None, [_vp, _i, _i, C.c_char_p, _i, C.c_int64]),
     "igd_ed137_pack": (_i, [_vp, C.POINTER(PackDesc)]),
+    "igd_ed137_keepalive": (_i, [_vp, _vp, _vp, _sz, C.c_int64, _vp, _i]),
     "igd_rx_track": (_i, [_vp, C.POINTER(RxTrackDesc)]),
     "igd_gate_arbitrate": (_i, [_vp, C.POINTER(ArbDesc)]),
     "igd_wav_size": (_sz, [_sz, _i]),

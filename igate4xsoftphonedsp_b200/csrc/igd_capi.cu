@@ -589,6 +589,29 @@ int igd_ed137_pack(igd_ctx *c, const igd_ed137_pack_desc *d)
     return finish(c, mem);
 }
 
+int igd_ed137_keepalive(igd_ctx *c, uint8_t *hdr20, igd_ed137_state *state, size_t C, int64_t now_ms,
+                        uint32_t *sizes, int mem)
+{
+    if (!c || (C && (!hdr20 || !state || !sizes))) return fail(c, IGD_EINVAL, "igd_ed137_keepalive: bad argument");
+    if (C == 0) return IGD_OK;
+    if (mem == IGD_MEM_DEVICE && (!aligned(hdr20, 4) || !aligned(state, 8) || !aligned(sizes, 4)))
+        return fail(c, IGD_EINVAL, "igd_ed137_keepalive: misaligned device pointer");
+    Bind b(c);
+    int rc;
+    const uint8_t *th = nullptr; const igd_ed137_state *ts = nullptr; uint32_t *dsz = nullptr;
+    if ((rc = in_arg(c, mem, 0, hdr20, C * IGD_PKT_HDR, &th))) return rc;
+    if ((rc = in_arg(c, mem, 1, state, C, &ts))) return rc;
+    if ((rc = out_arg(c, mem, 2, sizes, C, &dsz))) return rc;
+    uint8_t *dh = const_cast<uint8_t *>(th);
+    igd_ed137_state *ds = const_cast<igd_ed137_state *>(ts);
+    IGD_CUDA(c, igd_k_ed137_keepalive(cfg_of(c), dh, ds, C, (long long)now_ms, dsz));
+    c->launches++;
+    if ((rc = out_done(c, mem, hdr20, dh, C * IGD_PKT_HDR))) return rc;
+    if ((rc = out_done(c, mem, state, ds, C))) return rc;
+    if ((rc = out_done(c, mem, sizes, dsz, C))) return rc;
+    return finish(c, mem);
+}
+
 // ---------------------------------------------------------------- RX liveness, gate arbitration
 int igd_rx_track(igd_ctx *c, const igd_rx_track_desc *d)
 {

@@ -1245,6 +1245,28 @@ __global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d,
     last_src[c] = src;
 }
 
+// sendR2SStatus (TransportAdapter.cpp:422-633): thread per channel, one timer tick
+__global__ void __launch_bounds__(128) k_ed137_keepalive(uint8_t *__restrict__ hdr20, igd_ed137_state *__restrict__ state,
+                                                         size_t C, long long now, uint32_t *__restrict__ sizes)
+{
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    igd_ed137_state s = state[c];
+    uint32_t *h = reinterpret_cast<uint32_t *>(hdr20 + c * IGD_PKT_HDR);
+    uint32_t w0 = h[0];
+    const igd_tx_plan t = igd_ed137_r2s_step(s, now, (w0 >> 8) & 0x7Fu);
+    if (t.copy_payload) {                                   // the header fields are stamped into the send buffer
+        w0 |= 0x10u;                                                           // x = 1 (:495)
+        w0 = (w0 & ~0x8000u) | (t.marker ? 0x8000u : 0u);                      // m (:485-493)
+        if (t.pt123) w0 = (w0 & ~0x7F00u) | (123u << 8);
+        h[0] = w0;
+        h[3] = 0x01006701u;                                                    // 0x0167, 0x0001 big-endian
+        h[4] = bswap32(t.word);
+    }
+    sizes[c] = t.size;
+    state[c] = s;
+}
+
 // after the packets are assembled: remember the payload each adapter's send buffer ends up holding
 __global__ void __launch_bounds__(256) k_ed137_stale_update(const igd_ed137_pack_desc d,
                                                             const int32_t *__restrict__ last_src)
@@ -1608,6 +1630,13 @@ cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d)
     default:   // runtime leg count: leg state in shared memory (<= 64 * 32 * 8 B = 16 KB, 40 KB in all)
         k_gate_arbitrate<0><<<blocks, kArbThreads, stage + (size_t)kArbThreads * d.G * sizeof(igd_arb_leg), c.stream>>>(d);
     }
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_ed137_keepalive(const igd_launch_cfg &c, uint8_t *hdr20, igd_ed137_state *state, size_t C,
+                                  long long now, uint32_t *sizes)
+{
+    k_ed137_keepalive<<<(unsigned)((C + 127) / 128), 128, 0, c.stream>>>(hdr20, state, C, now, sizes);
     return cudaGetLastError();
 }
 

@@ -41,6 +41,8 @@ cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, cons
                               uint8_t *payload_out);
 cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc &d,
                              igd_tx_plan_rec *plan, int32_t *last_src);
+cudaError_t igd_k_ed137_keepalive(const igd_launch_cfg &c, uint8_t *hdr20, igd_ed137_state *state, size_t C,
+                                  long long now, uint32_t *sizes);
 cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d);
 cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d);
 cudaError_t igd_k_wav_image(const igd_launch_cfg &c, const uint8_t *payload, size_t n, int rate,

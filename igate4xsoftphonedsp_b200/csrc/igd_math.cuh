@@ -207,6 +207,77 @@ IGD_HD igd_tx_plan igd_ed137_tx_step(S &a, uint32_t payload_len, long long now)
     return r;
 }
 
+// Timer-driven keep-alive: sendR2SStatus (TransportAdapter.cpp:422-633), the twin of the step above.
+// It differs where the reference differs: no payload, the slave-enable "changed" values are NOT latched
+// (:513-516 vs :744-745), an extra Idle&&callIn branch (:585-589), and a packet only leaves when the PT
+// ends up 123 (:617-630).  The header it stamps lives in the adapter's send buffer, so whatever the
+// last call left in bytes 0..11 (incl. the PT in byte 1) is reused: `stale_pt` is that PT.
+// plan.size: 0 = nothing sent, 20 = keep-alive; plan.copy_payload is reused as "header fields were
+// written into the send buffer" (they persist even when nothing is sent).
+template <class S>
+IGD_HD igd_tx_plan igd_ed137_r2s_step(S &a, long long now, uint32_t stale_pt)
+{
+    igd_tx_plan r;
+    r.word = 0; r.size = 0; r.pt123 = 0; r.marker = 0; r.copy_payload = 0;
+    if (!a.radiostatus) return r;                                      // :429
+    const bool idle = a.calltype_flags & 1u, rxonly = a.calltype_flags & 2u,
+               txish = a.calltype_flags & 4u;
+    if (idle && a.callIn) { a.sqlstatus = 0; a.pttstatus = 0; }         // :444-448
+    const bool ptt = a.pttstatus != 0, sql = a.sqlstatus != 0, in = a.callIn != 0;
+    if ((ptt && !in) || (sql && in)) return r;                          // :449-454 audio is flowing
+    {
+        unsigned long long since = (unsigned long long)now - (unsigned long long)a.r2sSendtime;
+        unsigned long long ka = (unsigned long long)(long long)a.keepAlivePeroid;
+        if (since < ka && !a.firstR2SPacket) return r;                  // :457-460
+        if (since >= ka) a.r2sSendtime = now;                           // :463-473
+    }
+    r.copy_payload = 1;                                                 // header fields get written from here on
+    r.marker = (a.firstR2SPacket && a.packetCnt == 0) ? 1 : 0;          // :485-493
+    uint32_t w;
+    const bool stable = (a.txSlaveEnable == a.txSlaveEnableChanged) &&
+                        (a.rxSlaveEnable == a.rxSlaveEnableChanged) &&
+                        (a.trxSlaveEnableChangedCount >= 5);            // :499
+    if (!stable)                                                        // :513-516: count only, no latch
+        a.trxSlaveEnableChangedCount =
+            (uint8_t)(a.trxSlaveEnableChangedCount + 1 >= 5 ? 5 : a.trxSlaveEnableChangedCount + 1);
+    {
+        const uint32_t rx = a.rxSlaveEnable, tx = a.txSlaveEnable;
+        if (rx == 0 && tx == 0)      w = stable ? 0x00000000u : 0x00013100u;
+        else if (rx == 1 && tx == 1) w = 0x000131c0u;
+        else if (rx == 1 && tx == 0) w = 0x00013140u;
+        else if (rx == 0 && tx == 1) w = 0x00013180u;
+        else                         w = 0x00000000u;
+    }
+    if (sql) {                                                          // :531-546
+        a.sqlpriority = 0;
+        w |= 0x10000000u;
+        w |= 0x000000f8u & ((uint32_t)a.ed137_bssi << 3);
+    } else if (!ptt) {                                                  // :547-552
+        w |= 0x0fc00000u & (1u << 22);
+    }
+    if (ptt) {                                                          // :554-564
+        w |= 0x0fc00000u & ((uint32_t)a.pttid << 22);
+        w |= 0xe0000000u & ((uint32_t)a.pttpriority << 29);
+    }
+    r.word = w;
+    bool pt123 = false, leaves;
+    if (rxonly && !in) pt123 = true;                                    // :570-573
+    if (!ptt && !sql)               pt123 = true;                       // :580-584
+    else if (idle && in)            pt123 = true;                       // :585-589
+    else if (rxonly && !sql)        pt123 = true;                       // :590-594
+    else if (txish && !ptt && !sql) pt123 = true;                       // :595-598
+    else if (txish && ptt && in) {                                      // :599-610
+        if (!(a.callRecorder || sql)) pt123 = true;
+    }
+    r.pt123 = pt123 ? 1 : 0;
+    leaves = pt123 || stale_pt == 123;                                  // :617
+    if (!leaves) return r;
+    r.size = 20;
+    if (a.firstR2SPacket && a.packetCnt < 30) a.packetCnt++;            // :622-629
+    else if (a.packetCnt >= 30) a.firstR2SPacket = 0;
+    return r;
+}
+
 // ---------------------------------------------------------------- RX liveness
 // One tick of the receive side of one radio call: the state the reference keeps in
 // struct tp_adapter across transport_rtp_cb calls (TransportAdapter.cpp:240-316) plus the

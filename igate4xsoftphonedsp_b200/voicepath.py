@@ -357,6 +357,16 @@ class VoicePath:
         self._chk(self._lib.igd_ed137_pack(self._h, C.byref(d)))
         return pkts, sizes, bm
 
+    def ed137_keepalive(self, hdr20, state, now_ms):
+        """Batched sendR2SStatus: hdr20 u8 [C][20] (each adapter's send-buffer header, in/out), state [C]
+        (in/out) -> sizes [C] (20 where a keep-alive leaves, else 0)."""
+        mem = self._mode(hdr20, state)
+        Cn = hdr20.shape[0]
+        sizes = torch.empty((Cn,), dtype=torch.int32, device=hdr20.device) if mem == N.MEM_DEVICE else np.empty(Cn, np.uint32)
+        self._chk(self._lib.igd_ed137_keepalive(self._h, self._ptr(hdr20), self._ptr(state), Cn, int(now_ms),
+                                                self._ptr(sizes), mem))
+        return sizes
+
     # ------------------------------------------------------------ RX liveness, gate arbitration
     def rx_track(self, fields, state, present=None, now_ms0=0, tick_ms=20, r2s_period_ms=200, wd_ticks=2,
                  frame0=0):

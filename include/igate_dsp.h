@@ -299,6 +299,13 @@ typedef struct {
 } igd_ed137_pack_desc;
 int igd_ed137_pack(igd_ctx *ctx, const igd_ed137_pack_desc *d);
 
+/* Batched sendR2SStatus (TransportAdapter.cpp:422-633), the timer-driven keep-alive: one call at
+ * time now_ms for every channel.  hdr20 [C][20] is the header region of each adapter's send buffer
+ * (send_pkt_buff): read (the reference re-stamps whatever the last packet left there, PT included)
+ * and updated in place; sizes [C] = 20 where a keep-alive leaves (copy hdr20[c] to the wire), else 0. */
+int igd_ed137_keepalive(igd_ctx *ctx, uint8_t *hdr20, igd_ed137_state *state, size_t C, int64_t now_ms,
+                        uint32_t *sizes, int mem);
+
 /* -------------------------------------------------- RX liveness / call events
  * replaces: the receive-side state transport_rtp_cb keeps per call
  * (TransportAdapter.cpp:240-316: ed137_value / payloadsize latch :252-256,

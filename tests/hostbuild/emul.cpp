@@ -29,6 +29,12 @@ void emul_tx_step(igd_ed137_state *s, unsigned payload_len, long long now, unsig
     igd_tx_plan p = igd_ed137_tx_step(*s, payload_len, now);
     o[0] = p.word; o[1] = p.size; o[2] = p.pt123; o[3] = p.marker; o[4] = p.copy_payload;
 }
+// one sendR2SStatus call; plan out = {word, size, pt123, marker, header_written}
+void emul_r2s_step(igd_ed137_state *s, long long now, unsigned stale_pt, unsigned *o)
+{
+    igd_tx_plan p = igd_ed137_r2s_step(*s, now, stale_pt);
+    o[0] = p.word; o[1] = p.size; o[2] = p.pt123; o[3] = p.marker; o[4] = p.copy_payload;
+}
 // one RX tick: fields record, state in/out; returns IGD_RXE_* bits
 unsigned emul_rx_step(igd_rx_state *s, const igd_ed137_fields *f, int present, int wd, long long now, int period)
 {

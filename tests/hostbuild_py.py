@@ -28,6 +28,7 @@ def lib():
         L.emul_bytemean.argtypes = [C.c_int, C.c_int]
         L.emul_fields.argtypes = [C.c_uint, C.POINTER(C.c_uint)]
         L.emul_tx_step.argtypes = [C.c_void_p, C.c_uint, C.c_longlong, C.POINTER(C.c_uint)]
+        L.emul_r2s_step.argtypes = [C.c_void_p, C.c_longlong, C.c_uint, C.POINTER(C.c_uint)]
         L.emul_rx_step.restype = C.c_uint
         L.emul_rx_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int]
         L.emul_arb_tick.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]

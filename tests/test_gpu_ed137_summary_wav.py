@@ -156,3 +156,19 @@ def test_wav_image_reference_bytes(vp, golden_dir):
     assert clean[:4] == b"RIFF" and clean[20:22] == b"\x06\x00" and clean[22:24] == b"\x01\x00"
     assert clean[34:36] == b"\x08\x00" and clean[44:] == payload.tobytes()
     assert int.from_bytes(clean[40:44], "little") == payload.size and int.from_bytes(clean[4:8], "little") == 36 + payload.size
+
+
+def test_keepalive_matches_reference_sendR2SStatus(vp):
+    """batched sendR2SStatus (TransportAdapter.cpp:422-633) tick by tick against the oracle."""
+    import keepalive_cases as K
+    legs, hdr, ctl = K.make(300, 60, seed=5)
+    want_pk, want_sz, want_h = K.oracle_walk(legs, hdr, ctl)
+    st = K.initial_state(legs)
+    h = np.ascontiguousarray(hdr.copy())
+    for t in range(ctl.shape[0]):
+        K.apply_setters(st, ctl[t])
+        sz = vp.ed137_keepalive(h, st, 10_000 + 40 * t)
+        assert np.array_equal(sz, want_sz[t]), t
+        sent = sz == 20
+        assert np.array_equal(h[sent], want_pk[t][sent]), t
+    assert np.array_equal(h, want_h) and int(want_sz.sum()) > 0

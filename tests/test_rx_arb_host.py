@@ -119,3 +119,35 @@ def test_arbitration_device_math_matches_oracle():
             br[b] = bb[0]
         assert np.array_equal(got, want) and legs.tobytes() == wl.tobytes() and br.tobytes() == wb.tobytes()
         assert (want == 256).any()
+
+
+def test_keepalive_device_math_matches_oracle():
+    """igd_ed137_r2s_step (host build) against the oracle's sendR2SStatus restatement, header bytes included."""
+    import keepalive_cases as K
+    L = H.lib()
+    legs, hdr, ctl = K.make(40, 120, seed=2)
+    want_pk, want_sz, want_h = K.oracle_walk(legs, hdr, ctl)
+    st = K.initial_state(legs)
+    h = hdr.copy()
+    o = (C.c_uint * 5)()
+    T, Cn = ctl.shape
+    sent = 0
+    for t in range(T):
+        K.apply_setters(st, ctl[t])
+        for c in range(Cn):
+            s1 = st[c:c + 1].copy()
+            L.emul_r2s_step(s1.ctypes.data, 10_000 + 40 * t, int(h[c, 1] & 0x7F), o)
+            st[c] = s1[0]
+            word, size, pt123, marker, written = [int(x) for x in o]
+            if written:       # what k_ed137_keepalive stamps into the send buffer
+                h[c, 0] |= 0x10
+                h[c, 1] = (h[c, 1] & 0x7F) | (0x80 if marker else 0)
+                if pt123:
+                    h[c, 1] = (h[c, 1] & 0x80) | 123
+                h[c, 12:16] = [0x01, 0x67, 0x00, 0x01]
+                h[c, 16:20] = list(int(word).to_bytes(4, "big"))
+            assert size == want_sz[t, c], (t, c)
+            if size:
+                assert h[c].tobytes() == want_pk[t, c].tobytes(), (t, c)
+                sent += 1
+    assert np.array_equal(h, want_h) and sent > 100
