@@ -621,6 +621,185 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
     }
 }
 
+// ------------------------------------------------------------------------------------
+// Warp-autonomous fused kernel for ANY leg count (1..IGD_MAX_LEGS), e.g. the 32 inbound calls of a
+// CLIENT-mode softphone (roip_ed137.cpp:141-150).  Same building blocks as k_fused_w; what changes:
+//   * a warp's item is 3 consecutive bridge-frames, lane = ONE 16-sample chunk (10 lanes per
+//     bridge-frame, 30 of 32 lanes busy), so only 16 mix accumulators live across the legs;
+//   * the legs are walked in groups of four: per group the warp fetches 3 x (4 legs x 160 B) with
+//     three bulk copies (the groups of different bridge-frames are G*160 bytes apart) into a
+//     double-buffered, bank-conflict-free slot (bridge-frame stride 672 B == 2 mod 8 sixteenths),
+//     the next group is in flight while the current one is processed;
+//   * after every group lanes 0..11 finish that group's leg records; after the last group the mix
+//     is saturated / stored / compressed and lanes 0..2 finish the bridge records.
+constexpr int kGBf = 3;                    // bridge-frames per item
+constexpr int kGLegs = 4;                  // legs per group
+constexpr int kGStride = kGLegs * IGD_FRAME + 32;          // 672
+constexpr int kGSlotBytes = kGBf * kGStride;                // 2016
+constexpr int kGParts = (kGBf * kGLegs + kGBf) * kPst;      // leg + bridge partials per warp
+
+template <bool kSigned, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
+{
+    __shared__ uint64_t bars[kWarps * 2];
+    __shared__ __align__(16) uint32_t enc_tab[2][8];
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t lut_bytes = shared_addr(smem);
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, (uint32_t)t >> 5, 0);
+    const uint32_t slot_s = shared_addr(smem + kLutBytes) + warp * (2 * kGSlotBytes);
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes + (size_t)kWarps * 2 * kGSlotBytes) + (size_t)warp * kGParts;
+    uint2 *bpart = part + kGBf * kGLegs * kPst;
+    const uint32_t bar_s = shared_addr(bars) + warp * 16;
+
+    build_decode_lut_abs(lut, t, kWarps * 32);
+    if (t < 2) {
+        const enc_pk e = enc_pk_make(t);
+        enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
+        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4;
+    }
+    if (lane == 0) {
+        mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t G = (uint32_t)q.G, ngrp = (G + kGLegs - 1) / kGLegs;
+    const uint32_t total_bf = (uint32_t)q.total_bf;
+    const uint32_t items = (total_bf + kGBf - 1) / kGBf;
+    const uint32_t nw = gridDim.x * kWarps;
+    uint32_t item = warp * gridDim.x + blockIdx.x;
+    // unit = (item, leg group); the n-th unit of this warp lives in slot n & 1
+    auto fetch = [&](uint32_t it_idx, uint32_t grp, uint32_t n) {
+        const uint32_t bf0 = it_idx * kGBf;
+        const uint32_t left = total_bf - bf0;
+        const uint32_t nbf = left < (uint32_t)kGBf ? left : (uint32_t)kGBf;
+        const uint32_t legs = min((uint32_t)kGLegs, G - grp * kGLegs), bytes = legs * IGD_FRAME;
+        if (lane == 0) {
+            const uint32_t bs = bar_s + (n & 1u) * 8, dst = slot_s + (n & 1u) * kGSlotBytes;
+            mbar_expect_tx(bs, nbf * bytes);
+            const uint8_t *g = q.codes + ((size_t)bf0 * G + (size_t)grp * kGLegs) * IGD_FRAME;
+#pragma unroll
+            for (int k = 0; k < kGBf; k++)
+                if ((uint32_t)k < nbf) bulk_g2s(dst + k * kGStride, g + (size_t)k * G * IGD_FRAME, bytes, bs);
+        }
+    };
+    const bool worker = lane < kGBf * kChunks;
+    const uint32_t bfl = worker ? lane / kChunks : 0u, c = worker ? lane - bfl * kChunks : 0u;
+    const uint32_t src_off = bfl * kGStride + c * 16;
+    const uint32_t lane4 = lut_bytes + 4u * lane;
+    const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kGBf) % (uint32_t)q.B);
+    uint32_t b = (item * kGBf + bfl) % (uint32_t)q.B;
+    // gains (two packed words) and laws (4 bits) of one unit for this lane's bridge-frame
+    auto load_unit = [&](uint32_t it_idx, uint32_t grp, uint32_t bb, uint2 &gq, uint32_t &lw) {
+        gq = make_uint2(0u, 0u); lw = 0u;
+        const uint32_t bf = it_idx * kGBf + bfl;
+        if (!worker || it_idx >= items || bf >= total_bf) return;
+        const uint32_t legs = min((uint32_t)kGLegs, G - grp * kGLegs);
+        const uint16_t *gp = q.gain + (size_t)bf * G + grp * kGLegs;
+        const uint8_t *lp = q.law + (size_t)bb * G + grp * kGLegs;
+        uint32_t g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+        if (legs > 0) { g0 = __ldg(gp + 0); lw |= (uint32_t)(__ldg(lp + 0) & 1u); }
+        if (legs > 1) { g1 = __ldg(gp + 1); lw |= (uint32_t)(__ldg(lp + 1) & 1u) << 1; }
+        if (legs > 2) { g2 = __ldg(gp + 2); lw |= (uint32_t)(__ldg(lp + 2) & 1u) << 2; }
+        if (legs > 3) { g3 = __ldg(gp + 3); lw |= (uint32_t)(__ldg(lp + 3) & 1u) << 3; }
+        gq = make_uint2(g0 | (g1 << 16), g2 | (g3 << 16));
+    };
+    uint32_t n = 0;                       // units fetched so far == index of the unit being fetched next
+    if (item < items) fetch(item, 0, n);
+    uint2 gq; uint32_t lwq;
+    load_unit(item, 0, b, gq, lwq);
+
+    for (; item < items; item += nw) {
+        const uint32_t bf = item * kGBf + bfl;
+        const bool valid = worker && bf < total_bf;
+        const uint32_t b_next = (b + b_step >= (uint32_t)q.B) ? b + b_step - (uint32_t)q.B : b + b_step;
+        const uint32_t olaw = valid ? (uint32_t)(__ldg(q.out_law + b) & 1u) : 0u;
+        int acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = 0;
+        uint32_t n_open = 0;
+#pragma unroll 1
+        for (uint32_t grp = 0; grp < ngrp; grp++, n++) {
+            const uint32_t legs = min((uint32_t)kGLegs, G - grp * kGLegs);
+            const bool last = grp + 1 == ngrp;
+            const uint32_t it_n = last ? item + nw : item, grp_n = last ? 0u : grp + 1;
+            if (it_n < items) fetch(it_n, grp_n, n + 1);                 // the other slot was drained one unit ago
+            mbar_wait(bar_s + (n & 1u) * 8, (n >> 1) & 1u);
+            const uint2 gcur = gq;
+            const uint32_t lcur = lwq;
+            load_unit(it_n, grp_n, last ? b_next : b, gq, lwq);          // next unit's gains / laws ride in registers
+            const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
+            const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
+            const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
+                                       ((ory >> 16) ? 8u : 0u);
+            auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
+            n_open += (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y)));
+            const uint32_t src = slot_s + (n & 1u) * kGSlotBytes + src_off;
+            uint4 wh[kGLegs];
+#pragma unroll
+            for (int g = 0; g < kGLegs; g++)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
+                             : "r"(src + g * IGD_FRAME));
+#pragma unroll
+            for (int g = 0; g < kGLegs; g++) {
+                if ((uint32_t)g < legs) {                                 // warp-uniform
+                    const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
+                    uint2 ph;
+                    if (general) ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
+                    else if ((open_mask >> g) & 1u) ph = leg_chunk_u<kSigned, 1>(lb, wh[g], adj_of(g), 0, acc);
+                    else ph = leg_chunk_u<kSigned, 0>(lb, wh[g], 0u, 0, acc);
+                    if (valid) part[(bfl * kGLegs + g) * kPst + c] = ph;
+                }
+            }
+            __syncwarp();
+            if (lane < kGBf * kGLegs) {                                  // this group's leg records
+                const uint32_t fb = lane / kGLegs, g = lane - fb * kGLegs;
+                if (g < legs && item * kGBf + fb < total_bf) {
+                    const uint2 *src_p = part + lane * kPst;
+                    unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
+#pragma unroll
+                    for (int i = 0; i < kChunks; i++) {
+                        const uint2 v = src_p[i];
+                        sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
+                    }
+                    const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
+                    st16_stream(q.meter + ((size_t)(item * kGBf + fb) * G + grp * kGLegs + g), *reinterpret_cast<const uint4 *>(&r));
+                }
+            }
+            __syncwarp();
+        }
+        // ---- bridge output of this lane's chunk
+        enc_pk E;
+        {
+            const uint32_t *et = enc_tab[olaw];
+            const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
+            const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
+            E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
+        }
+        const size_t o16 = (size_t)bf * kChunks + c;
+        const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + o16 * 16, q.enc + o16 * 16, valid);
+        if (valid) bpart[bfl * kPst + c] = make_uint2(mo.x, mo.y | (n_open << 16));
+        __syncwarp();
+        if (lane < kGBf && item * kGBf + lane < total_bf) {
+            const uint2 *src_p = bpart + lane * kPst;
+            int esum = 0; uint32_t pk = 0;
+#pragma unroll
+            for (int i = 0; i < kChunks; i++) { esum += (int)src_p[i].x; pk = max(pk, src_p[i].y & 0xFFFFu); }
+            igd_bridge_rec r;
+            r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
+            r.n_open = (uint8_t)(src_p[0].y >> 16);
+            r.mix_peak = (uint16_t)pk;
+            q.bmeter[item * kGBf + lane] = r;
+        }
+        __syncwarp();
+        b = b_next;
+    }
+}
+
 // Any number of legs per bridge (1..IGD_MAX_LEGS): same algorithm, legs walked
 // in a loop with the partials reduced per leg through shared memory.
 template <int BFPC, bool kSigned>
@@ -1549,6 +1728,20 @@ cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
     return cudaGetLastError();
 }
 
+template <bool kSigned, int kWarps>
+cudaError_t launch_fused_g(const igd_launch_cfg &c, const FusedParams &q)
+{
+    auto kern = k_fused_g<kSigned, kWarps>;
+    const size_t smem = kLutBytes + (size_t)kWarps * 2 * kGSlotBytes + (size_t)kWarps * kGParts * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (q.total_bf + kGBf - 1) / kGBf;
+    long long grid = c.sm_count;
+    if (grid > items) grid = items;
+    kern<<<(int)grid, kWarps * 32, smem, c.stream>>>(q);
+    return cudaGetLastError();
+}
+
 template <int BFPC, bool kSigned>
 cudaError_t launch_fused_anyg(const igd_launch_cfg &c, const FusedParams &q)
 {
@@ -1586,6 +1779,11 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     if (fits32 && d.G == 4) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
     if (fits32 && d.G == 2) return sc ? launch_fused_w<2, true, 24>(c, q) : launch_fused_w<2, false, 24>(c, q);
     if (fits32 && d.G == 1) return sc ? launch_fused_w<1, true, 24>(c, q) : launch_fused_w<1, false, 24>(c, q);
+    // any other leg count: the warp-autonomous group walk (needs 16-byte aligned codes, which the C ABI
+    // checks, and 32-bit bridge-frame indices); the block-cooperative kernel is the last resort
+    if (q.total_bf < (1ll << 31) - (1ll << 24) && (long long)q.total_bf * d.G < (1ll << 32) &&
+        !getenv("IGD_FUSED_ANYG"))
+        return sc ? launch_fused_g<true, 24>(c, q) : launch_fused_g<false, 24>(c, q);
     return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
 }
 
