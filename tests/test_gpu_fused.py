@@ -215,3 +215,25 @@ def test_odd_gain_and_law_alignment_takes_the_generic_kernel(vp):
                            torch.from_numpy(out_law).to(dev), G)
     torch.cuda.synchronize()
     assert np.array_equal(got["mix"].cpu().numpy(), want[0]) and np.array_equal(got["enc"].cpu().numpy(), want[1])
+
+
+@pytest.mark.parametrize("G,B,F,flags", [(3, 7, 11, 0), (5, 2, 1, ig.F_SIGNED_CHAR), (6, 9, 5, 0), (7, 1, 2, 0),
+                                         (12, 5, 4, ig.F_SIGNED_CHAR), (31, 2, 3, 0), (32, 4, 7, 0)])
+def test_group_walk_kernel_any_leg_count(vp, G, B, F, flags):
+    """k_fused_g: ragged last leg group (G % 4 != 0), ragged last item (F*B % 3 != 0), both char signs,
+    reference gains and arbitrary ones in the same batch."""
+    codes, law, _, out_law = make(F, B, G, random_codes=True, seed=G + B)
+    rng = np.random.default_rng(G * 7 + F)
+    gain = rng.choice(np.array([0, 0, 0, 256, 256, 13, 64, 128, 511], np.uint16), (F, B * G))
+    gain[0] = rng.choice(np.array([0, 256], np.uint16), B * G)          # a frame on the one-instruction path
+    law = rng.integers(0, 2, B * G).astype(np.uint8)
+    sc = 1 if flags & ig.F_SIGNED_CHAR else 0
+    check(vp.process_batch(codes, law, gain, out_law, G, flags=flags),
+          O.process_batch(codes, law, gain, out_law, G, signed_char=sc))
+
+
+def test_block_cooperative_fallback_still_matches(vp, monkeypatch):
+    """the last-resort kernel for batches beyond 32-bit indices, forced through its dev switch"""
+    monkeypatch.setenv("IGD_FUSED_ANYG", "1")
+    codes, law, gain, out_law = make(4, 6, 5, random_codes=True, seed=1)
+    check(vp.process_batch(codes, law, gain, out_law, 5), O.process_batch(codes, law, gain, out_law, 5))
