@@ -133,13 +133,13 @@ def oracle_lib():
     return O
 
 
-def cpu_sample(seconds_target=12.0):
+def cpu_sample(seconds_target=12.0, threads=None):
     """Times the CPU oracle (reference-faithful scalar port, -O2) with all host threads on a
     bounded sample of the same workload.  Returns (channel-samples/s, cores, description)."""
     import numpy as np
     from igate4xsoftphonedsp_b200 import synth
     O = oracle_lib()
-    cores = os.cpu_count() or 1
+    cores = threads or os.cpu_count() or 1
     rng = np.random.default_rng(0)
     law, out_law = synth.laws(C), synth.out_laws(B)
 
@@ -339,7 +339,9 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, cores, desc = cpu_sample()
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}
+        v1, _, desc1 = cpu_sample(seconds_target=3.0, threads=1)     # also the single-thread figure
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+               "single_thread": {"value": v1, "sample": desc1}}
 
     if rank == 0:
         print(json.dumps({

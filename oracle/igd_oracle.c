@@ -88,20 +88,38 @@ uint8_t orc_lin2ulaw(int pcm)
     return (uint8_t)(((seg << 4) | ((pcm >> (seg + 3)) & 0x0F)) ^ mask);
 }
 
+/* Frame codec loops.  pjmedia's default build (PJMEDIA_HAS_ALAW_ULAW_TABLE) does not run the
+ * algorithmic routines per sample: alaw_ulaw_table.c fills lookup tables FROM them once and the
+ * codec indexes the tables.  The oracle does the same, so that the CPU baseline bench.py times is
+ * the deployed (table) form and not a slower one; the results are those of the routines above by
+ * construction (tests/test_oracle_pins.py checks table == routine on every input). */
+static int16_t g_dec_tab[2][256];
+static uint8_t g_enc_tab[2][65536];
+static pthread_once_t g_tab_once = PTHREAD_ONCE_INIT;
+static void build_tables(void)
+{
+    for (int c = 0; c < 256; c++) {
+        g_dec_tab[ORC_LAW_ALAW][c] = orc_alaw2lin((uint8_t)c);
+        g_dec_tab[ORC_LAW_ULAW][c] = orc_ulaw2lin((uint8_t)c);
+    }
+    for (int v = -32768; v < 32768; v++) {
+        g_enc_tab[ORC_LAW_ALAW][(uint16_t)v] = orc_lin2alaw(v);
+        g_enc_tab[ORC_LAW_ULAW][(uint16_t)v] = orc_lin2ulaw(v);
+    }
+}
+
 void orc_g711_decode(const uint8_t *codes, int16_t *pcm, size_t n, int law)
 {
-    if (law == ORC_LAW_ALAW)
-        for (size_t i = 0; i < n; i++) pcm[i] = orc_alaw2lin(codes[i]);
-    else
-        for (size_t i = 0; i < n; i++) pcm[i] = orc_ulaw2lin(codes[i]);
+    pthread_once(&g_tab_once, build_tables);
+    const int16_t *t = g_dec_tab[law == ORC_LAW_ALAW ? ORC_LAW_ALAW : ORC_LAW_ULAW];
+    for (size_t i = 0; i < n; i++) pcm[i] = t[codes[i]];
 }
 
 void orc_g711_encode(const int16_t *pcm, uint8_t *codes, size_t n, int law)
 {
-    if (law == ORC_LAW_ALAW)
-        for (size_t i = 0; i < n; i++) codes[i] = orc_lin2alaw(pcm[i]);
-    else
-        for (size_t i = 0; i < n; i++) codes[i] = orc_lin2ulaw(pcm[i]);
+    pthread_once(&g_tab_once, build_tables);
+    const uint8_t *t = g_enc_tab[law == ORC_LAW_ALAW ? ORC_LAW_ALAW : ORC_LAW_ULAW];
+    for (size_t i = 0; i < n; i++) codes[i] = t[(uint16_t)pcm[i]];
 }
 
 /* ======================================================================

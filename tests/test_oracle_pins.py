@@ -246,3 +246,14 @@ def test_threaded_oracle_equals_scalar():
     b = O.process_batch(codes, synth.laws(B * G), gain, synth.out_laws(B), G, threads=4)
     for x, y in zip(a, b):
         assert x.tobytes() == y.tobytes()
+
+
+def test_frame_codec_tables_equal_the_routines():
+    """orc_g711_decode / orc_g711_encode index tables (like pjmedia's default alaw_ulaw_table.c);
+    the tables must be the per-sample routines on every input."""
+    L = O.lib()
+    pcm = np.arange(-32768, 32768, dtype=np.int16)
+    codes = np.arange(256, dtype=np.uint8)
+    for law, enc1, dec1 in ((0, L.orc_lin2alaw, L.orc_alaw2lin), (1, L.orc_lin2ulaw, L.orc_ulaw2lin)):
+        assert O.g711_encode(pcm, law).tolist() == [enc1(int(v)) for v in pcm]
+        assert O.g711_decode(codes, law).tolist() == [dec1(int(c)) for c in codes]
