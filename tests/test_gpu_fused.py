@@ -237,3 +237,36 @@ def test_block_cooperative_fallback_still_matches(vp, monkeypatch):
     monkeypatch.setenv("IGD_FUSED_ANYG", "1")
     codes, law, gain, out_law = make(4, 6, 5, random_codes=True, seed=1)
     check(vp.process_batch(codes, law, gain, out_law, 5), O.process_batch(codes, law, gain, out_law, 5))
+
+
+@pytest.mark.parametrize("G,B,F", [(4, 37, 9), (4, 1, 1), (2, 5, 3), (1, 7, 1), (3, 5, 2), (32, 1, 5), (9, 4, 4)])
+def test_outputs_stay_inside_their_buffers(vp, G, B, F):
+    """ragged last item / last leg group: every output array sits between two guard bands inside one
+    allocation; the kernels must write all of it and nothing around it (compute-sanitizer is not available
+    on the pool, so the bounds are checked here)."""
+    import torch
+    dev = "cuda:0"
+    codes, law, gain, out_law = make(F, B, G, random_codes=True, seed=G * B + F)
+    want = O.process_batch(codes, law, gain, out_law, G)
+    guard = 4096
+    sizes = {"mix": F * B * 160 * 2, "enc": F * B * 160, "meter": F * B * G * 16, "bmeter": F * B * 4}
+    dt = {"mix": torch.int16, "enc": torch.uint8, "meter": torch.int32, "bmeter": torch.int32}
+    shape = {"mix": (F, B, 160), "enc": (F, B, 160), "meter": (F, B * G, 4), "bmeter": (F, B)}
+    arenas, out = {}, {}
+    for k, nbytes in sizes.items():
+        pad = (-nbytes) % 32
+        a = torch.full((guard + nbytes + pad + guard,), 0xA5, dtype=torch.uint8, device=dev)
+        arenas[k] = (a, nbytes)
+        out[k] = a[guard:guard + nbytes].view(dt[k]).reshape(shape[k])
+    # inputs with guard bands too: the kernels must not depend on what lies beyond them
+    cin = torch.full((guard + codes.size + guard,), 0x5A, dtype=torch.uint8, device=dev)
+    cin[guard:guard + codes.size] = torch.from_numpy(codes.reshape(-1)).to(dev)
+    got = vp.process_batch(cin[guard:guard + codes.size].reshape(codes.shape), torch.from_numpy(law).to(dev),
+                           torch.from_numpy(gain.view(np.int16)).to(dev), torch.from_numpy(out_law).to(dev), G, out=out)
+    torch.cuda.synchronize()
+    for k, (a, nbytes) in arenas.items():
+        assert bool((a[:guard] == 0xA5).all()) and bool((a[guard + nbytes:] == 0xA5).all()), f"{k}: wrote outside"
+    assert np.array_equal(got["mix"].cpu().numpy(), want[0]) and np.array_equal(got["enc"].cpu().numpy(), want[1])
+    assert np.array_equal(got["meter"].cpu().numpy().view(np.uint32)[..., :2].reshape(F, B * G, 2),
+                          want[2].view(np.uint32).reshape(F, B * G, 4)[..., :2])
+    assert got["bmeter"].cpu().numpy().tobytes() == want[3].tobytes()
