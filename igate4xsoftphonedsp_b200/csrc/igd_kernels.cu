@@ -1117,23 +1117,39 @@ __global__ void __launch_bounds__(256) k_ed137_parse_tile(const uint8_t *__restr
                                                           igd_ed137_fields *__restrict__ fields,
                                                           uint8_t *__restrict__ payload_out)
 {
-    __shared__ __align__(16) uint32_t img[kPktTile * kPktWords];
+    __shared__ __align__(128) uint32_t img[kPktTile * kPktWords];
     __shared__ uint32_t plen_s[kPktTile];
     const size_t first = (size_t)blockIdx.x * kPktTile;
     const uint32_t np = (uint32_t)min((size_t)kPktTile, npkts - first);
     const uint4 *src = reinterpret_cast<const uint4 *>(pkts + first * IGD_PKT_MAX);
-    const uint32_t nvec = (np * IGD_PKT_MAX + 15) / 16;      // the buffer holds whole packets: a partial
-    for (uint32_t j = threadIdx.x; j < nvec; j += blockDim.x) {   // last vector only exists when np*180 % 16 != 0
-        uint4 v;
-        if ((j + 1) * 16 <= np * IGD_PKT_MAX) v = __ldcs(src + j);
-        else {                                               // ragged tail of the whole buffer: word loads
-            const uint32_t *w = reinterpret_cast<const uint32_t *>(src + j);
-            const uint32_t left = (np * IGD_PKT_MAX - j * 16) / 4;
-            v.x = left > 0 ? w[0] : 0u; v.y = left > 1 ? w[1] : 0u; v.z = left > 2 ? w[2] : 0u; v.w = 0u;
+    const uint32_t tile_bytes = np * IGD_PKT_MAX;
+    if ((tile_bytes & 15u) == 0) {
+        // full tiles (and any tail whose size is a multiple of 16): ONE bulk async copy (TMA) stages the
+        // tile, completion on the CTA's mbarrier -- no registers, no LSU issue slots
+        __shared__ uint64_t bar;
+        const uint32_t bar_s = shared_addr(&bar);
+        if (threadIdx.x == 0) {
+            mbar_init(bar_s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(bar_s, tile_bytes);
+            bulk_g2s(shared_addr(img), src, tile_bytes, bar_s);
         }
-        reinterpret_cast<uint4 *>(img)[j] = v;
+        __syncthreads();                 // the barrier is initialised before anyone polls it
+        mbar_wait(bar_s, 0);
+    } else {
+        const uint32_t nvec = (tile_bytes + 15) / 16;
+        for (uint32_t j = threadIdx.x; j < nvec; j += blockDim.x) {
+            uint4 v;
+            if ((j + 1) * 16 <= tile_bytes) v = __ldcs(src + j);
+            else {                                               // ragged tail of the whole buffer: word loads
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(src + j);
+                const uint32_t left = (tile_bytes - j * 16) / 4;
+                v.x = left > 0 ? w[0] : 0u; v.y = left > 1 ? w[1] : 0u; v.z = left > 2 ? w[2] : 0u; v.w = 0u;
+            }
+            reinterpret_cast<uint4 *>(img)[j] = v;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (threadIdx.x < np) {
         const uint32_t p = threadIdx.x;
         const size_t i = first + p;
