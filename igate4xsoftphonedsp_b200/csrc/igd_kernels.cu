@@ -1550,17 +1550,28 @@ __global__ void __launch_bounds__(256) k_ed137_assemble(const igd_ed137_pack_des
 __global__ void __launch_bounds__(256) k_ed137_assemble_tile(const igd_ed137_pack_desc d,
                                                              const igd_tx_plan_rec *__restrict__ plan)
 {
-    __shared__ __align__(16) uint32_t img[kPktTile * kPktWords];
+    __shared__ __align__(128) uint32_t img[kPktTile * kPktWords];           // the 64 packets being built
+    __shared__ __align__(128) uint32_t pay[kPktTile * (IGD_FRAME / 4)];      // this tick's payloads of the tile
+    __shared__ uint64_t bar;
     __shared__ uint32_t size_s[kPktTile];
     __shared__ int32_t srcf_s[kPktTile];
     __shared__ uint32_t flag_s[kPktTile];
     __shared__ int bsum_s[kPktTile];
     __shared__ uint32_t chan_s[kPktTile];
     __shared__ int32_t frame_s[kPktTile];
+    __shared__ uint32_t not_full;                                            // some packet of the tile is not 180 bytes
     const size_t npkts = (size_t)d.F * d.C;
     const size_t first = (size_t)blockIdx.x * kPktTile;
     const uint32_t np = (uint32_t)min((size_t)kPktTile, npkts - first);
     const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0, quirks = (d.flags & IGD_F_REF_QUIRKS) != 0;
+    const uint32_t bar_s = shared_addr(&bar);
+    if (threadIdx.x == 0) {          // ONE bulk async copy (TMA) stages the tile's current payloads (np*160 contiguous bytes)
+        not_full = 0u;
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_s, np * IGD_FRAME);
+        bulk_g2s(shared_addr(pay), d.payload + first * IGD_FRAME, np * IGD_FRAME, bar_s);
+    }
     if (threadIdx.x < np) {
         const uint32_t p = threadIdx.x;
         const size_t i = first + p;
@@ -1583,21 +1594,20 @@ __global__ void __launch_bounds__(256) k_ed137_assemble_tile(const igd_ed137_pac
         if (quirks) { hs = bytesum4(h0, sc, hs); hs = bytesum4(h1, sc, hs); hs = bytesum4(h2, sc, hs); }
         bsum_s[p] = hs;
     }
-    __syncthreads();
+    __syncthreads();                 // barrier initialised, per-packet plan visible
+    if (threadIdx.x < np && size_s[threadIdx.x] != IGD_PKT_MAX) not_full = 1u;
+    mbar_wait(bar_s, 0);
     for (uint32_t j = threadIdx.x; j < np * kChunks; j += blockDim.x) {
         const uint32_t p = j / kChunks, ch = j - p * kChunks;
-        const size_t i = first + p;
         const uint32_t size = size_s[p];
         if (size == 0) continue;
         const bool audio = !(flag_s[p] & 1u);
         const size_t c = chan_s[p];
         const int32_t f = frame_s[p], sf = srcf_s[p];
-        uint4 cur = make_uint4(0u, 0u, 0u, 0u);
-        const bool need_cur = audio || (size > IGD_PKT_HDR && sf == f);
-        if (need_cur) cur = __ldcs(reinterpret_cast<const uint4 *>(d.payload + i * IGD_FRAME) + ch);
+        const uint4 cur = *reinterpret_cast<const uint4 *>(pay + p * (IGD_FRAME / 4) + ch * 4);
         if (size > IGD_PKT_HDR) {
             uint4 v = cur;
-            if (sf != f) {
+            if (sf != f) {           // quirk Q2: the send buffer still holds an older frame's payload
                 if (sf >= 0) v = __ldg(reinterpret_cast<const uint4 *>(d.payload + ((size_t)sf * d.C + c) * IGD_FRAME) + ch);
                 else if (d.stale_payload) v = __ldg(reinterpret_cast<const uint4 *>(d.stale_payload + c * IGD_FRAME) + ch);
                 else v = make_uint4(0u, 0u, 0u, 0u);
@@ -1607,9 +1617,7 @@ __global__ void __launch_bounds__(256) k_ed137_assemble_tile(const igd_ed137_pac
         }
         if (audio) {        // setOutgoingRTP (roip_ed137.cpp:6500-6536): clean = the payload bytes;
             int bs = 0;     // Q3 = ... + payload[0 .. 148) (TransportAdapter.cpp:654)
-            if (!quirks) {
-                bs = bytesum4(cur.x, sc, bs); bs = bytesum4(cur.y, sc, bs); bs = bytesum4(cur.z, sc, bs); bs = bytesum4(cur.w, sc, bs);
-            } else if (ch < 9) {
+            if (!quirks || ch < 9) {
                 bs = bytesum4(cur.x, sc, bs); bs = bytesum4(cur.y, sc, bs); bs = bytesum4(cur.z, sc, bs); bs = bytesum4(cur.w, sc, bs);
             } else {
                 bs = bytesum4(cur.x, sc, bs);                                  // bytes 144..147
@@ -1617,11 +1625,23 @@ __global__ void __launch_bounds__(256) k_ed137_assemble_tile(const igd_ed137_pac
             atomicAdd(&bsum_s[p], bs);
         }
     }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // the image is read by the async proxy below
     __syncthreads();
-    uint32_t *out = reinterpret_cast<uint32_t *>(d.pkts + first * IGD_PKT_MAX);
-    for (uint32_t w = threadIdx.x; w < np * kPktWords; w += blockDim.x) {
-        const uint32_t p = w / kPktWords, k = w - p * kPktWords;
-        if (4 * k < size_s[p]) out[w] = img[w];
+    const uint32_t tile_bytes = np * IGD_PKT_MAX;
+    if (!not_full && (tile_bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(d.pkts) & 15u) == 0) {
+        // every packet of the tile is a full 180-byte audio packet: ONE bulk async store (TMA) writes the image
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(d.pkts + first * IGD_PKT_MAX), "r"(shared_addr(img)), "r"(tile_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // smem must outlive the read
+        }
+    } else {
+        uint32_t *out = reinterpret_cast<uint32_t *>(d.pkts + first * IGD_PKT_MAX);
+        for (uint32_t w = threadIdx.x; w < np * kPktWords; w += blockDim.x) {
+            const uint32_t p = w / kPktWords, k = w - p * kPktWords;
+            if (4 * k < size_s[p]) out[w] = img[w];
+        }
     }
     if (threadIdx.x < np) {
         const uint32_t p = threadIdx.x;

@@ -77,4 +77,27 @@ ctl[..., 0] = 1
 ctl[..., 2] = 1
 timed("ed137_pack (plan+assemble)", lambda: vp.ed137_pack(rtp12, payload.reshape(Fp, Cp, 160), state, ctl=ctl),
       npk * (12 + 160 + 8 + 180 + 4 + 1), npk, "packets", reps=4)
+# ---- the same packet count shaped like BASELINE config 5 (65 536 channels): the sequential walks have 16x
+# more independent channels to hide their per-tick latency behind
+del pk, fields, payload, ev, rtp12, state, ctl
+torch.cuda.empty_cache()
+Fq, Cq = 52, 65536
+nq = Fq * Cq
+pk = torch.randint(0, 256, (nq, 180), dtype=torch.uint8, device=dev, generator=g)
+pk[:, 0] = 0x90
+pk[:, 1] = 8
+fields, payload = vp.ed137_parse(pk)
+st = torch.zeros((Cq, 4), dtype=torch.int32, device=dev)
+timed("k_rx_track @65536ch", lambda: vp.rx_track(fields.reshape(Fq, Cq, 4), st), nq * 24, nq, "packets")
+ev = vp.rx_track(fields.reshape(Fq, Cq, 4), st)
+legs = torch.zeros((Cq, 2), dtype=torch.int32, device=dev)
+br = torch.zeros((Cq // 4, 4), dtype=torch.int32, device=dev)
+timed("k_gate_arbitrate @65536ch", lambda: vp.gate_arbitrate(ev, legs, br, 4, N.ARB_CLIENT_PTT), nq * 6, nq, "leg-frames")
+rtp12 = torch.randint(0, 256, (Fq, Cq, 12), dtype=torch.uint8, device=dev, generator=g)
+state = torch.from_numpy(ig.make_state(Cq).view(np.uint8).reshape(Cq, 40)).to(dev)
+ctl = torch.zeros((Fq, Cq, 8), dtype=torch.uint8, device=dev)
+ctl[..., 0] = 1
+ctl[..., 2] = 1
+timed("ed137_pack @65536ch", lambda: vp.ed137_pack(rtp12, payload.reshape(Fq, Cq, 160), state, ctl=ctl),
+      nq * (12 + 160 + 8 + 180 + 4 + 1), nq, "packets", reps=4)
 print(json.dumps({"hbm_peak_gbs": PEAK, "rows": rows}, indent=1))
