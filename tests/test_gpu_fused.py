@@ -270,3 +270,35 @@ def test_outputs_stay_inside_their_buffers(vp, G, B, F):
     assert np.array_equal(got["meter"].cpu().numpy().view(np.uint32)[..., :2].reshape(F, B * G, 2),
                           want[2].view(np.uint32).reshape(F, B * G, 4)[..., :2])
     assert got["bmeter"].cpu().numpy().tobytes() == want[3].tobytes()
+
+
+def test_cfg5_full_size_65536_channels_1640_frames(vp):
+    """BASELINE config 5 at full length: 65 536 channels x 1640 frames = 17.2 GB of codes on one B200
+    (32 GB with the outputs); 64-bit offsets everywhere.  Sampled frames against the oracle, the encoded mix
+    against the stand-alone encoder on the whole batch, and the last bridge-frame's records."""
+    import torch
+    F, B, G = 1640, 16384, 4
+    Cn = B * G
+    dev = "cuda:0"
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 << 30:
+        pytest.skip("needs 40 GB of free device memory")
+    g = torch.Generator(device=dev).manual_seed(5)
+    codes = torch.randint(0, 256, (F, Cn, 160), dtype=torch.uint8, device=dev, generator=g)
+    law = torch.from_numpy(synth.laws(Cn)).to(dev)
+    out_law = torch.from_numpy(synth.out_laws(B)).to(dev)
+    gain = torch.from_numpy(synth.gains(F, B, G).view(np.int16)).to(dev)
+    got = vp.process_batch(codes, law, gain, out_law, G)
+    torch.cuda.synchronize()
+    fs = [0, 819, F - 1]
+    sel = torch.tensor(fs, device=dev)
+    want = O.process_batch(codes[sel].cpu().numpy(), law.cpu().numpy(), gain[sel].cpu().numpy().view(np.uint16),
+                           out_law.cpu().numpy(), G, threads=os.cpu_count() or 1)
+    sub = {"mix": got["mix"][sel].cpu().numpy(), "enc": got["enc"][sel].cpu().numpy(),
+           "meter": got["meter"][sel].cpu().numpy().view(ig.METER_DT).reshape(len(fs), Cn),
+           "bmeter": got["bmeter"][sel].cpu().numpy().view(ig.BRIDGE_DT).reshape(len(fs), B)}
+    check(sub, want)
+    for f0 in range(0, F, 410):          # enc == encode(mix), in slabs to bound the scratch
+        enc2 = vp.g711_encode(got["mix"][f0:f0 + 410], out_law)
+        torch.cuda.synchronize()
+        assert torch.equal(enc2, got["enc"][f0:f0 + 410])
