@@ -1806,10 +1806,10 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     q.num_tiles = 0;
     q.B = d.B; q.G = d.G; q.flags = d.flags;
     const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
-    // the warp-autonomous kernel indexes bridge-frames in 32 bits; anything larger (> 1.3 TB of
-    // codes at G = 1) cannot be resident on one GPU anyway and takes the generic kernel
+    // the warp-autonomous kernels index bridge-frames in 32 bits; anything larger (2^28 bridge-frames =
+    // 318 GB of traffic at G = 4) cannot be resident on one GPU anyway and takes the generic kernel
     // ... and reads a bridge-frame's G gains / a bridge's G laws as one 2G- / G-byte word
-    const bool fits32 = q.total_bf < (1ll << 31) - (1ll << 24) &&
+    const bool fits32 = q.total_bf < (1ll << 28) &&          // 16-sample chunk indices (10 per bridge-frame) stay below 2^32
                         (reinterpret_cast<uintptr_t>(d.gain_q7) & (size_t)(2 * d.G - 1) & 7u) == 0 &&
                         (d.G != 4 || (reinterpret_cast<uintptr_t>(d.law) & 3u) == 0);
     if (fits32 && d.G == 4) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
@@ -1817,7 +1817,7 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     if (fits32 && d.G == 1) return sc ? launch_fused_w<1, true, 24>(c, q) : launch_fused_w<1, false, 24>(c, q);
     // any other leg count: the warp-autonomous group walk (needs 16-byte aligned codes, which the C ABI
     // checks, and 32-bit bridge-frame indices); the block-cooperative kernel is the last resort
-    if (q.total_bf < (1ll << 31) - (1ll << 24) && (long long)q.total_bf * d.G < (1ll << 32) &&
+    if (q.total_bf < (1ll << 28) && (long long)q.total_bf * d.G < (1ll << 32) &&
         !getenv("IGD_FUSED_ANYG"))
         return sc ? launch_fused_g<true, 24>(c, q) : launch_fused_g<false, 24>(c, q);
     return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
