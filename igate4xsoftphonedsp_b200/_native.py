@@ -131,6 +131,7 @@ SYMBOLS = {
     "igd_gate_arbitrate": (_i, [_vp, C.POINTER(ArbDesc)]),
     "igd_wav_size": (_sz, [_sz, _i]),
     "igd_wav_image": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, C.POINTER(_sz), _i]),
+    "igd_wav_images": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _i, _i, _vp, _sz, _i]),
 }
 
 _lib = None

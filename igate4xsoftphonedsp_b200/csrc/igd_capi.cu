@@ -703,4 +703,30 @@ int igd_wav_image(igd_ctx *c, const uint8_t *payload, size_t n, int rate, int la
     return finish(c, mem);
 }
 
+int igd_wav_images(igd_ctx *c, const uint8_t *codes, size_t F, size_t C, const uint32_t *chans, size_t nchan,
+                   const uint8_t *law, int rate, int ref_quirks, uint8_t *out, size_t image_stride, int mem)
+{
+    const size_t need = igd_wav_size(F * IGD_FRAME, ref_quirks);
+    if (!c || (nchan && (!out || (F && !codes))) || (image_stride & 3) || image_stride < need || (!chans && nchan > C))
+        return fail(c, IGD_EINVAL, "igd_wav_images: bad argument (image_stride: multiple of 4, >= igd_wav_size)");
+    if (nchan == 0) return IGD_OK;
+    if (mem == IGD_MEM_DEVICE && (!aligned(codes, 4) || !aligned(out, 4)))
+        return fail(c, IGD_EINVAL, "igd_wav_images: misaligned device pointer");
+    if (chans && mem == IGD_MEM_HOST)
+        for (size_t k = 0; k < nchan; k++)
+            if (chans[k] >= C) return fail(c, IGD_EINVAL, "igd_wav_images: channel index out of range");
+    Bind b(c);
+    const uint8_t *dc, *dl = nullptr; const uint32_t *dch = nullptr; uint8_t *dout;
+    int rc;
+    if ((rc = in_arg(c, mem, 0, codes, F * C * IGD_FRAME, &dc))) return rc;
+    if (chans && (rc = in_arg(c, mem, 1, chans, nchan, &dch))) return rc;
+    if (law && (rc = in_arg(c, mem, 3, law, C, &dl))) return rc;
+    if ((rc = out_arg(c, mem, 2, out, nchan * image_stride, &dout))) return rc;
+    if (mem == IGD_MEM_HOST && image_stride > need) IGD_CUDA(c, cudaMemsetAsync(dout, 0, nchan * image_stride, c->stream));
+    IGD_CUDA(c, igd_k_wav_images(cfg_of(c), dc, F, C, dch, nchan, dl, rate, ref_quirks, dout, image_stride));
+    c->launches++;
+    if ((rc = out_done(c, mem, out, dout, nchan * image_stride))) return rc;
+    return finish(c, mem);
+}
+
 }  // extern "C"

@@ -1681,6 +1681,50 @@ __global__ void k_wav_image(const uint8_t *__restrict__ payload, size_t n, int r
     }
 }
 
+// Recorder sink for many calls at once: file image k = the WAV of channel chans[k], gathered from the
+// frame-major batch layout codes [F][C][160] (a channel's frames are C*160 bytes apart), written to
+// out + k*image_stride.  One warp moves one 160-byte frame (40 words in, 40 or 80 words out).
+__global__ void __launch_bounds__(256) k_wav_images(const uint8_t *__restrict__ codes, size_t F, size_t C,
+                                                    const uint32_t *__restrict__ chans, size_t nchan,
+                                                    const uint8_t *__restrict__ law_ch, int rate, int ref_quirks,
+                                                    uint8_t *__restrict__ out, size_t image_stride)
+{
+    const size_t n = F * IGD_FRAME;
+    const size_t body = ref_quirks ? 2 * n : n, total = 44 + body;
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t u = warp; u < nchan * (F + 1); u += nwarps) {       // unit F of a channel = its header
+        const size_t k = u / (F + 1), f = u - k * (F + 1);
+        const uint32_t ch = chans ? chans[k] : (uint32_t)k;
+        uint8_t *img = out + k * image_stride;
+        if (f == F) {
+            if (lane < 11) {
+                const uint32_t law = law_ch ? law_ch[ch] : (uint32_t)IGD_LAW_ULAW;
+                const uint32_t channels = ref_quirks ? 2 : 1, bits = ref_quirks ? 16 : 8;
+                const uint32_t fmt = ref_quirks ? 7u : (law == IGD_LAW_ALAW ? 6u : 7u);
+                const uint32_t align = bits / 8 * channels;
+                const uint32_t h[11] = {0x46464952u, (uint32_t)(total - 8), 0x45564157u, 0x20746d66u, 16u,
+                                        fmt | (channels << 16), (uint32_t)rate, (uint32_t)rate * align,
+                                        align | (bits << 16), 0x61746164u, (uint32_t)body};
+                reinterpret_cast<uint32_t *>(img)[lane] = h[lane];
+            }
+            continue;
+        }
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(codes + (f * C + ch) * IGD_FRAME);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(img + 44 + (ref_quirks ? 2 : 1) * f * IGD_FRAME);
+        for (uint32_t w = lane; w < IGD_FRAME / 4; w += 32) {
+            const uint32_t v = __ldcs(src + w);
+            if (ref_quirks) {                                            // every byte b -> {b, 0x00}
+                dst[2 * w] = __byte_perm(v, 0u, 0x4140);
+                dst[2 * w + 1] = __byte_perm(v, 0u, 0x4342);
+            } else {
+                dst[w] = v;
+            }
+        }
+    }
+}
+
 inline int grid_for(const igd_launch_cfg &c, size_t work_items, int threads, int per_sm)
 {
     size_t blocks = (work_items + threads - 1) / threads;
@@ -1893,6 +1937,15 @@ cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc 
     e = cudaGetLastError();
     if (e != cudaSuccess || !d.stale_payload) return e;
     k_ed137_stale_update<<<grid_for(c, (size_t)d.C * 32, 256, 8), 256, 0, c.stream>>>(d, last_src);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_wav_images(const igd_launch_cfg &c, const uint8_t *codes, size_t F, size_t C, const uint32_t *chans,
+                             size_t nchan, const uint8_t *law_ch, int rate, int ref_quirks, uint8_t *out,
+                             size_t image_stride)
+{
+    k_wav_images<<<grid_for(c, nchan * (F + 1) * 32, 256, 8), 256, 0, c.stream>>>(codes, F, C, chans, nchan, law_ch, rate,
+                                                                             ref_quirks, out, image_stride);
     return cudaGetLastError();
 }
 

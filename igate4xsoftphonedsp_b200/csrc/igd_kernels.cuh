@@ -45,6 +45,9 @@ cudaError_t igd_k_ed137_keepalive(const igd_launch_cfg &c, uint8_t *hdr20, igd_e
                                   long long now, uint32_t *sizes);
 cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d);
 cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d);
+cudaError_t igd_k_wav_images(const igd_launch_cfg &c, const uint8_t *codes, size_t F, size_t C, const uint32_t *chans,
+                             size_t nchan, const uint8_t *law_ch, int rate, int ref_quirks, uint8_t *out,
+                             size_t image_stride);
 cudaError_t igd_k_wav_image(const igd_launch_cfg &c, const uint8_t *payload, size_t n, int rate,
                             int law, int ref_quirks, uint8_t *out);
 

@@ -424,3 +424,23 @@ class VoicePath:
         self._chk(self._lib.igd_wav_image(self._h, self._ptr(payload), n, rate, law, int(ref_quirks),
                                           self._ptr(out), C.byref(ln), mem))
         return out
+
+    def wav_images(self, codes, chans=None, law=None, rate=8000, ref_quirks=False):
+        """WavWriter file images of many channels at once, gathered from codes u8 [F][C][160].
+        chans: u32 channel indices (None = every channel); law u8 [C] (None = u-law).
+        Returns u8 [len(chans)][image bytes]."""
+        mem = self._mode(codes, chans, law)
+        F, Cn = codes.shape[0], codes.shape[1]
+        nch = Cn if chans is None else (chans.numel() if mem == N.MEM_DEVICE else len(chans))
+        size = self._lib.igd_wav_size(F * N.FRAME, int(ref_quirks))
+        stride = (size + 3) & ~3
+        if mem == N.MEM_DEVICE:
+            out = torch.zeros((nch, stride), dtype=torch.uint8, device=codes.device)
+        else:
+            codes = np.ascontiguousarray(codes, dtype=np.uint8)
+            chans = None if chans is None else np.ascontiguousarray(chans, dtype=np.uint32)
+            law = None if law is None else np.ascontiguousarray(law, dtype=np.uint8)
+            out = np.zeros((nch, stride), dtype=np.uint8)
+        self._chk(self._lib.igd_wav_images(self._h, self._ptr(codes), F, Cn, self._ptr(chans), nch, self._ptr(law),
+                                           int(rate), int(ref_quirks), self._ptr(out), stride, mem))
+        return out[:, :size]

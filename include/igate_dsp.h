@@ -405,6 +405,14 @@ size_t igd_wav_size(size_t payload_bytes, int ref_quirks);
 int igd_wav_image(igd_ctx *ctx, const uint8_t *payload, size_t payload_bytes, int rate, int law,
                   int ref_quirks, uint8_t *out, size_t *out_len, int mem);
 
+/* The same sink for many calls at once, straight from the batch layout: image k is the WAV file of channel
+ * chans[k] (NULL: channel k) over all F frames of codes [F][C][160]; law [C] picks the format tag of the
+ * valid (non-quirk) header (NULL: u-law).  Image k starts at out + k*image_stride; image_stride must be a
+ * multiple of 4 and >= igd_wav_size(F*160, ref_quirks).  (Per-recording avg/max level as stored by
+ * Database::updateAudioRec, database.cpp:471-490, is igd_event_summary's output for that channel.)       */
+int igd_wav_images(igd_ctx *ctx, const uint8_t *codes, size_t F, size_t C, const uint32_t *chans, size_t nchan,
+                   const uint8_t *law, int rate, int ref_quirks, uint8_t *out, size_t image_stride, int mem);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -172,3 +172,28 @@ def test_keepalive_matches_reference_sendR2SStatus(vp):
         sent = sz == 20
         assert np.array_equal(h[sent], want_pk[t][sent]), t
     assert np.array_equal(h, want_h) and int(want_sz.sum()) > 0
+
+
+@pytest.mark.parametrize("quirks", [True, False])
+def test_wav_images_of_many_channels_from_the_batch_layout(vp, quirks):
+    """recorder sink for many calls at once: image k == the single-channel igd_wav_image / the oracle's
+    WavWriter restatement of that channel's frames, gathered out of codes [F][C][160]."""
+    F, Cn = 37, 23
+    rng = np.random.default_rng(3)
+    codes = rng.integers(0, 256, (F, Cn, 160), dtype=np.uint8)
+    law = rng.integers(0, 2, Cn).astype(np.uint8)
+    chans = np.array([22, 0, 7, 7, 13], np.uint32)
+    got = vp.wav_images(codes, chans, law, ref_quirks=quirks)
+    L = O.lib()
+    for k, ch in enumerate(chans):
+        pay = np.ascontiguousarray(codes[:, ch].reshape(-1))
+        one = vp.wav_image(pay, law=int(law[ch]), ref_quirks=quirks)
+        assert got[k].tobytes() == one.tobytes(), (k, ch)
+        if quirks:        # byte-for-byte the reference's WavWriter (WavWriter.cpp:63-156)
+            hdr = np.zeros(44, np.uint8)
+            body = np.zeros(2 * pay.size, np.uint8)
+            L.orc_wav_header(hdr.ctypes.data, 8000, pay.size)
+            L.orc_wav_body(pay.ctypes.data, pay.size, body.ctypes.data)
+            assert got[k].tobytes() == hdr.tobytes() + body.tobytes()
+    allc = vp.wav_images(codes, None, law, ref_quirks=quirks)
+    assert allc.shape[0] == Cn and allc[7].tobytes() == got[2].tobytes()
