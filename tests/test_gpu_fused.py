@@ -302,3 +302,40 @@ def test_cfg5_full_size_65536_channels_1640_frames(vp):
         enc2 = vp.g711_encode(got["mix"][f0:f0 + 410], out_law)
         torch.cuda.synchronize()
         assert torch.equal(enc2, got["enc"][f0:f0 + 410])
+
+
+def test_fuzz_shapes_gains_and_flags(vp):
+    """80 seeded random small batches: leg counts 1..32, ragged items and groups, every gain class
+    (shut / 2.0 / unity / sidetone / out-of-range), both char signs, host and device buffers."""
+    import torch
+    rng = np.random.default_rng(20261018)
+    gain_sets = [np.array([0, 256], np.uint16), np.array([0, 0, 0, 256], np.uint16), np.array([0], np.uint16),
+                 np.array([256], np.uint16), np.array([0, 256, 128], np.uint16),
+                 np.array([0, 13, 64, 128, 256, 300, 511, 65535], np.uint16)]
+    for case in range(80):
+        G = int(rng.choice([1, 2, 3, 4, 4, 4, 5, 8, 17, 32]))
+        B = int(rng.integers(1, 40 if G <= 8 else 6))
+        F = int(rng.integers(1, 12))
+        codes = rng.integers(0, 256, (F, B * G, 160), dtype=np.uint8)
+        if case % 7 == 0:
+            codes[:] = rng.choice(np.array([0x55, 0xD5, 0xFF, 0x7F, 0x00, 0x80, 0x2A, 0xAA], np.uint8), codes.shape)
+        law = rng.integers(0, 2, B * G).astype(np.uint8)
+        out_law = rng.integers(0, 2, B).astype(np.uint8)
+        gain = rng.choice(gain_sets[case % len(gain_sets)], (F, B * G))
+        flags = ig.F_SIGNED_CHAR if case % 3 == 0 else 0
+        want = O.process_batch(codes, law, gain, out_law, G, signed_char=1 if flags else 0)
+        if case % 2:
+            got = vp.process_batch(codes, law, gain, out_law, G, flags=flags)
+        else:
+            dev = "cuda:0"
+            r = vp.process_batch(torch.from_numpy(codes).to(dev), torch.from_numpy(law).to(dev),
+                                 torch.from_numpy(gain.view(np.int16)).to(dev), torch.from_numpy(out_law).to(dev), G,
+                                 flags=flags)
+            torch.cuda.synchronize()
+            got = {"mix": r["mix"].cpu().numpy(), "enc": r["enc"].cpu().numpy(),
+                   "meter": r["meter"].cpu().numpy().view(ig.METER_DT).reshape(F, B * G),
+                   "bmeter": r["bmeter"].cpu().numpy().view(ig.BRIDGE_DT).reshape(F, B)}
+        try:
+            check(got, want)
+        except AssertionError as e:
+            raise AssertionError(f"case {case}: G={G} B={B} F={F} flags={flags}: {e}")
