@@ -1,0 +1,719 @@
+// igd_fused.cu -- the fused decode -> meter -> gate/gain -> mix -> encode kernels (sm_100a) of the iGate4x voice path.
+//
+// Everything here is streaming integer/byte work bounded by HBM3e bandwidth or,
+// for the fused kernel, by instruction issue (see DESIGN.md "Kernels").  No
+// tensor cores: nothing on this path is a contraction.
+//
+// Common design points
+//  * 128-bit (LDG.128) loads / 128- and 256-bit (STG.E.ENL2.256) stores with the
+//    evict-first hint: every input byte is read once and every output written
+//    once, so nothing should stay in L2.
+//  * G.711 expansion through a 64 KB shared-memory table: one 32 KB table per law,
+//    row = code (128 B), column = lane, so a lookup can never bank-conflict and its
+//    byte address is ONE FMA-pipe instruction: IDP.4A(word, 0x80 << 8k, lane_base).
+//  * G.711 compression in ALU through the float-exponent trick of igd_math.cuh
+//    (no 64 KB encode table, no data-dependent bank conflicts).
+//  * Per-frame meters: exact integer partial sums per 16-sample chunk, combined
+//    through a padded shared-memory scratch (conflict-free LDS.64), dB via SFU lg2.
+//  * Persistent grids: a multiple of the SM count; the fused kernel runs one CTA of
+//    24 autonomous warps per SM, every warp with its own TMA slot and mbarrier.
+#include "igd_device.cuh"
+
+namespace {
+
+// ==================================================================== fused
+struct FusedParams {
+    const uint8_t *codes;
+    const uint8_t *law;
+    const uint16_t *gain;
+    const uint8_t *out_law;
+    int16_t *mix;
+    uint8_t *enc;
+    igd_meter_rec *meter;
+    igd_bridge_rec *bmeter;
+    long long total_bf;   // F*B bridge-frames
+    long long num_tiles;
+    int B, G;
+    unsigned flags;
+};
+
+constexpr uint32_t kSelGeneral = 0xFFFFFFFFu;
+// gain_q7 -> IDP.2A selector: 0 -> nothing, 128 -> x, 256 -> clamp16(2x); anything else
+// takes the general multiply / shift / clip path.
+__device__ __forceinline__ uint32_t gain_selector(uint32_t adj)
+{
+    return adj == 0u ? 0u : adj == 128u ? 0x0004u : adj == 256u ? 0x0100u : kSelGeneral;
+}
+
+// decode + meter + gain/accumulate one 16-sample chunk of one leg
+// kMode: 0 = gate shut (meter only), 1 = gain 1.0 / 2.0 through the IDP.2A selector,
+//        2 = arbitrary Q7 gain (multiply, shift, clip)
+template <bool kSigned, int kMode>
+__device__ __forceinline__ uint2 leg_chunk(uint32_t lane_base, uint4 w, uint32_t sel, int adj, int (&acc)[16])
+{
+    const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+    uint32_t sq = 0;               // sum of (x/4)^2: 16 * 8064^2 < 2^31
+    uint32_t mx = 0, mn = 0;       // packed running max / min of (x/4, clamp16(2x))
+    int bsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t e0 = lut_lookup<0>(lane_base, wd[j]);
+        const uint32_t e1 = lut_lookup<1>(lane_base, wd[j]);
+        const uint32_t e2 = lut_lookup<2>(lane_base, wd[j]);
+        const uint32_t e3 = lut_lookup<3>(lane_base, wd[j]);
+        // x/4 sign-extended from the low half (IDP.2A with a unit selector)
+        const int x0 = dp2a_lo(e0, 1u, 0), x1 = dp2a_lo(e1, 1u, 0);
+        const int x2 = dp2a_lo(e2, 1u, 0), x3 = dp2a_lo(e3, 1u, 0);
+        sq += (uint32_t)(x0 * x0) + (uint32_t)(x1 * x1) + (uint32_t)(x2 * x2) + (uint32_t)(x3 * x3);
+        mx = max_s16x2(max_s16x2(mx, e0), e1); mx = max_s16x2(max_s16x2(mx, e2), e3);
+        mn = min_s16x2(min_s16x2(mn, e0), e1); mn = min_s16x2(min_s16x2(mn, e2), e3);
+        bsum = kSigned ? __dp4a((int)wd[j], 0x01010101, bsum) : (int)__dp4a(wd[j], 0x01010101u, (uint32_t)bsum);
+        if (kMode == 1) {
+            acc[4 * j + 0] = dp2a_lo(e0, sel, acc[4 * j + 0]);
+            acc[4 * j + 1] = dp2a_lo(e1, sel, acc[4 * j + 1]);
+            acc[4 * j + 2] = dp2a_lo(e2, sel, acc[4 * j + 2]);
+            acc[4 * j + 3] = dp2a_lo(e3, sel, acc[4 * j + 3]);
+        } else if (kMode == 2) {
+            acc[4 * j + 0] += clamp16((4 * x0 * adj) >> 7);
+            acc[4 * j + 1] += clamp16((4 * x1 * adj) >> 7);
+            acc[4 * j + 2] += clamp16((4 * x2 * adj) >> 7);
+            acc[4 * j + 3] += clamp16((4 * x3 * adj) >> 7);
+        }
+    }
+    const int pmax = (int)(short)(mx & 0xFFFFu), pmin = (int)(short)(mn & 0xFFFFu);
+    return partial_pack(sq, (uint32_t)max(pmax, -pmin), bsum);
+}
+
+// bridge output of one 16-sample chunk: saturate, store PCM, compress, store codes
+template <bool kSigned>
+__device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_pk &E, int16_t *mix_dst,
+                                               uint8_t *enc_dst, bool do_store = true)
+{
+    uint32_t pk[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
+    if (do_store) st32_stream(mix_dst, pk);
+    uint32_t mx = max_s16x2(max_s16x2(pk[0], pk[1]), pk[2]), mn = min_s16x2(min_s16x2(pk[0], pk[1]), pk[2]);
+    mx = max_s16x2(max_s16x2(mx, pk[3]), pk[4]); mn = min_s16x2(min_s16x2(mn, pk[3]), pk[4]);
+    mx = max_s16x2(max_s16x2(mx, pk[5]), pk[6]); mn = min_s16x2(min_s16x2(mn, pk[5]), pk[6]);
+    mx = max_s16x2(mx, pk[7]); mn = min_s16x2(mn, pk[7]);
+    const int hi = max((int)(short)(mx & 0xFFFFu), (int)mx >> 16);
+    const int lo = min((int)(short)(mn & 0xFFFFu), (int)mn >> 16);
+    const uint4 e = encode16_packed(pk, E);
+    if (do_store) st16_stream(enc_dst, e);
+    int esum = 0;
+    if (kSigned) {
+        esum = __dp4a((int)e.x, 0x01010101, esum); esum = __dp4a((int)e.y, 0x01010101, esum);
+        esum = __dp4a((int)e.z, 0x01010101, esum); esum = __dp4a((int)e.w, 0x01010101, esum);
+    } else {
+        uint32_t u = __dp4a(e.x, 0x01010101u, 0u); u = __dp4a(e.y, 0x01010101u, u);
+        u = __dp4a(e.z, 0x01010101u, u); u = __dp4a(e.w, 0x01010101u, u);
+        esum = (int)u;
+    }
+    return make_uint2((uint32_t)esum, (uint32_t)max(hi, -lo));
+}
+
+// raw gain bits of one bridge-frame (G u16 values) in two registers
+template <int G>
+__device__ __forceinline__ uint2 load_gains(const uint16_t *g)
+{
+    if (G == 4) return *reinterpret_cast<const uint2 *>(g);
+    if (G == 2) return make_uint2(*reinterpret_cast<const uint32_t *>(g), 0u);
+    return make_uint2(*g, 0u);
+}
+
+// ------------------------------------------------------------------------------------
+// Warp-autonomous fused kernel (G in {1,2,4}): no cross-warp handshake at all.
+// A warp owns "items" of kBfPerItem = 6 consecutive bridge-frames (6*G*160 contiguous
+// code bytes) and strides over them on its own:
+//   * the item's codes are fetched by the warp's OWN bulk async copies (TMA, one per
+//     bridge-frame into a padded, bank-conflict-free slot), completion on the warp's
+//     private mbarrier; the copies of item i+1 are issued as soon as every lane holds
+//     the last codes of item i, so HBM latency hides behind half an item (~1.5 us) and
+//     ~77 KB per SM are in flight;
+//   * lane = two 16-sample chunks (c and c+5) of one bridge-frame, all G legs (5 lanes
+//     per bridge-frame, 30 of 32 lanes busy): per-bridge-frame setup (gains, laws,
+//     selectors, addresses) is paid once per 32 samples;
+//   * the per-chunk meter partials meet in the warp's private shared scratch after a
+//     __syncwarp; lanes 0..6G-1 finish one leg record each, the next 6 lanes one bridge
+//     record each.
+// Warps drift freely: nobody spins on a peer (the CTA-cooperative kernel above spends
+// ~16 % of its issue slots in mbarrier spin loops).
+//
+// Decode table of this kernel: low half |x|/4 (unsigned -> the frame peak is ONE packed
+// max per two samples, no min), high half clamp16(2x).  The one-instruction accumulate
+// covers the reference's gains 0.0 and 2.0; every other gain (sidetone 0.1, 0.5, 1.0)
+// takes the multiply/shift/clip path with the sign recovered from the high half.
+constexpr int kBfPerItem = 6;
+constexpr int kC32 = IGD_FRAME / 32;      // lanes per bridge-frame = 5
+// A slot is the item's 6*G*160 code bytes as they lie in HBM (ONE bulk copy).  Lane (bfl, c)
+// works on the 16-sample chunks (c + rot(bfl)) % 10 and that + 5; the per-bridge-frame rotation
+// (0,5,0,7,3,0) is the brute-forced minimum of LDS.128 bank conflicts for this layout (12
+// wavefronts instead of 8 per leg; padding the slot instead would cost six copies per item).
+template <int G> struct slot_geom {
+    static constexpr int kBfBytes = G * IGD_FRAME;
+    static constexpr int kSlotBytes = kBfPerItem * kBfBytes;
+};
+__device__ __forceinline__ uint32_t chunk_rotation(uint32_t bfl) { return (0x037050u >> (4 * bfl)) & 0xFu; }
+
+__device__ __forceinline__ void build_decode_lut_abs(uint32_t *lut, int tid, int nthreads)
+{
+    for (int i = tid; i < 2 * 256 * 32; i += nthreads) {
+        const uint32_t law = (uint32_t)i >> 13, code = ((uint32_t)i >> 5) & 255u;
+        const int x = law ? igd_ulaw2lin(code) : igd_alaw2lin(code);
+        const int y2 = min(max(2 * x, -32768), 32767);
+        lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)(abs(x) >> 2) & 0xFFFFu);
+    }
+}
+
+// bit 15 / 31 set for every non-zero 16-bit half of x
+__device__ __forceinline__ uint32_t nonzero_halves(uint32_t x)
+{
+    return (((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) & 0x80008000u;
+}
+
+// decode + meter + gain/accumulate one 16-sample chunk of one leg (|x|/4 table)
+// kMode: 0 = gate shut for the whole warp (meter only), 1 = gain 2.0 or shut through the
+//        IDP.2A selector (0x0100 / 0), 2 = arbitrary Q7 gain (multiply, shift, clip)
+template <bool kSigned, int kMode>
+__device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32_t sel, int adj, int (&acc)[16])
+{
+    const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+    uint32_t sq = 0;               // sum of (x/4)^2: 16 * 8064^2 < 2^31
+    uint32_t mx = 0;               // packed running max of (|x|/4, junk)
+    int bsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t e0 = lut_lookup<0>(lane_base, wd[j]);
+        const uint32_t e1 = lut_lookup<1>(lane_base, wd[j]);
+        const uint32_t e2 = lut_lookup<2>(lane_base, wd[j]);
+        const uint32_t e3 = lut_lookup<3>(lane_base, wd[j]);
+        // |x|/4 out of the low half on the ALU pipe (LOP3): everything else in this loop body is
+        // IDP/IMAD on the FMA pipe, which bounds this phase (measured: any IDP.2A here is slower)
+        const uint32_t x0 = e0 & 0xFFFFu, x1 = e1 & 0xFFFFu, x2 = e2 & 0xFFFFu, x3 = e3 & 0xFFFFu;
+        sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+        mx = max_u16x2(max_u16x2(mx, e0), e1); mx = max_u16x2(max_u16x2(mx, e2), e3);
+        bsum = kSigned ? __dp4a((int)wd[j], 0x01010101, bsum) : (int)__dp4a(wd[j], 0x01010101u, (uint32_t)bsum);
+        if (kMode == 1) {
+            acc[4 * j + 0] = dp2a_lo(e0, sel, acc[4 * j + 0]);
+            acc[4 * j + 1] = dp2a_lo(e1, sel, acc[4 * j + 1]);
+            acc[4 * j + 2] = dp2a_lo(e2, sel, acc[4 * j + 2]);
+            acc[4 * j + 3] = dp2a_lo(e3, sel, acc[4 * j + 3]);
+        } else if (kMode == 2) {
+            const int s0 = (int)e0 < 0 ? -(int)x0 : (int)x0, s1 = (int)e1 < 0 ? -(int)x1 : (int)x1;
+            const int s2 = (int)e2 < 0 ? -(int)x2 : (int)x2, s3 = (int)e3 < 0 ? -(int)x3 : (int)x3;
+            acc[4 * j + 0] += clamp16((4 * s0 * adj) >> 7);
+            acc[4 * j + 1] += clamp16((4 * s1 * adj) >> 7);
+            acc[4 * j + 2] += clamp16((4 * s2 * adj) >> 7);
+            acc[4 * j + 3] += clamp16((4 * s3 * adj) >> 7);
+        }
+    }
+    return make_uint2(sq, __byte_perm(mx, (uint32_t)bsum, 0x5410));   // {sq, peak/4 | bsum << 16}
+}
+
+template <int G, bool kSigned, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
+{
+    static_assert(kBfPerItem * G + kBfPerItem <= 32, "finish needs one lane per record");
+    using geom = slot_geom<G>;
+    constexpr int kLegParts = kBfPerItem * G * kPst, kBrParts = kBfPerItem * kPst;
+    __shared__ uint64_t bars[kWarps];
+    __shared__ __align__(16) uint32_t enc_tab[2][8];
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t lut_bytes = shared_addr(smem);
+
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, (uint32_t)t >> 5, 0);   // warp-uniform for the compiler too
+    const uint32_t slot_s = shared_addr(smem + kLutBytes) + warp * geom::kSlotBytes;
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes + (size_t)kWarps * geom::kSlotBytes) +
+                  (size_t)warp * (kLegParts + kBrParts);
+    uint2 *bpart = part + kLegParts;
+    const uint32_t bar_s = shared_addr(bars) + warp * 8;
+
+    build_decode_lut_abs(lut, t, kWarps * 32);
+    if (t < 2) {
+        const enc_pk e = enc_pk_make(t);
+        enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
+        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4;
+    }
+    if (lane == 0) {
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // bridge-frame and item indices fit 32 bits (the launcher checks total_bf < 2^31 - slack)
+    const uint32_t total_bf = (uint32_t)q.total_bf;
+    const uint32_t items = (total_bf + kBfPerItem - 1) / kBfPerItem;
+    const uint32_t nw = gridDim.x * kWarps;
+    uint32_t item = warp * gridDim.x + blockIdx.x;      // neighbouring items on different SMs
+    // one elected lane posts the byte count and issues the item's bulk async copy; every operand is
+    // warp-uniform (uniform datapath, no R2UR shuffles)
+    auto fetch = [&](uint32_t it_idx) {
+        const uint32_t bf0 = it_idx * kBfPerItem;
+        const uint32_t left = total_bf - bf0;
+        const uint32_t bytes = (left < (uint32_t)kBfPerItem ? left : (uint32_t)kBfPerItem) * geom::kBfBytes;
+        if (lane == 0) {
+            mbar_expect_tx(bar_s, bytes);
+            bulk_g2s(slot_s, q.codes + (size_t)bf0 * geom::kBfBytes, bytes, bar_s);
+        }
+    };
+    if (item < items) fetch(item);
+
+    const bool worker = lane < kBfPerItem * kC32;
+    const uint32_t bfl = worker ? lane / kC32 : 0u;
+    const uint32_t c0 = worker ? (lane - bfl * kC32 + chunk_rotation(bfl)) % kChunks : 0u;   // first chunk; second = +-5
+    const uint32_t src = slot_s + bfl * geom::kBfBytes;
+    const uint32_t lane4 = lut_bytes + 4u * lane;
+    const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kBfPerItem) % (uint32_t)q.B);
+    uint32_t b = (item * kBfPerItem + bfl) % (uint32_t)q.B;
+    auto load_laws = [&](uint32_t bb) -> uint32_t {      // the G leg laws (1 bit each) and the output law (bit 8)
+        uint32_t r = 0;
+        if (G == 4) {
+            const uint32_t lw = __ldg(reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4));
+            r = (lw & 1u) | ((lw >> 7) & 2u) | ((lw >> 14) & 4u) | ((lw >> 21) & 8u);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; g++) r |= (uint32_t)(__ldg(q.law + (size_t)bb * G + g) & 1u) << g;
+        }
+        return r | ((uint32_t)(__ldg(q.out_law + bb) & 1u) << 8);
+    };
+    uint2 gq = make_uint2(0u, 0u);
+    uint32_t lwq = 0u;
+    if (worker && item < items && item * kBfPerItem + bfl < total_bf) {
+        gq = load_gains<G>(q.gain + (size_t)(item * kBfPerItem + bfl) * G);
+        lwq = load_laws(b);
+    }
+
+    for (uint32_t it = 0; item < items; item += nw, it++) {
+        const uint32_t bf = item * kBfPerItem + bfl;
+        const uint32_t next = item + nw;
+        mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
+        const uint2 gcur = gq;
+        const uint32_t lcur = lwq;
+        const bool valid = worker && bf < total_bf;
+        {
+            b += b_step;
+            if (b >= (uint32_t)q.B) b -= (uint32_t)q.B;
+            const uint32_t bfn = bf + nw * kBfPerItem;
+            if (worker && next < items && bfn < total_bf) {      // next item's gains and laws ride in three registers
+                gq = load_gains<G>(q.gain + (size_t)bfn * G);
+                lwq = load_laws(b);
+            }
+        }
+        // every lane runs the same instruction stream (idle / tail lanes on stale bytes with all
+        // gates shut); only the stores are predicated, and the mode branches are warp-uniform
+        auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
+        // warp-wide OR of the gains (REDUX): anything but 0 / 256 anywhere in the warp -> general
+        // path; bit g of open_mask: some lane of the warp has leg g open
+        const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
+        const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
+        const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
+                                   ((ory >> 16) ? 8u : 0u);
+        // open legs of this lane's bridge-frame, pre-shifted into the high half of the bridge partial
+        // (every one of the ten partials carries it; the finish divides the sum by ten)
+        const uint32_t n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y))) << 16;
+#pragma unroll 1
+        for (int h = 0; h < 2; h++) {
+            const uint32_t ch = h == 0 ? c0 : (c0 >= (uint32_t)kC32 ? c0 - kC32 : c0 + kC32);   // this pass's chunk
+            uint4 wh[G];
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
+                             : "r"(src + g * IGD_FRAME + ch * 16));
+            if (h == 1) {        // every lane holds the rest of its codes: refill the slot
+                __syncwarp();
+                if (next < items) fetch(next);
+            }
+            uint2 *mypart = part + bfl * (G * kPst) + ch;
+            int acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) acc[i] = 0;
+            if (!general) {        // gains in {0, 2.0}: one IDP.2A per sample of an open leg
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
+                    const uint2 ph = (open_mask >> g) & 1u ? leg_chunk_u<kSigned, 1>(lb, wh[g], adj_of(g), 0, acc)
+                                                           : leg_chunk_u<kSigned, 0>(lb, wh[g], 0u, 0, acc);
+                    if (valid) mypart[g * kPst] = ph;
+                }
+            } else {               // arbitrary Q7 gains: multiply, shift, clip
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
+                    const uint2 ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
+                    if (valid) mypart[g * kPst] = ph;
+                }
+            }
+            enc_pk E;
+            {
+                const uint32_t *et = enc_tab[(lcur >> 8) & 1u];
+                const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
+                const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
+                E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
+            }
+            const uint32_t o16 = bf * kChunks + ch;     // 16-sample chunk index of the outputs
+            const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)o16 * 16, q.enc + (size_t)o16 * 16, valid);
+            if (valid) bpart[bfl * kPst + ch] = make_uint2(mo.x, mo.y | n_open16);
+        }
+        __syncwarp();
+        // ---- finish: one lane per record (leg records, then bridge records: bpart follows part,
+        // and both kinds of partial are {sum, max | sum << 16}, so the ten-partial walk is shared)
+        {
+            const uint32_t bf0 = item * kBfPerItem;
+            const uint2 *src_p = part + lane * kPst;
+            unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
+            if (lane < kBfPerItem * G + kBfPerItem) {
+#pragma unroll
+                for (int i = 0; i < kChunks; i++) {
+                    const uint2 v = src_p[i];
+                    sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
+                }
+            }
+            if (lane < kBfPerItem * G) {
+                if (bf0 + lane / G < total_bf) {
+                    const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
+                    st16_stream(q.meter + ((size_t)bf0 * G + lane), *reinterpret_cast<const uint4 *>(&r));
+                }
+            } else if (lane < kBfPerItem * G + kBfPerItem) {
+                const uint32_t j = lane - kBfPerItem * G;
+                if (bf0 + j < total_bf) {
+                    igd_bridge_rec r;
+                    r.bytemean_out = (uint8_t)igd_bytemean_from_sum((int)(uint32_t)sq, IGD_FRAME);
+                    r.n_open = (uint8_t)((uint32_t)bsum / kChunks);
+                    r.mix_peak = (uint16_t)(pk & 0xFFFFu);
+                    q.bmeter[bf0 + j] = r;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Warp-autonomous fused kernel for ANY leg count (1..IGD_MAX_LEGS), e.g. the 32 inbound calls of a
+// CLIENT-mode softphone (roip_ed137.cpp:141-150).  Same building blocks as k_fused_w; what changes:
+//   * a warp's item is 3 consecutive bridge-frames, lane = ONE 16-sample chunk (10 lanes per
+//     bridge-frame, 30 of 32 lanes busy), so only 16 mix accumulators live across the legs;
+//   * the legs are walked in groups of four: per group the warp fetches 3 x (4 legs x 160 B) with
+//     three bulk copies (the groups of different bridge-frames are G*160 bytes apart) into a
+//     double-buffered, bank-conflict-free slot (bridge-frame stride 672 B == 2 mod 8 sixteenths),
+//     the next group is in flight while the current one is processed;
+//   * after every group lanes 0..11 finish that group's leg records; after the last group the mix
+//     is saturated / stored / compressed and lanes 0..2 finish the bridge records.
+constexpr int kGBf = 3;                    // bridge-frames per item
+constexpr int kGLegs = 4;                  // legs per group
+constexpr int kGStride = kGLegs * IGD_FRAME + 32;          // 672
+constexpr int kGSlotBytes = kGBf * kGStride;                // 2016
+constexpr int kGParts = (kGBf * kGLegs + kGBf) * kPst;      // leg + bridge partials per warp
+
+template <bool kSigned, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
+{
+    __shared__ uint64_t bars[kWarps * 2];
+    __shared__ __align__(16) uint32_t enc_tab[2][8];
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t lut_bytes = shared_addr(smem);
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, (uint32_t)t >> 5, 0);
+    const uint32_t slot_s = shared_addr(smem + kLutBytes) + warp * (2 * kGSlotBytes);
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes + (size_t)kWarps * 2 * kGSlotBytes) + (size_t)warp * kGParts;
+    uint2 *bpart = part + kGBf * kGLegs * kPst;
+    const uint32_t bar_s = shared_addr(bars) + warp * 16;
+
+    build_decode_lut_abs(lut, t, kWarps * 32);
+    if (t < 2) {
+        const enc_pk e = enc_pk_make(t);
+        enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
+        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4;
+    }
+    if (lane == 0) {
+        mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t G = (uint32_t)q.G, ngrp = (G + kGLegs - 1) / kGLegs;
+    const uint32_t total_bf = (uint32_t)q.total_bf;
+    const uint32_t items = (total_bf + kGBf - 1) / kGBf;
+    const uint32_t nw = gridDim.x * kWarps;
+    uint32_t item = warp * gridDim.x + blockIdx.x;
+    // unit = (item, leg group); the n-th unit of this warp lives in slot n & 1
+    auto fetch = [&](uint32_t it_idx, uint32_t grp, uint32_t n) {
+        const uint32_t bf0 = it_idx * kGBf;
+        const uint32_t left = total_bf - bf0;
+        const uint32_t nbf = left < (uint32_t)kGBf ? left : (uint32_t)kGBf;
+        const uint32_t legs = min((uint32_t)kGLegs, G - grp * kGLegs), bytes = legs * IGD_FRAME;
+        if (lane == 0) {
+            const uint32_t bs = bar_s + (n & 1u) * 8, dst = slot_s + (n & 1u) * kGSlotBytes;
+            mbar_expect_tx(bs, nbf * bytes);
+            const uint8_t *g = q.codes + ((size_t)bf0 * G + (size_t)grp * kGLegs) * IGD_FRAME;
+#pragma unroll
+            for (int k = 0; k < kGBf; k++)
+                if ((uint32_t)k < nbf) bulk_g2s(dst + k * kGStride, g + (size_t)k * G * IGD_FRAME, bytes, bs);
+        }
+    };
+    const bool worker = lane < kGBf * kChunks;
+    const uint32_t bfl = worker ? lane / kChunks : 0u, c = worker ? lane - bfl * kChunks : 0u;
+    const uint32_t src_off = bfl * kGStride + c * 16;
+    const uint32_t lane4 = lut_bytes + 4u * lane;
+    const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kGBf) % (uint32_t)q.B);
+    uint32_t b = (item * kGBf + bfl) % (uint32_t)q.B;
+    // gains (two packed words) and laws (4 bits) of one unit for this lane's bridge-frame
+    auto load_unit = [&](uint32_t it_idx, uint32_t grp, uint32_t bb, uint2 &gq, uint32_t &lw) {
+        gq = make_uint2(0u, 0u); lw = 0u;
+        const uint32_t bf = it_idx * kGBf + bfl;
+        if (!worker || it_idx >= items || bf >= total_bf) return;
+        const uint32_t legs = min((uint32_t)kGLegs, G - grp * kGLegs);
+        const uint16_t *gp = q.gain + (size_t)bf * G + grp * kGLegs;
+        const uint8_t *lp = q.law + (size_t)bb * G + grp * kGLegs;
+        uint32_t g0 = 0, g1 = 0, g2 = 0, g3 = 0;
+        if (legs > 0) { g0 = __ldg(gp + 0); lw |= (uint32_t)(__ldg(lp + 0) & 1u); }
+        if (legs > 1) { g1 = __ldg(gp + 1); lw |= (uint32_t)(__ldg(lp + 1) & 1u) << 1; }
+        if (legs > 2) { g2 = __ldg(gp + 2); lw |= (uint32_t)(__ldg(lp + 2) & 1u) << 2; }
+        if (legs > 3) { g3 = __ldg(gp + 3); lw |= (uint32_t)(__ldg(lp + 3) & 1u) << 3; }
+        gq = make_uint2(g0 | (g1 << 16), g2 | (g3 << 16));
+    };
+    uint32_t n = 0;                       // units fetched so far == index of the unit being fetched next
+    if (item < items) fetch(item, 0, n);
+    uint2 gq; uint32_t lwq;
+    load_unit(item, 0, b, gq, lwq);
+
+    for (; item < items; item += nw) {
+        const uint32_t bf = item * kGBf + bfl;
+        const bool valid = worker && bf < total_bf;
+        const uint32_t b_next = (b + b_step >= (uint32_t)q.B) ? b + b_step - (uint32_t)q.B : b + b_step;
+        const uint32_t olaw = valid ? (uint32_t)(__ldg(q.out_law + b) & 1u) : 0u;
+        int acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = 0;
+        uint32_t n_open = 0;
+#pragma unroll 1
+        for (uint32_t grp = 0; grp < ngrp; grp++, n++) {
+            const uint32_t legs = min((uint32_t)kGLegs, G - grp * kGLegs);
+            const bool last = grp + 1 == ngrp;
+            const uint32_t it_n = last ? item + nw : item, grp_n = last ? 0u : grp + 1;
+            if (it_n < items) fetch(it_n, grp_n, n + 1);                 // the other slot was drained one unit ago
+            mbar_wait(bar_s + (n & 1u) * 8, (n >> 1) & 1u);
+            const uint2 gcur = gq;
+            const uint32_t lcur = lwq;
+            load_unit(it_n, grp_n, last ? b_next : b, gq, lwq);          // next unit's gains / laws ride in registers
+            const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
+            const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
+            const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
+                                       ((ory >> 16) ? 8u : 0u);
+            auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
+            n_open += (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y)));
+            const uint32_t src = slot_s + (n & 1u) * kGSlotBytes + src_off;
+            uint4 wh[kGLegs];
+#pragma unroll
+            for (int g = 0; g < kGLegs; g++)
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
+                             : "r"(src + g * IGD_FRAME));
+#pragma unroll
+            for (int g = 0; g < kGLegs; g++) {
+                if ((uint32_t)g < legs) {                                 // warp-uniform
+                    const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
+                    uint2 ph;
+                    if (general) ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
+                    else if ((open_mask >> g) & 1u) ph = leg_chunk_u<kSigned, 1>(lb, wh[g], adj_of(g), 0, acc);
+                    else ph = leg_chunk_u<kSigned, 0>(lb, wh[g], 0u, 0, acc);
+                    if (valid) part[(bfl * kGLegs + g) * kPst + c] = ph;
+                }
+            }
+            __syncwarp();
+            if (lane < kGBf * kGLegs) {                                  // this group's leg records
+                const uint32_t fb = lane / kGLegs, g = lane - fb * kGLegs;
+                if (g < legs && item * kGBf + fb < total_bf) {
+                    const uint2 *src_p = part + lane * kPst;
+                    unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
+#pragma unroll
+                    for (int i = 0; i < kChunks; i++) {
+                        const uint2 v = src_p[i];
+                        sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
+                    }
+                    const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
+                    st16_stream(q.meter + ((size_t)(item * kGBf + fb) * G + grp * kGLegs + g), *reinterpret_cast<const uint4 *>(&r));
+                }
+            }
+            __syncwarp();
+        }
+        // ---- bridge output of this lane's chunk
+        enc_pk E;
+        {
+            const uint32_t *et = enc_tab[olaw];
+            const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
+            const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
+            E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
+        }
+        const size_t o16 = (size_t)bf * kChunks + c;
+        const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + o16 * 16, q.enc + o16 * 16, valid);
+        if (valid) bpart[bfl * kPst + c] = make_uint2(mo.x, mo.y | (n_open << 16));
+        __syncwarp();
+        if (lane < kGBf && item * kGBf + lane < total_bf) {
+            const uint2 *src_p = bpart + lane * kPst;
+            int esum = 0; uint32_t pk = 0;
+#pragma unroll
+            for (int i = 0; i < kChunks; i++) { esum += (int)src_p[i].x; pk = max(pk, src_p[i].y & 0xFFFFu); }
+            igd_bridge_rec r;
+            r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
+            r.n_open = (uint8_t)(src_p[0].y >> 16);
+            r.mix_peak = (uint16_t)pk;
+            q.bmeter[item * kGBf + lane] = r;
+        }
+        __syncwarp();
+        b = b_next;
+    }
+}
+
+// Any number of legs per bridge (1..IGD_MAX_LEGS): same algorithm, legs walked
+// in a loop with the partials reduced per leg through shared memory.
+template <int BFPC, bool kSigned>
+__global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedParams q)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes);       // [BFPC][kPst]
+    uint2 *bpart = part + BFPC * kPst;                               // [BFPC][kPst]
+    const uint32_t lut_bytes = shared_addr(smem);
+    const int t = threadIdx.x, G = q.G;
+    const uint32_t lane = t & 31;
+    build_decode_lut(lut, t, BFPC * kChunks);
+    __syncthreads();
+    const int bfl = t / kChunks, p = t - bfl * kChunks;
+    for (long long tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x) {
+        const long long bf = tile * BFPC + bfl;
+        const bool valid = bf < q.total_bf;
+        const int b = valid ? (int)(bf % q.B) : 0;
+        int acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) acc[i] = 0;
+        for (int g = 0; g < G; g++) {
+            if (valid) {
+                const uint4 w = ld16_stream(q.codes + ((size_t)bf * G + g) * IGD_FRAME + p * 16);
+                const uint32_t a = q.gain[(size_t)bf * G + g];
+                const uint32_t sl = gain_selector(a), lb = lut_lane_base(lut_bytes, lane, q.law[(size_t)b * G + g]);
+                part[bfl * kPst + p] = sl == kSelGeneral ? leg_chunk<kSigned, 2>(lb, w, 0u, (int)a, acc)
+                                       : sl             ? leg_chunk<kSigned, 1>(lb, w, sl, 0, acc)
+                                                        : leg_chunk<kSigned, 0>(lb, w, 0u, 0, acc);
+            }
+            __syncthreads();
+            if (t < BFPC) {
+                const long long bf2 = tile * BFPC + t;
+                if (bf2 < q.total_bf) {
+                    unsigned long long sq = 0; uint32_t peak = 0; int bsum = 0;
+#pragma unroll
+                    for (int i = 0; i < kChunks; i++) partial_add(part[t * kPst + i], sq, peak, bsum);
+                    const igd_meter_rec r = meter_finish(sq << 4, peak << 2, bsum, true);
+                    st16_stream(q.meter + bf2 * G + g, *reinterpret_cast<const uint4 *>(&r));
+                }
+            }
+            __syncthreads();
+        }
+        if (valid)
+            bpart[bfl * kPst + p] = mix_out_chunk<kSigned>(acc, enc_pk_make(q.out_law[b]),
+                                                           q.mix + (size_t)bf * IGD_FRAME + p * 16,
+                                                           q.enc + (size_t)bf * IGD_FRAME + p * 16);
+        __syncthreads();
+        if (t < BFPC) {
+            const long long bf2 = tile * BFPC + t;
+            if (bf2 < q.total_bf) {
+                int esum = 0, mpeak = 0;
+#pragma unroll
+                for (int i = 0; i < kChunks; i++) { esum += (int)bpart[t * kPst + i].x; mpeak = max(mpeak, (int)bpart[t * kPst + i].y); }
+                int n_open = 0;
+                for (int g = 0; g < G; g++) n_open += q.gain[(size_t)bf2 * G + g] != 0;
+                igd_bridge_rec r;
+                r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
+                r.n_open = (uint8_t)n_open;
+                r.mix_peak = (uint16_t)mpeak;
+                q.bmeter[bf2] = r;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// ============================================================ launchers
+namespace {
+template <int G, bool kSigned, int kWarps>
+cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
+{
+    auto kern = k_fused_w<G, kSigned, kWarps>;
+    const size_t smem = kLutBytes + (size_t)kWarps * slot_geom<G>::kSlotBytes +
+                        (size_t)kWarps * (kBfPerItem * G * kPst + kBfPerItem * kPst) * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (q.total_bf + kBfPerItem - 1) / kBfPerItem;
+    long long grid = c.sm_count;
+    if (grid > items) grid = items;      // small ticks: one item per SM before a second warp gets one
+    kern<<<(int)grid, kWarps * 32, smem, c.stream>>>(q);
+    return cudaGetLastError();
+}
+
+template <bool kSigned, int kWarps>
+cudaError_t launch_fused_g(const igd_launch_cfg &c, const FusedParams &q)
+{
+    auto kern = k_fused_g<kSigned, kWarps>;
+    const size_t smem = kLutBytes + (size_t)kWarps * 2 * kGSlotBytes + (size_t)kWarps * kGParts * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (q.total_bf + kGBf - 1) / kGBf;
+    long long grid = c.sm_count;
+    if (grid > items) grid = items;
+    kern<<<(int)grid, kWarps * 32, smem, c.stream>>>(q);
+    return cudaGetLastError();
+}
+
+template <int BFPC, bool kSigned>
+cudaError_t launch_fused_anyg(const igd_launch_cfg &c, const FusedParams &q)
+{
+    const size_t smem = kLutBytes + (size_t)2 * BFPC * kPst * 8;
+    cudaError_t e = cudaFuncSetAttribute(k_fused_anyg<BFPC, kSigned>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fused_anyg<BFPC, kSigned>, BFPC * kChunks, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    FusedParams p = q;
+    p.num_tiles = (q.total_bf + BFPC - 1) / BFPC;
+    long long grid = (long long)c.sm_count * per_sm;
+    if (grid > p.num_tiles) grid = p.num_tiles;
+    k_fused_anyg<BFPC, kSigned><<<(int)grid, BFPC * kChunks, smem, c.stream>>>(p);
+    return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
+{
+    FusedParams q;
+    q.codes = d.codes; q.law = d.law; q.gain = d.gain_q7; q.out_law = d.out_law;
+    q.mix = d.mix; q.enc = d.enc; q.meter = d.meter; q.bmeter = d.bmeter;
+    q.total_bf = (long long)d.F * d.B;
+    q.num_tiles = 0;
+    q.B = d.B; q.G = d.G; q.flags = d.flags;
+    const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
+    // the warp-autonomous kernels index bridge-frames in 32 bits; anything larger (2^28 bridge-frames =
+    // 318 GB of traffic at G = 4) cannot be resident on one GPU anyway and takes the generic kernel
+    // ... and reads a bridge-frame's G gains / a bridge's G laws as one 2G- / G-byte word
+    const bool fits32 = q.total_bf < (1ll << 28) &&          // 16-sample chunk indices (10 per bridge-frame) stay below 2^32
+                        (reinterpret_cast<uintptr_t>(d.gain_q7) & (size_t)(2 * d.G - 1) & 7u) == 0 &&
+                        (d.G != 4 || (reinterpret_cast<uintptr_t>(d.law) & 3u) == 0);
+    if (fits32 && d.G == 4) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
+    if (fits32 && d.G == 2) return sc ? launch_fused_w<2, true, 24>(c, q) : launch_fused_w<2, false, 24>(c, q);
+    if (fits32 && d.G == 1) return sc ? launch_fused_w<1, true, 24>(c, q) : launch_fused_w<1, false, 24>(c, q);
+    // any other leg count: the warp-autonomous group walk (needs 16-byte aligned codes, which the C ABI
+    // checks, and 32-bit bridge-frame indices); the block-cooperative kernel is the last resort
+    if (q.total_bf < (1ll << 28) && (long long)q.total_bf * d.G < (1ll << 32) &&
+        !getenv("IGD_FUSED_ANYG"))
+        return sc ? launch_fused_g<true, 24>(c, q) : launch_fused_g<false, 24>(c, q);
+    return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
+}

@@ -1,5 +1,5 @@
 // igd_kernels.cuh -- launch interface between the C ABI (igd_capi.cu) and the
-// sm_100a kernels (igd_kernels.cu).  All pointers are device pointers.
+// sm_100a kernels (igd_fused.cu, igd_codec.cu, igd_packet.cu).  All pointers are device pointers.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

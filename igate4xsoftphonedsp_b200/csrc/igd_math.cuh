@@ -3,7 +3,7 @@
 // Everything here is __host__ __device__ so that tests/ can compile this very
 // file with g++ (-DIGD_HOST_EMUL) and check the integer/bit tricks against the
 // oracle on the CPU before a GPU run.  The product only ever runs them inside
-// the CUDA kernels of igd_kernels.cu.
+// the CUDA kernels of igd_fused.cu / igd_codec.cu / igd_packet.cu.
 #pragma once
 #include <stdint.h>
 

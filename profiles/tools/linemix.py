@@ -5,8 +5,9 @@ rep, so, ksub = sys.argv[1:4]
 nbf = float(sys.argv[4]) if len(sys.argv) > 4 else 1024 * 1640
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
-cub = [f for f in os.listdir(tmp) if f.startswith("igd_kernels.") and f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
+dis = []                          # every embedded cubin (one per translation unit)
+for cub in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+    dis += subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout.splitlines()
 # instruction list (offset, line, text) of the kernel
 ins, cur, on = [], None, False
 for l in dis:
