@@ -15,6 +15,11 @@ probe oracle/_ref/libigd_ref.so):   python tests/golden/make_golden.py
                           (oracle restates TransportAdapter.cpp:635-874)
   fused_cfg2.npz          BASELINE config 2 (4 legs, 2 u-law + 2 A-law), 75
                           frames: inputs + oracle outputs
+  rx_arb_keepalive.json   SHA-256 of the oracle's receive-side walk (transport_rtp_cb
+                          + R2S watchdog), gate arbitration (CLIENT PTT priority,
+                          SERVER best signal), sendR2SStatus and the
+                          PTTEventDataLogger message on the seeded cases of
+                          tests/rx_arb_cases.py / keepalive_cases.py
 """
 import ctypes as C
 import glob
@@ -109,6 +114,30 @@ def fused_cfg2():
     return sha(mix), sha(enc)
 
 
+def rx_arb_keepalive():
+    import keepalive_cases as K
+    import rx_arb_cases as R
+    from igate4xsoftphonedsp_b200 import _native as N
+    out = {}
+    pkts, sizes, present = R.make_rx_stream(300, 24, seed=3)
+    ev, st = R.oracle_rx_walk(pkts, sizes, present)
+    out["rx_walk"] = {"inputs": sha(pkts) + sha(sizes) + sha(present), "events": sha(ev), "state": sha(st),
+                      "edges": int(((ev["flags"] & N.RXE_EDGE) != 0).sum()),
+                      "hangups": int(((ev["flags"] & N.RXE_HANGUP) != 0).sum())}
+    for name, mode, G in (("client_ptt", N.ARB_CLIENT_PTT, 4), ("server_best", N.ARB_SERVER_BEST, 4)):
+        w = R.make_arb_words(200, 9, G, mode, seed=G)
+        gain, legs, br = R.oracle_arb_walk(w, G, mode)
+        out[name] = {"inputs": sha(w), "gain": sha(gain), "legs": sha(legs), "bridges": sha(br),
+                     "open_leg_frames": int((gain == 256).sum())}
+    legs, hdr, ctl = K.make(40, 120, seed=2)
+    pk, sz, hfin = K.oracle_walk(legs, hdr, ctl)
+    out["keepalive"] = {"packets": sha(pk), "sizes": sha(sz), "final_headers": sha(hfin), "sent": int((sz == 20).sum())}
+    buf = C.create_string_buffer(1024)
+    n = O.lib().orc_ptt_event_json(buf, 1024, 3, b"pptTest_released", 61.25, 70.5, 12.0412, b"sip:radio1@10.0.0.5", 133, 201, 17)
+    out["ptt_event_json"] = buf.raw[:n].decode()
+    return out
+
+
 def main():
     if not O.ref_available():
         sys.exit("oracle/_ref/libigd_ref.so missing: run `make -C oracle` where /root/reference exists")
@@ -123,6 +152,7 @@ def main():
                                                                     for f in range(min(4, pk.shape[0]))]})
     json.dump(scen, open(os.path.join(HERE, "ed137_tx_scenarios.json"), "w"), indent=1)
     print("fused_cfg2", fused_cfg2())
+    json.dump(rx_arb_keepalive(), open(os.path.join(HERE, "rx_arb_keepalive.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

@@ -257,3 +257,28 @@ def test_frame_codec_tables_equal_the_routines():
     for law, enc1, dec1 in ((0, L.orc_lin2alaw, L.orc_alaw2lin), (1, L.orc_lin2ulaw, L.orc_ulaw2lin)):
         assert O.g711_encode(pcm, law).tolist() == [enc1(int(v)) for v in pcm]
         assert O.g711_decode(codes, law).tolist() == [dec1(int(c)) for c in codes]
+
+
+def test_rx_arb_keepalive_golden_is_stable(golden_dir):
+    """the oracle's receive walk, gate arbitration, sendR2SStatus and event message on the seeded cases
+    are pinned by committed hashes (tests/golden/make_golden.py -> rx_arb_keepalive.json)."""
+    import ctypes as C
+    import keepalive_cases as K
+    import rx_arb_cases as R
+    from igate4xsoftphonedsp_b200 import _native as N
+    g = json.load(open(os.path.join(golden_dir, "rx_arb_keepalive.json")))
+    pkts, sizes, present = R.make_rx_stream(300, 24, seed=3)
+    assert sha(pkts) + sha(sizes) + sha(present) == g["rx_walk"]["inputs"]
+    ev, st = R.oracle_rx_walk(pkts, sizes, present)
+    assert sha(ev) == g["rx_walk"]["events"] and sha(st) == g["rx_walk"]["state"]
+    for name, mode in (("client_ptt", N.ARB_CLIENT_PTT), ("server_best", N.ARB_SERVER_BEST)):
+        w = R.make_arb_words(200, 9, 4, mode, seed=4)
+        assert sha(w) == g[name]["inputs"]
+        gain, legs, br = R.oracle_arb_walk(w, 4, mode)
+        assert (sha(gain), sha(legs), sha(br)) == (g[name]["gain"], g[name]["legs"], g[name]["bridges"])
+    legs, hdr, ctl = K.make(40, 120, seed=2)
+    pk, sz, hfin = K.oracle_walk(legs, hdr, ctl)
+    assert (sha(pk), sha(sz), sha(hfin)) == (g["keepalive"]["packets"], g["keepalive"]["sizes"], g["keepalive"]["final_headers"])
+    buf = C.create_string_buffer(1024)
+    n = O.lib().orc_ptt_event_json(buf, 1024, 3, b"pptTest_released", 61.25, 70.5, 12.0412, b"sip:radio1@10.0.0.5", 133, 201, 17)
+    assert buf.raw[:n].decode() == g["ptt_event_json"]
