@@ -5,8 +5,16 @@
 namespace {
 
 // ============================================================ stand-alone G.711
-// codes -> PCM.  One thread per 16 codes.  law_ch != nullptr: law of chunk i is
-// law_ch[(i / 10) % nch] (frames of 160 samples laid out [frame][channel]).
+// law of 16-sample chunk i when frames are laid out [frame][channel]: law_ch[(i / 10) % nch].  The chunk
+// index fits 32 bits for anything below 64 G samples; 64-bit division would cost ~80 instructions per chunk.
+__device__ __forceinline__ uint32_t chunk_law(const uint8_t *law_ch, int law, size_t i, size_t nchunk, size_t nch)
+{
+    if (!law_ch) return (uint32_t)law;
+    if (nchunk <= 0xFFFFFFFFull) return law_ch[((uint32_t)i / (uint32_t)kChunks) % (uint32_t)nch];
+    return law_ch[(i / kChunks) % nch];
+}
+
+// codes -> PCM.  One thread per 16 codes, shared-memory table, one 256-bit store.
 __global__ void __launch_bounds__(512) k_g711_decode(const uint8_t *__restrict__ codes,
                                                      const uint8_t *__restrict__ law_ch, int law,
                                                      int16_t *__restrict__ pcm, size_t n, size_t nch)
@@ -19,7 +27,7 @@ __global__ void __launch_bounds__(512) k_g711_decode(const uint8_t *__restrict__
     const size_t nchunk = n / 16;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunk;
          i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t lw = law_ch ? law_ch[(i / kChunks) % nch] : (uint32_t)law;
+        const uint32_t lw = chunk_law(law_ch, law, i, nchunk, nch);
         const uint32_t lb = lut_lane_base(lut_s, lane, lw);
         const uint4 w = ld16_stream(codes + i * 16);
         const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
@@ -48,12 +56,20 @@ __global__ void __launch_bounds__(256) k_g711_encode(const int16_t *__restrict__
                                                      uint8_t *__restrict__ codes, size_t n, size_t nch)
 {
     const size_t nchunk = n / 16;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nchunk;
-         i += (size_t)gridDim.x * blockDim.x) {
-        const int lw = law_ch ? law_ch[(i / kChunks) % nch] : law;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < nchunk; i += 2 * stride) {       // two chunks per trip: two 32-byte loads in flight
+        uint32_t pa[8], pb[8];
+        ld32_stream(pcm + i * 16, pa);
+        ld32_stream(pcm + (i + stride) * 16, pb);
+        st16_stream(codes + i * 16, encode16_packed(pa, enc_pk_make((int)chunk_law(law_ch, law, i, nchunk, nch))));
+        st16_stream(codes + (i + stride) * 16,
+                    encode16_packed(pb, enc_pk_make((int)chunk_law(law_ch, law, i + stride, nchunk, nch))));
+    }
+    if (i < nchunk) {
         uint32_t pk[8];
         ld32_stream(pcm + i * 16, pk);
-        st16_stream(codes + i * 16, encode16_packed(pk, enc_pk_make(lw)));
+        st16_stream(codes + i * 16, encode16_packed(pk, enc_pk_make((int)chunk_law(law_ch, law, i, nchunk, nch))));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         for (size_t i = nchunk * 16; i < n; i++) {
