@@ -576,7 +576,6 @@ int igd_ed137_pack(igd_ctx *c, const igd_ed137_pack_desc *d)
             return rc;
         dstale = const_cast<uint8_t *>(tmp2);
     }
-    if (mem == IGD_MEM_HOST) IGD_CUDA(c, cudaMemsetAsync(dpk, 0, n * d->out_stride, c->stream));
     k.rtp12 = drtp; k.payload = dpay; k.ctl = dctl; k.state = dst; k.pkts = dpk; k.sizes = dsz; k.bytemean_out = dbm;
     k.stale_payload = dstale;
     IGD_CUDA(c, igd_k_ed137_pack(cfg_of(c), k, static_cast<igd_tx_plan_rec *>(dplan), static_cast<int32_t *>(dlast)));

@@ -399,6 +399,8 @@ __global__ void __launch_bounds__(256) k_ed137_assemble(const igd_ed137_pack_des
         const size_t c = i % (size_t)d.C;
         if (lane == 0) d.sizes[i] = r.size;
         int bsum = 0;
+        // the bytes of the slot past the packet are defined (zero): nobody has to clear the buffer first
+        for (uint32_t k = r.size / 4 + lane; k < d.out_stride / 4; k += 32) out[k] = 0u;
         if (r.size == 0) {
             if (lane == 0) d.bytemean_out[i] = 0;
             continue;
@@ -543,7 +545,7 @@ __global__ void __launch_bounds__(256) k_ed137_assemble_tile(const igd_ed137_pac
         uint32_t *out = reinterpret_cast<uint32_t *>(d.pkts + first * IGD_PKT_MAX);
         for (uint32_t w = threadIdx.x; w < np * kPktWords; w += blockDim.x) {
             const uint32_t p = w / kPktWords, k = w - p * kPktWords;
-            if (4 * k < size_s[p]) out[w] = img[w];
+            out[w] = 4 * k < size_s[p] ? img[w] : 0u;              // past the packet the slot reads zero
         }
     }
     if (threadIdx.x < np) {

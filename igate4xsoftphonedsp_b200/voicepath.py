@@ -338,7 +338,7 @@ class VoicePath:
         F, Cn = rtp12.shape[0], rtp12.shape[1]
         if mem == N.MEM_DEVICE:
             dev = rtp12.device
-            pkts = torch.zeros((F, Cn, out_stride), dtype=torch.uint8, device=dev)
+            pkts = torch.empty((F, Cn, out_stride), dtype=torch.uint8, device=dev)   # the kernels define every byte
             sizes = torch.empty((F, Cn), dtype=torch.int32, device=dev)
             bm = torch.empty((F, Cn), dtype=torch.uint8, device=dev)
         else:

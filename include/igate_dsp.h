@@ -269,7 +269,8 @@ typedef struct {
  *        payload [F][C][160]  its G.711 payload (payload_len bytes each)
  *        ctl     [F][C]       (NULL = keep the state's own flags)
  *        now_ms0, tick_ms     currenttime of frame f = now_ms0 + f*tick_ms
- *   out: pkts    [F][C][out_stride]  packet bytes (out_stride >= 180)
+ *   out: pkts    [F][C][out_stride]  packet bytes (out_stride >= 180); the bytes of a slot past
+ *                             sizes[f][c] are written as zero
  *        sizes   [F][C]       0 = suppressed by the keep-alive throttle,
  *                             20 = header only, 20+payload_len = with payload
  *        bytemean_out [F][C]  setOutgoingRTP level (roip_ed137.cpp:6500-6536) of
