@@ -443,6 +443,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
     const uint32_t items = (total_bf + kGBf - 1) / kGBf;
     const uint32_t nw = gridDim.x * kWarps;
     uint32_t item = warp * gridDim.x + blockIdx.x;
+    const size_t row_bytes = (size_t)G * IGD_FRAME;       // a bridge-frame's legs
     // unit = (item, leg group); the n-th unit of this warp lives in slot n & 1
     auto fetch = [&](uint32_t it_idx, uint32_t grp, uint32_t n) {
         const uint32_t bf0 = it_idx * kGBf;
@@ -452,10 +453,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
         if (lane == 0) {
             const uint32_t bs = bar_s + (n & 1u) * 8, dst = slot_s + (n & 1u) * kGSlotBytes;
             mbar_expect_tx(bs, nbf * bytes);
-            const uint8_t *g = q.codes + ((size_t)bf0 * G + (size_t)grp * kGLegs) * IGD_FRAME;
-#pragma unroll
-            for (int k = 0; k < kGBf; k++)
-                if ((uint32_t)k < nbf) bulk_g2s(dst + k * kGStride, g + (size_t)k * G * IGD_FRAME, bytes, bs);
+            const uint8_t *g0 = q.codes + ((size_t)bf0 * G + (size_t)grp * kGLegs) * IGD_FRAME;
+            if (nbf == (uint32_t)kGBf) {          // whole item: three copies, row pointers by addition
+                const uint8_t *g1 = g0 + row_bytes, *g2 = g1 + row_bytes;
+                bulk_g2s(dst, g0, bytes, bs);
+                bulk_g2s(dst + kGStride, g1, bytes, bs);
+                bulk_g2s(dst + 2 * kGStride, g2, bytes, bs);
+            } else {
+                bulk_g2s(dst, g0, bytes, bs);
+                if (nbf > 1) bulk_g2s(dst + kGStride, g0 + row_bytes, bytes, bs);
+            }
         }
     };
     const bool worker = lane < kGBf * kChunks;
