@@ -1,4 +1,5 @@
-"""Raw host<->device copy bandwidth of the box (pinned vs write-combined, H2D alone vs with a concurrent D2H), at 1 GPU\nor under torchrun at N GPUs: the ceiling of bench.py's e2e leg.  gpurun -- 'python profiles/tools/pcie_probe.py'"""
+"""Raw host<->device copy bandwidth of the box (pinned vs write-combined, H2D alone vs with a concurrent D2H), at 1 GPU
+or under torchrun at N GPUs: the ceiling of bench.py's e2e leg.  gpurun -- 'python profiles/tools/pcie_probe.py'"""
 import ctypes, os, sys, time, torch
 import torch.distributed as dist
 rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
