@@ -33,4 +33,4 @@ def test_example_runs_one_tick_on_the_gpu():
     # four radios keying PTT types 0..3 in one tick: the priority PTT (leg 3) wins (roip_ed137.cpp:6157-6177)
     assert [ln.split("gain_q7 ")[1].split()[0] for ln in out[:4]] == ["0", "0", "0", "256"]
     assert all("bytemean 213 peak 8" in ln for ln in out[:4])          # A-law silence 0xD5 decodes to +8
-    assert out[4] == "bridge: 1 legs open, outgoing byte-mean 213, mix[0] 16"   # 2.0 * 8, re-encoded
+    assert out[4] == "bridge: 1 legs open, outgoing byte-mean 212, mix[0] 16"   # 2.0 * 8 = 16 -> A-law 0xD4
