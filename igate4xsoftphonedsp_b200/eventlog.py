@@ -48,3 +48,16 @@ def vu_meter_json(in_level, out_level, in_db, out_db):
         parts.append(f"\"in{n}\":{_qnum(in_level[i])},\"out{n}\":{_qnum(out_level[i])}")
         parts.append(f"\"in{n}dB\":{_qnum(in_db[i])},\"out{n}dB\":{_qnum(out_db[i])}")
     return "{" + ",".join(parts) + "}"
+
+
+def vu_meter_json_from_records(meter, bmeter):
+    """The VU feed of one tick for the four softphones of a box, from the fused kernel's records:
+    meter = the igd_meter_rec of the leg each softphone listens to (4 records), bmeter = the
+    igd_bridge_rec of each softphone's bridge (4 records).  in<N> / out<N> = peak amplitude (0..32768) of the
+    received leg / of the mix, in<N>dB / out<N>dB = the same in dBFS (20*log10(peak/32768), -inf for silence)."""
+    def db(p):
+        return 20.0 * math.log10(p / 32768.0) if p > 0 else float("-inf")
+    pin = [int(m["hi"]) >> 16 for m in meter]
+    pout = [int(b["mix_peak"]) for b in bmeter]
+    return vu_meter_json(pin, pout, [db(p) for p in pin], [db(p) for p in pout])
+

@@ -53,3 +53,16 @@ std::string igd_vu_meter_json(const double in_level[4], const double out_level[4
     m += "}";
     return m;
 }
+
+std::string igd_vu_meter_json_from_records(const igd_meter_rec meter[4], const igd_bridge_rec bmeter[4])
+{
+    double in[4], out[4], indb[4], outdb[4];
+    for (int i = 0; i < 4; i++) {
+        in[i] = (double)IGD_METER_PEAK(meter[i]);
+        out[i] = (double)bmeter[i].mix_peak;
+        indb[i] = in[i] > 0 ? 20.0 * log10(in[i] / 32768.0) : -INFINITY;
+        outdb[i] = out[i] > 0 ? 20.0 * log10(out[i] / 32768.0) : -INFINITY;
+    }
+    return igd_vu_meter_json(in, out, indb, outdb);
+}
+

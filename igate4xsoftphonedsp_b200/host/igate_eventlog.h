@@ -26,3 +26,6 @@ std::string igd_ptt_released_json(int softPhoneID, const igd_summary_rec &rec, c
 // level = linear level, dB = its dB value, index i = softphone i+1 (roip_ed137.cpp:7688-7712)
 std::string igd_vu_meter_json(const double in_level[4], const double out_level[4], const double in_db[4],
                               const double out_db[4]);
+// the same message straight from the fused kernel's records of one tick: meter[i] = the leg softphone i+1
+// listens to, bmeter[i] = its bridge; level = peak amplitude (0..32768), dB = 20*log10(peak/32768)
+std::string igd_vu_meter_json_from_records(const igd_meter_rec meter[4], const igd_bridge_rec bmeter[4]);

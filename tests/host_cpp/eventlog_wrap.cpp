@@ -23,4 +23,8 @@ size_t w_vu(char *out, size_t cap, const double *a, const double *b, const doubl
 {
     return put(out, cap, igd_vu_meter_json(a, b, c, d));
 }
+size_t w_vu_rec(char *out, size_t cap, const igd_meter_rec *m, const igd_bridge_rec *b)
+{
+    return put(out, cap, igd_vu_meter_json_from_records(m, b));
+}
 }

@@ -30,6 +30,8 @@ def cxx():
     L.w_ptt_released.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_char_p]
     L.w_vu.restype = C.c_size_t
     L.w_vu.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.w_vu_rec.restype = C.c_size_t
+    L.w_vu_rec.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -78,3 +80,17 @@ def test_vu_meter_message():
     for k in range(1, 5):
         assert {f"in{k}", f"out{k}", f"in{k}dB", f"out{k}dB"} <= set(m)
     assert m["menuID"] == "broadcastVUMeter" and m["in2"] == 2000.5
+
+
+def test_vu_meter_message_from_kernel_records():
+    L = cxx()
+    meter = np.zeros(4, N.METER_DT)
+    bm = np.zeros(4, N.BRIDGE_DT)
+    meter["hi"] = np.array([16384, 0, 32768, 8], np.uint32) << 16
+    bm["mix_peak"] = [32767, 16, 0, 1000]
+    buf = C.create_string_buffer(2048)
+    n = L.w_vu_rec(buf, 2048, meter.ctypes.data, bm.ctypes.data)
+    py = E.vu_meter_json_from_records(meter, bm)
+    assert buf.raw[:n].decode() == py
+    assert '"in1":16384' in py and '"in1dB":-6.0206' in py and '"in2dB":-inf' in py and '"out3dB":-inf' in py
+
