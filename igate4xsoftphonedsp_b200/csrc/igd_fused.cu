@@ -126,19 +126,20 @@ __device__ __forceinline__ uint2 load_gains(const uint16_t *g)
 // Warp-autonomous fused kernel (G in {1,2,4}): no cross-warp handshake at all.
 // A warp owns "items" of kBfPerItem = 6 consecutive bridge-frames (6*G*160 contiguous
 // code bytes) and strides over them on its own:
-//   * the item's codes are fetched by the warp's OWN bulk async copies (TMA, one per
-//     bridge-frame into a padded, bank-conflict-free slot), completion on the warp's
-//     private mbarrier; the copies of item i+1 are issued as soon as every lane holds
+//   * the item's codes are fetched by the warp's OWN bulk async copy (TMA, one copy of
+//     the contiguous item into the warp's private slot), completion on the warp's
+//     private mbarrier; the copy of item i+1 is issued as soon as every lane holds
 //     the last codes of item i, so HBM latency hides behind half an item (~1.5 us) and
-//     ~77 KB per SM are in flight;
-//   * lane = two 16-sample chunks (c and c+5) of one bridge-frame, all G legs (5 lanes
+//     ~90 KB per SM are in flight;
+//   * lane = two 16-sample chunks (c' and c'+5, c' rotated per bridge-frame, see
+//     chunk_rotation) of one bridge-frame, all G legs (5 lanes
 //     per bridge-frame, 30 of 32 lanes busy): per-bridge-frame setup (gains, laws,
 //     selectors, addresses) is paid once per 32 samples;
 //   * the per-chunk meter partials meet in the warp's private shared scratch after a
 //     __syncwarp; lanes 0..6G-1 finish one leg record each, the next 6 lanes one bridge
 //     record each.
-// Warps drift freely: nobody spins on a peer (the CTA-cooperative kernel above spends
-// ~16 % of its issue slots in mbarrier spin loops).
+// Warps drift freely: nobody spins on a peer (the CTA-cooperative first version of this kernel
+// spent ~16 % of its issue slots in mbarrier spin loops).
 //
 // Decode table of this kernel: low half |x|/4 (unsigned -> the frame peak is ONE packed
 // max per two samples, no min), high half clamp16(2x).  The one-instruction accumulate
