@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
     const uint32_t lane4 = lut_bytes + 4u * lane;
     const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kGBf) % (uint32_t)q.B);
     uint32_t b = (item * kGBf + bfl) % (uint32_t)q.B;
+    const bool wide = (G & 3u) == 0u && (reinterpret_cast<uintptr_t>(q.gain) & 7u) == 0 && (reinterpret_cast<uintptr_t>(q.law) & 3u) == 0;
     // gains (two packed words) and laws (4 bits) of one unit for this lane's bridge-frame
     auto load_unit = [&](uint32_t it_idx, uint32_t grp, uint32_t bb, uint2 &gq, uint32_t &lw) {
         gq = make_uint2(0u, 0u); lw = 0u;
@@ -480,6 +481,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
         const uint32_t legs = min((uint32_t)kGLegs, G - grp * kGLegs);
         const uint16_t *gp = q.gain + (size_t)bf * G + grp * kGLegs;
         const uint8_t *lp = q.law + (size_t)bb * G + grp * kGLegs;
+        if (wide) {                          // G % 4 == 0 and aligned arrays: one 8-byte and one 4-byte load
+            gq = __ldg(reinterpret_cast<const uint2 *>(gp));
+            const uint32_t l4 = __ldg(reinterpret_cast<const uint32_t *>(lp));
+            lw = (l4 & 1u) | ((l4 >> 7) & 2u) | ((l4 >> 14) & 4u) | ((l4 >> 21) & 8u);
+            return;
+        }
         uint32_t g0 = 0, g1 = 0, g2 = 0, g3 = 0;
         if (legs > 0) { g0 = __ldg(gp + 0); lw |= (uint32_t)(__ldg(lp + 0) & 1u); }
         if (legs > 1) { g1 = __ldg(gp + 1); lw |= (uint32_t)(__ldg(lp + 1) & 1u) << 1; }
