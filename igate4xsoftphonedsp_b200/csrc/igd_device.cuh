@@ -227,6 +227,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar_s, uint32_t parity)
         "@!p bra WAIT_%=;\n\t}"
         ::"r"(bar_s), "r"(parity) : "memory");
 }
+// orders this thread's earlier generic-proxy shared accesses before later async-proxy (TMA) ones
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 // TMA bulk copy global -> shared (UBLKCP): no registers, no LSU issue slots; the
 // bytes land asynchronously and complete_tx on the mbarrier.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_s, const void *src, uint32_t bytes, uint32_t bar_s)

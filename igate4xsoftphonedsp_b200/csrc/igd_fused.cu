@@ -128,9 +128,9 @@ __device__ __forceinline__ uint2 load_gains(const uint16_t *g)
 // code bytes) and strides over them on its own:
 //   * the item's codes are fetched by the warp's OWN bulk async copy (TMA, one copy of
 //     the contiguous item into the warp's private slot), completion on the warp's
-//     private mbarrier; the copy of item i+1 is issued as soon as every lane holds
-//     the last codes of item i, so HBM latency hides behind half an item (~1.5 us) and
-//     ~90 KB per SM are in flight;
+//     private mbarrier; the copy of item i+1 is issued once every lane has consumed
+//     the last codes of item i (proxy fence, then the copy), so HBM latency hides behind
+//     the rest of the item and ~90 KB per SM are in flight;
 //   * lane = two 16-sample chunks (c' and c'+5, c' rotated per bridge-frame, see
 //     chunk_rotation) of one bridge-frame, all G legs (5 lanes
 //     per bridge-frame, 30 of 32 lanes busy): per-bridge-frame setup (gains, laws,
@@ -325,10 +325,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                 asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                              : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
                              : "r"(src + g * IGD_FRAME + ch * 16));
-            if (h == 1) {        // every lane holds the rest of its codes: refill the slot
-                __syncwarp();
-                if (next < items) fetch(next);
-            }
             uint2 *mypart = part + bfl * (G * kPst) + ch;
             int acc[16];
 #pragma unroll
@@ -348,6 +344,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                     const uint2 ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
                     if (valid) mypart[g * kPst] = ph;
                 }
+            }
+            if (h == 1) {
+                // Every lane has consumed the rest of its codes: refill the slot.  The fence orders the
+                // slot reads (generic proxy) before the bulk copy's writes (async proxy); placed here,
+                // after the lookups that depend on those reads, it has nothing left to wait for.
+                // (Issuing the copy right behind the LDS, unfenced, lost the race at G = 1: a 960-byte
+                // copy that hits L2 overtook loads still queued behind the other warps' table lookups
+                // -- profiles/tools/determinism_soak.py.)
+                fence_proxy_async();
+                __syncwarp();
+                if (next < items) fetch(next);
             }
             enc_pk E;
             {
@@ -513,7 +520,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
             const uint32_t legs = min((uint32_t)kGLegs, G - grp * kGLegs);
             const bool last = grp + 1 == ngrp;
             const uint32_t it_n = last ? item + nw : item, grp_n = last ? 0u : grp + 1;
-            if (it_n < items) fetch(it_n, grp_n, n + 1);                 // the other slot was drained one unit ago
+            // the other slot was drained one unit ago (its loads were consumed by that unit's lookups);
+            // the fence makes that generic-before-async order formal
+            fence_proxy_async();
+            if (it_n < items) fetch(it_n, grp_n, n + 1);
             mbar_wait(bar_s + (n & 1u) * 8, (n >> 1) & 1u);
             const uint2 gcur = gq;
             const uint32_t lcur = lwq;

@@ -339,3 +339,33 @@ def test_fuzz_shapes_gains_and_flags(vp):
             check(got, want)
         except AssertionError as e:
             raise AssertionError(f"case {case}: G={G} B={B} F={F} flags={flags}: {e}")
+
+
+@pytest.mark.parametrize("G,B,F", [(1, 999, 77), (1, 64, 500), (1, 4096, 50), (2, 999, 40), (4, 333, 40),
+                                   (3, 200, 30), (32, 16, 60)])
+def test_slot_refill_is_ordered_after_the_reads_many_items_per_warp(vp, G, B, F):
+    """Every warp walks several items and the codes sit in L2, so a refill copy lands as early as it
+    can: repeated launches on the same device inputs must equal the oracle every time (the first
+    G = 1 kernel lost this race -- its refill overtook loads that were issued but not complete)."""
+    import torch
+    dev = "cuda:0"
+    rng = np.random.default_rng(G * 7919 + B)
+    codes = rng.integers(0, 256, (F, B * G, 160), dtype=np.uint8)
+    law = rng.integers(0, 2, B * G).astype(np.uint8)
+    out_law = rng.integers(0, 2, B).astype(np.uint8)
+    gain = rng.choice(np.array([0, 0, 256], np.uint16), (F, B * G))
+    if G == 3:
+        gain[::5] = 128
+    want = O.process_batch(codes, law, gain, out_law, G, threads=8)
+    d_codes, d_law = torch.from_numpy(codes).to(dev), torch.from_numpy(law).to(dev)
+    d_gain, d_out = torch.from_numpy(gain.view(np.int16)).to(dev), torch.from_numpy(out_law).to(dev)
+    for rep in range(6):
+        r = vp.process_batch(d_codes, d_law, d_gain, d_out, G)
+        torch.cuda.synchronize()
+        got = {"mix": r["mix"].cpu().numpy(), "enc": r["enc"].cpu().numpy(),
+               "meter": r["meter"].cpu().numpy().view(ig.METER_DT).reshape(F, B * G),
+               "bmeter": r["bmeter"].cpu().numpy().view(ig.BRIDGE_DT).reshape(F, B)}
+        try:
+            check(got, want)
+        except AssertionError as e:
+            raise AssertionError(f"launch {rep}: {e}")
