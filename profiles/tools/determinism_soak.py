@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Soak: the fused path re-run many times on the same device-resident inputs must reproduce its outputs bit for
+"""Soak: the fused path (and then the packet path / state machines) re-run many times on the same device-resident inputs must reproduce its outputs bit for
 bit (a race in the per-warp slot refill / partial scratch hand-over would show up as a rare mismatch).
 gpurun -- 'python profiles/tools/determinism_soak.py'"""
 import os
@@ -35,4 +35,53 @@ for G, B, F, reps in ((4, 1024, 400, 300), (4, 37, 11, 2000), (32, 64, 200, 200)
             bad += 1
             print(f"MISMATCH G={G} B={B} F={F} rep {r}")
     print(f"G={G} B={B} F={F}: {reps} runs identical" if bad == 0 else f"G={G}: mismatches so far {bad}")
+
+# ---- the packet path and the per-channel state machines: same host inputs, repeated calls, byte-identical outputs
+from igate4xsoftphonedsp_b200 import _native as N          # noqa: E402
+
+rng = np.random.default_rng(5)
+F, Cn, G = 50, 4096, 4
+pk = rng.integers(0, 256, (F * Cn, 180), dtype=np.uint8)
+pk[:, 0] = 0x90
+pk[:, 1] = rng.choice(np.array([8, 0, 123, 18, 96], np.uint8), F * Cn)
+sizes = rng.choice(np.array([180, 180, 180, 20, 12, 100, 8], np.uint32), F * Cn)
+rtp12 = rng.integers(0, 256, (F, Cn, 12), dtype=np.uint8)
+pay = rng.integers(0, 256, (F, Cn, 160), dtype=np.uint8)
+ctl = np.zeros((F, Cn), dtype=N.CTL_DT)
+for name in ("pttstatus", "sqlstatus", "pttpriority", "ed137_bssi", "pttid", "callRecorder"):
+    ctl[name] = rng.integers(0, 2, (F, Cn)).astype(np.uint8)
+present = (rng.integers(0, 4, (F, Cn)) != 0).astype(np.uint8)
+
+
+def blob(*arrs):
+    return b"".join(np.ascontiguousarray(a).tobytes() for a in arrs if a is not None)
+
+
+def once():
+    out = []
+    fields, payload = vp.ed137_parse(pk, sizes)
+    out.append(blob(fields, payload))
+    st = np.zeros(Cn, dtype=N.STATE_DT)
+    out.append(blob(*vp.ed137_pack(rtp12, pay, st, ctl, now_ms0=1000, flags=ig.F_REF_QUIRKS), st))
+    rxs = np.zeros(Cn, dtype=N.RX_STATE_DT)
+    ev = vp.rx_track(fields.reshape(F, Cn), rxs, present, now_ms0=1000)
+    out.append(blob(ev, rxs))
+    for mode in (N.ARB_CLIENT_PTT, N.ARB_SERVER_BEST):
+        legs, br = np.zeros(Cn, dtype=N.ARB_LEG_DT), np.zeros(Cn // G, dtype=N.ARB_BRIDGE_DT)
+        gq = vp.gate_arbitrate(ev, legs, br, G, mode=mode)
+        out.append(blob(gq, legs, br))
+    r = vp.process_batch(pay, synth.laws(Cn), gq, synth.out_laws(Cn // G), G)
+    out.append(blob(*vp.event_summary(r["meter"], gq)))
+    out.append(blob(vp.wav_images(pay[:, :64], ref_quirks=True)))
+    return out
+
+
+ref = once()
+names = ("parse", "pack", "rx_track", "arb_client", "arb_server", "summary", "wav_images")
+for r in range(40):
+    for nme, a, b in zip(names, ref, once()):
+        if a != b:
+            bad += 1
+            print(f"MISMATCH {nme} rep {r}")
+print("packet path / state machines: 40 runs identical" if bad == 0 else f"mismatches {bad}")
 print("SOAK", "OK" if bad == 0 else f"FAILED ({bad})")
