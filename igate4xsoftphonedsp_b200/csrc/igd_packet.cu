@@ -201,24 +201,28 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
 // ============================================================ gate arbitration
 // One thread per bridge walks its frames through checkEvents()'s gate decisions
 // (igd_math.cuh: igd_arb_client_tick / igd_arb_server_best_tick); the leg state of
-// the block's bridges lives in shared memory for the walk.
+// the block's bridges lives in registers (G in {1,2,4}) or shared memory for the walk.
+// A block owns `bpb` <= 64 bridges (the launcher shrinks bpb until the grid covers the
+// SMs several times: the walk over F is sequential per bridge, so few bridges x many
+// frames must not sit on a handful of SMs); all 64 threads stage the words / gains of
+// a run of ticks through shared memory with coalesced rows.
 constexpr int kArbThreads = 64;
 constexpr int kArbStageWords = 4096;     // words (and gains) of a run of ticks staged per block
 template <int kG> struct arb_legs {      // compile-time leg count: the leg state lives in registers
     igd_arb_leg v[kG > 0 ? kG : 1];
 };
 template <int kG>
-__global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_desc d)
+__global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_desc d, const int bpb)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     const int G = kG > 0 ? kG : d.G;
-    const int bpb = kArbThreads;                                        // bridges per block
     uint32_t *words_s = reinterpret_cast<uint32_t *>(smem);             // [T][bpb*G]
     uint16_t *gain_s = reinterpret_cast<uint16_t *>(words_s + kArbStageWords);   // [T][bpb*G]
     igd_arb_leg *legs_s = reinterpret_cast<igd_arb_leg *>(gain_s + kArbStageWords);   // [bpb][G] (runtime G only)
     const int b0 = blockIdx.x * bpb;
     const int b = b0 + threadIdx.x;
     const int nb = min(bpb, d.B - b0);
+    const bool owner = (int)threadIdx.x < nb;                            // this thread walks bridge b
     const int row = nb * G;                                             // words of this block per tick
     const int T = max(1, kArbStageWords / (bpb * G));                   // ticks per staged run
     const size_t Cn = (size_t)d.B * G;
@@ -226,32 +230,32 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
     igd_arb_leg *legs;
     if (kG > 0) {
         legs = lr.v;
-        if (b < d.B) {
+        if (owner) {
 #pragma unroll
             for (int g = 0; g < (kG > 0 ? kG : 1); g++) lr.v[g] = d.legs[(size_t)b * G + g];
         }
     } else {
         for (int k = threadIdx.x; k < row; k += kArbThreads) legs_s[k] = d.legs[(size_t)b0 * G + k];
-        legs = legs_s + threadIdx.x * G;
+        legs = legs_s + (owner ? threadIdx.x : 0) * G;
     }
     igd_arb_bridge br;
-    if (b < d.B) br = d.bridges[b];
+    if (owner) br = d.bridges[b];
     const uint8_t *act = d.active ? d.active + (size_t)b * G : nullptr;
     uint32_t act_mask = 0xFFFFFFFFu;                                    // G <= 32 legs
-    if (act && b < d.B) {
+    if (act && owner) {
         act_mask = 0;
         for (int g = 0; g < G; g++) act_mask |= (act[g] != 0 ? 1u : 0u) << g;
     }
     for (int f0 = 0; f0 < d.F; f0 += T) {
         const int nt = min(T, d.F - f0);
         __syncthreads();
-        for (int t = 0; t < nt; t++) {                                  // coalesced: a tick's words are contiguous
+        for (int k = threadIdx.x; k < nt * row; k += kArbThreads) {      // coalesced: a tick's words are contiguous
+            const int t = k / row, j = k - t * row;
             const uint8_t *wrow = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)(f0 + t) * Cn + (size_t)b0 * G) * d.word_stride;
-            for (int j = threadIdx.x; j < row; j += kArbThreads)
-                words_s[t * row + j] = *reinterpret_cast<const uint32_t *>(wrow + (size_t)j * d.word_stride);
+            words_s[k] = *reinterpret_cast<const uint32_t *>(wrow + (size_t)j * d.word_stride);
         }
         __syncthreads();
-        if (b < d.B) {
+        if (owner) {
             for (int t = 0; t < nt; t++) {
                 const uint32_t *wt = words_s + t * row + threadIdx.x * G;
                 auto word = [&](int g) { return wt[g]; };
@@ -271,15 +275,15 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
             }
         }
         __syncthreads();
-        for (int t = 0; t < nt; t++) {
-            uint16_t *grow = d.gain_q7 + (size_t)(f0 + t) * Cn + (size_t)b0 * G;
-            for (int j = threadIdx.x; j < row; j += kArbThreads) grow[j] = gain_s[t * row + j];
+        for (int k = threadIdx.x; k < nt * row; k += kArbThreads) {
+            const int t = k / row, j = k - t * row;
+            d.gain_q7[(size_t)(f0 + t) * Cn + (size_t)b0 * G + j] = gain_s[k];
         }
     }
     __syncthreads();
-    if (b < d.B) d.bridges[b] = br;
+    if (owner) d.bridges[b] = br;
     if (kG > 0) {
-        if (b < d.B) {
+        if (owner) {
 #pragma unroll
             for (int g = 0; g < (kG > 0 ? kG : 1); g++) d.legs[(size_t)b * G + g] = lr.v[g];
         }
@@ -656,14 +660,18 @@ cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d)
 
 cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d)
 {
-    const unsigned blocks = (unsigned)((d.B + kArbThreads - 1) / kArbThreads);
+    // bridges per block: 64, or fewer so that the grid is ~4 blocks per SM (the walk over F is sequential)
+    const int want_blocks = 4 * (c.sm_count > 0 ? c.sm_count : 148);
+    int bpb = (d.B + want_blocks - 1) / want_blocks;
+    bpb = bpb < 1 ? 1 : bpb > kArbThreads ? kArbThreads : bpb;
+    const unsigned blocks = (unsigned)((d.B + bpb - 1) / bpb);
     const size_t stage = (size_t)kArbStageWords * 6;
     switch (d.G) {
-    case 1: k_gate_arbitrate<1><<<blocks, kArbThreads, stage, c.stream>>>(d); break;
-    case 2: k_gate_arbitrate<2><<<blocks, kArbThreads, stage, c.stream>>>(d); break;
-    case 4: k_gate_arbitrate<4><<<blocks, kArbThreads, stage, c.stream>>>(d); break;
+    case 1: k_gate_arbitrate<1><<<blocks, kArbThreads, stage, c.stream>>>(d, bpb); break;
+    case 2: k_gate_arbitrate<2><<<blocks, kArbThreads, stage, c.stream>>>(d, bpb); break;
+    case 4: k_gate_arbitrate<4><<<blocks, kArbThreads, stage, c.stream>>>(d, bpb); break;
     default:   // runtime leg count: leg state in shared memory (<= 64 * 32 * 8 B = 16 KB, 40 KB in all)
-        k_gate_arbitrate<0><<<blocks, kArbThreads, stage + (size_t)kArbThreads * d.G * sizeof(igd_arb_leg), c.stream>>>(d);
+        k_gate_arbitrate<0><<<blocks, kArbThreads, stage + (size_t)kArbThreads * d.G * sizeof(igd_arb_leg), c.stream>>>(d, bpb);
     }
     return cudaGetLastError();
 }
