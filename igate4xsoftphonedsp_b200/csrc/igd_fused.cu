@@ -119,11 +119,12 @@ __device__ __forceinline__ uint2 load_gains(const uint16_t *g)
 {
     if (G == 4) return *reinterpret_cast<const uint2 *>(g);
     if (G == 2) return make_uint2(*reinterpret_cast<const uint32_t *>(g), 0u);
+    if (G == 3) return make_uint2((uint32_t)g[0] | ((uint32_t)g[1] << 16), (uint32_t)g[2]);   // 6-byte rows: halfword loads
     return make_uint2(*g, 0u);
 }
 
 // ------------------------------------------------------------------------------------
-// Warp-autonomous fused kernel (G in {1,2,4}): no cross-warp handshake at all.
+// Warp-autonomous fused kernel (G in {1,2,3,4}): no cross-warp handshake at all.
 // A warp owns "items" of kBfPerItem = 6 consecutive bridge-frames (6*G*160 contiguous
 // code bytes) and strides over them on its own:
 //   * the item's codes are fetched by the warp's OWN bulk async copy (TMA, one copy of
@@ -735,6 +736,7 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     if (fits32 && d.G == 4) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
     if (fits32 && d.G == 2) return sc ? launch_fused_w<2, true, 24>(c, q) : launch_fused_w<2, false, 24>(c, q);
     if (fits32 && d.G == 1) return sc ? launch_fused_w<1, true, 24>(c, q) : launch_fused_w<1, false, 24>(c, q);
+    if (q.total_bf < (1ll << 28) && d.G == 3) return sc ? launch_fused_w<3, true, 24>(c, q) : launch_fused_w<3, false, 24>(c, q);
     // any other leg count: the warp-autonomous group walk (needs 16-byte aligned codes, which the C ABI
     // checks, and 32-bit bridge-frame indices); the block-cooperative kernel is the last resort
     if (q.total_bf < (1ll << 28) && (long long)q.total_bf * d.G < (1ll << 32) &&

@@ -4,7 +4,7 @@ import igate4xsoftphonedsp_b200 as ig
 from igate4xsoftphonedsp_b200 import synth
 vp = ig.VoicePath(0); vp.use_torch_stream()
 dev = torch.device("cuda", 0)
-for G in (4, 3, 8, 32):
+for G in (4, 2, 1, 3, 8, 32):
     Cn = 4096; B = Cn // G if Cn % G == 0 else 1365; Cn = B * G; F = 1640
     g = torch.Generator(device=dev).manual_seed(1)
     codes = torch.randint(0, 256, (F, Cn, 160), dtype=torch.uint8, device=dev, generator=g)
@@ -19,5 +19,5 @@ for G in (4, 3, 8, 32):
     for _ in range(5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); f(); b.record(); torch.cuda.synchronize(); best = min(best, a.elapsed_time(b))
-    nbytes = F * B * (G * 160 + 480 + G * 16)
+    nbytes = F * B * (G * 160 + 480 + G * 16)          # SURVEY 8(d) accounting (bridge record not counted)
     print(f"G={G} B={B}: {best:.3f} ms  {nbytes / best / 1e6:.0f} GB/s  {nbytes / best / 1e6 / 6552.6:.1%}")
