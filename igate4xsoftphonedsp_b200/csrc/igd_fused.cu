@@ -419,6 +419,39 @@ constexpr int kGStride = kGLegs * IGD_FRAME + 32;          // 672
 constexpr int kGSlotBytes = kGBf * kGStride;                // 2016
 constexpr int kGParts = (kGBf * kGLegs + kGBf) * kPst;      // leg + bridge partials per warp
 
+// Meter-only table of k_fused_g for legs shut in the whole warp: clean 32-bit |x|/4 entries (no
+// extract before the square), indexed by the 7 magnitude bits of the code (the sign of both laws
+// is bit 7), rows of 256 B = [law][lane column] so that ONE PRMT builds the lookup offset
+// (code << 8 | law << 7 | lane << 2): the address moves from the FMA pipe (IDP.4A) to the ALU.
+constexpr int kMlutBytes = 128 * 256;
+__device__ __forceinline__ void build_meter_lut(uint32_t *mlut, int tid, int nthreads)
+{
+    for (int i = tid; i < kMlutBytes / 4; i += nthreads) {
+        const uint32_t code = (uint32_t)i >> 6, law = ((uint32_t)i >> 5) & 1u;
+        const int x = law ? igd_ulaw2lin(code) : igd_alaw2lin(code);
+        mlut[i] = (uint32_t)(abs(x) >> 2);
+    }
+}
+template <bool kSigned>
+__device__ __forceinline__ uint2 leg_chunk_shut(const uint8_t *mlut, uint32_t lanereg, uint4 w)
+{
+    const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
+    uint32_t sq = 0, mx = 0;
+    int bsum = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t wm = wd[j] & 0x7F7F7F7Fu;
+        const uint32_t e0 = *reinterpret_cast<const uint32_t *>(mlut + __byte_perm(wm, lanereg, 0x7604));
+        const uint32_t e1 = *reinterpret_cast<const uint32_t *>(mlut + __byte_perm(wm, lanereg, 0x7614));
+        const uint32_t e2 = *reinterpret_cast<const uint32_t *>(mlut + __byte_perm(wm, lanereg, 0x7624));
+        const uint32_t e3 = *reinterpret_cast<const uint32_t *>(mlut + __byte_perm(wm, lanereg, 0x7634));
+        sq += e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+        mx = max_u16x2(max_u16x2(mx, e0), e1); mx = max_u16x2(max_u16x2(mx, e2), e3);
+        bsum = kSigned ? __dp4a((int)wd[j], 0x01010101, bsum) : (int)__dp4a(wd[j], 0x01010101u, (uint32_t)bsum);
+    }
+    return make_uint2(sq, __byte_perm(mx, (uint32_t)bsum, 0x5410));
+}
+
 template <bool kSigned, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
 {
@@ -430,12 +463,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
     const int t = threadIdx.x;
     const uint32_t lane = t & 31;
     const uint32_t warp = __shfl_sync(0xFFFFFFFFu, (uint32_t)t >> 5, 0);
-    const uint32_t slot_s = shared_addr(smem + kLutBytes) + warp * (2 * kGSlotBytes);
-    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes + (size_t)kWarps * 2 * kGSlotBytes) + (size_t)warp * kGParts;
+    const uint8_t *mlut = smem + kLutBytes;
+    const uint32_t slot_s = shared_addr(smem + kLutBytes + kMlutBytes) + warp * (2 * kGSlotBytes);
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes + kMlutBytes + (size_t)kWarps * 2 * kGSlotBytes) + (size_t)warp * kGParts;
     uint2 *bpart = part + kGBf * kGLegs * kPst;
     const uint32_t bar_s = shared_addr(bars) + warp * 16;
 
     build_decode_lut_abs(lut, t, kWarps * 32);
+    build_meter_lut(reinterpret_cast<uint32_t *>(smem + kLutBytes), t, kWarps * 32);
     if (t < 2) {
         const enc_pk e = enc_pk_make(t);
         enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
@@ -549,7 +584,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
                     uint2 ph;
                     if (general) ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
                     else if ((open_mask >> g) & 1u) ph = leg_chunk_u<kSigned, 1>(lb, wh[g], adj_of(g), 0, acc);
-                    else ph = leg_chunk_u<kSigned, 0>(lb, wh[g], 0u, 0, acc);
+                    else ph = leg_chunk_shut<kSigned>(mlut, 4u * lane + (((lcur >> g) & 1u) << 7), wh[g]);
                     if (valid) part[(bfl * kGLegs + g) * kPst + c] = ph;
                 }
             }
@@ -689,7 +724,7 @@ template <bool kSigned, int kWarps>
 cudaError_t launch_fused_g(const igd_launch_cfg &c, const FusedParams &q)
 {
     auto kern = k_fused_g<kSigned, kWarps>;
-    const size_t smem = kLutBytes + (size_t)kWarps * 2 * kGSlotBytes + (size_t)kWarps * kGParts * 8;
+    const size_t smem = kLutBytes + kMlutBytes + (size_t)kWarps * 2 * kGSlotBytes + (size_t)kWarps * kGParts * 8;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long items = (q.total_bf + kGBf - 1) / kGBf;
