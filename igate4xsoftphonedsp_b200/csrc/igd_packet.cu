@@ -101,6 +101,40 @@ __global__ void __launch_bounds__(256) k_ed137_parse_tile(const uint8_t *__restr
     }
 }
 
+// Fields only (no payload wanted, e.g. the RX front-end feeding k_rx_track): one thread per packet
+// reads the three header words it needs -- 1-2 DRAM sectors per packet instead of the whole packet.
+__global__ void __launch_bounds__(256) k_ed137_fields(const uint8_t *__restrict__ pkts,
+                                                      const uint32_t *__restrict__ sizes, size_t npkts,
+                                                      size_t stride, igd_ed137_fields *__restrict__ fields)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npkts) return;
+    const uint32_t *pw = reinterpret_cast<const uint32_t *>(pkts + i * stride);
+    const uint32_t size = sizes ? sizes[i] : (uint32_t)stride;
+    const uint32_t navail = min(size, (uint32_t)stride) / 4;
+    const uint32_t w0 = navail > 0 ? __ldg(pw) : 0u, w3 = navail > 3 ? __ldg(pw + 3) : 0u, w4 = navail > 4 ? __ldg(pw + 4) : 0u;
+    const uint32_t pt = (w0 >> 8) & 0x7Fu;
+    const bool too_short = size < IGD_PKT_HDR;
+    const uint32_t plen_raw = size - IGD_PKT_HDR;
+    const bool dropped = too_short || plen_raw >= 1024u;
+    const bool accepted = !too_short && (pt == 8 || pt == 0 || pt == 18 || pt == 123);
+    igd_ed137_fields f;
+    const uint32_t word = accepted ? bswap32(w4) : 0u;
+    const igd_edf e = igd_ed137_fields_of(word);
+    f.word = word;
+    f.length_raw = accepted ? (uint16_t)(w3 >> 16) : (uint16_t)0;
+    f.payload_len = (uint16_t)(dropped ? 0u : min(plen_raw, (uint32_t)IGD_FRAME));
+    f.pt = (uint8_t)pt;
+    f.accepted = accepted;
+    f.keepalive = (!too_short && pt == 123);
+    f.ptt_type = (uint8_t)e.ptt_type;
+    f.ptt_id = (uint8_t)e.ptt_id;
+    f.squelch = (uint8_t)e.squelch;
+    f.bss = (uint8_t)e.bss;
+    f.flags = (uint8_t)(e.flags | (dropped ? IGD_EDF_DROPPED : 0u));
+    *reinterpret_cast<uint4 *>(fields + i) = *reinterpret_cast<const uint4 *>(&f);
+}
+
 __global__ void __launch_bounds__(256) k_ed137_parse(const uint8_t *__restrict__ pkts,
                                                      const uint32_t *__restrict__ sizes, size_t npkts,
                                                      size_t stride, igd_ed137_fields *__restrict__ fields,
@@ -641,6 +675,10 @@ cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, cons
                               size_t npkts, size_t stride, igd_ed137_fields *fields,
                               uint8_t *payload_out)
 {
+    if (!payload_out && npkts > 0) {
+        k_ed137_fields<<<(unsigned)((npkts + 255) / 256), 256, 0, c.stream>>>(pkts, sizes, npkts, stride, fields);
+        return cudaGetLastError();
+    }
     const bool al16 = ((reinterpret_cast<uintptr_t>(pkts) | reinterpret_cast<uintptr_t>(payload_out)) & 15) == 0;
     if (stride == IGD_PKT_MAX && al16 && npkts > 0) {
         const size_t tiles = (npkts + kPktTile - 1) / kPktTile;

@@ -63,6 +63,7 @@ pk = torch.randint(0, 256, (npk, 180), dtype=torch.uint8, device=dev, generator=
 pk[:, 0] = 0x90
 pk[:, 1] = 8
 timed("k_ed137_parse", lambda: vp.ed137_parse(pk), npk * (180 + 16 + 160), npk, "packets")
+timed("k_ed137_fields (header only)", lambda: vp.ed137_parse(pk, want_payload=False), npk * (20 + 16), npk, "packets")
 fields, payload = vp.ed137_parse(pk)
 st = torch.zeros((Cp, 4), dtype=torch.int32, device=dev)
 timed("k_rx_track", lambda: vp.rx_track(fields.reshape(Fp, Cp, 4), st), npk * 24, npk, "packets")
