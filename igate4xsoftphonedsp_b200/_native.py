@@ -70,6 +70,14 @@ class BatchDesc(C.Structure):
                 ("mix", C.c_void_p), ("enc", C.c_void_p), ("meter", C.c_void_p), ("bmeter", C.c_void_p)]
 
 
+class PacketsDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("F", C.c_int32), ("B", C.c_int32),
+                ("G", C.c_int32), ("flags", C.c_uint32),
+                ("pkts", C.c_void_p), ("fields", C.c_void_p), ("law", C.c_void_p), ("gain_q7", C.c_void_p),
+                ("out_law", C.c_void_p),
+                ("mix", C.c_void_p), ("enc", C.c_void_p), ("meter", C.c_void_p), ("bmeter", C.c_void_p)]
+
+
 class PackDesc(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("F", C.c_int32), ("C", C.c_int32),
                 ("flags", C.c_uint32), ("payload_len", C.c_uint32), ("out_stride", C.c_uint32),
@@ -121,6 +129,7 @@ SYMBOLS = {
     "igd_gain_q7": (_i, [C.c_float]),
     "igd_mix": (_i, [_vp, _vp, _vp, _sz, _sz, _i, _vp, _i]),
     "igd_process_batch": (_i, [_vp, C.POINTER(BatchDesc)]),
+    "igd_process_packets": (_i, [_vp, C.POINTER(PacketsDesc)]),
     "igd_event_summary": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _i]),
     "igd_ed137_parse": (_i, [_vp, _vp, _vp, _sz, _sz, _vp, _vp, _i]),
     "igd_calltype_flags": (C.c_uint, [C.c_char_p]),

@@ -471,6 +471,43 @@ int igd_process_batch(igd_ctx *c, const igd_batch_desc *d)
     return IGD_OK;
 }
 
+int igd_process_packets(igd_ctx *c, const igd_packets_desc *d)
+{
+    if (!c || !d || d->struct_size != sizeof(igd_packets_desc))
+        return fail(c, IGD_EINVAL, "igd_process_packets: bad descriptor");
+    if (d->F < 0 || d->B < 0) return fail(c, IGD_EINVAL, "igd_process_packets: bad shape");
+    if (d->G != 4)
+        return fail(c, IGD_EINVAL, "igd_process_packets: G must be 4 (use igd_ed137_parse + igd_process_batch)");
+    if (d->F == 0 || d->B == 0) return IGD_OK;
+    if (!d->pkts || !d->fields || !d->law || !d->gain_q7 || !d->out_law || !d->mix || !d->enc || !d->meter || !d->bmeter)
+        return fail(c, IGD_EINVAL, "igd_process_packets: null buffer");
+    const size_t F = d->F, B = d->B, C = B * 4;
+    Bind b(c);
+    if (d->mem == IGD_MEM_DEVICE &&
+        (!aligned(d->pkts, 16) || !aligned(d->fields, 16) || !aligned(d->mix, 32) || !aligned(d->enc, 16) ||
+         !aligned(d->meter, 16) || !aligned(d->gain_q7, 8) || !aligned(d->law, 4) || !aligned(d->bmeter, 4)))
+        return fail(c, IGD_EINVAL, "igd_process_packets: misaligned device pointer");
+    igd_packets_desc k = *d;
+    k.mem = IGD_MEM_DEVICE;
+    int rc;
+    if ((rc = in_arg(c, d->mem, 0, d->pkts, F * C * IGD_PKT_MAX, &k.pkts))) return rc;
+    if ((rc = in_arg(c, d->mem, 1, d->fields, F * C, &k.fields))) return rc;
+    if ((rc = in_arg(c, d->mem, 2, d->law, C, &k.law))) return rc;
+    if ((rc = in_arg(c, d->mem, 3, d->gain_q7, F * C, &k.gain_q7))) return rc;
+    if ((rc = in_arg(c, d->mem, 4, d->out_law, B, &k.out_law))) return rc;
+    if ((rc = out_arg(c, d->mem, 5, d->mix, F * B * IGD_FRAME, &k.mix))) return rc;
+    if ((rc = out_arg(c, d->mem, 6, d->enc, F * B * IGD_FRAME, &k.enc))) return rc;
+    if ((rc = out_arg(c, d->mem, 7, d->meter, F * C, &k.meter))) return rc;
+    if ((rc = out_arg(c, d->mem, 8, d->bmeter, F * B, &k.bmeter))) return rc;
+    IGD_CUDA(c, igd_k_fused_packets(cfg_of(c), k));
+    c->launches++;
+    if ((rc = out_done(c, d->mem, d->mix, k.mix, F * B * IGD_FRAME))) return rc;
+    if ((rc = out_done(c, d->mem, d->enc, k.enc, F * B * IGD_FRAME))) return rc;
+    if ((rc = out_done(c, d->mem, d->meter, k.meter, F * C))) return rc;
+    if ((rc = out_done(c, d->mem, d->bmeter, k.bmeter, F * B))) return rc;
+    return finish(c, d->mem);
+}
+
 // ---------------------------------------------------------------- summary
 int igd_event_summary(igd_ctx *c, const igd_meter_rec *meter, const uint16_t *gain, size_t F, size_t C,
                       igd_summary_rec *out, igd_summary_db *db, int mem)

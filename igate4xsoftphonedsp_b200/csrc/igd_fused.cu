@@ -31,6 +31,7 @@ struct FusedParams {
     uint8_t *enc;
     igd_meter_rec *meter;
     igd_bridge_rec *bmeter;
+    const igd_ed137_fields *fields;   // packet form only: [F][C], payload_len is read
     long long total_bf;   // F*B bridge-frames
     long long num_tiles;
     int B, G;
@@ -152,8 +153,9 @@ constexpr int kC32 = IGD_FRAME / 32;      // lanes per bridge-frame = 5
 // works on the 16-sample chunks (c + rot(bfl)) % 10 and that + 5; the per-bridge-frame rotation
 // (0,5,0,7,3,0) is the brute-forced minimum of LDS.128 bank conflicts for this layout (12
 // wavefronts instead of 8 per leg; padding the slot instead would cost six copies per item).
-template <int G> struct slot_geom {
-    static constexpr int kBfBytes = G * IGD_FRAME;
+template <int G, bool kPkt = false> struct slot_geom {
+    static constexpr int kLegBytes = kPkt ? IGD_PKT_MAX : IGD_FRAME;   // packet form: the raw 180-byte packets
+    static constexpr int kBfBytes = G * kLegBytes;
     static constexpr int kSlotBytes = kBfPerItem * kBfBytes;
 };
 __device__ __forceinline__ uint32_t chunk_rotation(uint32_t bfl) { return (0x037050u >> (4 * bfl)) & 0xFu; }
@@ -213,12 +215,29 @@ __device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32
     return make_uint2(sq, __byte_perm(mx, (uint32_t)bsum, 0x5410));   // {sq, peak/4 | bsum << 16}
 }
 
-template <int G, bool kSigned, int kWarps>
+// payload bytes past `rem` (bytes of payload left at this chunk's start) read as zero, like the
+// payload array igd_ed137_parse writes
+__device__ __forceinline__ uint4 clip_chunk(uint4 w, int rem)
+{
+    uint32_t v[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int rb = rem - 4 * k;
+        v[k] = rb >= 4 ? v[k] : rb <= 0 ? 0u : (v[k] & ((1u << (8 * rb)) - 1u));
+    }
+    return make_uint4(v[0], v[1], v[2], v[3]);
+}
+
+// kPkt: the codes are read straight out of the raw ED-137 packets ([F][C][180], payload at byte 20,
+// payload_len from the parsed fields) -- the item is still ONE contiguous bulk copy (6 * G * 180 B),
+// the payload array between igd_ed137_parse and this kernel is never materialised.
+template <int G, bool kSigned, int kWarps, bool kPkt = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
 {
     static_assert(kBfPerItem * G + kBfPerItem <= 32, "finish needs one lane per record");
-    using geom = slot_geom<G>;
-    constexpr int kLegParts = kBfPerItem * G * kPst, kBrParts = kBfPerItem * kPst;
+    using geom = slot_geom<G, kPkt>;
+    constexpr int kP = kPkt ? kChunks : kPst;      // partial stride: the bigger packet slots leave no room for the pad column
+    constexpr int kLegParts = kBfPerItem * G * kP, kBrParts = kBfPerItem * kP;
     __shared__ uint64_t bars[kWarps];
     __shared__ __align__(16) uint32_t enc_tab[2][8];
     extern __shared__ __align__(128) uint8_t smem[];
@@ -282,11 +301,20 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         }
         return r | ((uint32_t)(__ldg(q.out_law + bb) & 1u) << 8);
     };
+    auto load_plens = [&](uint32_t bfi) -> uint32_t {    // packet form: the G payload lengths (<= 160) of a bridge-frame, one byte each
+        uint32_t r = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            r |= min((uint32_t)__ldg(&q.fields[(size_t)bfi * G + g].payload_len), (uint32_t)IGD_FRAME) << (8 * g);
+        return r;
+    };
+    constexpr uint32_t kFullPlens = G == 4 ? 0xA0A0A0A0u : G == 3 ? 0x00A0A0A0u : G == 2 ? 0x0000A0A0u : 0x000000A0u;
     uint2 gq = make_uint2(0u, 0u);
-    uint32_t lwq = 0u;
+    uint32_t lwq = 0u, plq = kFullPlens;
     if (worker && item < items && item * kBfPerItem + bfl < total_bf) {
         gq = load_gains<G>(q.gain + (size_t)(item * kBfPerItem + bfl) * G);
         lwq = load_laws(b);
+        if (kPkt) plq = load_plens(item * kBfPerItem + bfl);
     }
 
     for (uint32_t it = 0; item < items; item += nw, it++) {
@@ -294,7 +322,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         const uint32_t next = item + nw;
         mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
         const uint2 gcur = gq;
-        const uint32_t lcur = lwq;
+        const uint32_t lcur = lwq, plcur = plq;
         const bool valid = worker && bf < total_bf;
         {
             b += b_step;
@@ -303,6 +331,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             if (worker && next < items && bfn < total_bf) {      // next item's gains and laws ride in three registers
                 gq = load_gains<G>(q.gain + (size_t)bfn * G);
                 lwq = load_laws(b);
+                if (kPkt) plq = load_plens(bfn);
             }
         }
         // every lane runs the same instruction stream (idle / tail lanes on stale bytes with all
@@ -317,16 +346,31 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         // open legs of this lane's bridge-frame, pre-shifted into the high half of the bridge partial
         // (every one of the ten partials carries it; the finish divides the sum by ten)
         const uint32_t n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y))) << 16;
+        // packet form: some packet of this item is shorter than 180 bytes (keep-alive, truncated) -> clip its chunks
+        const bool ragged = kPkt && __any_sync(0xFFFFFFFFu, valid && plcur != kFullPlens);
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const uint32_t ch = h == 0 ? c0 : (c0 >= (uint32_t)kC32 ? c0 - kC32 : c0 + kC32);   // this pass's chunk
             uint4 wh[G];
 #pragma unroll
-            for (int g = 0; g < G; g++)
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                             : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
-                             : "r"(src + g * IGD_FRAME + ch * 16));
-            uint2 *mypart = part + bfl * (G * kPst) + ch;
+            for (int g = 0; g < G; g++) {
+                if (!kPkt) {
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
+                                 : "r"(src + g * IGD_FRAME + ch * 16));
+                } else {          // payload at byte 20 of a 180-byte packet: 4-byte aligned only
+                    const uint32_t a = src + g * IGD_PKT_MAX + IGD_PKT_HDR + ch * 16;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wh[g].x) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(wh[g].y) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(wh[g].z) : "r"(a));
+                    asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(wh[g].w) : "r"(a));
+                }
+            }
+            if (kPkt && ragged) {
+#pragma unroll
+                for (int g = 0; g < G; g++) wh[g] = clip_chunk(wh[g], (int)((plcur >> (8 * g)) & 0xFFu) - (int)ch * 16);
+            }
+            uint2 *mypart = part + bfl * (G * kP) + ch;
             int acc[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) acc[i] = 0;
@@ -336,14 +380,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                     const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
                     const uint2 ph = (open_mask >> g) & 1u ? leg_chunk_u<kSigned, 1>(lb, wh[g], adj_of(g), 0, acc)
                                                            : leg_chunk_u<kSigned, 0>(lb, wh[g], 0u, 0, acc);
-                    if (valid) mypart[g * kPst] = ph;
+                    if (valid) mypart[g * kP] = ph;
                 }
             } else {               // arbitrary Q7 gains: multiply, shift, clip
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
                     const uint2 ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
-                    if (valid) mypart[g * kPst] = ph;
+                    if (valid) mypart[g * kP] = ph;
                 }
             }
             if (h == 1) {
@@ -366,14 +410,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             }
             const uint32_t o16 = bf * kChunks + ch;     // 16-sample chunk index of the outputs
             const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)o16 * 16, q.enc + (size_t)o16 * 16, valid);
-            if (valid) bpart[bfl * kPst + ch] = make_uint2(mo.x, mo.y | n_open16);
+            if (valid) bpart[bfl * kP + ch] = make_uint2(mo.x, mo.y | n_open16);
         }
         __syncwarp();
         // ---- finish: one lane per record (leg records, then bridge records: bpart follows part,
         // and both kinds of partial are {sum, max | sum << 16}, so the ten-partial walk is shared)
         {
             const uint32_t bf0 = item * kBfPerItem;
-            const uint2 *src_p = part + lane * kPst;
+            const uint2 *src_p = part + lane * kP;
             unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
             if (lane < kBfPerItem * G + kBfPerItem) {
 #pragma unroll
@@ -705,12 +749,13 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
 
 // ============================================================ launchers
 namespace {
-template <int G, bool kSigned, int kWarps>
+template <int G, bool kSigned, int kWarps, bool kPkt = false>
 cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
 {
-    auto kern = k_fused_w<G, kSigned, kWarps>;
-    const size_t smem = kLutBytes + (size_t)kWarps * slot_geom<G>::kSlotBytes +
-                        (size_t)kWarps * (kBfPerItem * G * kPst + kBfPerItem * kPst) * 8;
+    auto kern = k_fused_w<G, kSigned, kWarps, kPkt>;
+    constexpr int kP = kPkt ? kChunks : kPst;
+    const size_t smem = kLutBytes + (size_t)kWarps * slot_geom<G, kPkt>::kSlotBytes +
+                        (size_t)kWarps * (kBfPerItem * G * kP + kBfPerItem * kP) * 8;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const long long items = (q.total_bf + kBfPerItem - 1) / kBfPerItem;
@@ -758,6 +803,7 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     FusedParams q;
     q.codes = d.codes; q.law = d.law; q.gain = d.gain_q7; q.out_law = d.out_law;
     q.mix = d.mix; q.enc = d.enc; q.meter = d.meter; q.bmeter = d.bmeter;
+    q.fields = nullptr;
     q.total_bf = (long long)d.F * d.B;
     q.num_tiles = 0;
     q.B = d.B; q.G = d.G; q.flags = d.flags;
@@ -778,4 +824,19 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
         !getenv("IGD_FUSED_ANYG"))
         return sc ? launch_fused_g<true, 24>(c, q) : launch_fused_g<false, 24>(c, q);
     return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
+}
+
+// packets in: [F][B*4][180] raw ED-137 packets + their parsed fields (payload_len) instead of codes
+cudaError_t igd_k_fused_packets(const igd_launch_cfg &c, const igd_packets_desc &d)
+{
+    FusedParams q;
+    q.codes = d.pkts; q.fields = d.fields; q.law = d.law; q.gain = d.gain_q7; q.out_law = d.out_law;
+    q.mix = d.mix; q.enc = d.enc; q.meter = d.meter; q.bmeter = d.bmeter;
+    q.total_bf = (long long)d.F * d.B;
+    q.num_tiles = 0;
+    q.B = d.B; q.G = d.G; q.flags = d.flags;
+    if (d.G != 4 || q.total_bf >= (1ll << 28) || (reinterpret_cast<uintptr_t>(d.gain_q7) & 7u) ||
+        (reinterpret_cast<uintptr_t>(d.law) & 3u))
+        return cudaErrorInvalidValue;
+    return (d.flags & IGD_F_SIGNED_CHAR) ? launch_fused_w<4, true, 24, true>(c, q) : launch_fused_w<4, false, 24, true>(c, q);
 }

@@ -33,6 +33,7 @@ cudaError_t igd_k_level_percent(const igd_launch_cfg &c, const int32_t *v, size_
 cudaError_t igd_k_mix(const igd_launch_cfg &c, const int16_t *pcm, const uint16_t *gain,
                       size_t nframes, size_t nbridges, int legs, int16_t *mix);
 cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d);
+cudaError_t igd_k_fused_packets(const igd_launch_cfg &c, const igd_packets_desc &d);
 cudaError_t igd_k_event_summary(const igd_launch_cfg &c, const igd_meter_rec *meter,
                                 const uint16_t *gain, size_t F, size_t C, igd_summary_rec *out,
                                 igd_summary_db *db);

@@ -293,6 +293,42 @@ class VoicePath:
         self._chk(self._lib.igd_process_batch(self._h, C.byref(d)))
         return o
 
+    def process_packets(self, pkts, fields, law, gain_q7, out_law, legs=4, flags=0, out=None):
+        """process_batch with the codes read straight out of the raw ED-137 packets.
+
+        pkts u8 [F][B*legs][180] as received; fields [F][B*legs] from ed137_parse (payload_len
+        is read; payload bytes past it count as zero); the rest as process_batch.  Identical
+        results to ed137_parse(...)[1] fed to process_batch; legs must be 4.
+        """
+        mem = self._mode(pkts, fields, law, gain_q7, out_law)
+        F, Cn, n = pkts.shape
+        if n != N.PKT_MAX or Cn % legs:
+            raise IgdError("pkts must be [F][B*legs][180]")
+        B = Cn // legs
+        if mem == N.MEM_DEVICE:
+            if pkts.dtype != torch.uint8 or law.dtype != torch.uint8 or out_law.dtype != torch.uint8:
+                raise IgdError("pkts/law/out_law must be uint8")
+            o = out if out is not None else self.alloc_outputs(F, B, legs)
+        else:
+            pkts = np.ascontiguousarray(pkts, dtype=np.uint8)
+            fields = np.ascontiguousarray(fields, dtype=N.FIELDS_DT)
+            law = np.ascontiguousarray(law, dtype=np.uint8)
+            gain_q7 = np.ascontiguousarray(gain_q7, dtype=np.uint16)
+            out_law = np.ascontiguousarray(out_law, dtype=np.uint8)
+            o = out if out is not None else {
+                "mix": np.empty((F, B, N.FRAME), dtype=np.int16),
+                "enc": np.empty((F, B, N.FRAME), dtype=np.uint8),
+                "meter": np.empty((F, Cn), dtype=N.METER_DT),
+                "bmeter": np.empty((F, B), dtype=N.BRIDGE_DT),
+            }
+        if law.shape[0] != Cn or out_law.shape[0] != B or tuple(gain_q7.shape) != (F, Cn):
+            raise IgdError("law / out_law / gain_q7 shapes do not match pkts")
+        d = N.PacketsDesc(C.sizeof(N.PacketsDesc), mem, F, B, legs, flags,
+                          self._ptr(pkts), self._ptr(fields), self._ptr(law), self._ptr(gain_q7), self._ptr(out_law),
+                          self._ptr(o["mix"]), self._ptr(o["enc"]), self._ptr(o["meter"]), self._ptr(o["bmeter"]))
+        self._chk(self._lib.igd_process_packets(self._h, C.byref(d)))
+        return o
+
     # ------------------------------------------------------------ summary
     def event_summary(self, meter, gain_q7, want_db=True):
         """meter [F][C] records, gain_q7 [F][C] -> (summary [C], db [C])."""

@@ -307,6 +307,34 @@ int igd_ed137_pack(igd_ctx *ctx, const igd_ed137_pack_desc *d);
 int igd_ed137_keepalive(igd_ctx *ctx, uint8_t *hdr20, igd_ed137_state *state, size_t C, int64_t now_ms,
                         uint32_t *sizes, int mem);
 
+/* ------------------------------------------- fused voice path, packets in
+ * The same computation as igd_process_batch with the codes read straight out
+ * of the raw ED-137 packets: pkts [F][B*G][IGD_PKT_MAX] as received
+ * (transport_rtp_cb, TransportAdapter.cpp:240-316: payload = bytes 20..size),
+ * fields [F][B*G] from igd_ed137_parse (payload_len is read: payload bytes
+ * past it count as zero, exactly the payload array igd_ed137_parse would
+ * write).  Results are identical to igd_ed137_parse(payload_out) followed by
+ * igd_process_batch on that payload; the payload array is never materialised.
+ * G must be 4 (the reference's four radios per softphone, roip_ed137.cpp:130-139);
+ * other leg counts take the two-call form (IGD_EINVAL here).  Device pointers:
+ * pkts 16-byte aligned, the rest as for igd_process_batch.                       */
+typedef struct {
+    uint32_t struct_size;        /* = sizeof(igd_packets_desc)                    */
+    int32_t mem;
+    int32_t F, B, G;
+    uint32_t flags;              /* IGD_F_SIGNED_CHAR                             */
+    const uint8_t *pkts;
+    const igd_ed137_fields *fields;
+    const uint8_t *law;
+    const uint16_t *gain_q7;
+    const uint8_t *out_law;
+    int16_t *mix;
+    uint8_t *enc;
+    igd_meter_rec *meter;
+    igd_bridge_rec *bmeter;
+} igd_packets_desc;
+int igd_process_packets(igd_ctx *ctx, const igd_packets_desc *d);
+
 /* -------------------------------------------------- RX liveness / call events
  * replaces: the receive-side state transport_rtp_cb keeps per call
  * (TransportAdapter.cpp:240-316: ed137_value / payloadsize latch :252-256,

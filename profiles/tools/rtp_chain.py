@@ -2,7 +2,8 @@
 """SURVEY.md 8(d) "with RTP" accounting: the whole path on device-resident buffers, raw ED-137 packets in ->
 ED-137 packets out, at the bench shape (4096 channels x 1640 frames):
 
-    k_ed137_parse_tile -> k_rx_track -> k_gate_arbitrate -> k_fused_w -> ed137_pack (plan + assemble)
+    k_ed137_fields -> k_rx_track -> k_gate_arbitrate -> k_fused_w<packets> -> ed137_pack (plan + assemble)
+    (IGD_CHAIN_TWO_CALL=1: k_ed137_parse_tile with payload -> ... -> k_fused_w on the payload array)
 
 Prints one JSON object: channel-samples/s of the chain, per-stage device times (CUDA events), the
 algorithmic figure (1284 B per bridge-frame = 1184 core + 20 (G + 1) header bytes) and the bytes the chain
@@ -60,18 +61,25 @@ names = ("parse", "rx_track", "gate_arbitrate", "fused", "pack")
 res = {}
 
 
+FUSED_PKT = os.environ.get("IGD_CHAIN_TWO_CALL", "") == ""      # default: the fused kernel reads the packets itself
+pk3 = pk.view(F, C, 180)
+
+
 def chain(ev=None):
     def mark(i):
         if ev is not None:
             ev[i].record()
     mark(0)
-    fields, payload = vp.ed137_parse(pk)
+    fields, payload = vp.ed137_parse(pk, want_payload=not FUSED_PKT)
     mark(1)
     events = vp.rx_track(fields.view(F, C, 4), rx_state)
     mark(2)
     gain = vp.gate_arbitrate(events, legs, bridges, G, N.ARB_CLIENT_PTT)
     mark(3)
-    vp.process_batch(payload.view(F, C, 160), law, gain, out_law, G, out=out)
+    if FUSED_PKT:
+        vp.process_packets(pk3, fields, law, gain, out_law, G, out=out)
+    else:
+        vp.process_batch(payload.view(F, C, 160), law, gain, out_law, G, out=out)
     mark(4)
     pkts, sizes, bm = vp.ed137_pack(rtp12, out["enc"], tx_state, ctl)
     mark(5)
@@ -94,10 +102,10 @@ acc /= steps
 tot /= steps
 fields, events, gain, pkts, sizes = res["last"]
 open_frac = float((gain != 0).float().mean())
-moved = F * (C * (180 + 160 + 16)            # parse: packets in, payload + fields out
+moved = F * ((C * (64 + 16) + B * (1184 + 80 + 64) if FUSED_PKT       # header sectors in, fields out; fused reads whole packets + fields
+              else C * (180 + 160 + 16) + B * 1184)                     # parse: packets in, payload + fields out; fused on the payload
              + C * (16 + 8)                   # rx_track: fields in, events out
              + C * (8 + 2)                    # gate_arbitrate: events in, gains out
-             + B * 1184                       # fused
              + B * (12 + 160 + 8 + 180 + 5))  # pack: header + payload + control in, packet + size + level out
 alg = F * B * (1184 + 20 * (G + 1))
 peak = 6552.6
@@ -106,6 +114,7 @@ try:
 except Exception:
     pass
 print(json.dumps({
+    "form": "fields-only parse + igd_process_packets" if FUSED_PKT else "igd_ed137_parse (payload) + igd_process_batch",
     "workload": f"{C} channels ({B} bridges x {G} legs) x {F} frames, raw 180-byte ED-137 packets in, {B} x {F} packets out",
     "ms_per_step": tot, "channel_samples_per_s": C * F * 160 / (tot * 1e-3),
     "stage_ms": {n: round(float(t), 4) for n, t in zip(names, acc)},

@@ -1,0 +1,76 @@
+"""GPU parity of igd_process_packets (the fused path reading the codes straight out of the raw
+ED-137 packets) against the oracle on the payload igd_ed137_parse extracts from the same packets:
+transport_rtp_cb's payload rule (TransportAdapter.cpp:240-316: bytes 20..size, nothing for a
+keep-alive / truncated / dropped packet) composed with the decode -> meter -> mix -> encode path."""
+import numpy as np
+import pytest
+import torch
+
+import oracle_py as O
+import igate4xsoftphonedsp_b200 as ig
+from igate4xsoftphonedsp_b200 import _native as N
+from test_gpu_fused import check
+
+pytestmark = pytest.mark.gpu
+G = 4
+
+
+def make(F, B, seed, ragged, gains=(0, 0, 256)):
+    rng = np.random.default_rng(seed)
+    Cn = B * G
+    pk = rng.integers(0, 256, (F, Cn, 180), dtype=np.uint8)
+    pk[..., 0] = 0x90
+    pk[..., 1] = rng.choice(np.array([8, 0, 8, 0, 123, 18, 96], np.uint8), (F, Cn))
+    if ragged:
+        sizes = rng.choice(np.array([180, 180, 180, 180, 20, 12, 100, 21, 179, 37, 8, 200, 1100, 0], np.uint32), (F, Cn))
+    else:
+        sizes = np.full((F, Cn), 180, np.uint32)
+    law = rng.integers(0, 2, Cn).astype(np.uint8)
+    out_law = rng.integers(0, 2, B).astype(np.uint8)
+    gain = rng.choice(np.array(gains, np.uint16), (F, Cn))
+    return pk, sizes, law, gain, out_law
+
+
+def want_of(vp, pk, sizes, law, gain, out_law, signed=0):
+    F, Cn, _ = pk.shape
+    fields, payload = vp.ed137_parse(pk.reshape(F * Cn, 180), sizes.reshape(-1))
+    return fields.reshape(F, Cn), O.process_batch(payload.reshape(F, Cn, 160), law, gain, out_law, G,
+                                                  signed_char=signed, threads=8)
+
+
+@pytest.mark.parametrize("F,B,ragged", [(7, 5, True), (3, 1, True), (1, 1, False), (40, 64, False), (50, 333, True),
+                                        (77, 250, False)])
+def test_packets_in_equals_parse_then_process_batch(vp, F, B, ragged):
+    pk, sizes, law, gain, out_law = make(F, B, 100 * F + B, ragged)
+    fields, want = want_of(vp, pk, sizes, law, gain, out_law)
+    check(vp.process_packets(pk, fields, law, gain, out_law), want)
+
+
+def test_packets_in_general_gains_and_signed_char(vp):
+    pk, sizes, law, gain, out_law = make(9, 13, 5, True, gains=(0, 13, 64, 128, 256, 300))
+    fields, want = want_of(vp, pk, sizes, law, gain, out_law, signed=1)
+    check(vp.process_packets(pk, fields, law, gain, out_law, flags=ig.F_SIGNED_CHAR), want)
+
+
+def test_packets_in_device_pointers_repeated_launches(vp):
+    """many items per warp, L2-resident packets, device buffers: every launch equals the oracle."""
+    F, B = 60, 400
+    pk, sizes, law, gain, out_law = make(F, B, 77, True)
+    fields, want = want_of(vp, pk, sizes, law, gain, out_law)
+    dev = "cuda:0"
+    d = [torch.from_numpy(a).to(dev) for a in (pk, fields.view(np.int32).reshape(F, B * G, 4), law,
+                                               gain.view(np.int16), out_law)]
+    for rep in range(4):
+        r = vp.process_packets(*d)
+        torch.cuda.synchronize()
+        got = {"mix": r["mix"].cpu().numpy(), "enc": r["enc"].cpu().numpy(),
+               "meter": r["meter"].cpu().numpy().view(ig.METER_DT).reshape(F, B * G),
+               "bmeter": r["bmeter"].cpu().numpy().view(ig.BRIDGE_DT).reshape(F, B)}
+        check(got, want)
+
+
+def test_packets_in_rejects_other_leg_counts(vp):
+    pk = np.zeros((1, 6, 180), np.uint8)
+    with pytest.raises(ig.IgdError):
+        vp.process_packets(pk, np.zeros((1, 6), N.FIELDS_DT), np.zeros(6, np.uint8), np.zeros((1, 6), np.uint16),
+                           np.zeros(2, np.uint8), legs=3)
