@@ -76,6 +76,25 @@ def once():
     return out
 
 
+# ---- the packet form of the fused kernel (same slot refill, 4320-byte items): device inputs, many launches
+pk_d = torch.from_numpy(pk.reshape(F, Cn, 180)).to(dev)
+sz = rng.choice(np.array([180, 180, 180, 20, 100, 179], np.uint32), F * Cn)
+fields_h, _ = vp.ed137_parse(pk, sz, want_payload=False)
+fields_d = torch.from_numpy(fields_h.view(np.int32).reshape(F * Cn, 4)).to(dev)
+law_d, ol_d = torch.from_numpy(synth.laws(Cn)).to(dev), torch.from_numpy(synth.out_laws(Cn // G)).to(dev)
+gain_d = torch.from_numpy(synth.gains(F, Cn // G, G).view(np.int16)).to(dev)
+refp = None
+for r in range(300):
+    o = vp.process_packets(pk_d, fields_d, law_d, gain_d, ol_d)
+    h = tuple(int(o[k].view(torch.uint8).to(torch.int64).sum()) ^ int((o[k].view(torch.uint8).flatten().to(torch.int64) *
+              (torch.arange(o[k].numel() * o[k].element_size(), device=dev) % 1000003 + 1)).sum()) for k in ("mix", "enc", "meter", "bmeter"))
+    if refp is None:
+        refp = h
+    elif h != refp:
+        bad += 1
+        print(f"MISMATCH process_packets rep {r}")
+print("process_packets: 300 runs identical" if bad == 0 else f"mismatches {bad}")
+
 ref = once()
 names = ("parse", "pack", "rx_track", "arb_client", "arb_server", "summary", "wav_images")
 for r in range(40):
