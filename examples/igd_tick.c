@@ -1,6 +1,7 @@
 /* igd_tick.c -- the C ABI from plain C (C99): one 20 ms tick of a 4-radio bridge through the GPU path.
  *   gcc -std=c99 -Iinclude examples/igd_tick.c -Ligate4xsoftphonedsp_b200 -ligate_dsp -o igd_tick
- * Packets in -> parse -> receive-side liveness -> PTT arbitration -> decode/meter/mix/encode -> levels. */
+ * Packets in -> header parse -> receive-side liveness -> PTT arbitration -> decode/meter/mix/encode straight
+ * out of the packets (igd_process_packets; the payload array is never materialised) -> levels. */
 #include <stdio.h>
 #include <string.h>
 
@@ -16,7 +17,7 @@ int main(void)
         fprintf(stderr, "igd_init failed: %d\n", rc);
         return 1;
     }
-    static uint8_t pkts[C][IGD_PKT_MAX], payload[C][IGD_FRAME];
+    static uint8_t pkts[C][IGD_PKT_MAX];
     uint32_t sizes[C];
     for (int c = 0; c < C; c++) {              /* radio c keys PTT type c (0 = idle ... 3 = priority) */
         const uint32_t word = (uint32_t)c << 29;
@@ -28,7 +29,7 @@ int main(void)
         sizes[c] = IGD_PKT_MAX;
     }
     igd_ed137_fields fields[C];
-    rc = igd_ed137_parse(ctx, &pkts[0][0], sizes, C, IGD_PKT_MAX, fields, &payload[0][0], IGD_MEM_HOST);
+    rc = igd_ed137_parse(ctx, &pkts[0][0], sizes, C, IGD_PKT_MAX, fields, NULL /* no payload array */, IGD_MEM_HOST);
 
     igd_rx_state rxs[C];
     igd_rx_event ev[C];
@@ -49,9 +50,9 @@ int main(void)
     static uint8_t enc[B][IGD_FRAME];
     igd_meter_rec meter[C];
     igd_bridge_rec bm[B];
-    igd_batch_desc d = {sizeof d, IGD_MEM_HOST, F, B, G, 0, &payload[0][0], law, gain, out_law,
-                        &mix[0][0], &enc[0][0], meter, bm};
-    if (rc == IGD_OK) rc = igd_process_batch(ctx, &d);
+    igd_packets_desc d = {sizeof d, IGD_MEM_HOST, F, B, G, 0, &pkts[0][0], fields, law, gain, out_law,
+                          &mix[0][0], &enc[0][0], meter, bm};
+    if (rc == IGD_OK) rc = igd_process_packets(ctx, &d);
     if (rc != IGD_OK) {
         fprintf(stderr, "error %d: %s\n", rc, igd_last_error(ctx));
         igd_shutdown(ctx);
