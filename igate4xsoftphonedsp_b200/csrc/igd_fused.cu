@@ -169,6 +169,31 @@ __device__ __forceinline__ void build_decode_lut_abs(uint32_t *lut, int tid, int
         lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)(abs(x) >> 2) & 0xFFFFu);
     }
 }
+// Wide form (k_fused_g): 8-byte entries {(|x|/4)^2, |x|/4 | clamp16(2x) << 16} -- the square comes
+// out of the table with the sample (one LDS.64), so the meter needs no extract and no multiply per
+// sample.  Row = code, 16 columns of 8 bytes (128 B, the same 64 KB as 32 columns of 4 bytes): a
+// 64-bit shared load is served per half-warp, lanes l and l + 16 share a column, no bank conflicts.
+// Twice the shared-memory bytes per lookup: +5..7 % for k_fused_g (one chunk per lane, issue-bound),
+// -26 % for k_fused_w at G = 4, which then sits on the shared-memory bandwidth at every gate density.
+__device__ __forceinline__ void build_decode_lut_wide(uint32_t *lut, int tid, int nthreads)
+{
+    uint2 *lut2 = reinterpret_cast<uint2 *>(lut);
+    for (int i = tid; i < 2 * 256 * 16; i += nthreads) {
+        const uint32_t law = (uint32_t)i >> 12, code = ((uint32_t)i >> 4) & 255u;
+        const int x = law ? igd_ulaw2lin(code) : igd_alaw2lin(code);
+        const int y2 = min(max(2 * x, -32768), 32767);
+        const uint32_t q = (uint32_t)(abs(x) >> 2);
+        lut2[i] = make_uint2(q * q, ((uint32_t)y2 << 16) | q);
+    }
+}
+template <int K>
+__device__ __forceinline__ uint2 lut_lookup2(uint32_t lane_base, uint32_t word)
+{
+    const uint32_t a = __dp4a(word, 0x80u << (8 * K), lane_base);
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
 
 // bit 15 / 31 set for every non-zero 16-bit half of x
 __device__ __forceinline__ uint32_t nonzero_halves(uint32_t x)
@@ -179,7 +204,7 @@ __device__ __forceinline__ uint32_t nonzero_halves(uint32_t x)
 // decode + meter + gain/accumulate one 16-sample chunk of one leg (|x|/4 table)
 // kMode: 0 = gate shut for the whole warp (meter only), 1 = gain 2.0 or shut through the
 //        IDP.2A selector (0x0100 / 0), 2 = arbitrary Q7 gain (multiply, shift, clip)
-template <bool kSigned, int kMode>
+template <bool kSigned, int kMode, bool kWide = false>
 __device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32_t sel, int adj, int (&acc)[16])
 {
     const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
@@ -188,14 +213,20 @@ __device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32
     int bsum = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const uint32_t e0 = lut_lookup<0>(lane_base, wd[j]);
-        const uint32_t e1 = lut_lookup<1>(lane_base, wd[j]);
-        const uint32_t e2 = lut_lookup<2>(lane_base, wd[j]);
-        const uint32_t e3 = lut_lookup<3>(lane_base, wd[j]);
-        // |x|/4 out of the low half on the ALU pipe (LOP3): everything else in this loop body is
-        // IDP/IMAD on the FMA pipe, which bounds this phase (measured: any IDP.2A here is slower)
-        const uint32_t x0 = e0 & 0xFFFFu, x1 = e1 & 0xFFFFu, x2 = e2 & 0xFFFFu, x3 = e3 & 0xFFFFu;
-        sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+        uint32_t e0, e1, e2, e3;
+        if (kWide) {
+            const uint2 t0 = lut_lookup2<0>(lane_base, wd[j]), t1 = lut_lookup2<1>(lane_base, wd[j]);
+            const uint2 t2 = lut_lookup2<2>(lane_base, wd[j]), t3 = lut_lookup2<3>(lane_base, wd[j]);
+            e0 = t0.y; e1 = t1.y; e2 = t2.y; e3 = t3.y;
+            sq += (t0.x + t1.x) + (t2.x + t3.x);      // the squares ride in the table: two IADD3 per four samples
+        } else {
+            e0 = lut_lookup<0>(lane_base, wd[j]); e1 = lut_lookup<1>(lane_base, wd[j]);
+            e2 = lut_lookup<2>(lane_base, wd[j]); e3 = lut_lookup<3>(lane_base, wd[j]);
+            // |x|/4 out of the low half on the ALU pipe (LOP3): everything else in this loop body is
+            // IDP/IMAD on the FMA pipe, which bounds this phase (measured: any IDP.2A here is slower)
+            const uint32_t x0 = e0 & 0xFFFFu, x1 = e1 & 0xFFFFu, x2 = e2 & 0xFFFFu, x3 = e3 & 0xFFFFu;
+            sq += x0 * x0 + x1 * x1 + x2 * x2 + x3 * x3;
+        }
         mx = max_u16x2(max_u16x2(mx, e0), e1); mx = max_u16x2(max_u16x2(mx, e2), e3);
         bsum = kSigned ? __dp4a((int)wd[j], 0x01010101, bsum) : (int)__dp4a(wd[j], 0x01010101u, (uint32_t)bsum);
         if (kMode == 1) {
@@ -204,6 +235,7 @@ __device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32
             acc[4 * j + 2] = dp2a_lo(e2, sel, acc[4 * j + 2]);
             acc[4 * j + 3] = dp2a_lo(e3, sel, acc[4 * j + 3]);
         } else if (kMode == 2) {
+            const uint32_t x0 = e0 & 0xFFFFu, x1 = e1 & 0xFFFFu, x2 = e2 & 0xFFFFu, x3 = e3 & 0xFFFFu;
             const int s0 = (int)e0 < 0 ? -(int)x0 : (int)x0, s1 = (int)e1 < 0 ? -(int)x1 : (int)x1;
             const int s2 = (int)e2 < 0 ? -(int)x2 : (int)x2, s3 = (int)e3 < 0 ? -(int)x3 : (int)x3;
             acc[4 * j + 0] += clamp16((4 * s0 * adj) >> 7);
@@ -513,7 +545,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
     uint2 *bpart = part + kGBf * kGLegs * kPst;
     const uint32_t bar_s = shared_addr(bars) + warp * 16;
 
-    build_decode_lut_abs(lut, t, kWarps * 32);
+    build_decode_lut_wide(lut, t, kWarps * 32);
     build_meter_lut(reinterpret_cast<uint32_t *>(smem + kLutBytes), t, kWarps * 32);
     if (t < 2) {
         const enc_pk e = enc_pk_make(t);
@@ -556,7 +588,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
     const bool worker = lane < kGBf * kChunks;
     const uint32_t bfl = worker ? lane / kChunks : 0u, c = worker ? lane - bfl * kChunks : 0u;
     const uint32_t src_off = bfl * kGStride + c * 16;
-    const uint32_t lane4 = lut_bytes + 4u * lane;
+    const uint32_t lane4 = lut_bytes + 8u * (lane & 15u);
     const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kGBf) % (uint32_t)q.B);
     uint32_t b = (item * kGBf + bfl) % (uint32_t)q.B;
     const bool wide = (G & 3u) == 0u && (reinterpret_cast<uintptr_t>(q.gain) & 7u) == 0 && (reinterpret_cast<uintptr_t>(q.law) & 3u) == 0;
@@ -626,8 +658,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
                 if ((uint32_t)g < legs) {                                 // warp-uniform
                     const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
                     uint2 ph;
-                    if (general) ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
-                    else if ((open_mask >> g) & 1u) ph = leg_chunk_u<kSigned, 1>(lb, wh[g], adj_of(g), 0, acc);
+                    if (general) ph = leg_chunk_u<kSigned, 2, true>(lb, wh[g], 0u, (int)adj_of(g), acc);
+                    else if ((open_mask >> g) & 1u) ph = leg_chunk_u<kSigned, 1, true>(lb, wh[g], adj_of(g), 0, acc);
                     else ph = leg_chunk_shut<kSigned>(mlut, 4u * lane + (((lcur >> g) & 1u) << 7), wh[g]);
                     if (valid) part[(bfl * kGLegs + g) * kPst + c] = ph;
                 }

@@ -9,7 +9,7 @@ for G in (4, 2, 1, 3, 8, 32):
     g = torch.Generator(device=dev).manual_seed(1)
     codes = torch.randint(0, 256, (F, Cn, 160), dtype=torch.uint8, device=dev, generator=g)
     law = torch.from_numpy(synth.laws(Cn)).to(dev)
-    gain = torch.zeros((F, B, G), dtype=torch.int16, device=dev); gain[:, :, :(int(os.environ['IGD_SWEEP_OPEN']) if 'IGD_SWEEP_OPEN' in os.environ else max(1, G // 2))] = 256   # default: half of the legs open
+    gain = torch.zeros((F, B, G), dtype=torch.int16, device=dev); gain[:, :, :(int(os.environ['IGD_SWEEP_OPEN']) if os.environ.get('IGD_SWEEP_OPEN') else max(1, G // 2))] = 256   # default: half of the legs open
     gain = gain.reshape(F, Cn).contiguous()
     out_law = torch.from_numpy(synth.out_laws(B)).to(dev)
     out = vp.alloc_outputs(F, B, G)
