@@ -267,6 +267,7 @@ template <int G, bool kSigned, int kWarps, bool kPkt = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
 {
     static_assert(kBfPerItem * G + kBfPerItem <= 32, "finish needs one lane per record");
+    static_assert(!kPkt || G == 4, "packet form: the aligned-window offsets assume 720-byte bridge-frames");
     using geom = slot_geom<G, kPkt>;
     constexpr int kP = kPkt ? kChunks : kPst;      // partial stride: the bigger packet slots leave no room for the pad column
     constexpr int kLegParts = kBfPerItem * G * kP, kBrParts = kBfPerItem * kP;
@@ -390,12 +391,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                                  : "=r"(wh[g].x), "=r"(wh[g].y), "=r"(wh[g].z), "=r"(wh[g].w)
                                  : "r"(src + g * IGD_FRAME + ch * 16));
-                } else {          // payload at byte 20 of a 180-byte packet: 4-byte aligned only
-                    const uint32_t a = src + g * IGD_PKT_MAX + IGD_PKT_HDR + ch * 16;
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wh[g].x) : "r"(a));
-                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(wh[g].y) : "r"(a));
-                    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(wh[g].z) : "r"(a));
-                    asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(wh[g].w) : "r"(a));
+                } else {
+                    // payload at byte 20 of a 180-byte packet.  With G = 4 a bridge-frame is 720 = 45 * 16
+                    // bytes, so the chunk of leg g starts (4 g + 4) % 16 bytes past a 16-byte boundary -- a
+                    // compile-time offset: read the aligned 32-byte window with two LDS.128 (one for
+                    // g = 3) and pick the four words by register name (four 4-byte loads per chunk
+                    // would be 4-way bank conflicts: the lanes' chunks are 16 bytes apart).
+                    const int kOff = ((4 * g + 4) % 16) / 4;                   // words into the window (constant once unrolled)
+                    const uint32_t a = src + g * IGD_PKT_MAX + IGD_PKT_HDR + ch * 16 - 4 * kOff;
+                    uint32_t v[8];
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(a));
+                    if (kOff != 0)
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4+16];"
+                                     : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(a));
+                    wh[g] = make_uint4(v[kOff], v[kOff + 1], v[kOff + 2], v[kOff + 3]);
                 }
             }
             if (kPkt && ragged) {
