@@ -200,19 +200,28 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
     igd_rx_state s = d.state[c];
-    constexpr int kAhead = 8;            // the walk is sequential, its inputs are not: fetch 8 frames ahead
-    for (int f0 = 0; f0 < d.F; f0 += kAhead) {
-        uint4 raw[kAhead];
-        uint8_t pres[kAhead];
+    // The walk is sequential, its inputs are not: the fields of the NEXT run of 8 frames are in flight
+    // while this run is walked (with a few thousand channels there is one warp per SM and nothing
+    // else to hide the latency behind).
+    constexpr int kAhead = 8;
+    uint4 raw[kAhead], nraw[kAhead];
+    uint8_t pres[kAhead], npres[kAhead];
+    auto fetch = [&](int f0, uint4 (&r)[kAhead], uint8_t (&p)[kAhead]) {
 #pragma unroll
         for (int u = 0; u < kAhead; u++) {
             const int f = f0 + u;
             if (f < d.F) {
                 const size_t i = (size_t)f * d.C + c;
-                raw[u] = __ldg(reinterpret_cast<const uint4 *>(d.fields + i));
-                pres[u] = d.present ? d.present[i] : (uint8_t)1;
+                r[u] = __ldg(reinterpret_cast<const uint4 *>(d.fields + i));
+                p[u] = d.present ? d.present[i] : (uint8_t)1;
             }
         }
+    };
+    fetch(0, nraw, npres);
+    for (int f0 = 0; f0 < d.F; f0 += kAhead) {
+#pragma unroll
+        for (int u = 0; u < kAhead; u++) { raw[u] = nraw[u]; pres[u] = npres[u]; }
+        fetch(f0 + kAhead, nraw, npres);
 #pragma unroll
         for (int u = 0; u < kAhead; u++) {
             const int f = f0 + u;
