@@ -197,3 +197,24 @@ def test_wav_images_of_many_channels_from_the_batch_layout(vp, quirks):
             assert got[k].tobytes() == hdr.tobytes() + body.tobytes()
     allc = vp.wav_images(codes, None, law, ref_quirks=quirks)
     assert allc.shape[0] == Cn and allc[7].tobytes() == got[2].tobytes()
+
+
+@pytest.mark.parametrize("stride,device", [(180, False), (180, True), (184, False), (64, False)])
+def test_header_only_parse_equals_the_full_parse(vp, stride, device):
+    """payload_out = NULL takes the thread-per-packet header kernel: same field records as the tile /
+    warp-per-packet kernels on ragged sizes, unknown payload types and short strides."""
+    import torch
+    rng = np.random.default_rng(stride)
+    n = 3001
+    pk = rng.integers(0, 256, (n, stride), dtype=np.uint8)
+    pk[:, 1] = rng.choice(np.array([8, 0, 123, 18, 96, 0x88, 0xFB], np.uint8), n)
+    sizes = rng.choice(np.array([stride, stride, 180, 20, 19, 12, 0, 100, 21, 1100, 2000], np.uint32), n)
+    if device:
+        dpk, dsz = torch.from_numpy(pk).to("cuda:0"), torch.from_numpy(sizes.view(np.int32)).to("cuda:0")
+        full = vp.ed137_parse(dpk, dsz)[0].cpu().numpy()
+        hdr = vp.ed137_parse(dpk, dsz, want_payload=False)[0].cpu().numpy()
+    else:
+        full = vp.ed137_parse(pk, sizes)[0]
+        hdr = vp.ed137_parse(pk, sizes, want_payload=False)[0]
+    assert full.tobytes() == hdr.tobytes()
+    assert vp.ed137_parse(pk, None, want_payload=False)[0].tobytes() == vp.ed137_parse(pk, None)[0].tobytes()
