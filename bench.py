@@ -3,7 +3,7 @@
 path on N B200s (BASELINE.json metric), with its HBM roofline, the end-to-end
 number through the C ABI with host buffers, and the CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cfg4]
 
 One "step" = one pass of the fused kernel over one resident batch of
 BASELINE config 3: 4096 channels (1024 bridges x 4 legs) x 1640 frames of
@@ -195,8 +195,22 @@ def main():
     ap.add_argument("--frames", type=int, default=F, help="frames per step (default: the config-3 value)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg")
+    ap.add_argument("--cfg4", action="store_true",
+                    help="BASELINE config 4 instead of config 3: 1 M channel-seconds (1024 bridges x 4 legs x 12207 frames "
+                         "= 5.0e7 channel-frames) as ONE fixed job whose bridges are split over the ranks (strong scaling); "
+                         "device-resident legs only")
     args = ap.parse_args()
-    if args.frames != F:
+    if args.cfg4:
+        world_ = int(os.environ.get("WORLD_SIZE", "1"))
+        if 1024 % world_:
+            raise SystemExit("--cfg4 needs a rank count that divides 1024 bridges")
+        globals()["B"] = 1024 // world_
+        globals()["C"] = globals()["B"] * G
+        globals()["F"] = 12207
+        globals()["WORKLOAD"] = (f"cfg4: 1 M channel-seconds = 4096 channels (1024 bridges x {G} legs) x 12207 frames of 20 ms, "
+                                 f"bridges split over {world_} rank(s) ({globals()['B']} bridges each), noise+tone, gates 2-of-4 open at gain 2.0")
+        args.no_e2e = args.no_cpu = True
+    if not args.cfg4 and args.frames != F:
         globals()["F"] = args.frames
         globals()["WORKLOAD"] = WORKLOAD.replace("x 1640 frames", f"x {args.frames} frames (non-default)")
     if args.impl == "reference":
@@ -347,7 +361,7 @@ def main():
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int16", "data": "synthetic",
+            "scaling": "strong" if args.cfg4 else "weak", "vs_baseline": None, "dtype": "u8/int16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_codes_bytes": C * F * FRAME, "l2": "inputs larger than L2",
                        "parallelism": f"bridges sharded over {world} GPU(s), no data-path collective",
                        "summaries_gathered_to_rank0": n_summaries},
