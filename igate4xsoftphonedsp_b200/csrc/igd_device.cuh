@@ -57,14 +57,27 @@ __device__ __forceinline__ int clamp16(int v) { return min(max(v, -32768), 32767
 // the sample after the reference's open-gate gain 2.0 (SLOT_VOLUME, Functions.cpp:
 // 1682) with pjmedia's per-port clip.  One IDP.2A then selects 4*(x/4) (gain 1.0),
 // clamp16(2x) (gain 2.0) or nothing (gate shut) AND accumulates it into the mix.
+// Fills a [2 laws][256 codes][32 lane columns] table: every warp takes runs of 32 (law, code) pairs,
+// lane l computes the entry of pair l ONCE, and the 32 entries are broadcast row by row
+// (shuffle + one conflict-free store per row) -- 1/30th of the instructions of computing every
+// replica, which is what a one-tick launch of the fused kernel mostly consisted of.
+template <class F>
+__device__ __forceinline__ void fill_lut32(uint32_t *lut, int warp, int lane, int nwarps, F entry_of)
+{
+    for (int base = warp * 32; base < 2 * 256; base += nwarps * 32) {
+        const uint32_t idx = (uint32_t)(base + lane);
+        const uint32_t mine = entry_of(idx >> 8, idx & 255u);
+#pragma unroll 8
+        for (int k = 0; k < 32; k++) lut[(base + k) * 32 + lane] = __shfl_sync(0xFFFFFFFFu, mine, k);
+    }
+}
 __device__ __forceinline__ void build_decode_lut(uint32_t *lut, int tid, int nthreads)
 {
-    for (int i = tid; i < 2 * 256 * 32; i += nthreads) {
-        const uint32_t law = (uint32_t)i >> 13, code = ((uint32_t)i >> 5) & 255u;
+    fill_lut32(lut, tid >> 5, tid & 31, nthreads >> 5, [](uint32_t law, uint32_t code) {      // nthreads: a multiple of 32
         const int x = law ? igd_ulaw2lin(code) : igd_alaw2lin(code);
         const int y2 = min(max(2 * x, -32768), 32767);
-        lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)(x >> 2) & 0xFFFFu);
-    }
+        return ((uint32_t)y2 << 16) | ((uint32_t)(x >> 2) & 0xFFFFu);
+    });
 }
 // shared-window byte address of this lane's column in the table of `law`
 __device__ __forceinline__ uint32_t lut_lane_base(uint32_t lut_s, uint32_t lane, uint32_t law)

@@ -160,14 +160,13 @@ template <int G, bool kPkt = false> struct slot_geom {
 };
 __device__ __forceinline__ uint32_t chunk_rotation(uint32_t bfl) { return (0x037050u >> (4 * bfl)) & 0xFu; }
 
-__device__ __forceinline__ void build_decode_lut_abs(uint32_t *lut, int tid, int nthreads)
+__device__ __forceinline__ void build_decode_lut_abs(uint32_t *lut, int warp, int lane, int nwarps)
 {
-    for (int i = tid; i < 2 * 256 * 32; i += nthreads) {
-        const uint32_t law = (uint32_t)i >> 13, code = ((uint32_t)i >> 5) & 255u;
+    fill_lut32(lut, warp, lane, nwarps, [](uint32_t law, uint32_t code) {
         const int x = law ? igd_ulaw2lin(code) : igd_alaw2lin(code);
         const int y2 = min(max(2 * x, -32768), 32767);
-        lut[i] = ((uint32_t)y2 << 16) | ((uint32_t)(abs(x) >> 2) & 0xFFFFu);
-    }
+        return ((uint32_t)y2 << 16) | ((uint32_t)(abs(x) >> 2) & 0xFFFFu);
+    });
 }
 // Wide form (k_fused_g): 8-byte entries {(|x|/4)^2, |x|/4 | clamp16(2x) << 16} -- the square comes
 // out of the table with the sample (one LDS.64), so the meter needs no extract and no multiply per
@@ -286,7 +285,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
     uint2 *bpart = part + kLegParts;
     const uint32_t bar_s = shared_addr(bars) + warp * 8;
 
-    build_decode_lut_abs(lut, t, kWarps * 32);
+    build_decode_lut_abs(lut, (int)warp, (int)lane, kWarps);
     if (t < 2) {
         const enc_pk e = enc_pk_make(t);
         enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
