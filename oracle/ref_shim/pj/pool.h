@@ -1,0 +1,5 @@
+/* <pj/pool.h> for the reference-backed oracle build: see igd_pj_stub.h (test infrastructure only). */
+#ifndef IGD_REF_SHIM_PJ_POOL_H
+#define IGD_REF_SHIM_PJ_POOL_H
+#include "../igd_pj_stub.h"
+#endif

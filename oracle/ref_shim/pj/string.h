@@ -1,0 +1,5 @@
+/* <pj/string.h> for the reference-backed oracle build: see igd_pj_stub.h (test infrastructure only). */
+#ifndef IGD_REF_SHIM_PJ_STRING_H
+#define IGD_REF_SHIM_PJ_STRING_H
+#include "../igd_pj_stub.h"
+#endif

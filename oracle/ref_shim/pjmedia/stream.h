@@ -1,0 +1,5 @@
+/* <pjmedia/stream.h> for the reference-backed oracle build: see igd_pj_stub.h (test infrastructure only). */
+#ifndef IGD_REF_SHIM_PJMEDIA_STREAM_H
+#define IGD_REF_SHIM_PJMEDIA_STREAM_H
+#include "../igd_pj_stub.h"
+#endif

@@ -11,8 +11,15 @@ probe oracle/_ref/libigd_ref.so):   python tests/golden/make_golden.py
                           (start/wav_write/stop) for wavwriter_payload.bin
   g711_pins.json          SHA-256 of the four G.711 tables
                           + ITU known answers
-  ed137_tx_scenarios.json sender scenarios and the packets the ORACLE emits
-                          (oracle restates TransportAdapter.cpp:635-874)
+  ed137_tx_scenarios.json sender scenarios and the packets the REFERENCE'S OWN
+                          transport_send_rtp emits (TransportAdapter.cpp compiled from
+                          /root/reference into oracle/_ref/libigd_ref_ta.so, driven through
+                          tp->op->send_rtp by tests/ref_py.run_tx)
+  ref_pins.json           SHA-256 digests of the REFERENCE run (same library) on every
+                          shared seeded case: sender scenarios (both `char` signs), sendR2SStatus,
+                          the transport_rtp_cb walk, checkEvents gate arbitration (CLIENT / SERVER
+                          best signal) and the PTTEventDataLogger messages; the oracle has to
+                          reproduce them (tests/test_ref_pins.py)
   fused_cfg2.npz          BASELINE config 2 (4 legs, 2 u-law + 2 A-law), 75
                           frames: inputs + oracle outputs
   rx_arb_keepalive.json   SHA-256 of the oracle's receive-side walk (transport_rtp_cb
@@ -38,6 +45,7 @@ sys.path.insert(0, ROOT)
 import oracle_py as O  # noqa: E402
 from igate4xsoftphonedsp_b200 import synth  # noqa: E402
 from tx_scenarios import SCENARIOS, run_oracle  # noqa: E402
+import ref_py as RP  # noqa: E402
 
 
 def sha(a):
@@ -138,21 +146,65 @@ def rx_arb_keepalive():
     return out
 
 
+def ref_pins():
+    """the digest tests/test_ref_pins._oracle_digest computes with the oracle, computed with the REFERENCE"""
+    import keepalive_cases as K
+    import rx_arb_cases as R
+    from igate4xsoftphonedsp_b200 import _native as N
+    out = {"generated_from": "reference",
+           "how": "oracle/_ref/libigd_ref_ta{,_sc}.so = /root/reference/TransportAdapter.cpp + line-range extracts of "
+                  "roip_ed137.cpp / Functions.cpp (oracle/ref_extract.sh), driven by tests/ref_py.py",
+           "tx": {}}
+    for s in SCENARIOS:
+        pk, sz, bm, _ = RP.run_tx(s)
+        out["tx"][s["name"]] = {"packets": sha(pk), "sizes": sha(sz), "bytemean": sha(bm), "bytes": int(sz.sum())}
+    pk, sz, bm, _ = RP.run_tx(SCENARIOS[0], signed_char=1)
+    out["tx_signed_char"] = {"packets": sha(pk), "bytemean": sha(bm)}
+    legs, hdr, ctl = K.make(40, 120, seed=2)
+    pk, sz, hf = RP.run_keepalive(legs, hdr, ctl)
+    out["keepalive"] = {"packets": sha(pk), "sizes": sha(sz), "final_headers": sha(hf)}
+    pkts, sizes, present = R.make_rx_stream(300, 24, seed=3)
+    ev, st = RP.run_rx(pkts, R.ref_comparable_sizes(sizes), present)
+    out["rx_walk"] = {"events": sha(ev), "state": sha(st)}
+    for name, mode, G in (("client_ptt", N.ARB_CLIENT_PTT, 4), ("server_best", N.ARB_SERVER_BEST, 4)):
+        w = R.make_arb_words(200, 9, G, mode, seed=G)
+        g, lg, br = RP.run_arb(w, G, mode)
+        out[name] = {"gain": sha(g), "legs": sha(lg), "bridges": sha(br)}
+    import test_ref_pins as TP
+    msgs = []
+    Rf = RP.lib(0)
+    for seed in (1, 2, 3):
+        meter, gain, s, bm = TP._event_case(seed)
+        Rf.refapp_reset(RP.SERVER, 1)
+        buf = C.create_string_buffer(2048)
+        Rf.refapp_ptt_event(0, b"pptTest_pressed", 4.0, b"sip:radio1@10.0.0.5", 3, buf, 2048)
+        for f in range(meter.shape[0]):
+            if gain[f, 0]:
+                Rf.refapp_keeplog(0, float(s[f]) / 160.0, int(bm[f]))
+        Rf.refapp_ptt_event(0, b"pptTest_released", 0.0, b"sip:radio1@10.0.0.5", 3, buf, 2048)
+        msgs.append(buf.value.decode())
+    out["event_messages"] = msgs
+    return out
+
+
 def main():
-    if not O.ref_available():
-        sys.exit("oracle/_ref/libigd_ref.so missing: run `make -C oracle` where /root/reference exists")
+    if not O.ref_available() or not RP.available():
+        sys.exit("oracle/_ref/libigd_ref*.so missing: run `make -C oracle` where /root/reference exists")
     json.dump(ref_headers(), open(os.path.join(HERE, "ed137_ref_headers.json"), "w"), indent=1)
     print("wavwriter_ref.bin", wavwriter(), "bytes")
     json.dump(g711_pins(), open(os.path.join(HERE, "g711_pins.json"), "w"), indent=1)
     scen = []
     for s in SCENARIOS:
-        pk, sizes, bm, st = run_oracle(s)
+        pk, sizes, bm, st = RP.run_tx(s)          # the reference's own transport_send_rtp
+        opk, osz, obm, _ = run_oracle(s)
+        assert np.array_equal(pk, opk) and np.array_equal(sizes, osz) and np.array_equal(bm, obm), s["name"]
         scen.append({"name": s["name"], "sha256_packets": sha(pk), "sizes": sizes.tolist(),
                      "bytemean": bm.tolist(), "first_packets_hex": [pk[f, 0, :sizes[f, 0]].tobytes().hex()
                                                                     for f in range(min(4, pk.shape[0]))]})
     json.dump(scen, open(os.path.join(HERE, "ed137_tx_scenarios.json"), "w"), indent=1)
     print("fused_cfg2", fused_cfg2())
     json.dump(rx_arb_keepalive(), open(os.path.join(HERE, "rx_arb_keepalive.json"), "w"), indent=1)
+    json.dump(ref_pins(), open(os.path.join(HERE, "ref_pins.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

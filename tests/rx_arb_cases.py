@@ -47,6 +47,20 @@ def make_rx_stream(F, Cn, seed=0):
     return pkts, sizes, present
 
 
+def ref_comparable_sizes(sizes):
+    """The same stream restricted to sizes on which the REFERENCE's behaviour is defined, so that it can be
+    replayed through the reference's own transport_rtp_cb (tests/ref_py.run_rx):
+      * 276 < size < 1044: the reference copies size-20 bytes into its 256-byte payload_buff
+        (TransportAdapter.cpp:286-287 tests `< 1024`), overwriting payload_bufSize and the send buffers,
+        and setIncomingRTP then sizes a stack array from the overwritten length (roip_ed137.cpp:6553);
+      * size < 20: the reference reads pt / ed137 / length through the header cast (:248-256) beyond the
+        received bytes, i.e. whatever the socket buffer still holds.
+    The oracle and the CUDA path cap the copy at 256 bytes and do not latch a word from a packet shorter than
+    its header; both kinds are mapped onto the reference's own drop rule (size - 20 >= 1024)."""
+    bad = ((sizes > 276) & (sizes < 1044)) | (sizes < 20)
+    return np.where(bad, 1044 + (sizes % 7), sizes).astype(np.uint32)
+
+
 def oracle_rx_walk(pkts, sizes, present, now0=1000, tick=20, period=200, wd_ticks=2, frame0=0, state=None):
     """-> events (RX_EVENT_DT [F][C]), final state (RX_STATE_DT [C])"""
     L = O.lib()
