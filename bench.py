@@ -44,12 +44,15 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the fused kernel from the committed ncu capture, if any."""
+def ncu_traffic(algorithmic_bytes_per_launch):
+    """dram bytes per launch of the fused kernel from the committed ncu capture -- only for the launch shape the
+    capture was taken on (same algorithmic bytes per launch); any other shape reports null."""
     p = os.path.join(ROOT, "profiles", "fused_traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            t = json.load(open(p))
+            if int(t.get("algorithmic_bytes_per_launch", -1)) == int(algorithmic_bytes_per_launch):
+                return t.get("dram_bytes_per_launch")
         except Exception:
             return None
     return None
@@ -133,34 +136,59 @@ def oracle_lib():
     return O
 
 
-def cpu_sample(seconds_target=12.0, threads=None):
-    """Times the CPU oracle (reference-faithful scalar port, -O2) with all host threads on a
-    bounded sample of the same workload.  Returns (channel-samples/s, cores, description)."""
+def seeded_codes_host(nf, ch0=0):
+    """The bench workload's input codes for frames [0, nf) generated on the host: the same seeded noise+tone
+    family as the GPU arm (synth.pcm_noise_tone), encoded by the oracle (used by --impl reference, which must
+    not touch the GPU path; the ours arm hands its own device-generated codes to the CPU leg instead)."""
+    import numpy as np
+    from igate4xsoftphonedsp_b200 import synth
+    O = oracle_lib()
+    law = synth.laws(C, ch0)
+    codes = np.empty((nf, C, FRAME), np.uint8)
+    step = 512
+    for c0 in range(0, C, step):
+        pcm = synth.pcm_noise_tone(nf, min(step, C - c0), ch0=ch0 + c0)
+        for k in range(pcm.shape[1]):
+            codes[:, c0 + k] = O.g711_encode(pcm[:, k], int(law[c0 + k]))
+    return codes
+
+
+def cpu_sample(seconds_target=12.0, threads=None, codes=None, gpu_out=None):
+    """Times the CPU oracle (reference-faithful scalar port, -O2) with all host threads on a bounded sample of
+    the SAME workload: the seeded noise+tone codes and the 2-of-4 gate pattern of the GPU arm (frames [0, nf)).
+    codes: host copy of the GPU arm's input codes (ours arm) or None (generated on the host).
+    gpu_out: the GPU arm's outputs for the same frames -> the CPU outputs are byte-compared with them.
+    Returns (channel-samples/s, cores, description, outputs_equal or None)."""
     import numpy as np
     from igate4xsoftphonedsp_b200 import synth
     O = oracle_lib()
     cores = threads or os.cpu_count() or 1
-    rng = np.random.default_rng(0)
     law, out_law = synth.laws(C), synth.out_laws(B)
+    if codes is None:
+        codes = seeded_codes_host(min(F, 256))
 
-    def make(nf):
-        return rng.integers(0, 256, (nf, C, FRAME), dtype=np.uint8), synth.gains(nf, B, G)
-
-    def run(codes, gain, out=None):
+    def run(nf, out=None):
         t0 = time.perf_counter()
-        O.process_batch(codes, law, gain, out_law, G, threads=cores, out=out)
-        return time.perf_counter() - t0
+        res = O.process_batch(codes[:nf], law, synth.gains(nf, B, G), out_law, G, threads=cores, out=out)
+        return time.perf_counter() - t0, res
 
-    t = run(*make(8))                            # calibration (also warms the thread pool / pages)
-    nf = int(max(8, min(F, 8 * seconds_target / max(t, 1e-6))))
-    sample = make(nf)                            # generated once; >> CPU caches, so passes do not get cheaper
+    t, _ = run(8)                                # calibration (also warms the thread pool / pages)
+    nf = int(max(8, min(codes.shape[0], 8 * seconds_target / max(t, 1e-6))))
     outs = O.alloc_outputs(nf, C, G)             # pre-faulted output buffers, reused by every pass
     passes, dt = 0, 0.0
     while dt < seconds_target and passes < 64:   # bounded: repeat the sample until ~seconds_target of CPU work
-        dt += run(*sample, out=outs)
+        d, _ = run(nf, out=outs)
+        dt += d
         passes += 1
+    equal = None
+    if gpu_out is not None:
+        equal = bool(np.array_equal(outs[0], gpu_out["mix"][:nf]) and np.array_equal(outs[1], gpu_out["enc"][:nf]) and
+                     np.array_equal(outs[2].view(np.uint32).reshape(nf, C, 4)[..., :2],
+                                    gpu_out["meter"][:nf].view(np.uint32).reshape(nf, C, 4)[..., :2]) and
+                     outs[3].tobytes() == gpu_out["bmeter"][:nf].tobytes())
     return (C * nf * FRAME * passes / dt, cores,
-            f"{C} channels x {nf} frames x {passes} passes, {cores} threads, {dt:.1f} s")
+            f"{C} channels x frames [0,{nf}) of the seeded noise+tone workload x {passes} passes, {cores} threads, {dt:.1f} s",
+            equal)
 
 
 def run_reference(args):
@@ -171,8 +199,9 @@ def run_reference(args):
         return
     vals = []
     desc, cores = "", 1
+    codes = seeded_codes_host(min(F, 256))
     for i in range(args.warmup + args.steps):
-        v, cores, desc = cpu_sample(seconds_target=max(2.0, 60.0 / max(1, args.warmup + args.steps)))
+        v, cores, desc, _ = cpu_sample(seconds_target=max(2.0, 60.0 / max(1, args.warmup + args.steps)), codes=codes)
         if i >= args.warmup:
             vals.append(v)
     value = sum(vals) / len(vals)
@@ -199,7 +228,22 @@ def main():
                     help="BASELINE config 4 instead of config 3: 1 M channel-seconds (1024 bridges x 4 legs x 12207 frames "
                          "= 5.0e7 channel-frames) as ONE fixed job whose bridges are split over the ranks (strong scaling); "
                          "device-resident legs only")
+    ap.add_argument("--cfg5", action="store_true",
+                    help="BASELINE config 5: one mixed-codec batch of 65536 channels (16384 bridges x 4 legs, A-law / u-law "
+                         "alternating) x 100 frames, bridges split over the ranks (strong scaling), per-channel dBFS "
+                         "summaries gathered to rank 0 over NCCL and checked against the oracle; device-resident legs only")
     args = ap.parse_args()
+    if args.cfg5:
+        world_ = int(os.environ.get("WORLD_SIZE", "1"))
+        if 16384 % world_:
+            raise SystemExit("--cfg5 needs a rank count that divides 16384 bridges")
+        globals()["B"] = 16384 // world_
+        globals()["C"] = globals()["B"] * G
+        globals()["F"] = 100
+        globals()["WORKLOAD"] = (f"cfg5: mixed-codec batch of 65536 channels (16384 bridges x {G} legs, A-law/u-law alternating) x 100 "
+                                 f"frames of 20 ms, bridges split over {world_} rank(s) ({globals()['B']} bridges each), noise+tone, "
+                                 "gates 2-of-4 open at gain 2.0, per-channel summaries gathered to rank 0")
+        args.no_e2e = args.no_cpu = True
     if args.cfg4:
         world_ = int(os.environ.get("WORLD_SIZE", "1"))
         if 1024 % world_:
@@ -210,7 +254,7 @@ def main():
         globals()["WORKLOAD"] = (f"cfg4: 1 M channel-seconds = 4096 channels (1024 bridges x {G} legs) x 12207 frames of 20 ms, "
                                  f"bridges split over {world_} rank(s) ({globals()['B']} bridges each), noise+tone, gates 2-of-4 open at gain 2.0")
         args.no_e2e = args.no_cpu = True
-    if not args.cfg4 and args.frames != F:
+    if not args.cfg4 and not args.cfg5 and args.frames != F:
         globals()["F"] = args.frames
         globals()["WORKLOAD"] = WORKLOAD.replace("x 1640 frames", f"x {args.frames} frames (non-default)")
     if args.impl == "reference":
@@ -292,31 +336,56 @@ def main():
     avg_launch_s = (total_ms / args.steps) * 1e-3
     achieved = BYTES_PER_BF * B * F / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "k_fused_w<G=4, 24 autonomous warps/SM, per-warp TMA slot>", "peak_source": peak_src,
+                "traffic": ncu_traffic(BYTES_PER_BF * B * F), "kernel": "k_fused_w<G=4, 24 autonomous warps/SM, per-warp TMA slot>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_BF * B * F,
                 "launch_ms": {"avg": total_ms / args.steps, "min": per_launch_ms[0], "max": per_launch_ms[-1]}}
 
     # ---- parity spot check on the timed outputs (oracle as checker, outside the timed region)
-    parity = None
+    parity, parity_frames = None, 0
     if rank == 0:
         O = oracle_lib()
-        fs = [0, 25, F - 1]
+        fs = sorted({0, F - 1} | {int(x) for x in np.random.default_rng(args.steps).choice(F, size=min(F, 64), replace=False)})
         sel = torch.tensor(fs, device=dev)
         want = O.process_batch(codes[sel].cpu().numpy(), law.cpu().numpy(), gain_np[fs], out_law.cpu().numpy(), G,
                                threads=os.cpu_count() or 1)
         parity = bool(np.array_equal(out["mix"][sel].cpu().numpy(), want[0]) and
                       np.array_equal(out["enc"][sel].cpu().numpy(), want[1]) and
                       np.array_equal(out["meter"][sel].cpu().numpy().view(np.uint32)[..., :2].reshape(len(fs), C, 2),
-                                     want[2].view(np.uint32).reshape(len(fs), C, 4)[..., :2]))
+                                     want[2].view(np.uint32).reshape(len(fs), C, 4)[..., :2]) and
+                      out["bmeter"][sel].cpu().numpy().tobytes() == want[3].tobytes())
+        parity_frames = len(fs)
 
     # ---- per-channel summaries gathered to rank 0 (the only collective; outside the timed region)
     summ, _ = vp.event_summary(out["meter"], gain, want_db=False)
     torch.cuda.synchronize()
     gathered = sharding.gather_records(summ, world * B, G) if world > 1 else summ
     n_summaries = int(gathered.shape[0]) if rank == 0 else None
+    # content check of the gathered records ON HARDWARE: rank 0 regenerates two bridges of EVERY rank from the seed
+    # (GPU encoder for the codes, as the ranks did), runs the oracle on them and compares the records that came
+    # over NCCL bit for bit
+    summaries_parity = None
+    if rank == 0:
+        O = oracle_lib()
+        gath = gathered.cpu().numpy().view(np.uint8).reshape(-1, 32).copy().view(O.SUMMARY_DT).reshape(-1)
+        ok = True
+        for r in range(world):
+            for b_off in (0, B - 1):
+                chs = (r * B + b_off) * G
+                p_ = synth.pcm_noise_tone_torch(F, G, dev, ch0=chs)
+                lw = synth.laws(G, chs)
+                cd = vp.g711_encode(p_, torch.from_numpy(lw).to(dev)).cpu().numpy()
+                gn = synth.gains(F, 1, G)
+                _, _, mt, _ = O.process_batch(cd, lw, gn, synth.out_laws(1, r * B + b_off), G)
+                want_s = O.event_summary(mt, gn)
+                ok = ok and gath[chs:chs + G].tobytes() == want_s.tobytes()
+        summaries_parity = bool(ok)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + kernel + D2H every step
+    # ---- end to end through the C ABI with HOST buffers (pinned), H2D + kernel + D2H every step.
+    # Headline form: what a gateway takes back -- the encoded bridge output (packet payloads), the per-leg meter
+    # records and the bridge records; the int16 mix stays on the device (igd_batch_desc.mix = NULL).  The form with
+    # every output, r01's, is reported beside it.
     e2e = None
+    h_codes = None
     if not args.no_e2e:
         affinity0 = os.sched_getaffinity(0)
         numa = pin_to_gpu_numa_node(local)      # the pinned buffers are first-touched on the GPU's own NUMA node
@@ -334,37 +403,55 @@ def main():
             t.zero_()                           # first touch while bound
         os.sched_setaffinity(0, affinity0)      # the CPU legs below use every host core again
         esteps = max(2, min(args.steps, 5))
-        for _ in range(2):
-            vp.process_batch(h_in["codes"], h_in["law"], h_in["gain"], h_in["out_law"], G, out=h_out)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(esteps):
-            vp.process_batch(h_in["codes"], h_in["law"], h_in["gain"], h_in["out_law"], G, out=h_out)
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         h2d = h_in["codes"].nbytes + h_in["gain"].nbytes + h_in["law"].nbytes + h_in["out_law"].nbytes
-        d2h = sum(v.nbytes for v in h_out.values())
-        e2e_ok = bool(torch.equal(h_out_t["mix"], out["mix"].cpu()) and torch.equal(h_out_t["enc"], out["enc"].cpu()))
-        e2e = {"value": samples_per_step * esteps / float(dt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": esteps, "matches_device_path": e2e_ok, "host_buffers": numa}
+
+        def e2e_leg(names):
+            o = {k: h_out[k] for k in names}
+            for _ in range(2):
+                vp.process_batch(h_in["codes"], h_in["law"], h_in["gain"], h_in["out_law"], G, out=o)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                vp.process_batch(h_in["codes"], h_in["law"], h_in["gain"], h_in["out_law"], G, out=o)
+            barrier()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return samples_per_step * esteps / float(dt.item()), sum(v.nbytes for v in o.values())
+
+        v_all, d2h_all = e2e_leg(("mix", "enc", "meter", "bmeter"))
+        ok_all = bool(torch.equal(h_out_t["mix"], out["mix"].cpu()) and torch.equal(h_out_t["enc"], out["enc"].cpu()))
+        for k in ("enc", "meter", "bmeter"):
+            h_out_t[k].zero_()
+        v_gw, d2h_gw = e2e_leg(("enc", "meter", "bmeter"))
+        ok_gw = bool(torch.equal(h_out_t["enc"], out["enc"].cpu()) and torch.equal(h_out_t["meter"], out["meter"].cpu()) and
+                     torch.equal(h_out_t["bmeter"], out["bmeter"].cpu()))
+        e2e = {"value": v_gw, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_gw, "steps": esteps,
+               "outputs": ["enc", "meter", "bmeter"], "matches_device_path": ok_gw, "host_buffers": numa,
+               "all_outputs": {"value": v_all, "d2h_bytes_per_step": d2h_all, "outputs": ["mix", "enc", "meter", "bmeter"],
+                               "matches_device_path": ok_all},
+               "note": "PCIe-bound: the input codes alone are h2d_bytes_per_step; profiles/tools/pcie_probe.py gives the box's copy rates"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, desc = cpu_sample()
-        v1, _, desc1 = cpu_sample(seconds_target=3.0, threads=1)     # also the single-thread figure
+        # same inputs as the GPU arm (its own device-generated codes, copied to the host), outputs byte-compared
+        host_codes = h_codes.numpy() if h_codes is not None else codes.cpu().numpy()
+        gpu_out = {"mix": out["mix"].cpu().numpy(), "enc": out["enc"].cpu().numpy(),
+                   "meter": out["meter"].cpu().numpy(), "bmeter": out["bmeter"].cpu().numpy()}
+        v, cores, desc, equal = cpu_sample(codes=host_codes, gpu_out=gpu_out)
+        v1, _, desc1, _ = cpu_sample(seconds_target=3.0, threads=1, codes=host_codes)   # also the single-thread figure
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
-               "single_thread": {"value": v1, "sample": desc1}}
+               "outputs_equal_gpu": equal, "single_thread": {"value": v1, "sample": desc1}}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.cfg4 else "weak", "vs_baseline": None, "dtype": "u8/int16", "data": "synthetic",
+            "scaling": "strong" if (args.cfg4 or args.cfg5) else "weak", "vs_baseline": None, "dtype": "u8/int16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_codes_bytes": C * F * FRAME, "l2": "inputs larger than L2",
                        "parallelism": f"bridges sharded over {world} GPU(s), no data-path collective",
-                       "summaries_gathered_to_rank0": n_summaries},
+                       "summaries_gathered_to_rank0": n_summaries, "summaries_parity_vs_oracle": summaries_parity,
+                       "parity_frames_checked": parity_frames},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "parity_vs_oracle_on_timed_output": parity,
         }))

@@ -18,7 +18,7 @@ PKT_HDR = 20
 PKT_MAX = 180
 LAW_ALAW, LAW_ULAW = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-F_SIGNED_CHAR, F_REF_QUIRKS = 0x1, 0x2
+F_SIGNED_CHAR, F_REF_QUIRKS, F_GENERIC_KERNEL = 0x1, 0x2, 0x4
 CT_IDLE, CT_RXONLY, CT_TXISH = 0x1, 0x2, 0x4
 EDF_ACTIVE, EDF_RRC, EDF_MAIN_TX, EDF_MAIN_RX, EDF_DROPPED = 0x01, 0x02, 0x04, 0x08, 0x10
 
@@ -52,8 +52,10 @@ ARB_LEG_DT = np.dtype([("last", "u1"), ("msec", "u1"), ("on", "u1"), ("rssi", "i
                        ("reserved", "<u2")])
 ARB_BRIDGE_DT = np.dtype([("ptt_level", "<i4"), ("sqlStatusCount", "<i4"), ("sqlStatusOn", "u1"),
                           ("reserved", "u1", (7,))])
-RXE_PACKET, RXE_AUDIO, RXE_EDGE, RXE_DROPPED, RXE_LATE, RXE_HANGUP = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20
+RXE_PACKET, RXE_AUDIO, RXE_EDGE, RXE_DROPPED, RXE_LATE, RXE_HANGUP, RXE_FRAME = 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40
 ARB_CLIENT_PTT, ARB_SERVER_BEST = 0, 1
+ARB_F_SILENCE = 0x1
+GAIN_NO_AUDIO = 0x8000
 assert CTL_DT.itemsize == 8 and RX_STATE_DT.itemsize == 16 and RX_EVENT_DT.itemsize == 8
 assert ARB_LEG_DT.itemsize == 8 and ARB_BRIDGE_DT.itemsize == 16
 
@@ -96,7 +98,7 @@ class RxTrackDesc(C.Structure):
 
 class ArbDesc(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("F", C.c_int32), ("B", C.c_int32),
-                ("G", C.c_int32), ("mode", C.c_int32), ("word_stride", C.c_uint32), ("reserved", C.c_uint32),
+                ("G", C.c_int32), ("mode", C.c_int32), ("word_stride", C.c_uint32), ("flags", C.c_uint32),
                 ("words", C.c_void_p), ("active", C.c_void_p), ("legs", C.c_void_p), ("bridges", C.c_void_p),
                 ("gain_q7", C.c_void_p)]
 

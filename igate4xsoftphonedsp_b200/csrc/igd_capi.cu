@@ -50,8 +50,13 @@ int fail(igd_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
 
 struct Bind {
     igd_ctx *c;
-    explicit Bind(igd_ctx *ctx) : c(ctx) { cudaSetDevice(ctx->device); }
+    cudaError_t err;
+    explicit Bind(igd_ctx *ctx) : c(ctx), err(cudaSetDevice(ctx->device)) {}
 };
+// binds the calling thread to the context's device; a failure is an error of the call, not ignored
+#define IGD_BIND(c)  \
+    Bind b(c);       \
+    if (b.err != cudaSuccess) return fail((c), IGD_ECUDA, "cudaSetDevice", b.err)
 
 igd_launch_cfg cfg_of(igd_ctx *c)
 {
@@ -147,8 +152,16 @@ int igd_init(int device, igd_ctx **out)
         return IGD_ECUDA;
     }
     c->stream = c->own_stream;
-    for (auto &s : c->copy_streams) cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
-    for (auto &e : c->ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    bool ok = true;
+    for (auto &s : c->copy_streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto &e : c->ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {          // never run with a null copy stream / event
+        for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+        for (auto &s : c->copy_streams) if (s) cudaStreamDestroy(s);
+        cudaStreamDestroy(c->own_stream);
+        delete c;
+        return IGD_ECUDA;
+    }
     *out = c;
     return IGD_OK;
 }
@@ -184,7 +197,7 @@ int igd_use_own_stream(igd_ctx *c)
 int igd_sync(igd_ctx *c)
 {
     if (!c) return IGD_EINVAL;
-    Bind b(c);
+    IGD_BIND(c);
     IGD_CUDA(c, cudaStreamSynchronize(c->stream));
     return IGD_OK;
 }
@@ -229,7 +242,7 @@ void igd_dev_free(igd_ctx *c, void *p)
 int igd_copy_to_device(igd_ctx *c, void *dst, const void *src, size_t bytes)
 {
     if (!c) return IGD_EINVAL;
-    Bind b(c);
+    IGD_BIND(c);
     IGD_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
     IGD_CUDA(c, cudaStreamSynchronize(c->stream));
     return IGD_OK;
@@ -237,7 +250,7 @@ int igd_copy_to_device(igd_ctx *c, void *dst, const void *src, size_t bytes)
 int igd_copy_to_host(igd_ctx *c, void *dst, const void *src, size_t bytes)
 {
     if (!c) return IGD_EINVAL;
-    Bind b(c);
+    IGD_BIND(c);
     IGD_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     IGD_CUDA(c, cudaStreamSynchronize(c->stream));
     return IGD_OK;
@@ -252,7 +265,7 @@ static int g711_decode_impl(igd_ctx *c, const uint8_t *codes, const uint8_t *law
     if (n == 0) return IGD_OK;
     if (mem == IGD_MEM_DEVICE && (!aligned(codes, 16) || !aligned(pcm, 32)))
         return fail(c, IGD_EINVAL, "igd_g711_decode: device pointers must be 16/32-byte aligned");
-    Bind b(c);
+    IGD_BIND(c);
     const uint8_t *dc; const uint8_t *dl = nullptr; int16_t *dp;
     int rc;
     if ((rc = in_arg(c, mem, 0, codes, n, &dc))) return rc;
@@ -283,7 +296,7 @@ static int g711_encode_impl(igd_ctx *c, const int16_t *pcm, const uint8_t *law_c
     if (n == 0) return IGD_OK;
     if (mem == IGD_MEM_DEVICE && (!aligned(codes, 16) || !aligned(pcm, 32)))
         return fail(c, IGD_EINVAL, "igd_g711_encode: device pointers must be 16/32-byte aligned");
-    Bind b(c);
+    IGD_BIND(c);
     const int16_t *dp; const uint8_t *dl = nullptr; uint8_t *dc;
     int rc;
     if ((rc = in_arg(c, mem, 0, pcm, n, &dp))) return rc;
@@ -313,7 +326,7 @@ int igd_frame_meter(igd_ctx *c, const int16_t *pcm, size_t nframes, igd_meter_re
     if (nframes == 0) return IGD_OK;
     if (mem == IGD_MEM_DEVICE && (!aligned(pcm, 32) || !aligned(out, 16)))
         return fail(c, IGD_EINVAL, "igd_frame_meter: device pointers must be 32/16-byte aligned");
-    Bind b(c);
+    IGD_BIND(c);
     const int16_t *dp; igd_meter_rec *dout;
     int rc;
     if ((rc = in_arg(c, mem, 0, pcm, nframes * IGD_FRAME, &dp))) return rc;
@@ -329,7 +342,7 @@ int igd_bytemean(igd_ctx *c, const uint8_t *payloads, size_t n, size_t len, size
 {
     if (!c || (n && (!payloads || !out)) || stride < len) return fail(c, IGD_EINVAL, "igd_bytemean: bad argument");
     if (n == 0) return IGD_OK;
-    Bind b(c);
+    IGD_BIND(c);
     const uint8_t *dp; uint8_t *dout;
     int rc;
     if ((rc = in_arg(c, mem, 0, payloads, (n - 1) * stride + len, &dp))) return rc;
@@ -344,7 +357,7 @@ int igd_level_percent(igd_ctx *c, const int32_t *v, size_t n, int32_t *out, int 
 {
     if (!c || (n && (!v || !out))) return fail(c, IGD_EINVAL, "igd_level_percent: bad argument");
     if (n == 0) return IGD_OK;
-    Bind b(c);
+    IGD_BIND(c);
     const int32_t *dv; int32_t *dout;
     int rc;
     if ((rc = in_arg(c, mem, 0, v, n, &dv))) return rc;
@@ -370,7 +383,7 @@ int igd_mix(igd_ctx *c, const int16_t *pcm, const uint16_t *gain, size_t F, size
     if (F == 0 || B == 0) return IGD_OK;
     if (mem == IGD_MEM_DEVICE && (!aligned(pcm, 16) || !aligned(mix, 16)))
         return fail(c, IGD_EINVAL, "igd_mix: device pointers must be 16-byte aligned");
-    Bind b(c);
+    IGD_BIND(c);
     const int16_t *dp; const uint16_t *dg; int16_t *dm;
     int rc;
     if ((rc = in_arg(c, mem, 0, pcm, F * B * G * IGD_FRAME, &dp))) return rc;
@@ -383,6 +396,122 @@ int igd_mix(igd_ctx *c, const int16_t *pcm, const uint16_t *gain, size_t F, size
 }
 
 // ---------------------------------------------------------------- fused path
+namespace {
+
+// One description of both entry points: codes (160 B per leg-frame) or raw packets (180 B + a 16-byte
+// field record per leg-frame) in; any subset of {mix, enc, meter, bmeter} out.
+struct FusedJob {
+    bool packets;
+    size_t F, B, G;
+    unsigned flags;
+    const uint8_t *in;                 // codes or pkts
+    const igd_ed137_fields *fields;    // packets only
+    const uint8_t *law, *out_law;
+    const uint16_t *gain;
+    int16_t *mix;
+    uint8_t *enc;
+    igd_meter_rec *meter;
+    igd_bridge_rec *bmeter;
+};
+
+cudaError_t launch_fused_job(igd_ctx *c, const FusedJob &j, size_t nf, const uint8_t *in, const igd_ed137_fields *fields,
+                             const uint8_t *law, const uint16_t *gain, const uint8_t *out_law, int16_t *mix,
+                             uint8_t *enc, igd_meter_rec *meter, igd_bridge_rec *bmeter)
+{
+    if (j.packets) {
+        igd_packets_desc k;
+        memset(&k, 0, sizeof k);
+        k.struct_size = sizeof k; k.mem = IGD_MEM_DEVICE; k.F = (int32_t)nf; k.B = (int32_t)j.B; k.G = (int32_t)j.G;
+        k.flags = j.flags; k.pkts = in; k.fields = fields; k.law = law; k.gain_q7 = gain; k.out_law = out_law;
+        k.mix = mix; k.enc = enc; k.meter = meter; k.bmeter = bmeter;
+        return igd_k_fused_packets(cfg_of(c), k);
+    }
+    igd_batch_desc k;
+    memset(&k, 0, sizeof k);
+    k.struct_size = sizeof k; k.mem = IGD_MEM_DEVICE; k.F = (int32_t)nf; k.B = (int32_t)j.B; k.G = (int32_t)j.G;
+    k.flags = j.flags; k.codes = in; k.law = law; k.gain_q7 = gain; k.out_law = out_law;
+    k.mix = mix; k.enc = enc; k.meter = meter; k.bmeter = bmeter;
+    return igd_k_fused(cfg_of(c), k);
+}
+
+// Host buffers: staged through the GPU in frame chunks so that the H2D copy of chunk k+1, the kernel of
+// chunk k and the D2H copy of chunk k-1 overlap (three streams, two buffers).  Only the outputs the caller
+// asked for are copied back -- the int16 mix alone is 57 % of the full result set.
+int fused_job_host(igd_ctx *c, const FusedJob &j)
+{
+    const size_t F = j.F, B = j.B, C = j.B * j.G;
+    const size_t leg_bytes = j.packets ? (size_t)IGD_PKT_MAX : (size_t)IGD_FRAME;
+    int rc;
+    const uint8_t *dlaw, *dol;
+    if ((rc = in_arg(c, IGD_MEM_HOST, 0, j.law, C, &dlaw))) return rc;
+    if ((rc = in_arg(c, IGD_MEM_HOST, 1, j.out_law, B, &dol))) return rc;
+    // chunk size: ~32 MiB of input per chunk, at least 1 frame
+    // (measured on B200 / PCIe gen5: 4 / 8 / 16 / 32 / 64 MiB -> 3.2 / 4.0 / 4.6 / 4.8 / 4.8e10 channel-samples/s)
+    size_t fc = (32u << 20) / (C * leg_bytes);
+    if (fc < 1) fc = 1;
+    if (fc > F) fc = F;
+    const size_t nchunks = (F + fc - 1) / fc;
+    const int nbuf = nchunks > 1 ? 2 : 1;
+    void *din, *dgain, *dfields = nullptr, *dmix = nullptr, *denc = nullptr, *dmeter = nullptr, *dbm = nullptr;
+    if ((rc = scratch(c, 2, nbuf * fc * C * leg_bytes, &din))) return rc;
+    if ((rc = scratch(c, 3, nbuf * fc * C * sizeof(uint16_t), &dgain))) return rc;
+    if (j.packets && (rc = scratch(c, 8, nbuf * fc * C * sizeof(igd_ed137_fields), &dfields))) return rc;
+    if (j.mix && (rc = scratch(c, 4, nbuf * fc * B * IGD_FRAME * sizeof(int16_t), &dmix))) return rc;
+    if (j.enc && (rc = scratch(c, 5, nbuf * fc * B * IGD_FRAME, &denc))) return rc;
+    if (j.meter && (rc = scratch(c, 6, nbuf * fc * C * sizeof(igd_meter_rec), &dmeter))) return rc;
+    if (j.bmeter && (rc = scratch(c, 7, nbuf * fc * B * sizeof(igd_bridge_rec), &dbm))) return rc;
+    cudaStream_t sin = c->copy_streams[0], sout = c->copy_streams[1];
+    // ev[0..1]: input of buffer i ready; ev[2..3]: kernel on buffer i done; ev[4..5]: output drained
+    bool out_pending[2] = {false, false};
+    auto chunk = [&](size_t ch) -> int {
+        const int i = (int)(ch % nbuf);
+        const size_t f0 = ch * fc, nf = (f0 + fc <= F) ? fc : F - f0;
+        uint8_t *bi = static_cast<uint8_t *>(din) + (size_t)i * fc * C * leg_bytes;
+        uint16_t *bg = static_cast<uint16_t *>(dgain) + (size_t)i * fc * C;
+        igd_ed137_fields *bf = j.packets ? static_cast<igd_ed137_fields *>(dfields) + (size_t)i * fc * C : nullptr;
+        int16_t *bm = j.mix ? static_cast<int16_t *>(dmix) + (size_t)i * fc * B * IGD_FRAME : nullptr;
+        uint8_t *be = j.enc ? static_cast<uint8_t *>(denc) + (size_t)i * fc * B * IGD_FRAME : nullptr;
+        igd_meter_rec *bmt = j.meter ? static_cast<igd_meter_rec *>(dmeter) + (size_t)i * fc * C : nullptr;
+        igd_bridge_rec *bbr = j.bmeter ? static_cast<igd_bridge_rec *>(dbm) + (size_t)i * fc * B : nullptr;
+        // the input buffer may only be overwritten once the kernel that read it is done
+        if (ch >= (size_t)nbuf) IGD_CUDA(c, cudaStreamWaitEvent(sin, c->ev[2 + i], 0));
+        IGD_CUDA(c, cudaMemcpyAsync(bi, j.in + f0 * C * leg_bytes, nf * C * leg_bytes, cudaMemcpyHostToDevice, sin));
+        IGD_CUDA(c, cudaMemcpyAsync(bg, j.gain + f0 * C, nf * C * sizeof(uint16_t), cudaMemcpyHostToDevice, sin));
+        if (j.packets)
+            IGD_CUDA(c, cudaMemcpyAsync(bf, j.fields + f0 * C, nf * C * sizeof(igd_ed137_fields), cudaMemcpyHostToDevice, sin));
+        IGD_CUDA(c, cudaEventRecord(c->ev[i], sin));
+        IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[i], 0));
+        // the output buffer may only be overwritten once its previous D2H is done
+        if (out_pending[i]) IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[4 + i], 0));
+        IGD_CUDA(c, launch_fused_job(c, j, nf, bi, bf, dlaw, bg, dol, bm, be, bmt, bbr));
+        c->launches++;
+        IGD_CUDA(c, cudaEventRecord(c->ev[2 + i], c->stream));
+        IGD_CUDA(c, cudaStreamWaitEvent(sout, c->ev[2 + i], 0));
+        if (j.mix)
+            IGD_CUDA(c, cudaMemcpyAsync(j.mix + f0 * B * IGD_FRAME, bm, nf * B * IGD_FRAME * sizeof(int16_t), cudaMemcpyDeviceToHost, sout));
+        if (j.enc)
+            IGD_CUDA(c, cudaMemcpyAsync(j.enc + f0 * B * IGD_FRAME, be, nf * B * IGD_FRAME, cudaMemcpyDeviceToHost, sout));
+        if (j.meter)
+            IGD_CUDA(c, cudaMemcpyAsync(j.meter + f0 * C, bmt, nf * C * sizeof(igd_meter_rec), cudaMemcpyDeviceToHost, sout));
+        if (j.bmeter)
+            IGD_CUDA(c, cudaMemcpyAsync(j.bmeter + f0 * B, bbr, nf * B * sizeof(igd_bridge_rec), cudaMemcpyDeviceToHost, sout));
+        IGD_CUDA(c, cudaEventRecord(c->ev[4 + i], sout));
+        out_pending[i] = true;
+        return IGD_OK;
+    };
+    rc = IGD_OK;
+    for (size_t ch = 0; ch < nchunks && rc == IGD_OK; ch++) rc = chunk(ch);
+    // also on an error: nothing may still be copying from / into the caller's buffers or the scratch when we return
+    const cudaError_t e0 = cudaStreamSynchronize(sin), e1 = cudaStreamSynchronize(sout), e2 = cudaStreamSynchronize(c->stream);
+    if (rc != IGD_OK) return rc;
+    if (e0 != cudaSuccess) return fail(c, IGD_ECUDA, "cudaStreamSynchronize(copy in)", e0);
+    if (e1 != cudaSuccess) return fail(c, IGD_ECUDA, "cudaStreamSynchronize(copy out)", e1);
+    if (e2 != cudaSuccess) return fail(c, IGD_ECUDA, "cudaStreamSynchronize", e2);
+    return IGD_OK;
+}
+
+}  // namespace
+
 int igd_process_batch(igd_ctx *c, const igd_batch_desc *d)
 {
     if (!c || !d || d->struct_size != sizeof(igd_batch_desc))
@@ -390,10 +519,11 @@ int igd_process_batch(igd_ctx *c, const igd_batch_desc *d)
     if (d->F < 0 || d->B < 0 || d->G < 1 || d->G > IGD_MAX_LEGS)
         return fail(c, IGD_EINVAL, "igd_process_batch: bad shape");
     if (d->F == 0 || d->B == 0) return IGD_OK;
-    if (!d->codes || !d->law || !d->gain_q7 || !d->out_law || !d->mix || !d->enc || !d->meter || !d->bmeter)
-        return fail(c, IGD_EINVAL, "igd_process_batch: null buffer");
-    const size_t F = d->F, B = d->B, G = d->G, C = B * G;
-    Bind b(c);
+    if (!d->codes || !d->law || !d->gain_q7 || !d->out_law)
+        return fail(c, IGD_EINVAL, "igd_process_batch: null input buffer");
+    if (!d->mix && !d->enc && !d->meter && !d->bmeter)
+        return fail(c, IGD_EINVAL, "igd_process_batch: no output requested (mix, enc, meter, bmeter are all NULL)");
+    IGD_BIND(c);
     if (d->mem == IGD_MEM_DEVICE) {
         if (!aligned(d->codes, 16) || !aligned(d->mix, 32) || !aligned(d->enc, 16) || !aligned(d->meter, 16) ||
             !aligned(d->gain_q7, 2) || !aligned(d->bmeter, 4))
@@ -402,73 +532,11 @@ int igd_process_batch(igd_ctx *c, const igd_batch_desc *d)
         c->launches++;
         return IGD_OK;
     }
-    // Host buffers: stage through the GPU in frame chunks so that the H2D copy of
-    // chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap.
-    igd_batch_desc k = *d;
-    k.mem = IGD_MEM_DEVICE;
-    int rc;
-    const uint8_t *dlaw, *dol;
-    if ((rc = in_arg(c, IGD_MEM_HOST, 0, d->law, C, &dlaw))) return rc;
-    if ((rc = in_arg(c, IGD_MEM_HOST, 1, d->out_law, B, &dol))) return rc;
-    k.law = dlaw; k.out_law = dol;
-    // chunk size: ~32 MiB of codes per chunk, at least 1 frame
-    // (measured on B200 / PCIe gen5: 4 / 8 / 16 / 32 / 64 MiB -> 3.2 / 4.0 / 4.6 / 4.8 / 4.8e10 channel-samples/s)
-    size_t fc = (32u << 20) / (C * IGD_FRAME);
-    if (fc < 1) fc = 1;
-    if (fc > F) fc = F;
-    const size_t nchunks = (F + fc - 1) / fc;
-    const int nbuf = nchunks > 1 ? 2 : 1;
-    void *dcodes, *dgain, *dmix, *denc, *dmeter, *dbm;
-    if ((rc = scratch(c, 2, nbuf * fc * C * IGD_FRAME, &dcodes))) return rc;
-    if ((rc = scratch(c, 3, nbuf * fc * C * sizeof(uint16_t), &dgain))) return rc;
-    if ((rc = scratch(c, 4, nbuf * fc * B * IGD_FRAME * sizeof(int16_t), &dmix))) return rc;
-    if ((rc = scratch(c, 5, nbuf * fc * B * IGD_FRAME, &denc))) return rc;
-    if ((rc = scratch(c, 6, nbuf * fc * C * sizeof(igd_meter_rec), &dmeter))) return rc;
-    if ((rc = scratch(c, 7, nbuf * fc * B * sizeof(igd_bridge_rec), &dbm))) return rc;
-    // law tables were queued on c->stream; copies below run on the copy streams
-    IGD_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
-    cudaStream_t sin = c->copy_streams[0], sout = c->copy_streams[1];
-    // ev[0..1]: input of buffer i ready; ev[2..3]: kernel on buffer i done; ev[4..5]: output drained
-    bool out_pending[2] = {false, false};
-    for (size_t ch = 0; ch < nchunks; ch++) {
-        const int i = (int)(ch % nbuf);
-        const size_t f0 = ch * fc, nf = (f0 + fc <= F) ? fc : F - f0;
-        uint8_t *bc = static_cast<uint8_t *>(dcodes) + (size_t)i * fc * C * IGD_FRAME;
-        uint16_t *bg = static_cast<uint16_t *>(dgain) + (size_t)i * fc * C;
-        int16_t *bm = static_cast<int16_t *>(dmix) + (size_t)i * fc * B * IGD_FRAME;
-        uint8_t *be = static_cast<uint8_t *>(denc) + (size_t)i * fc * B * IGD_FRAME;
-        igd_meter_rec *bmt = static_cast<igd_meter_rec *>(dmeter) + (size_t)i * fc * C;
-        igd_bridge_rec *bbr = static_cast<igd_bridge_rec *>(dbm) + (size_t)i * fc * B;
-        // the input buffer may only be overwritten once the kernel that read it is done
-        if (ch >= (size_t)nbuf) IGD_CUDA(c, cudaStreamWaitEvent(sin, c->ev[2 + i], 0));
-        IGD_CUDA(c, cudaMemcpyAsync(bc, d->codes + f0 * C * IGD_FRAME, nf * C * IGD_FRAME,
-                                    cudaMemcpyHostToDevice, sin));
-        IGD_CUDA(c, cudaMemcpyAsync(bg, d->gain_q7 + f0 * C, nf * C * sizeof(uint16_t),
-                                    cudaMemcpyHostToDevice, sin));
-        IGD_CUDA(c, cudaEventRecord(c->ev[i], sin));
-        IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[i], 0));
-        // the output buffer may only be overwritten once its previous D2H is done
-        if (out_pending[i]) IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[4 + i], 0));
-        k.F = (int32_t)nf;
-        k.codes = bc; k.gain_q7 = bg; k.mix = bm; k.enc = be; k.meter = bmt; k.bmeter = bbr;
-        IGD_CUDA(c, igd_k_fused(cfg_of(c), k));
-        c->launches++;
-        IGD_CUDA(c, cudaEventRecord(c->ev[2 + i], c->stream));
-        IGD_CUDA(c, cudaStreamWaitEvent(sout, c->ev[2 + i], 0));
-        IGD_CUDA(c, cudaMemcpyAsync(d->mix + f0 * B * IGD_FRAME, bm, nf * B * IGD_FRAME * sizeof(int16_t),
-                                    cudaMemcpyDeviceToHost, sout));
-        IGD_CUDA(c, cudaMemcpyAsync(d->enc + f0 * B * IGD_FRAME, be, nf * B * IGD_FRAME,
-                                    cudaMemcpyDeviceToHost, sout));
-        IGD_CUDA(c, cudaMemcpyAsync(d->meter + f0 * C, bmt, nf * C * sizeof(igd_meter_rec),
-                                    cudaMemcpyDeviceToHost, sout));
-        IGD_CUDA(c, cudaMemcpyAsync(d->bmeter + f0 * B, bbr, nf * B * sizeof(igd_bridge_rec),
-                                    cudaMemcpyDeviceToHost, sout));
-        IGD_CUDA(c, cudaEventRecord(c->ev[4 + i], sout));
-        out_pending[i] = true;
-    }
-    IGD_CUDA(c, cudaStreamSynchronize(sout));
-    IGD_CUDA(c, cudaStreamSynchronize(c->stream));
-    return IGD_OK;
+    FusedJob j;
+    j.packets = false; j.F = d->F; j.B = d->B; j.G = d->G; j.flags = d->flags;
+    j.in = d->codes; j.fields = nullptr; j.law = d->law; j.out_law = d->out_law; j.gain = d->gain_q7;
+    j.mix = d->mix; j.enc = d->enc; j.meter = d->meter; j.bmeter = d->bmeter;
+    return fused_job_host(c, j);
 }
 
 int igd_process_packets(igd_ctx *c, const igd_packets_desc *d)
@@ -479,33 +547,24 @@ int igd_process_packets(igd_ctx *c, const igd_packets_desc *d)
     if (d->G != 4)
         return fail(c, IGD_EINVAL, "igd_process_packets: G must be 4 (use igd_ed137_parse + igd_process_batch)");
     if (d->F == 0 || d->B == 0) return IGD_OK;
-    if (!d->pkts || !d->fields || !d->law || !d->gain_q7 || !d->out_law || !d->mix || !d->enc || !d->meter || !d->bmeter)
-        return fail(c, IGD_EINVAL, "igd_process_packets: null buffer");
-    const size_t F = d->F, B = d->B, C = B * 4;
-    Bind b(c);
-    if (d->mem == IGD_MEM_DEVICE &&
-        (!aligned(d->pkts, 16) || !aligned(d->fields, 16) || !aligned(d->mix, 32) || !aligned(d->enc, 16) ||
-         !aligned(d->meter, 16) || !aligned(d->gain_q7, 8) || !aligned(d->law, 4) || !aligned(d->bmeter, 4)))
-        return fail(c, IGD_EINVAL, "igd_process_packets: misaligned device pointer");
-    igd_packets_desc k = *d;
-    k.mem = IGD_MEM_DEVICE;
-    int rc;
-    if ((rc = in_arg(c, d->mem, 0, d->pkts, F * C * IGD_PKT_MAX, &k.pkts))) return rc;
-    if ((rc = in_arg(c, d->mem, 1, d->fields, F * C, &k.fields))) return rc;
-    if ((rc = in_arg(c, d->mem, 2, d->law, C, &k.law))) return rc;
-    if ((rc = in_arg(c, d->mem, 3, d->gain_q7, F * C, &k.gain_q7))) return rc;
-    if ((rc = in_arg(c, d->mem, 4, d->out_law, B, &k.out_law))) return rc;
-    if ((rc = out_arg(c, d->mem, 5, d->mix, F * B * IGD_FRAME, &k.mix))) return rc;
-    if ((rc = out_arg(c, d->mem, 6, d->enc, F * B * IGD_FRAME, &k.enc))) return rc;
-    if ((rc = out_arg(c, d->mem, 7, d->meter, F * C, &k.meter))) return rc;
-    if ((rc = out_arg(c, d->mem, 8, d->bmeter, F * B, &k.bmeter))) return rc;
-    IGD_CUDA(c, igd_k_fused_packets(cfg_of(c), k));
-    c->launches++;
-    if ((rc = out_done(c, d->mem, d->mix, k.mix, F * B * IGD_FRAME))) return rc;
-    if ((rc = out_done(c, d->mem, d->enc, k.enc, F * B * IGD_FRAME))) return rc;
-    if ((rc = out_done(c, d->mem, d->meter, k.meter, F * C))) return rc;
-    if ((rc = out_done(c, d->mem, d->bmeter, k.bmeter, F * B))) return rc;
-    return finish(c, d->mem);
+    if (!d->pkts || !d->fields || !d->law || !d->gain_q7 || !d->out_law)
+        return fail(c, IGD_EINVAL, "igd_process_packets: null input buffer");
+    if (!d->mix && !d->enc && !d->meter && !d->bmeter)
+        return fail(c, IGD_EINVAL, "igd_process_packets: no output requested (mix, enc, meter, bmeter are all NULL)");
+    IGD_BIND(c);
+    if (d->mem == IGD_MEM_DEVICE) {
+        if (!aligned(d->pkts, 16) || !aligned(d->fields, 16) || !aligned(d->mix, 32) || !aligned(d->enc, 16) ||
+            !aligned(d->meter, 16) || !aligned(d->gain_q7, 8) || !aligned(d->law, 4) || !aligned(d->bmeter, 4))
+            return fail(c, IGD_EINVAL, "igd_process_packets: misaligned device pointer");
+        IGD_CUDA(c, igd_k_fused_packets(cfg_of(c), *d));
+        c->launches++;
+        return IGD_OK;
+    }
+    FusedJob j;
+    j.packets = true; j.F = d->F; j.B = d->B; j.G = d->G; j.flags = d->flags;
+    j.in = d->pkts; j.fields = d->fields; j.law = d->law; j.out_law = d->out_law; j.gain = d->gain_q7;
+    j.mix = d->mix; j.enc = d->enc; j.meter = d->meter; j.bmeter = d->bmeter;
+    return fused_job_host(c, j);
 }
 
 // ---------------------------------------------------------------- summary
@@ -514,7 +573,7 @@ int igd_event_summary(igd_ctx *c, const igd_meter_rec *meter, const uint16_t *ga
 {
     if (!c || (C && (!out || (F && (!meter || !gain))))) return fail(c, IGD_EINVAL, "igd_event_summary: bad argument");
     if (C == 0) return IGD_OK;
-    Bind b(c);
+    IGD_BIND(c);
     const igd_meter_rec *dm; const uint16_t *dg; igd_summary_rec *dout; igd_summary_db *ddb = nullptr;
     int rc;
     if ((rc = in_arg(c, mem, 0, meter, F * C, &dm))) return rc;
@@ -561,7 +620,7 @@ int igd_ed137_parse(igd_ctx *c, const uint8_t *pkts, const uint32_t *sizes, size
     if (npkts == 0) return IGD_OK;
     if (mem == IGD_MEM_DEVICE && (!aligned(pkts, 4) || !aligned(fields, 16) || (payload_out && !aligned(payload_out, 4))))
         return fail(c, IGD_EINVAL, "igd_ed137_parse: misaligned device pointer");
-    Bind b(c);
+    IGD_BIND(c);
     const uint8_t *dp; const uint32_t *ds = nullptr; igd_ed137_fields *df; uint8_t *dpo = nullptr;
     int rc;
     if ((rc = in_arg(c, mem, 0, pkts, npkts * stride, &dp))) return rc;
@@ -579,13 +638,17 @@ int igd_ed137_pack(igd_ctx *c, const igd_ed137_pack_desc *d)
 {
     if (!c || !d || d->struct_size != sizeof(igd_ed137_pack_desc))
         return fail(c, IGD_EINVAL, "igd_ed137_pack: bad descriptor");
-    if (d->F < 0 || d->C < 0 || d->payload_len > IGD_FRAME || (d->payload_len & 3) ||
+    if (d->F < 0 || d->C < 0 || d->payload_len == 0 || d->payload_len > IGD_FRAME || (d->payload_len & 3) ||
         d->out_stride < IGD_PKT_HDR + d->payload_len || (d->out_stride & 3))
-        return fail(c, IGD_EINVAL, "igd_ed137_pack: bad shape (payload_len and out_stride must be multiples of 4)");
+        return fail(c, IGD_EINVAL, "igd_ed137_pack: bad shape (payload_len in 4..160 and out_stride must be multiples of 4)");
     if (d->F == 0 || d->C == 0) return IGD_OK;
     if (!d->rtp12 || !d->payload || !d->state || !d->pkts || !d->sizes || !d->bytemean_out)
         return fail(c, IGD_EINVAL, "igd_ed137_pack: null buffer");
-    Bind b(c);
+    if (d->mem == IGD_MEM_DEVICE &&
+        (!aligned(d->rtp12, 4) || !aligned(d->payload, 4) || !aligned(d->pkts, 4) || !aligned(d->sizes, 4) ||
+         !aligned(d->state, 8) || (d->ctl && !aligned(d->ctl, 8)) || (d->stale_payload && !aligned(d->stale_payload, 4))))
+        return fail(c, IGD_EINVAL, "igd_ed137_pack: misaligned device pointer (4 bytes; state / ctl 8)");
+    IGD_BIND(c);
     const size_t n = (size_t)d->F * d->C;
     const int mem = d->mem;
     igd_ed137_pack_desc k = *d;
@@ -632,7 +695,7 @@ int igd_ed137_keepalive(igd_ctx *c, uint8_t *hdr20, igd_ed137_state *state, size
     if (C == 0) return IGD_OK;
     if (mem == IGD_MEM_DEVICE && (!aligned(hdr20, 4) || !aligned(state, 8) || !aligned(sizes, 4)))
         return fail(c, IGD_EINVAL, "igd_ed137_keepalive: misaligned device pointer");
-    Bind b(c);
+    IGD_BIND(c);
     int rc;
     const uint8_t *th = nullptr; const igd_ed137_state *ts = nullptr; uint32_t *dsz = nullptr;
     if ((rc = in_arg(c, mem, 0, hdr20, C * IGD_PKT_HDR, &th))) return rc;
@@ -658,7 +721,7 @@ int igd_rx_track(igd_ctx *c, const igd_rx_track_desc *d)
     const int mem = d->mem;
     if (mem == IGD_MEM_DEVICE && (!aligned(d->fields, 16) || !aligned(d->state, 16) || !aligned(d->events, 8)))
         return fail(c, IGD_EINVAL, "igd_rx_track: misaligned device pointer");
-    Bind b(c);
+    IGD_BIND(c);
     const size_t n = (size_t)d->F * d->C;
     igd_rx_track_desc k = *d;
     int rc;
@@ -689,7 +752,7 @@ int igd_gate_arbitrate(igd_ctx *c, const igd_arb_desc *d)
     const int mem = d->mem;
     if (mem == IGD_MEM_DEVICE && (!aligned(d->words, 4) || !aligned(d->legs, 8) || !aligned(d->bridges, 4)))
         return fail(c, IGD_EINVAL, "igd_gate_arbitrate: misaligned device pointer");
-    Bind b(c);
+    IGD_BIND(c);
     const size_t Cn = (size_t)d->B * d->G, n = (size_t)d->F * Cn;
     igd_arb_desc k = *d;
     int rc;
@@ -726,7 +789,7 @@ int igd_wav_image(igd_ctx *c, const uint8_t *payload, size_t n, int rate, int la
 {
     if (!c || !out || (n && !payload)) return fail(c, IGD_EINVAL, "igd_wav_image: bad argument");
     if (mem == IGD_MEM_DEVICE && !aligned(out, 4)) return fail(c, IGD_EINVAL, "igd_wav_image: misaligned output");
-    Bind b(c);
+    IGD_BIND(c);
     const size_t total = igd_wav_size(n, ref_quirks);
     const uint8_t *dp; uint8_t *dout;
     int rc;
@@ -751,7 +814,7 @@ int igd_wav_images(igd_ctx *c, const uint8_t *codes, size_t F, size_t C, const u
     if (chans && mem == IGD_MEM_HOST)
         for (size_t k = 0; k < nchan; k++)
             if (chans[k] >= C) return fail(c, IGD_EINVAL, "igd_wav_images: channel index out of range");
-    Bind b(c);
+    IGD_BIND(c);
     const uint8_t *dc, *dl = nullptr; const uint32_t *dch = nullptr; uint8_t *dout;
     int rc;
     if ((rc = in_arg(c, mem, 0, codes, F * C * IGD_FRAME, &dc))) return rc;

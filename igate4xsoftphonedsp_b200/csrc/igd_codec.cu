@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) k_mix(const int16_t *__restrict__ pcm, co
         for (int k = 0; k < 8; k++) acc[k] = 0;
         for (int g = 0; g < G; g++) {
             const int a = gain[bf * G + g];
-            if (a == 0) continue;
+            if (a == 0 || (a & (int)IGD_GAIN_NO_AUDIO)) continue;
             const uint4 w = ld16_stream(pcm + ((size_t)bf * G + g) * IGD_FRAME + p * 8);
             const uint32_t wd[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(32 * kSumSlices) k_event_summary(const igd_met
             for (int u = 0; u < kAhead; u++) {
                 const long long f = f0 + (long long)u * kSumSlices;
                 g[u] = f < F ? (uint32_t)gain[(size_t)f * C + c] : 0u;
+                if (g[u] & IGD_GAIN_NO_AUDIO) g[u] = 0u;      // no audio frame on this tick: no level either
             }
 #pragma unroll
             for (int u = 0; u < kAhead; u++) {
@@ -259,12 +260,9 @@ __global__ void __launch_bounds__(32 * kSumSlices) k_event_summary(const igd_met
 cudaError_t igd_k_g711_decode(const igd_launch_cfg &c, const uint8_t *codes, const uint8_t *law_ch,
                               int law, int16_t *pcm, size_t n, size_t nch)
 {
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_g711_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutBytes);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    // per launch, like the fused launchers: the attribute is per device, a process may hold contexts on several
+    cudaError_t e = cudaFuncSetAttribute(k_g711_decode, cudaFuncAttributeMaxDynamicSharedMemorySize, kLutBytes);
+    if (e != cudaSuccess) return e;
     const int threads = 512;
     k_g711_decode<<<grid_for(c, n / 16 + 1, threads, 3), threads, kLutBytes, c.stream>>>(codes, law_ch, law, pcm, n,
                                                                                   nch ? nch : 1);

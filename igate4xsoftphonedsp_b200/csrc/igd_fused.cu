@@ -88,12 +88,12 @@ __device__ __forceinline__ uint2 leg_chunk(uint32_t lane_base, uint4 w, uint32_t
 // bridge output of one 16-sample chunk: saturate, store PCM, compress, store codes
 template <bool kSigned>
 __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_pk &E, int16_t *mix_dst,
-                                               uint8_t *enc_dst, bool do_store = true)
+                                               uint8_t *enc_dst, bool st_mix, bool st_enc)
 {
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
-    if (do_store) st32_stream(mix_dst, pk);
+    if (st_mix) st32_stream(mix_dst, pk);
     uint32_t mx = max_s16x2(max_s16x2(pk[0], pk[1]), pk[2]), mn = min_s16x2(min_s16x2(pk[0], pk[1]), pk[2]);
     mx = max_s16x2(max_s16x2(mx, pk[3]), pk[4]); mn = min_s16x2(min_s16x2(mn, pk[3]), pk[4]);
     mx = max_s16x2(max_s16x2(mx, pk[5]), pk[6]); mn = min_s16x2(min_s16x2(mn, pk[5]), pk[6]);
@@ -101,7 +101,7 @@ __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_p
     const int hi = max((int)(short)(mx & 0xFFFFu), (int)mx >> 16);
     const int lo = min((int)(short)(mn & 0xFFFFu), (int)mn >> 16);
     const uint4 e = encode16_packed(pk, E);
-    if (do_store) st16_stream(enc_dst, e);
+    if (st_enc) st16_stream(enc_dst, e);
     int esum = 0;
     if (kSigned) {
         esum = __dp4a((int)e.x, 0x01010101, esum); esum = __dp4a((int)e.y, 0x01010101, esum);
@@ -194,6 +194,16 @@ __device__ __forceinline__ uint2 lut_lookup2(uint32_t lane_base, uint32_t word)
     return v;
 }
 
+// IGD_GAIN_NO_AUDIO (bit 15 of a gain): the leg-frame is silent.  Clears every flagged half (the leg then
+// walks the shut path like any closed gate) and returns the flags as one bit per leg in `sil`.
+__device__ __forceinline__ uint2 split_no_audio(uint2 raw, uint32_t &sil)
+{
+    const uint32_t fx = raw.x & 0x80008000u, fy = raw.y & 0x80008000u;
+    sil = ((fx >> 15) & 1u) | ((fx >> 30) & 2u) | (((fy >> 15) & 1u) << 2) | (((fy >> 30) & 2u) << 2);
+    // a flagged half 0x8000 becomes a 0xFFFF mask: (f >> 15) * 0xFFFF
+    return make_uint2(raw.x & ~((fx >> 15) * 0xFFFFu), raw.y & ~((fy >> 15) * 0xFFFFu));
+}
+
 // bit 15 / 31 set for every non-zero 16-bit half of x
 __device__ __forceinline__ uint32_t nonzero_halves(uint32_t x)
 {
@@ -246,22 +256,9 @@ __device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32
     return make_uint2(sq, __byte_perm(mx, (uint32_t)bsum, 0x5410));   // {sq, peak/4 | bsum << 16}
 }
 
-// payload bytes past `rem` (bytes of payload left at this chunk's start) read as zero, like the
-// payload array igd_ed137_parse writes
-__device__ __forceinline__ uint4 clip_chunk(uint4 w, int rem)
-{
-    uint32_t v[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int rb = rem - 4 * k;
-        v[k] = rb >= 4 ? v[k] : rb <= 0 ? 0u : (v[k] & ((1u << (8 * rb)) - 1u));
-    }
-    return make_uint4(v[0], v[1], v[2], v[3]);
-}
-
-// kPkt: the codes are read straight out of the raw ED-137 packets ([F][C][180], payload at byte 20,
-// payload_len from the parsed fields) -- the item is still ONE contiguous bulk copy (6 * G * 180 B),
-// the payload array between igd_ed137_parse and this kernel is never materialised.
+// kPkt: the codes are read straight out of the raw ED-137 packets ([F][C][180], payload at byte 20) -- the
+// item is still ONE contiguous bulk copy (6 * G * 180 B), the payload array between igd_ed137_parse and
+// this kernel is never materialised; a packet that is not a whole audio frame (parsed fields) is silent.
 template <int G, bool kSigned, int kWarps, bool kPkt = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
 {
@@ -333,28 +330,33 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         }
         return r | ((uint32_t)(__ldg(q.out_law + bb) & 1u) << 8);
     };
-    auto load_plens = [&](uint32_t bfi) -> uint32_t {    // packet form: the G payload lengths (<= 160) of a bridge-frame, one byte each
-        uint32_t r = 0;
+    // packet form: a leg whose packet is not a whole audio frame (keep-alive, truncated, dropped, absent) is
+    // silent -- its gain gets IGD_GAIN_NO_AUDIO, the bytes of its slot are never interpreted
+    auto mark_no_audio = [&](uint2 g, uint32_t bfi) -> uint2 {
+        const uint32_t *fw = reinterpret_cast<const uint32_t *>(q.fields + (size_t)bfi * G);
 #pragma unroll
-        for (int g = 0; g < G; g++)
-            r |= min((uint32_t)__ldg(&q.fields[(size_t)bfi * G + g].payload_len), (uint32_t)IGD_FRAME) << (8 * g);
-        return r;
+        for (int l = 0; l < G; l++) {
+            if (igd_fields_no_audio(__ldg(fw + 4 * l + 1), __ldg(fw + 4 * l + 2), __ldg(fw + 4 * l + 3))) {
+                if (l < 2) g.x |= 0x8000u << (16 * l); else g.y |= 0x8000u << (16 * (l - 2));
+            }
+        }
+        return g;
     };
-    constexpr uint32_t kFullPlens = G == 4 ? 0xA0A0A0A0u : G == 3 ? 0x00A0A0A0u : G == 2 ? 0x0000A0A0u : 0x000000A0u;
     uint2 gq = make_uint2(0u, 0u);
-    uint32_t lwq = 0u, plq = kFullPlens;
+    uint32_t lwq = 0u;
     if (worker && item < items && item * kBfPerItem + bfl < total_bf) {
         gq = load_gains<G>(q.gain + (size_t)(item * kBfPerItem + bfl) * G);
         lwq = load_laws(b);
-        if (kPkt) plq = load_plens(item * kBfPerItem + bfl);
+        if (kPkt) gq = mark_no_audio(gq, item * kBfPerItem + bfl);
     }
 
     for (uint32_t it = 0; item < items; item += nw, it++) {
         const uint32_t bf = item * kBfPerItem + bfl;
         const uint32_t next = item + nw;
         mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
-        const uint2 gcur = gq;
-        const uint32_t lcur = lwq, plcur = plq;
+        uint32_t silent;                                      // bit g: leg g of this lane's bridge-frame has no audio
+        const uint2 gcur = split_no_audio(gq, silent);
+        const uint32_t lcur = lwq;
         const bool valid = worker && bf < total_bf;
         {
             b += b_step;
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             if (worker && next < items && bfn < total_bf) {      // next item's gains and laws ride in three registers
                 gq = load_gains<G>(q.gain + (size_t)bfn * G);
                 lwq = load_laws(b);
-                if (kPkt) plq = load_plens(bfn);
+                if (kPkt) gq = mark_no_audio(gq, bfn);
             }
         }
         // every lane runs the same instruction stream (idle / tail lanes on stale bytes with all
@@ -378,8 +380,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         // open legs of this lane's bridge-frame, pre-shifted into the high half of the bridge partial
         // (every one of the ten partials carries it; the finish divides the sum by ten)
         const uint32_t n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y))) << 16;
-        // packet form: some packet of this item is shorter than 180 bytes (keep-alive, truncated) -> clip its chunks
-        const bool ragged = kPkt && __any_sync(0xFFFFFFFFu, valid && plcur != kFullPlens);
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const uint32_t ch = h == 0 ? c0 : (c0 >= (uint32_t)kC32 ? c0 - kC32 : c0 + kC32);   // this pass's chunk
@@ -406,10 +406,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                                      : "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(a));
                     wh[g] = make_uint4(v[kOff], v[kOff + 1], v[kOff + 2], v[kOff + 3]);
                 }
-            }
-            if (kPkt && ragged) {
-#pragma unroll
-                for (int g = 0; g < G; g++) wh[g] = clip_chunk(wh[g], (int)((plcur >> (8 * g)) & 0xFFu) - (int)ch * 16);
             }
             uint2 *mypart = part + bfl * (G * kP) + ch;
             int acc[16];
@@ -450,7 +446,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                 E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
             }
             const uint32_t o16 = bf * kChunks + ch;     // 16-sample chunk index of the outputs
-            const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)o16 * 16, q.enc + (size_t)o16 * 16, valid);
+            const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)o16 * 16, q.enc + (size_t)o16 * 16,
+                                                    valid && q.mix != nullptr, valid && q.enc != nullptr);
             if (valid) bpart[bfl * kP + ch] = make_uint2(mo.x, mo.y | n_open16);
         }
         __syncwarp();
@@ -460,7 +457,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             const uint32_t bf0 = item * kBfPerItem;
             const uint2 *src_p = part + lane * kP;
             unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
-            if (lane < kBfPerItem * G + kBfPerItem) {
+            // the record of leg (lane / G, lane % G): the lanes of that bridge-frame hold its no-audio flags
+            const uint32_t sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / G) * kC32) & 31) >> (lane % G)) & 1u;
+            if (lane < kBfPerItem * G + kBfPerItem && !(lane < kBfPerItem * G && sil_rec)) {
 #pragma unroll
                 for (int i = 0; i < kChunks; i++) {
                     const uint2 v = src_p[i];
@@ -468,13 +467,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                 }
             }
             if (lane < kBfPerItem * G) {
-                if (bf0 + lane / G < total_bf) {
+                if (bf0 + lane / G < total_bf && q.meter != nullptr) {
                     const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
                     st16_stream(q.meter + ((size_t)bf0 * G + lane), *reinterpret_cast<const uint4 *>(&r));
                 }
             } else if (lane < kBfPerItem * G + kBfPerItem) {
                 const uint32_t j = lane - kBfPerItem * G;
-                if (bf0 + j < total_bf) {
+                if (bf0 + j < total_bf && q.bmeter != nullptr) {
                     igd_bridge_rec r;
                     r.bytemean_out = (uint8_t)igd_bytemean_from_sum((int)(uint32_t)sq, IGD_FRAME);
                     r.n_open = (uint8_t)((uint32_t)bsum / kChunks);
@@ -646,7 +645,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
             fence_proxy_async();
             if (it_n < items) fetch(it_n, grp_n, n + 1);
             mbar_wait(bar_s + (n & 1u) * 8, (n >> 1) & 1u);
-            const uint2 gcur = gq;
+            uint32_t silent;                                             // bit g: leg g of this group has no audio on this lane's bridge-frame
+            const uint2 gcur = split_no_audio(gq, silent);
             const uint32_t lcur = lwq;
             load_unit(it_n, grp_n, last ? b_next : b, gq, lwq);          // next unit's gains / laws ride in registers
             const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
@@ -674,14 +674,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
                 }
             }
             __syncwarp();
+            // the record of leg (lane / 4, lane % 4): the lanes of that bridge-frame hold its no-audio flags
+            const uint32_t sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / kGLegs) * kChunks) & 31) >> (lane % kGLegs)) & 1u;
             if (lane < kGBf * kGLegs) {                                  // this group's leg records
                 const uint32_t fb = lane / kGLegs, g = lane - fb * kGLegs;
-                if (g < legs && item * kGBf + fb < total_bf) {
+                if (g < legs && item * kGBf + fb < total_bf && q.meter != nullptr) {
                     const uint2 *src_p = part + lane * kPst;
                     unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
 #pragma unroll
                     for (int i = 0; i < kChunks; i++) {
-                        const uint2 v = src_p[i];
+                        const uint2 v = sil_rec ? make_uint2(0u, 0u) : src_p[i];
                         sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
                     }
                     const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
@@ -699,10 +701,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
             E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
         }
         const size_t o16 = (size_t)bf * kChunks + c;
-        const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + o16 * 16, q.enc + o16 * 16, valid);
+        const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + o16 * 16, q.enc + o16 * 16, valid && q.mix != nullptr,
+                                                valid && q.enc != nullptr);
         if (valid) bpart[bfl * kPst + c] = make_uint2(mo.x, mo.y | (n_open << 16));
         __syncwarp();
-        if (lane < kGBf && item * kGBf + lane < total_bf) {
+        if (lane < kGBf && item * kGBf + lane < total_bf && q.bmeter != nullptr) {
             const uint2 *src_p = bpart + lane * kPst;
             int esum = 0; uint32_t pk = 0;
 #pragma unroll
@@ -745,7 +748,8 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
                 const uint4 w = ld16_stream(q.codes + ((size_t)bf * G + g) * IGD_FRAME + p * 16);
                 const uint32_t a = q.gain[(size_t)bf * G + g];
                 const uint32_t sl = gain_selector(a), lb = lut_lane_base(lut_bytes, lane, q.law[(size_t)b * G + g]);
-                part[bfl * kPst + p] = sl == kSelGeneral ? leg_chunk<kSigned, 2>(lb, w, 0u, (int)a, acc)
+                part[bfl * kPst + p] = (a & IGD_GAIN_NO_AUDIO) ? make_uint2(0u, 0u)                 // silent leg-frame
+                                       : sl == kSelGeneral ? leg_chunk<kSigned, 2>(lb, w, 0u, (int)a, acc)
                                        : sl             ? leg_chunk<kSigned, 1>(lb, w, sl, 0, acc)
                                                         : leg_chunk<kSigned, 0>(lb, w, 0u, 0, acc);
             }
@@ -757,7 +761,7 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
 #pragma unroll
                     for (int i = 0; i < kChunks; i++) partial_add(part[t * kPst + i], sq, peak, bsum);
                     const igd_meter_rec r = meter_finish(sq << 4, peak << 2, bsum, true);
-                    st16_stream(q.meter + bf2 * G + g, *reinterpret_cast<const uint4 *>(&r));
+                    if (q.meter) st16_stream(q.meter + bf2 * G + g, *reinterpret_cast<const uint4 *>(&r));
                 }
             }
             __syncthreads();
@@ -765,16 +769,20 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
         if (valid)
             bpart[bfl * kPst + p] = mix_out_chunk<kSigned>(acc, enc_pk_make(q.out_law[b]),
                                                            q.mix + (size_t)bf * IGD_FRAME + p * 16,
-                                                           q.enc + (size_t)bf * IGD_FRAME + p * 16);
+                                                           q.enc + (size_t)bf * IGD_FRAME + p * 16, q.mix != nullptr,
+                                                           q.enc != nullptr);
         __syncthreads();
         if (t < BFPC) {
             const long long bf2 = tile * BFPC + t;
-            if (bf2 < q.total_bf) {
+            if (bf2 < q.total_bf && q.bmeter != nullptr) {
                 int esum = 0, mpeak = 0;
 #pragma unroll
                 for (int i = 0; i < kChunks; i++) { esum += (int)bpart[t * kPst + i].x; mpeak = max(mpeak, (int)bpart[t * kPst + i].y); }
                 int n_open = 0;
-                for (int g = 0; g < G; g++) n_open += q.gain[(size_t)bf2 * G + g] != 0;
+                for (int g = 0; g < G; g++) {
+                    const uint32_t a = q.gain[(size_t)bf2 * G + g];
+                    n_open += a != 0 && !(a & IGD_GAIN_NO_AUDIO);
+                }
                 igd_bridge_rec r;
                 r.bytemean_out = (uint8_t)igd_bytemean_from_sum(esum, IGD_FRAME);
                 r.n_open = (uint8_t)n_open;
@@ -852,6 +860,7 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     // the warp-autonomous kernels index bridge-frames in 32 bits; anything larger (2^28 bridge-frames =
     // 318 GB of traffic at G = 4) cannot be resident on one GPU anyway and takes the generic kernel
     // ... and reads a bridge-frame's G gains / a bridge's G laws as one 2G- / G-byte word
+    if (d.flags & IGD_F_GENERIC_KERNEL) return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
     const bool fits32 = q.total_bf < (1ll << 28) &&          // 16-sample chunk indices (10 per bridge-frame) stay below 2^32
                         (reinterpret_cast<uintptr_t>(d.gain_q7) & (size_t)(2 * d.G - 1) & 7u) == 0 &&
                         (d.G != 4 || (reinterpret_cast<uintptr_t>(d.law) & 3u) == 0);
@@ -861,8 +870,7 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     if (q.total_bf < (1ll << 28) && d.G == 3) return sc ? launch_fused_w<3, true, 24>(c, q) : launch_fused_w<3, false, 24>(c, q);
     // any other leg count: the warp-autonomous group walk (needs 16-byte aligned codes, which the C ABI
     // checks, and 32-bit bridge-frame indices); the block-cooperative kernel is the last resort
-    if (q.total_bf < (1ll << 28) && (long long)q.total_bf * d.G < (1ll << 32) &&
-        !getenv("IGD_FUSED_ANYG"))
+    if (q.total_bf < (1ll << 28) && (long long)q.total_bf * d.G < (1ll << 32))
         return sc ? launch_fused_g<true, 24>(c, q) : launch_fused_g<false, 24>(c, q);
     return sc ? launch_fused_anyg<32, true>(c, q) : launch_fused_anyg<32, false>(c, q);
 }

@@ -299,6 +299,7 @@ IGD_HD uint32_t igd_rx_step(S &a, const FL &f, bool present, bool run_watchdog, 
         } else if (f.pt != 123) {                                     // :298-307
             a.r2sPacket = now;
             ev |= 0x02u;                                              // IGD_RXE_AUDIO
+            if ((f.pt == 0 || f.pt == 8) && f.payload_len == 160) ev |= 0x40u;   // IGD_RXE_FRAME: a whole G.711 frame
             if (!a.rtpAudio) ev |= 0x04u;                             // IGD_RXE_EDGE -> setIncomingED137Value
             a.rtpAudio = 1;
         } else {                                                      // :308-315
@@ -318,6 +319,15 @@ IGD_HD uint32_t igd_rx_step(S &a, const FL &f, bool present, bool run_watchdog, 
         }
     }
     return ev;
+}
+
+// A leg-frame the fused path must not decode: its packet (igd_ed137_fields words 1..3) is not a whole G.711
+// audio frame -- pt other than 0 / 8, payload_len != 160, dropped, or absent (size 0 parses as payload_len 0).
+// The same rule as IGD_RXE_FRAME above.
+IGD_HD bool igd_fields_no_audio(uint32_t w1, uint32_t w2, uint32_t w3)
+{
+    const uint32_t plen = w1 >> 16, pt = w2 & 0xFFu, flags = w3 >> 24;
+    return !(pt == 0u || pt == 8u) || plen != 160u || (flags & 0x10u) != 0u;
 }
 
 // ---------------------------------------------------------------- gate arbitration

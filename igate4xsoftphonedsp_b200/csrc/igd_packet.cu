@@ -318,9 +318,15 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
             }
         }
         __syncthreads();
+        const bool mark = (d.flags & IGD_ARB_F_SILENCE) != 0u && d.word_stride >= 8u;
         for (int k = threadIdx.x; k < nt * row; k += kArbThreads) {
             const int t = k / row, j = k - t * row;
-            d.gain_q7[(size_t)(f0 + t) * Cn + (size_t)b0 * G + j] = gain_s[k];
+            uint16_t gv = gain_s[k];
+            if (mark) {      // words are igd_rx_event records: no whole audio frame on this tick -> the leg is silent
+                const uint8_t *ev = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)(f0 + t) * Cn + (size_t)b0 * G + j) * d.word_stride;
+                if (!(ev[4] & IGD_RXE_FRAME)) gv |= (uint16_t)IGD_GAIN_NO_AUDIO;
+            }
+            d.gain_q7[(size_t)(f0 + t) * Cn + (size_t)b0 * G + j] = gv;
         }
     }
     __syncthreads();
@@ -648,7 +654,8 @@ __global__ void __launch_bounds__(256) k_wav_images(const uint8_t *__restrict__ 
     const size_t nwarps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t u = warp; u < nchan * (F + 1); u += nwarps) {       // unit F of a channel = its header
         const size_t k = u / (F + 1), f = u - k * (F + 1);
-        const uint32_t ch = chans ? chans[k] : (uint32_t)k;
+        uint32_t ch = chans ? chans[k] : (uint32_t)k;
+        if (ch >= C) ch = (uint32_t)(C - 1);             // device-side index list: never read outside the batch
         uint8_t *img = out + k * image_stride;
         if (f == F) {
             if (lane < 11) {

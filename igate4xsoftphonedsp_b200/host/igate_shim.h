@@ -11,8 +11,12 @@
 // per tick.  All arithmetic runs on the GPU; this file holds no codec, meter or
 // header math.
 //
-// Built against pjproject the PJ types come from <pjsua.h>; without it (this
-// repo's tests) minimal stand-ins are declared below.
+// The adapter is a REAL `pjmedia_transport`: its struct starts with `pjmedia_transport base` whose
+// `op` points at a 12-entry `pjmedia_transport_op` (the table of TransportAdapter.cpp:59-73), so PJSIP
+// drives it exactly as it drives the reference's: `tp->op->attach` registers the shim's RTP callback
+// with the slave (UDP) transport, `tp->op->send_rtp` stages the conference bridge's packet, the other
+// entries pass through to the slave transport, `tp->op->destroy` closes it.  PJ types come from the
+// real pjproject headers when IGD_HAVE_PJSIP is defined, else from igate_pj_compat.h.
 #pragma once
 #include <stddef.h>
 #include <stdint.h>
@@ -20,20 +24,7 @@
 #include <string>
 
 #include "../../include/igate_dsp.h"
-
-#ifndef __PJ_TYPES_H__
-typedef int pj_status_t;
-typedef int pj_bool_t;
-typedef uint8_t pj_uint8_t;
-typedef uint16_t pj_uint16_t;
-typedef uint32_t pj_uint32_t;
-typedef size_t pj_size_t;
-typedef long pj_ssize_t;
-typedef int pjsua_call_id;
-#define PJ_SUCCESS 0
-struct pjmedia_transport;   // opaque handle, as handed around by the reference
-struct pjmedia_endpt;
-#endif
+#include "igate_pj_compat.h"
 
 // wire image of the reference's struct custom_rtp_hdr (ed137_rtp.h:22-47)
 #pragma pack(push, 1)
@@ -56,6 +47,11 @@ struct igd_bank;
 igd_bank *igd_bank_open(int device, int max_channels);
 void igd_bank_close(igd_bank *bank);
 void igd_bank_set_default(igd_bank *bank);    // the bank pjmedia_custom_tp_adapter_create allocates from
+// Clock behind the reference's QDateTime::currentMSecsSinceEpoch() calls (adapter creation stamps
+// r2sPacket / r2sSendtime, TransportAdapter.cpp:122-123; getR2SStatus(NULL), :324; sendR2SStatus, :426).
+// Default: the wall clock.  A gateway that runs on a media clock (or a replay) installs its own.
+typedef long long (*igd_clock_fn)(void *user);
+void igd_bank_set_clock(igd_bank *bank, igd_clock_fn fn, void *user);
 igd_ctx *igd_bank_ctx(igd_bank *bank);
 
 // ---- reference signatures (TransportAdapter.h:18-38), same names and argument meaning
@@ -74,6 +70,11 @@ pj_status_t setAdapterPttId(pjmedia_transport *tp, int pttid);
 pj_status_t setcallRecorder(pjmedia_transport *tp, bool val);
 pj_status_t setCallType(pjmedia_transport *tp, char const *calltype);
 long long getR2SStatus(pjmedia_transport *tp);
+// TransportAdapter.h:38 (body TransportAdapter.cpp:422-633): the timer-driven keep-alive of ONE adapter, now:
+// one igd_ed137_keepalive launch for its channel; a 20-byte PT-123 packet leaves through the slave transport
+// when the reference's would.  igd_bank_keepalive does the same for every adapter of the bank in one launch.
+void sendR2SStatus(pjmedia_transport *tp);
+int igd_bank_keepalive(igd_bank *bank, long long now_ms);
 
 // ---- RoIP_ED137 field getters (Functions.cpp:1001-1179), per adapter instead of per call id
 int get_IPRadioBss(pjmedia_transport *tp);
@@ -91,11 +92,15 @@ pj_status_t igd_submit_tx(pjmedia_transport *tp, const void *pkt, pj_size_t size
 pj_status_t igd_submit_rx(pjmedia_transport *tp, const void *pkt, pj_ssize_t size);
 typedef void (*igd_send_fn)(void *user, pjmedia_transport *tp, const void *pkt, pj_size_t size);
 // runs the staged TX packets of this tick through igd_ed137_pack and hands every packet that the
-// reference would have given to pjmedia_transport_send_rtp() to `send`; returns packets sent or <0
+// reference would have given to pjmedia_transport_send_rtp() to `send`; send == NULL: to the adapter's
+// slave transport, pjmedia_transport_send_rtp(slave_tp, pkt, size) as TransportAdapter.cpp:848 does.
+// Returns packets sent or <0
 int igd_bank_flush_tx(igd_bank *bank, long long now_ms, unsigned flags, igd_send_fn send, void *user);
 // runs the staged RX packets through igd_ed137_parse (+ the byte-mean meter); afterwards the getters
-// above return the new values; `stream_cb` (may be NULL) receives the audio packets (PT != 123) like
-// stream_rtp_cb does in the reference.  Returns packets parsed or <0
+// above return the new values; `stream_cb` receives the audio packets (PT != 123) like stream_rtp_cb
+// does in the reference; stream_cb == NULL: the callback the stream registered through tp->op->attach
+// (adapter->stream_rtp_cb(adapter->stream_user_data, pkt, size), TransportAdapter.cpp:301).
+// Returns packets parsed or <0
 int igd_bank_flush_rx(igd_bank *bank, long long now_ms, igd_send_fn stream_cb, void *user);
 
 // events the receive side raises (what transport_rtp_cb / the 40 ms watchdog did inline):

@@ -56,7 +56,10 @@ def gather_records(local, nbridges, legs, group=None, dst=0):
     else:
         assert local.shape[0] == sizes[rank]
         flat = local.contiguous().view(torch.uint8).reshape(-1)
-        itemsize = flat.numel() // max(sizes[rank], 1) if sizes[rank] else local[0:0].element_size()
+        # bytes per record from the record shape, also on a rank that owns no bridge (world > nbridges)
+        itemsize = local.element_size()
+        for d in local.shape[1:]:
+            itemsize *= int(d)
         buf = torch.zeros(nmax * itemsize, dtype=torch.uint8, device=local.device)
         buf[: flat.numel()] = flat
     outs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None

@@ -247,21 +247,36 @@ class VoicePath:
         return out
 
     # ------------------------------------------------------------ fused path
-    def alloc_outputs(self, F, B, G):
-        """Device output buffers for process_batch (torch)."""
-        dev = f"cuda:{self.device}"
-        return {
-            "mix": torch.empty((F, B, N.FRAME), dtype=torch.int16, device=dev),
-            "enc": torch.empty((F, B, N.FRAME), dtype=torch.uint8, device=dev),
-            "meter": torch.empty((F, B * G, 4), dtype=torch.int32, device=dev),
-            "bmeter": torch.empty((F, B), dtype=torch.int32, device=dev),
-        }
+    OUTPUTS = ("mix", "enc", "meter", "bmeter")
 
-    def process_batch(self, codes, law, gain_q7, out_law, legs, flags=0, out=None):
+    def alloc_outputs(self, F, B, G, want=OUTPUTS):
+        """Device output buffers for process_batch (torch); `want` selects which outputs exist."""
+        dev = f"cuda:{self.device}"
+        o = {
+            "mix": lambda: torch.empty((F, B, N.FRAME), dtype=torch.int16, device=dev),
+            "enc": lambda: torch.empty((F, B, N.FRAME), dtype=torch.uint8, device=dev),
+            "meter": lambda: torch.empty((F, B * G, 4), dtype=torch.int32, device=dev),
+            "bmeter": lambda: torch.empty((F, B), dtype=torch.int32, device=dev),
+        }
+        return {k: o[k]() for k in want}
+
+    @staticmethod
+    def _host_outputs(F, B, Cn, want):
+        o = {
+            "mix": lambda: np.empty((F, B, N.FRAME), dtype=np.int16),
+            "enc": lambda: np.empty((F, B, N.FRAME), dtype=np.uint8),
+            "meter": lambda: np.empty((F, Cn), dtype=N.METER_DT),
+            "bmeter": lambda: np.empty((F, B), dtype=N.BRIDGE_DT),
+        }
+        return {k: o[k]() for k in want}
+
+    def process_batch(self, codes, law, gain_q7, out_law, legs, flags=0, out=None, want=OUTPUTS):
         """decode -> meter -> gate/gain -> mix -> encode in one pass.
 
         codes u8 [F][B*legs][160]; law u8 [B*legs]; gain_q7 u16 [F][B*legs]
-        (0 = gate shut); out_law u8 [B].  Returns dict(mix, enc, meter, bmeter).
+        (0 = gate shut, bit 15 = GAIN_NO_AUDIO); out_law u8 [B].  Returns dict(mix, enc, meter, bmeter);
+        `want` (or the keys of `out`) selects a subset: an output that is not asked for is neither
+        stored nor copied back (the int16 mix is 57 % of the result bytes).
         """
         mem = self._mode(codes, law, gain_q7, out_law)
         F, Cn, n = codes.shape
@@ -273,32 +288,29 @@ class VoicePath:
                 raise IgdError("codes/law/out_law must be uint8")
             if gain_q7.dtype not in (torch.int16, torch.uint16):
                 raise IgdError("gain_q7 must be a 16-bit tensor")
-            o = out if out is not None else self.alloc_outputs(F, B, legs)
+            o = out if out is not None else self.alloc_outputs(F, B, legs, want)
         else:
             codes = np.ascontiguousarray(codes, dtype=np.uint8)
             law = np.ascontiguousarray(law, dtype=np.uint8)
             gain_q7 = np.ascontiguousarray(gain_q7, dtype=np.uint16)
             out_law = np.ascontiguousarray(out_law, dtype=np.uint8)
-            o = out if out is not None else {
-                "mix": np.empty((F, B, N.FRAME), dtype=np.int16),
-                "enc": np.empty((F, B, N.FRAME), dtype=np.uint8),
-                "meter": np.empty((F, Cn), dtype=N.METER_DT),
-                "bmeter": np.empty((F, B), dtype=N.BRIDGE_DT),
-            }
+            o = out if out is not None else self._host_outputs(F, B, Cn, want)
         if law.shape[0] != Cn or out_law.shape[0] != B or tuple(gain_q7.shape) != (F, Cn):
             raise IgdError("law / out_law / gain_q7 shapes do not match codes")
         d = N.BatchDesc(C.sizeof(N.BatchDesc), mem, F, B, legs, flags,
                         self._ptr(codes), self._ptr(law), self._ptr(gain_q7), self._ptr(out_law),
-                        self._ptr(o["mix"]), self._ptr(o["enc"]), self._ptr(o["meter"]), self._ptr(o["bmeter"]))
+                        self._ptr(o.get("mix")), self._ptr(o.get("enc")), self._ptr(o.get("meter")),
+                        self._ptr(o.get("bmeter")))
         self._chk(self._lib.igd_process_batch(self._h, C.byref(d)))
         return o
 
-    def process_packets(self, pkts, fields, law, gain_q7, out_law, legs=4, flags=0, out=None):
+    def process_packets(self, pkts, fields, law, gain_q7, out_law, legs=4, flags=0, out=None, want=OUTPUTS):
         """process_batch with the codes read straight out of the raw ED-137 packets.
 
-        pkts u8 [F][B*legs][180] as received; fields [F][B*legs] from ed137_parse (payload_len
-        is read; payload bytes past it count as zero); the rest as process_batch.  Identical
-        results to ed137_parse(...)[1] fed to process_batch; legs must be 4.
+        pkts u8 [F][B*legs][180] as received; fields [F][B*legs] from ed137_parse; the rest as
+        process_batch.  A leg-frame whose packet is not a whole G.711 audio frame (keep-alive,
+        truncated, dropped, absent) is silent (GAIN_NO_AUDIO); otherwise identical results to
+        ed137_parse(...)[1] fed to process_batch; legs must be 4.
         """
         mem = self._mode(pkts, fields, law, gain_q7, out_law)
         F, Cn, n = pkts.shape
@@ -308,24 +320,20 @@ class VoicePath:
         if mem == N.MEM_DEVICE:
             if pkts.dtype != torch.uint8 or law.dtype != torch.uint8 or out_law.dtype != torch.uint8:
                 raise IgdError("pkts/law/out_law must be uint8")
-            o = out if out is not None else self.alloc_outputs(F, B, legs)
+            o = out if out is not None else self.alloc_outputs(F, B, legs, want)
         else:
             pkts = np.ascontiguousarray(pkts, dtype=np.uint8)
             fields = np.ascontiguousarray(fields, dtype=N.FIELDS_DT)
             law = np.ascontiguousarray(law, dtype=np.uint8)
             gain_q7 = np.ascontiguousarray(gain_q7, dtype=np.uint16)
             out_law = np.ascontiguousarray(out_law, dtype=np.uint8)
-            o = out if out is not None else {
-                "mix": np.empty((F, B, N.FRAME), dtype=np.int16),
-                "enc": np.empty((F, B, N.FRAME), dtype=np.uint8),
-                "meter": np.empty((F, Cn), dtype=N.METER_DT),
-                "bmeter": np.empty((F, B), dtype=N.BRIDGE_DT),
-            }
+            o = out if out is not None else self._host_outputs(F, B, Cn, want)
         if law.shape[0] != Cn or out_law.shape[0] != B or tuple(gain_q7.shape) != (F, Cn):
             raise IgdError("law / out_law / gain_q7 shapes do not match pkts")
         d = N.PacketsDesc(C.sizeof(N.PacketsDesc), mem, F, B, legs, flags,
                           self._ptr(pkts), self._ptr(fields), self._ptr(law), self._ptr(gain_q7), self._ptr(out_law),
-                          self._ptr(o["mix"]), self._ptr(o["enc"]), self._ptr(o["meter"]), self._ptr(o["bmeter"]))
+                          self._ptr(o.get("mix")), self._ptr(o.get("enc")), self._ptr(o.get("meter")),
+                          self._ptr(o.get("bmeter")))
         self._chk(self._lib.igd_process_packets(self._h, C.byref(d)))
         return o
 
@@ -424,10 +432,12 @@ class VoicePath:
         self._chk(self._lib.igd_rx_track(self._h, C.byref(d)))
         return events
 
-    def gate_arbitrate(self, words, legs, bridges, G, mode=N.ARB_CLIENT_PTT, active=None):
+    def gate_arbitrate(self, words, legs, bridges, G, mode=N.ARB_CLIENT_PTT, active=None, silence=False):
         """checkEvents() gate decisions.  words: u32 [F][B*G] or an RX_EVENT_DT array [F][B*G]
         (its .word is read in place); legs [B*G] (ARB_LEG_DT) and bridges [B] (ARB_BRIDGE_DT)
-        are updated in place.  Returns gain_q7 u16 [F][B*G] for process_batch."""
+        are updated in place.  Returns gain_q7 u16 [F][B*G] for process_batch.
+        silence=True (words must be rx_track events): ticks without a whole audio frame
+        (no RXE_FRAME) carry GAIN_NO_AUDIO, i.e. the leg is silent while keep-alives arrive."""
         mem = self._mode(words, legs, bridges, active)
         F, Cn = words.shape[0], words.shape[1]
         B = Cn // G
@@ -440,7 +450,10 @@ class VoicePath:
             if active is not None:
                 active = np.ascontiguousarray(active, dtype=np.uint8)
             gain = np.empty((F, Cn), dtype=np.uint16)
-        d = N.ArbDesc(C.sizeof(N.ArbDesc), mem, F, B, int(G), int(mode), stride, 0, self._ptr(words),
+        if silence and stride != 8:
+            raise ValueError("silence=True needs the rx_track events as `words`")
+        d = N.ArbDesc(C.sizeof(N.ArbDesc), mem, F, B, int(G), int(mode), stride, N.ARB_F_SILENCE if silence else 0,
+                      self._ptr(words),
                       self._ptr(active), self._ptr(legs), self._ptr(bridges), self._ptr(gain))
         self._chk(self._lib.igd_gate_arbitrate(self._h, C.byref(d)))
         return gain

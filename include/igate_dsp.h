@@ -58,6 +58,9 @@ enum {
 #define IGD_F_REF_QUIRKS 0x2u    /* quirks Q2/Q3 of SURVEY.md Appendix A in the
                                     packet path (stale payload; outgoing byte-mean
                                     over header+payload)                          */
+#define IGD_F_GENERIC_KERNEL 0x4u /* diagnostic (igd_process_batch): run the block-cooperative kernel that
+                                    serves batches beyond 32-bit indices instead of the warp-autonomous
+                                    ones; same results, slower                                       */
 
 typedef struct igd_ctx igd_ctx;
 
@@ -151,13 +154,28 @@ int igd_mix(igd_ctx *ctx, const int16_t *pcm, const uint16_t *gain_q7, size_t nf
  * Layout (frame-major = arrival order of one 20 ms tick):
  *   codes   [F][B*G][160] u8     G.711 payloads of every leg
  *   law     [B*G] u8             IGD_LAW_* per leg
- *   gain_q7 [F][B*G] u16         adj per leg and frame; 0 = gate shut
+ *   gain_q7 [F][B*G] u16         adj per leg and frame; 0 = gate shut.  Bit 15
+ *                                (IGD_GAIN_NO_AUDIO) = no audio frame arrived for this
+ *                                leg on this tick (keep-alive, lost / truncated packet):
+ *                                the reference never hands such a packet to the stream
+ *                                (TransportAdapter.cpp:298-315), so its bridge hears the
+ *                                stream's silence.  The leg adds nothing to the mix
+ *                                whatever the low bits say, is not counted in n_open, its
+ *                                meter record is digital silence (sum 0, peak 0, byte-mean
+ *                                0, -inf dB) and igd_event_summary skips the frame.  The
+ *                                code bytes of such a leg-frame are not interpreted.
  *   out_law [B] u8               law the bridge output is encoded with
  *   mix     [F][B][160] i16      bridge output PCM
  *   enc     [F][B][160] u8       bridge output, G.711
  *   meter   [F][B*G] igd_meter_rec
  *   bmeter  [F][B]   igd_bridge_rec
- * Device pointers must be 16-byte aligned (32 for mix).                          */
+ * Any of the four outputs may be NULL (not all): it is then neither stored nor, for
+ * host buffers, copied back -- a gateway that only forwards packets and levels leaves
+ * mix NULL and moves 43 % of the result bytes.
+ * Device pointers must be 16-byte aligned (32 for mix).  Host buffers (ideally from
+ * igd_host_alloc) are staged in frame chunks: the H2D copy of chunk k+1, the kernel of
+ * chunk k and the D2H copy of chunk k-1 overlap; the call returns when all is done.  */
+#define IGD_GAIN_NO_AUDIO 0x8000u
 typedef struct {
     uint32_t struct_size;        /* = sizeof(igd_batch_desc)                      */
     int32_t mem;                 /* IGD_MEM_HOST or IGD_MEM_DEVICE (all pointers) */
@@ -311,10 +329,13 @@ int igd_ed137_keepalive(igd_ctx *ctx, uint8_t *hdr20, igd_ed137_state *state, si
  * The same computation as igd_process_batch with the codes read straight out
  * of the raw ED-137 packets: pkts [F][B*G][IGD_PKT_MAX] as received
  * (transport_rtp_cb, TransportAdapter.cpp:240-316: payload = bytes 20..size),
- * fields [F][B*G] from igd_ed137_parse (payload_len is read: payload bytes
- * past it count as zero, exactly the payload array igd_ed137_parse would
- * write).  Results are identical to igd_ed137_parse(payload_out) followed by
- * igd_process_batch on that payload; the payload array is never materialised.
+ * fields [F][B*G] from igd_ed137_parse.  A leg-frame whose packet is not a whole
+ * G.711 audio frame -- pt other than 0 / 8 (the R2S keep-alive is pt 123), fewer
+ * than 160 payload bytes, dropped, or absent (size 0) -- is silent exactly as if
+ * its gain carried IGD_GAIN_NO_AUDIO (the same rule as IGD_RXE_FRAME): the reference
+ * never gives such a packet's bytes to the decoder.  Otherwise the results are
+ * identical to igd_ed137_parse(payload_out) followed by igd_process_batch on that
+ * payload with those gains; the payload array is never materialised.
  * G must be 4 (the reference's four radios per softphone, roip_ed137.cpp:130-139);
  * other leg counts take the two-call form (IGD_EINVAL here).  Device pointers:
  * pkts 16-byte aligned, the rest as for igd_process_batch.                       */
@@ -363,6 +384,9 @@ typedef struct {
 #define IGD_RXE_DROPPED 0x08u    /* oversized / truncated packet (:286-291)        */
 #define IGD_RXE_LATE 0x10u       /* watchdog: now - r2sPacket > 3*r2s_period       */
 #define IGD_RXE_HANGUP 0x20u     /* watchdog: sixth late tick in a row, hang up    */
+#define IGD_RXE_FRAME 0x40u      /* a whole G.711 audio frame arrived: forwarded (pt 0 / 8) with
+                                    160 payload bytes -- what the fused path may decode; without
+                                    it the leg is silent on this tick (IGD_GAIN_NO_AUDIO)          */
 typedef struct {
     uint32_t struct_size;
     int32_t mem;
@@ -393,6 +417,12 @@ int igd_rx_track(igd_ctx *ctx, const igd_rx_track_desc *d);
  * MUTE/UNMUTE are taken as gain 0 / 256 (Functions.cpp:1664-1705 with its
  * sidetone / group-mute side conditions left to the host).                     */
 enum { IGD_ARB_CLIENT_PTT = 0, IGD_ARB_SERVER_BEST = 1 };
+/* words are igd_rx_event records read in place (word_stride 8): every gain written for a tick whose
+ * event lacks IGD_RXE_FRAME carries IGD_GAIN_NO_AUDIO, i.e. the leg is silent on ticks on which no
+ * whole audio frame arrived (the PTT hold-off keeps a gate open for five ticks while the radio already
+ * sends 20-byte keep-alives, roip_ed137.cpp:6140-6147; the reference's bridge hears stream silence
+ * then).  The arbitration state itself is unaffected.                                              */
+#define IGD_ARB_F_SILENCE 0x1u
 typedef struct {
     uint8_t last;                /* lastTx (CLIENT) / lastRx (SERVER)             */
     uint8_t msec;                /* lastTxmsec / lastRxmsec                       */
@@ -414,7 +444,7 @@ typedef struct {
     int32_t mode;                /* IGD_ARB_*                                     */
     uint32_t word_stride;        /* bytes between consecutive words: 4 for a plain
                                     u32 array, 8 to read igd_rx_event.word in place */
-    uint32_t reserved;
+    uint32_t flags;              /* IGD_ARB_F_*                                   */
     const void *words;           /* [F][B*G] latched ED-137 words, host order     */
     const uint8_t *active;       /* [B*G] leg takes part (callState...); NULL = all */
     igd_arb_leg *legs;           /* [B*G], updated in place                       */

@@ -213,7 +213,7 @@ void orc_mix_frame(const int16_t *const *legs, const uint16_t *adj, int nlegs,
     for (int i = 0; i < n; i++) {
         int acc = 0;
         for (int g = 0; g < nlegs; g++)
-            if (adj[g] != 0)
+            if (adj[g] != 0 && !(adj[g] & ORC_GAIN_NO_AUDIO))
                 acc += orc_apply_gain(legs[g][i], adj[g]);
         mix[i] = (int16_t)clamp16(acc);
     }
@@ -238,6 +238,16 @@ void orc_process_batch_range(const orc_batch *b, int b0, int b1)
                 size_t ch = (size_t)br * G + g;
                 const uint8_t *codes = b->codes + ((size_t)f * C + ch) * N;
                 uint64_t s; uint32_t pk;
+                if (adj[g] & ORC_GAIN_NO_AUDIO) {
+                    /* no audio frame arrived for this leg on this tick (keep-alive, lost or truncated
+                     * packet): transport_rtp_cb never hands such a packet to the stream
+                     * (TransportAdapter.cpp:298-315), the bridge hears the stream's silence */
+                    memset(pcm[g], 0, sizeof pcm[g]);
+                    if (b->meter)
+                        meter_pack(&b->meter[(size_t)f * C + ch], 0, 0, 0, N);
+                    legp[g] = pcm[g];
+                    continue;
+                }
                 orc_g711_decode(codes, pcm[g], N, b->law[ch]);
                 orc_frame_power(pcm[g], N, &s, &pk);
                 if (b->meter)
@@ -309,8 +319,8 @@ void orc_event_summary(const orc_meter_rec *meter, const uint16_t *gain_q7,
         r.sum_s = 0; r.max_s = 0; r.min_s = 255ull * ORC_FRAME;
         for (int f = 0; f < F; f++) {
             size_t i = (size_t)f * C + c;
-            if (gain_q7[i] == 0)
-                continue;                                  /* eventPttSQL_In_LoggingOn */
+            if (gain_q7[i] == 0 || (gain_q7[i] & ORC_GAIN_NO_AUDIO))
+                continue;                                  /* eventPttSQL_In_LoggingOn; no level without audio */
             uint64_t s = (uint64_t)meter[i].sumsq_lo | ((uint64_t)(meter[i].hi & 0xFF) << 32);
             uint8_t bm = (uint8_t)(meter[i].hi >> 8);
             r.count += 1;                                  /* :2131 */

@@ -97,6 +97,9 @@ void orc_mix_frame(const int16_t *const *legs, const uint16_t *adj, int nlegs,
                    int n, int16_t *mix);
 
 /* ---------------- fused per-frame voice path ------------------------------ */
+/* gain_q7 bit 15: no audio frame arrived for the leg on this tick (TransportAdapter.cpp:298-315: keep-alives
+ * and dropped packets never reach the stream) -> silent leg-frame, see include/igate_dsp.h IGD_GAIN_NO_AUDIO */
+#define ORC_GAIN_NO_AUDIO 0x8000u
 typedef struct {
     int F, B, G;                     /* frames, bridges, legs per bridge       */
     const uint8_t *codes;            /* [F][B*G][160]                          */

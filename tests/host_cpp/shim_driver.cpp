@@ -53,6 +53,10 @@ int main(int argc, char **argv)
         fread(&flags, 4, 1, in) != 1 || fread(&now0, 8, 1, in) != 1) return 2;
     igd_bank *bank = igd_bank_open(0, C);
     if (!bank) { fprintf(stderr, "igd_bank_open failed (no sm_100 GPU?)\n"); return 3; }
+    // scenarios run on their own clock: the adapter constructor stamps r2sSendtime / r2sPacket from it
+    static long long clock_now;
+    clock_now = now0;
+    igd_bank_set_clock(bank, [](void *u) { return *static_cast<long long *>(u); }, &clock_now);
     std::vector<pjmedia_transport *> tps(C);
     std::vector<int32_t> slave(2 * C);
     for (int c = 0; c < C; c++) {
@@ -64,15 +68,11 @@ int main(int argc, char **argv)
                                              "", keepalive, 1, 1) != PJ_SUCCESS) return 4;
         if (slave[2 * c] >= 0) setTxRxSlaveEnable(tps[c], slave[2 * c], slave[2 * c + 1]);
     }
-    // the adapter constructor stamps wall-clock time; scenarios use their own clock
-    // (r2sSendtime is part of the sender state the batched call carries)
     std::vector<igd_ed137_ctl> ctl((size_t)F * C);
     std::vector<uint8_t> rtp12((size_t)F * C * 12), payload((size_t)F * C * 160);
     if (fread(ctl.data(), 8, ctl.size(), in) != ctl.size() || fread(rtp12.data(), 1, rtp12.size(), in) != rtp12.size() ||
         fread(payload.data(), 1, payload.size(), in) != payload.size()) return 2;
     fclose(in);
-    extern void igd_test_set_sendtime(pjmedia_transport *, long long);
-    for (int c = 0; c < C; c++) igd_test_set_sendtime(tps[c], now0);
 
     Out o;
     o.pkts.assign((size_t)F * C * 180, 0);
@@ -87,8 +87,6 @@ int main(int argc, char **argv)
     ev.C = C;
     ev.tps = &tps;
     igd_bank_set_event_cb(bank, on_event, &ev);
-    extern void igd_test_set_r2spacket(pjmedia_transport *, long long);
-    for (int c = 0; c < C; c++) igd_test_set_r2spacket(tps[c], now0);
     for (int f = 0; f < F; f++) {
         o.f = f;
         ev.f = f;

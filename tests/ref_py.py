@@ -231,7 +231,8 @@ def run_rx(pkts, sizes, present, now0=1000, tick=20, period=200, wd_ticks=2, fra
                 fwd = R.refta_rx(h, p.ctypes.data, n, p.size)
                 after = state(R, h)
                 if fwd == 1:
-                    flags |= N.RXE_AUDIO
+                    from rx_arb_cases import frame_flag
+                    flags |= N.RXE_AUDIO | frame_flag(pkts[f, c], n)
                 elif after.rtpAudio == before.rtpAudio and (n < 20 or n - 20 >= 1024):
                     flags |= N.RXE_DROPPED          # :289-290: stamped r2sPacket and returned
                 if R.refapp_checkEvents_calls() != calls:

@@ -47,6 +47,12 @@ def make_rx_stream(F, Cn, seed=0):
     return pkts, sizes, present
 
 
+def frame_flag(pkt, size):
+    """IGD_RXE_FRAME: a forwarded packet that is a whole G.711 audio frame (pt 0 / 8, 160 payload bytes) -- the
+    build's own notion (include/igate_dsp.h), derived from what the reference forwards to the stream"""
+    return N.RXE_FRAME if (int(pkt[1]) & 0x7F) in (0, 8) and size == 180 else 0
+
+
 def ref_comparable_sizes(sizes):
     """The same stream restricted to sizes on which the REFERENCE's behaviour is defined, so that it can be
     replayed through the reference's own transport_rtp_cb (tests/ref_py.run_rx):
@@ -88,7 +94,7 @@ def oracle_rx_walk(pkts, sizes, present, now0=1000, tick=20, period=200, wd_tick
                 if r < 0:
                     flags |= N.RXE_DROPPED
                 elif r == 1:
-                    flags |= N.RXE_AUDIO
+                    flags |= N.RXE_AUDIO | frame_flag(pkts[f, c], n)
                 if a.checkEvents_calls != calls:
                     flags |= N.RXE_EDGE
             if wd_ticks > 0 and (frame0 + f) % wd_ticks == wd_ticks - 1:

@@ -232,11 +232,13 @@ def test_group_walk_kernel_any_leg_count(vp, G, B, F, flags):
           O.process_batch(codes, law, gain, out_law, G, signed_char=sc))
 
 
-def test_block_cooperative_fallback_still_matches(vp, monkeypatch):
-    """the last-resort kernel for batches beyond 32-bit indices, forced through its dev switch"""
-    monkeypatch.setenv("IGD_FUSED_ANYG", "1")
+def test_block_cooperative_fallback_still_matches(vp):
+    """the last-resort kernel for batches beyond 32-bit indices, forced through IGD_F_GENERIC_KERNEL"""
+    from igate4xsoftphonedsp_b200 import _native as N
     codes, law, gain, out_law = make(4, 6, 5, random_codes=True, seed=1)
-    check(vp.process_batch(codes, law, gain, out_law, 5), O.process_batch(codes, law, gain, out_law, 5))
+    check(vp.process_batch(codes, law, gain, out_law, 5, flags=N.F_GENERIC_KERNEL), O.process_batch(codes, law, gain, out_law, 5))
+    codes, law, gain, out_law = make(3, 9, 4, random_codes=True, seed=2)
+    check(vp.process_batch(codes, law, gain, out_law, 4, flags=N.F_GENERIC_KERNEL), O.process_batch(codes, law, gain, out_law, 4))
 
 
 @pytest.mark.parametrize("G,B,F", [(4, 37, 9), (4, 1, 1), (2, 5, 3), (1, 7, 1), (3, 5, 2), (32, 1, 5), (9, 4, 4)])

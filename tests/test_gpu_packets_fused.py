@@ -1,7 +1,8 @@
 """GPU parity of igd_process_packets (the fused path reading the codes straight out of the raw
 ED-137 packets) against the oracle on the payload igd_ed137_parse extracts from the same packets:
-transport_rtp_cb's payload rule (TransportAdapter.cpp:240-316: bytes 20..size, nothing for a
-keep-alive / truncated / dropped packet) composed with the decode -> meter -> mix -> encode path."""
+transport_rtp_cb's rule (TransportAdapter.cpp:240-316: payload = bytes 20..size; a keep-alive never
+reaches the stream, so the leg is silent -- as is a truncated / dropped / absent packet) composed
+with the decode -> meter -> mix -> encode path."""
 import numpy as np
 import pytest
 import torch
@@ -31,10 +32,17 @@ def make(F, B, seed, ragged, gains=(0, 0, 256)):
     return pk, sizes, law, gain, out_law
 
 
+def no_audio(pk, sizes):
+    """a packet that is not a whole G.711 audio frame: the leg is silent on that tick (IGD_GAIN_NO_AUDIO rule)"""
+    pt = pk[..., 1] & 0x7F
+    return ~(((pt == 0) | (pt == 8)) & (sizes == 180))
+
+
 def want_of(vp, pk, sizes, law, gain, out_law, signed=0):
     F, Cn, _ = pk.shape
     fields, payload = vp.ed137_parse(pk.reshape(F * Cn, 180), sizes.reshape(-1))
-    return fields.reshape(F, Cn), O.process_batch(payload.reshape(F, Cn, 160), law, gain, out_law, G,
+    g = np.where(no_audio(pk, sizes), gain | N.GAIN_NO_AUDIO, gain).astype(np.uint16)
+    return fields.reshape(F, Cn), O.process_batch(payload.reshape(F, Cn, 160), law, g, out_law, G,
                                                   signed_char=signed, threads=8)
 
 

@@ -83,6 +83,7 @@ def _host_parse(pkts, sizes):
     f["keepalive"] = ~short & (pt == 123)
     dropped = short | (sz - 20 >= 1024)
     f["flags"] = np.where(dropped, N.EDF_DROPPED, 0)
+    f["payload_len"] = np.where(dropped, 0, sz - 20)
     return f
 
 
