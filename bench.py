@@ -176,7 +176,7 @@ def cpu_sample(seconds_target=12.0, threads=None, codes=None, gpu_out=None):
     nf = int(max(8, min(codes.shape[0], 8 * seconds_target / max(t, 1e-6))))
     outs = O.alloc_outputs(nf, C, G)             # pre-faulted output buffers, reused by every pass
     passes, dt = 0, 0.0
-    while dt < seconds_target and passes < 64:   # bounded: repeat the sample until ~seconds_target of CPU work
+    while dt < seconds_target and passes < 4096:   # bounded: repeat the sample until ~seconds_target of CPU work
         d, _ = run(nf, out=outs)
         dt += d
         passes += 1

@@ -93,7 +93,19 @@ class RxTrackDesc(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("F", C.c_int32), ("C", C.c_int32),
                 ("tick_ms", C.c_int32), ("r2s_period_ms", C.c_int32), ("wd_ticks", C.c_int32),
                 ("frame0", C.c_int32), ("now_ms0", C.c_int64),
-                ("fields", C.c_void_p), ("present", C.c_void_p), ("state", C.c_void_p), ("events", C.c_void_p)]
+                ("fields", C.c_void_p), ("present", C.c_void_p), ("state", C.c_void_p), ("events", C.c_void_p),
+                ("sizes", C.c_void_p)]
+
+
+class GatewayDesc(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("mem", C.c_int32), ("F", C.c_int32), ("B", C.c_int32), ("G", C.c_int32),
+                ("flags", C.c_uint32), ("arb_mode", C.c_int32), ("tick_ms", C.c_int32), ("r2s_period_ms", C.c_int32),
+                ("wd_ticks", C.c_int32), ("frame0", C.c_int32), ("reserved", C.c_int32), ("now_ms0", C.c_int64),
+                ("rx_pkts", C.c_void_p), ("rx_sizes", C.c_void_p), ("law", C.c_void_p), ("active", C.c_void_p),
+                ("rx_state", C.c_void_p), ("arb_legs", C.c_void_p), ("arb_bridges", C.c_void_p),
+                ("out_law", C.c_void_p), ("tx_rtp12", C.c_void_p), ("tx_ctl", C.c_void_p), ("tx_state", C.c_void_p),
+                ("tx_pkts", C.c_void_p), ("tx_sizes", C.c_void_p), ("rx_events", C.c_void_p), ("gain_q7", C.c_void_p),
+                ("meter", C.c_void_p), ("bmeter", C.c_void_p), ("mix", C.c_void_p), ("enc", C.c_void_p)]
 
 
 class ArbDesc(C.Structure):
@@ -140,6 +152,7 @@ SYMBOLS = {
     "igd_ed137_keepalive": (_i, [_vp, _vp, _vp, _sz, C.c_int64, _vp, _i]),
     "igd_rx_track": (_i, [_vp, C.POINTER(RxTrackDesc)]),
     "igd_gate_arbitrate": (_i, [_vp, C.POINTER(ArbDesc)]),
+    "igd_gateway_process": (_i, [_vp, C.POINTER(GatewayDesc)]),
     "igd_wav_size": (_sz, [_sz, _i]),
     "igd_wav_image": (_i, [_vp, _vp, _sz, _i, _i, _i, _vp, C.POINTER(_sz), _i]),
     "igd_wav_images": (_i, [_vp, _vp, _sz, _sz, _vp, _sz, _vp, _i, _i, _vp, _sz, _i]),

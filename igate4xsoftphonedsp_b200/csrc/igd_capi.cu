@@ -14,7 +14,7 @@
 #include "igd_kernels.cuh"
 
 namespace {
-constexpr int kSlots = 12;
+constexpr int kSlots = 13;
 }
 
 struct igd_ctx {
@@ -727,6 +727,7 @@ int igd_rx_track(igd_ctx *c, const igd_rx_track_desc *d)
     int rc;
     if ((rc = in_arg(c, mem, 0, d->fields, n, &k.fields))) return rc;
     if (d->present && (rc = in_arg(c, mem, 1, d->present, n, &k.present))) return rc;
+    if (d->sizes && (rc = in_arg(c, mem, 4, d->sizes, n, &k.sizes))) return rc;
     {
         const igd_rx_state *tmp = nullptr;
         if ((rc = in_arg(c, mem, 2, d->state, (size_t)d->C, &tmp))) return rc;
@@ -775,6 +776,136 @@ int igd_gate_arbitrate(igd_ctx *c, const igd_arb_desc *d)
     if ((rc = out_done(c, mem, d->legs, k.legs, Cn))) return rc;
     if ((rc = out_done(c, mem, d->bridges, k.bridges, (size_t)d->B))) return rc;
     if ((rc = out_done(c, mem, d->gain_q7, k.gain_q7, n))) return rc;
+    return finish(c, mem);
+}
+
+// ---------------------------------------------------------------- gateway: packets in, packets out
+int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
+{
+    if (!c || !d || d->struct_size != sizeof(igd_gateway_desc))
+        return fail(c, IGD_EINVAL, "igd_gateway_process: bad descriptor");
+    if (d->F < 0 || d->B < 0 || d->wd_ticks < 0 || (d->arb_mode != IGD_ARB_CLIENT_PTT && d->arb_mode != IGD_ARB_SERVER_BEST))
+        return fail(c, IGD_EINVAL, "igd_gateway_process: bad shape / mode");
+    if (d->G != 4) return fail(c, IGD_EINVAL, "igd_gateway_process: G must be 4");
+    if (d->F == 0 || d->B == 0) return IGD_OK;
+    if (!d->rx_pkts || !d->law || !d->rx_state || !d->arb_legs || !d->arb_bridges || !d->out_law || !d->tx_rtp12 ||
+        !d->tx_state || !d->tx_pkts || !d->tx_sizes)
+        return fail(c, IGD_EINVAL, "igd_gateway_process: null buffer");
+    const int mem = d->mem;
+    if (mem == IGD_MEM_DEVICE &&
+        (!aligned(d->rx_pkts, 16) || (d->rx_sizes && !aligned(d->rx_sizes, 4)) || !aligned(d->law, 4) ||
+         !aligned(d->rx_state, 16) || !aligned(d->arb_legs, 8) || !aligned(d->arb_bridges, 4) || !aligned(d->tx_rtp12, 4) ||
+         (d->tx_ctl && !aligned(d->tx_ctl, 8)) || !aligned(d->tx_state, 8) || !aligned(d->tx_pkts, 4) ||
+         !aligned(d->tx_sizes, 4) || (d->rx_events && !aligned(d->rx_events, 8)) || (d->gain_q7 && !aligned(d->gain_q7, 8)) ||
+         (d->meter && !aligned(d->meter, 16)) || (d->bmeter && !aligned(d->bmeter, 4)) || (d->mix && !aligned(d->mix, 32)) ||
+         (d->enc && !aligned(d->enc, 16))))
+        return fail(c, IGD_EINVAL, "igd_gateway_process: misaligned device pointer");
+    IGD_BIND(c);
+    const size_t F = d->F, B = d->B, Cn = B * 4, n = F * Cn, nb = F * B;
+    int rc;
+    // ---- inputs (host form: staged; slots 0..5 in, 6..11 scratch / out)
+    const uint8_t *dpk, *dlaw, *dact = nullptr, *dol, *drtp; const uint32_t *dsz = nullptr; const igd_ed137_ctl *dctl = nullptr;
+    if ((rc = in_arg(c, mem, 0, d->rx_pkts, n * IGD_PKT_MAX, &dpk))) return rc;
+    if (d->rx_sizes && (rc = in_arg(c, mem, 1, d->rx_sizes, n, &dsz))) return rc;
+    void *small = nullptr;       // law, active, out_law, states in one staged block (host form)
+    igd_rx_state *drx; igd_arb_leg *dleg; igd_arb_bridge *dbr; igd_ed137_state *dtx;
+    if (mem == IGD_MEM_DEVICE) {
+        dlaw = d->law; dact = d->active; dol = d->out_law;
+        drx = d->rx_state; dleg = d->arb_legs; dbr = d->arb_bridges; dtx = d->tx_state;
+    } else {
+        const size_t o_law = 0, o_act = o_law + ((Cn + 15) & ~(size_t)15), o_ol = o_act + ((Cn + 15) & ~(size_t)15),
+                     o_rx = o_ol + ((B + 15) & ~(size_t)15), o_leg = o_rx + Cn * sizeof(igd_rx_state),
+                     o_br = o_leg + Cn * sizeof(igd_arb_leg), o_tx = o_br + B * sizeof(igd_arb_bridge),
+                     total = o_tx + B * sizeof(igd_ed137_state);
+        if ((rc = scratch(c, 2, total, &small))) return rc;
+        uint8_t *sb = static_cast<uint8_t *>(small);
+        IGD_CUDA(c, cudaMemcpyAsync(sb + o_law, d->law, Cn, cudaMemcpyHostToDevice, c->stream));
+        if (d->active) IGD_CUDA(c, cudaMemcpyAsync(sb + o_act, d->active, Cn, cudaMemcpyHostToDevice, c->stream));
+        IGD_CUDA(c, cudaMemcpyAsync(sb + o_ol, d->out_law, B, cudaMemcpyHostToDevice, c->stream));
+        IGD_CUDA(c, cudaMemcpyAsync(sb + o_rx, d->rx_state, Cn * sizeof(igd_rx_state), cudaMemcpyHostToDevice, c->stream));
+        IGD_CUDA(c, cudaMemcpyAsync(sb + o_leg, d->arb_legs, Cn * sizeof(igd_arb_leg), cudaMemcpyHostToDevice, c->stream));
+        IGD_CUDA(c, cudaMemcpyAsync(sb + o_br, d->arb_bridges, B * sizeof(igd_arb_bridge), cudaMemcpyHostToDevice, c->stream));
+        IGD_CUDA(c, cudaMemcpyAsync(sb + o_tx, d->tx_state, B * sizeof(igd_ed137_state), cudaMemcpyHostToDevice, c->stream));
+        dlaw = sb + o_law; dact = d->active ? sb + o_act : nullptr; dol = sb + o_ol;
+        drx = reinterpret_cast<igd_rx_state *>(sb + o_rx); dleg = reinterpret_cast<igd_arb_leg *>(sb + o_leg);
+        dbr = reinterpret_cast<igd_arb_bridge *>(sb + o_br); dtx = reinterpret_cast<igd_ed137_state *>(sb + o_tx);
+    }
+    if ((rc = in_arg(c, mem, 3, d->tx_rtp12, nb * 12, &drtp))) return rc;
+    if (d->tx_ctl && (rc = in_arg(c, mem, 4, d->tx_ctl, nb, &dctl))) return rc;
+    // ---- intermediates that never cross the API: field records, events, gains, sender plan
+    void *dfields, *dplan, *dlast, *dev_s = nullptr, *dgain_s = nullptr;
+    if ((rc = scratch(c, 5, n * sizeof(igd_ed137_fields), &dfields))) return rc;
+    if ((rc = scratch(c, 6, nb * sizeof(igd_tx_plan_rec) + B * sizeof(int32_t), &dplan))) return rc;
+    dlast = static_cast<uint8_t *>(dplan) + nb * sizeof(igd_tx_plan_rec);
+    igd_rx_event *dev; uint16_t *dgain;
+    if (mem == IGD_MEM_DEVICE && d->rx_events) dev = d->rx_events;
+    else { if ((rc = scratch(c, 7, n * sizeof(igd_rx_event), &dev_s))) return rc; dev = static_cast<igd_rx_event *>(dev_s); }
+    if (mem == IGD_MEM_DEVICE && d->gain_q7) dgain = d->gain_q7;
+    else { if ((rc = scratch(c, 8, n * sizeof(uint16_t), &dgain_s))) return rc; dgain = static_cast<uint16_t *>(dgain_s); }
+    // ---- outputs
+    uint8_t *dtp; uint32_t *dts; igd_meter_rec *dmt = nullptr; igd_bridge_rec *dbm = nullptr; int16_t *dmix = nullptr; uint8_t *denc = nullptr;
+    if ((rc = out_arg(c, mem, 9, d->tx_pkts, nb * IGD_PKT_MAX, &dtp))) return rc;
+    if ((rc = out_arg(c, mem, 10, d->tx_sizes, nb, &dts))) return rc;
+    if (mem == IGD_MEM_DEVICE) { dmt = d->meter; dbm = d->bmeter; dmix = d->mix; denc = d->enc; }
+    else {
+        // host form: the optional record / PCM outputs share slot 11
+        const size_t o_mt = 0, o_bm = o_mt + (d->meter ? n * sizeof(igd_meter_rec) : 0), o_mx = (o_bm + (d->bmeter ? nb * sizeof(igd_bridge_rec) : 0) + 31) & ~(size_t)31,
+                     o_en = o_mx + (d->mix ? nb * IGD_FRAME * sizeof(int16_t) : 0), total = o_en + (d->enc ? nb * IGD_FRAME : 0);
+        void *ob = nullptr;
+        if (total && (rc = scratch(c, 11, total, &ob))) return rc;
+        uint8_t *o8 = static_cast<uint8_t *>(ob);
+        if (d->meter) dmt = reinterpret_cast<igd_meter_rec *>(o8 + o_mt);
+        if (d->bmeter) dbm = reinterpret_cast<igd_bridge_rec *>(o8 + o_bm);
+        if (d->mix) dmix = reinterpret_cast<int16_t *>(o8 + o_mx);
+        if (d->enc) denc = o8 + o_en;
+    }
+    const igd_launch_cfg k = cfg_of(c);
+    // 1. header fields of every received packet (transport_rtp_cb's view of the header)
+    IGD_CUDA(c, igd_k_ed137_parse(k, dpk, dsz, n, IGD_PKT_MAX, static_cast<igd_ed137_fields *>(dfields), nullptr));
+    // 2. liveness / latch / edge walk
+    igd_rx_track_desc rx;
+    memset(&rx, 0, sizeof rx);
+    rx.struct_size = sizeof rx; rx.mem = IGD_MEM_DEVICE; rx.F = d->F; rx.C = (int32_t)Cn; rx.tick_ms = d->tick_ms;
+    rx.r2s_period_ms = d->r2s_period_ms; rx.wd_ticks = d->wd_ticks; rx.frame0 = d->frame0; rx.now_ms0 = d->now_ms0;
+    rx.fields = static_cast<igd_ed137_fields *>(dfields); rx.present = nullptr; rx.state = drx; rx.events = dev;
+    rx.sizes = dsz;              // a leg without a packet on a tick has size 0: not a packet for the walk
+    IGD_CUDA(c, igd_k_rx_track(k, rx));
+    // 3. gate decisions; ticks without a whole audio frame carry IGD_GAIN_NO_AUDIO
+    igd_arb_desc ar;
+    memset(&ar, 0, sizeof ar);
+    ar.struct_size = sizeof ar; ar.mem = IGD_MEM_DEVICE; ar.F = d->F; ar.B = d->B; ar.G = 4; ar.mode = d->arb_mode;
+    ar.word_stride = 8; ar.flags = IGD_ARB_F_SILENCE; ar.words = dev; ar.active = dact; ar.legs = dleg; ar.bridges = dbr;
+    ar.gain_q7 = dgain;
+    IGD_CUDA(c, igd_k_gate_arbitrate(k, ar));
+    // 4. sender walk of the B outgoing calls
+    igd_ed137_pack_desc pk;
+    memset(&pk, 0, sizeof pk);
+    pk.struct_size = sizeof pk; pk.mem = IGD_MEM_DEVICE; pk.F = d->F; pk.C = d->B; pk.flags = d->flags & IGD_F_SIGNED_CHAR;
+    pk.payload_len = IGD_FRAME; pk.out_stride = IGD_PKT_MAX; pk.tick_ms = d->tick_ms; pk.now_ms0 = d->now_ms0;
+    pk.rtp12 = drtp; pk.payload = nullptr; pk.ctl = dctl; pk.state = dtx;
+    IGD_CUDA(c, igd_k_ed137_plan(k, pk, static_cast<igd_tx_plan_rec *>(dplan), static_cast<int32_t *>(dlast)));
+    // 5. decode -> meter -> mix -> encode -> packets
+    igd_packets_desc fp;
+    memset(&fp, 0, sizeof fp);
+    fp.struct_size = sizeof fp; fp.mem = IGD_MEM_DEVICE; fp.F = d->F; fp.B = d->B; fp.G = 4; fp.flags = d->flags & IGD_F_SIGNED_CHAR;
+    fp.pkts = dpk; fp.fields = nullptr; fp.law = dlaw; fp.gain_q7 = dgain; fp.out_law = dol;
+    fp.mix = dmix; fp.enc = denc; fp.meter = dmt; fp.bmeter = dbm;
+    IGD_CUDA(c, igd_k_fused_gateway(k, fp, static_cast<igd_tx_plan_rec *>(dplan), drtp, dtp, dts));
+    c->launches += 5;
+    if (mem == IGD_MEM_HOST) {
+        if ((rc = out_done(c, mem, d->tx_pkts, dtp, nb * IGD_PKT_MAX))) return rc;
+        if ((rc = out_done(c, mem, d->tx_sizes, dts, nb))) return rc;
+        if (d->rx_events && (rc = out_done(c, mem, d->rx_events, dev, n))) return rc;
+        if (d->gain_q7 && (rc = out_done(c, mem, d->gain_q7, dgain, n))) return rc;
+        if (d->meter && (rc = out_done(c, mem, d->meter, dmt, n))) return rc;
+        if (d->bmeter && (rc = out_done(c, mem, d->bmeter, dbm, nb))) return rc;
+        if (d->mix && (rc = out_done(c, mem, d->mix, dmix, nb * IGD_FRAME))) return rc;
+        if (d->enc && (rc = out_done(c, mem, d->enc, denc, nb * IGD_FRAME))) return rc;
+        if ((rc = out_done(c, mem, d->rx_state, drx, Cn))) return rc;
+        if ((rc = out_done(c, mem, d->arb_legs, dleg, Cn))) return rc;
+        if ((rc = out_done(c, mem, d->arb_bridges, dbr, B))) return rc;
+        if ((rc = out_done(c, mem, d->tx_state, dtx, B))) return rc;
+    }
     return finish(c, mem);
 }
 

@@ -176,6 +176,8 @@ struct enc_pk {
     uint32_t hi_pos, hi_x;       // packed upper clip of t so that t+bias <= 0x7FFF
     uint32_t thr;                // packed 256 (A-law) / 0 (u-law)
     uint32_t mask4;              // output XOR mask for x>=0, replicated per byte
+    uint32_t zero2;              // packed (0, 0) in a register the compiler cannot fold: max.s16x2(x, 0) with a
+                                 // literal makes it rebuild the constant (PRMT RZ) for every packed pair
 };
 __device__ __forceinline__ enc_pk enc_pk_make(int law)
 {
@@ -187,6 +189,7 @@ __device__ __forceinline__ enc_pk enc_pk_make(int law)
     e.hi_pos = hp * 0x10001u;   e.hi_x = (hp ^ hn) * 0x10001u;
     e.thr = (uint32_t)L.thr * 0x10001u;
     e.mask4 = L.mpos * 0x01010101u;
+    e.zero2 = 0u;
     return e;
 }
 // two packed samples -> the float whose bits [26:19] are seg<<4|mant, per sample
@@ -195,7 +198,11 @@ __device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t 
     const uint32_t sgn = prmt_full<0xBB99>(pk, 0u);                 // sign of each half, replicated
     uint32_t t = pk ^ sgn;                                          // |x| or |x|-1
     t = min_u16x2(t, E.hi_pos ^ (sgn & E.hi_x));                    // u-law clip
+#ifdef IGD_X_ZERO2
+    const uint32_t p = max_s16x2(add_16x2(t, E.bias_pos ^ (sgn & E.bias_x)), E.zero2);
+#else
     const uint32_t p = max_s16x2(add_16x2(t, E.bias_pos ^ (sgn & E.bias_x)), 0u);
+#endif
     const uint32_t P = add_16x2(p, max_u16x2(p, E.thr));            // leading one -> segment
     // 8388608.0f + P per half, built on the FMA pipe (IDP.2A picks the half and adds the magic;
     // the compressor is ALU-bound, a PRMT here measured 4 % slower)

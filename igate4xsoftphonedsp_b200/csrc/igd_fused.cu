@@ -31,7 +31,12 @@ struct FusedParams {
     uint8_t *enc;
     igd_meter_rec *meter;
     igd_bridge_rec *bmeter;
-    const igd_ed137_fields *fields;   // packet form only: [F][C], payload_len is read
+    const igd_ed137_fields *fields;   // packet form only: [F][C]; NULL = the gains already carry IGD_GAIN_NO_AUDIO
+    // packets OUT (gateway form): the bridge output leaves as finished ED-137 packets, one sender per bridge
+    const igd_tx_plan_rec *plan;      // [F][B] from the sender walk (k_ed137_plan)
+    const uint8_t *rtp12;             // [F][B][12] the PJSIP-built RTP headers
+    uint8_t *tx_pkts;                 // [F][B][180]
+    uint32_t *tx_sizes;               // [F][B]
     long long total_bf;   // F*B bridge-frames
     long long num_tiles;
     int B, G;
@@ -88,12 +93,19 @@ __device__ __forceinline__ uint2 leg_chunk(uint32_t lane_base, uint4 w, uint32_t
 // bridge output of one 16-sample chunk: saturate, store PCM, compress, store codes
 template <bool kSigned>
 __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_pk &E, int16_t *mix_dst,
-                                               uint8_t *enc_dst, bool st_mix, bool st_enc)
+                                               uint8_t *enc_dst, bool st_mix, bool st_enc, uint4 *enc_out = nullptr)
 {
     uint32_t pk[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
     if (st_mix) st32_stream(mix_dst, pk);
+#ifdef IGD_X_NOPEAK      // measurement only: what the bridge record's mix_peak costs
+    const uint4 e_np = encode16_packed(pk, E);
+    if (st_enc) st16_stream(enc_dst, e_np);
+    uint32_t u_np = __dp4a(e_np.x, 0x01010101u, 0u); u_np = __dp4a(e_np.y, 0x01010101u, u_np);
+    u_np = __dp4a(e_np.z, 0x01010101u, u_np); u_np = __dp4a(e_np.w, 0x01010101u, u_np);
+    return make_uint2(u_np, 0u);
+#endif
     uint32_t mx = max_s16x2(max_s16x2(pk[0], pk[1]), pk[2]), mn = min_s16x2(min_s16x2(pk[0], pk[1]), pk[2]);
     mx = max_s16x2(max_s16x2(mx, pk[3]), pk[4]); mn = min_s16x2(min_s16x2(mn, pk[3]), pk[4]);
     mx = max_s16x2(max_s16x2(mx, pk[5]), pk[6]); mn = min_s16x2(min_s16x2(mn, pk[5]), pk[6]);
@@ -102,6 +114,7 @@ __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_p
     const int lo = min((int)(short)(mn & 0xFFFFu), (int)mn >> 16);
     const uint4 e = encode16_packed(pk, E);
     if (st_enc) st16_stream(enc_dst, e);
+    if (enc_out) *enc_out = e;
     int esum = 0;
     if (kSigned) {
         esum = __dp4a((int)e.x, 0x01010101, esum); esum = __dp4a((int)e.y, 0x01010101, esum);
@@ -259,7 +272,10 @@ __device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32
 // kPkt: the codes are read straight out of the raw ED-137 packets ([F][C][180], payload at byte 20) -- the
 // item is still ONE contiguous bulk copy (6 * G * 180 B), the payload array between igd_ed137_parse and
 // this kernel is never materialised; a packet that is not a whole audio frame (parsed fields) is silent.
-template <int G, bool kSigned, int kWarps, bool kPkt = false>
+// kTx: the bridge output leaves as finished 180-byte ED-137 packets -- header from the sender plan (k_ed137_plan)
+// and the PJSIP RTP header, payload = this tick's encoded mix, every byte of a slot past the packet's size zero
+// (the bytes k_ed137_assemble_tile writes without IGD_F_REF_QUIRKS): no enc[] round trip, no assembly kernel.
+template <int G, bool kSigned, int kWarps, bool kPkt = false, bool kTx = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
 {
     static_assert(kBfPerItem * G + kBfPerItem <= 32, "finish needs one lane per record");
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
     if (t < 2) {
         const enc_pk e = enc_pk_make(t);
         enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
-        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4;
+        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4; enc_tab[t][6] = 0u; enc_tab[t][7] = 0u;
     }
     if (lane == 0) {
         mbar_init(bar_s, 1);
@@ -347,15 +363,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
     if (worker && item < items && item * kBfPerItem + bfl < total_bf) {
         gq = load_gains<G>(q.gain + (size_t)(item * kBfPerItem + bfl) * G);
         lwq = load_laws(b);
-        if (kPkt) gq = mark_no_audio(gq, item * kBfPerItem + bfl);
+        if (kPkt && q.fields) gq = mark_no_audio(gq, item * kBfPerItem + bfl);
+        if (kTx) lwq |= (uint32_t)(__ldg(&q.plan[item * kBfPerItem + bfl].size) > IGD_PKT_HDR) << 9;   // bit 9: the packet carries the payload
     }
 
+    const bool want_mix = q.mix != nullptr, want_enc = q.enc != nullptr, want_meter = q.meter != nullptr,
+               want_bmeter = q.bmeter != nullptr;
     for (uint32_t it = 0; item < items; item += nw, it++) {
         const uint32_t bf = item * kBfPerItem + bfl;
         const uint32_t next = item + nw;
         mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
-        uint32_t silent;                                      // bit g: leg g of this lane's bridge-frame has no audio
-        const uint2 gcur = split_no_audio(gq, silent);
+        uint2 gcur = gq;
         const uint32_t lcur = lwq;
         const bool valid = worker && bf < total_bf;
         {
@@ -365,7 +383,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             if (worker && next < items && bfn < total_bf) {      // next item's gains and laws ride in three registers
                 gq = load_gains<G>(q.gain + (size_t)bfn * G);
                 lwq = load_laws(b);
-                if (kPkt) gq = mark_no_audio(gq, bfn);
+                if (kPkt && q.fields) gq = mark_no_audio(gq, bfn);
+                if (kTx) lwq |= (uint32_t)(__ldg(&q.plan[bfn].size) > IGD_PKT_HDR) << 9;
             }
         }
         // every lane runs the same instruction stream (idle / tail lanes on stale bytes with all
@@ -373,7 +392,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
         // warp-wide OR of the gains (REDUX): anything but 0 / 256 anywhere in the warp -> general
         // path; bit g of open_mask: some lane of the warp has leg g open
-        const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
+        uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
+        // IGD_GAIN_NO_AUDIO anywhere in the warp (rare: keep-alive / lost-packet ticks): clear those legs' gains
+        // -- they then walk the shut path -- and remember them for the records.  Warp-uniform branch.
+        uint32_t silent = 0u;                                 // bit g: leg g of this lane's bridge-frame has no audio
+        const bool any_silent = ((orx | ory) & 0x80008000u) != 0u;
+        if (any_silent) {
+            gcur = split_no_audio(gcur, silent);
+            orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x); ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
+        }
         const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
         const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
                                    ((ory >> 16) ? 8u : 0u);
@@ -444,10 +471,22 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                 const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
                 const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
                 E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
+#ifdef IGD_X_ZERO2
+                E.zero2 = et[6];
+#else
+                E.zero2 = 0u;
+#endif
             }
             const uint32_t o16 = bf * kChunks + ch;     // 16-sample chunk index of the outputs
+            uint4 ev;
             const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + (size_t)o16 * 16, q.enc + (size_t)o16 * 16,
-                                                    valid && q.mix != nullptr, valid && q.enc != nullptr);
+                                                    valid && want_mix, valid && want_enc, kTx ? &ev : nullptr);
+            if (kTx && valid) {      // payload bytes [20 + 16 ch, +16) of the packet slot (4-byte aligned): the codes, or zeros
+                uint32_t *tp = reinterpret_cast<uint32_t *>(q.tx_pkts + (size_t)bf * IGD_PKT_MAX + IGD_PKT_HDR + ch * 16);
+                const bool pay = (lcur >> 9) & 1u;
+                __stcs(tp, pay ? ev.x : 0u); __stcs(tp + 1, pay ? ev.y : 0u);
+                __stcs(tp + 2, pay ? ev.z : 0u); __stcs(tp + 3, pay ? ev.w : 0u);
+            }
             if (valid) bpart[bfl * kP + ch] = make_uint2(mo.x, mo.y | n_open16);
         }
         __syncwarp();
@@ -458,7 +497,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             const uint2 *src_p = part + lane * kP;
             unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
             // the record of leg (lane / G, lane % G): the lanes of that bridge-frame hold its no-audio flags
-            const uint32_t sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / G) * kC32) & 31) >> (lane % G)) & 1u;
+            uint32_t sil_rec = 0u;
+            if (any_silent) sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / G) * kC32) & 31) >> (lane % G)) & 1u;
             if (lane < kBfPerItem * G + kBfPerItem && !(lane < kBfPerItem * G && sil_rec)) {
 #pragma unroll
                 for (int i = 0; i < kChunks; i++) {
@@ -467,13 +507,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                 }
             }
             if (lane < kBfPerItem * G) {
-                if (bf0 + lane / G < total_bf && q.meter != nullptr) {
+                if (bf0 + lane / G < total_bf && want_meter) {
                     const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
                     st16_stream(q.meter + ((size_t)bf0 * G + lane), *reinterpret_cast<const uint4 *>(&r));
                 }
             } else if (lane < kBfPerItem * G + kBfPerItem) {
                 const uint32_t j = lane - kBfPerItem * G;
-                if (bf0 + j < total_bf && q.bmeter != nullptr) {
+                if (kTx && bf0 + j < total_bf) {      // the packet's 20-byte header (TransportAdapter.cpp:715-800) and its size
+                    const uint32_t *pr = reinterpret_cast<const uint32_t *>(q.plan + (bf0 + j));
+                    const uint32_t pw = __ldg(pr), psf = __ldg(pr + 1);      // word; size | flags << 16
+                    const uint32_t psize = psf & 0xFFFFu, pfl = psf >> 16;
+                    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(q.rtp12 + (size_t)(bf0 + j) * 12);
+                    uint32_t v0 = __ldg(hdr) | 0x10u;                                          // x = 1 (:725)
+                    v0 = (v0 & ~0x8000u) | ((pfl & 2u) ? 0x8000u : 0u);                        // m (:715-723)
+                    if (pfl & 1u) v0 = (v0 & ~0x7F00u) | (123u << 8);                          // pt = 123
+                    uint32_t *tp = reinterpret_cast<uint32_t *>(q.tx_pkts + (size_t)(bf0 + j) * IGD_PKT_MAX);
+                    const bool any = psize != 0u;
+                    tp[0] = any ? v0 : 0u; tp[1] = any ? __ldg(hdr + 1) : 0u; tp[2] = any ? __ldg(hdr + 2) : 0u;
+                    tp[3] = any ? 0x01006701u : 0u;                                            // 0x0167, 0x0001 big-endian
+                    tp[4] = any ? __byte_perm(pw, 0u, 0x0123) : 0u;                            // htonl (:800)
+                    q.tx_sizes[bf0 + j] = psize;
+                }
+                if (bf0 + j < total_bf && want_bmeter) {
                     igd_bridge_rec r;
                     r.bytemean_out = (uint8_t)igd_bytemean_from_sum((int)(uint32_t)sq, IGD_FRAME);
                     r.n_open = (uint8_t)((uint32_t)bsum / kChunks);
@@ -645,11 +700,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
             fence_proxy_async();
             if (it_n < items) fetch(it_n, grp_n, n + 1);
             mbar_wait(bar_s + (n & 1u) * 8, (n >> 1) & 1u);
-            uint32_t silent;                                             // bit g: leg g of this group has no audio on this lane's bridge-frame
-            const uint2 gcur = split_no_audio(gq, silent);
+            uint2 gcur = gq;
             const uint32_t lcur = lwq;
             load_unit(it_n, grp_n, last ? b_next : b, gq, lwq);          // next unit's gains / laws ride in registers
-            const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
+            uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
+            uint32_t silent = 0u;                                        // bit g: leg g of this group has no audio on this lane's bridge-frame
+            const bool any_silent = ((orx | ory) & 0x80008000u) != 0u;   // warp-uniform, rare
+            if (any_silent) {
+                gcur = split_no_audio(gcur, silent);
+                orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x); ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
+            }
             const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
             const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
                                        ((ory >> 16) ? 8u : 0u);
@@ -675,7 +735,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
             }
             __syncwarp();
             // the record of leg (lane / 4, lane % 4): the lanes of that bridge-frame hold its no-audio flags
-            const uint32_t sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / kGLegs) * kChunks) & 31) >> (lane % kGLegs)) & 1u;
+            uint32_t sil_rec = 0u;
+            if (any_silent) sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / kGLegs) * kChunks) & 31) >> (lane % kGLegs)) & 1u;
             if (lane < kGBf * kGLegs) {                                  // this group's leg records
                 const uint32_t fb = lane / kGLegs, g = lane - fb * kGLegs;
                 if (g < legs && item * kGBf + fb < total_bf && q.meter != nullptr) {
@@ -699,6 +760,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
             const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
             const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
             E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
+            E.zero2 = 0u;
         }
         const size_t o16 = (size_t)bf * kChunks + c;
         const uint2 mo = mix_out_chunk<kSigned>(acc, E, q.mix + o16 * 16, q.enc + o16 * 16, valid && q.mix != nullptr,
@@ -798,10 +860,10 @@ __global__ void __launch_bounds__(BFPC * kChunks, 2) k_fused_anyg(const FusedPar
 
 // ============================================================ launchers
 namespace {
-template <int G, bool kSigned, int kWarps, bool kPkt = false>
+template <int G, bool kSigned, int kWarps, bool kPkt = false, bool kTx = false>
 cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
 {
-    auto kern = k_fused_w<G, kSigned, kWarps, kPkt>;
+    auto kern = k_fused_w<G, kSigned, kWarps, kPkt, kTx>;
     constexpr int kP = kPkt ? kChunks : kPst;
     const size_t smem = kLutBytes + (size_t)kWarps * slot_geom<G, kPkt>::kSlotBytes +
                         (size_t)kWarps * (kBfPerItem * G * kP + kBfPerItem * kP) * 8;
@@ -853,6 +915,7 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     q.codes = d.codes; q.law = d.law; q.gain = d.gain_q7; q.out_law = d.out_law;
     q.mix = d.mix; q.enc = d.enc; q.meter = d.meter; q.bmeter = d.bmeter;
     q.fields = nullptr;
+    q.plan = nullptr; q.rtp12 = nullptr; q.tx_pkts = nullptr; q.tx_sizes = nullptr;
     q.total_bf = (long long)d.F * d.B;
     q.num_tiles = 0;
     q.B = d.B; q.G = d.G; q.flags = d.flags;
@@ -881,6 +944,7 @@ cudaError_t igd_k_fused_packets(const igd_launch_cfg &c, const igd_packets_desc 
     FusedParams q;
     q.codes = d.pkts; q.fields = d.fields; q.law = d.law; q.gain = d.gain_q7; q.out_law = d.out_law;
     q.mix = d.mix; q.enc = d.enc; q.meter = d.meter; q.bmeter = d.bmeter;
+    q.plan = nullptr; q.rtp12 = nullptr; q.tx_pkts = nullptr; q.tx_sizes = nullptr;
     q.total_bf = (long long)d.F * d.B;
     q.num_tiles = 0;
     q.B = d.B; q.G = d.G; q.flags = d.flags;
@@ -888,4 +952,22 @@ cudaError_t igd_k_fused_packets(const igd_launch_cfg &c, const igd_packets_desc 
         (reinterpret_cast<uintptr_t>(d.law) & 3u))
         return cudaErrorInvalidValue;
     return (d.flags & IGD_F_SIGNED_CHAR) ? launch_fused_w<4, true, 24, true>(c, q) : launch_fused_w<4, false, 24, true>(c, q);
+}
+
+// gateway form: packets in (gains carry IGD_GAIN_NO_AUDIO, no field records needed) -> packets out
+cudaError_t igd_k_fused_gateway(const igd_launch_cfg &c, const igd_packets_desc &d, const igd_tx_plan_rec *plan,
+                                const uint8_t *tx_rtp12, uint8_t *tx_pkts, uint32_t *tx_sizes)
+{
+    FusedParams q;
+    q.codes = d.pkts; q.fields = d.fields; q.law = d.law; q.gain = d.gain_q7; q.out_law = d.out_law;
+    q.mix = d.mix; q.enc = d.enc; q.meter = d.meter; q.bmeter = d.bmeter;
+    q.plan = plan; q.rtp12 = tx_rtp12; q.tx_pkts = tx_pkts; q.tx_sizes = tx_sizes;
+    q.total_bf = (long long)d.F * d.B;
+    q.num_tiles = 0;
+    q.B = d.B; q.G = d.G; q.flags = d.flags;
+    if (d.G != 4 || q.total_bf >= (1ll << 28) || (reinterpret_cast<uintptr_t>(d.gain_q7) & 7u) ||
+        (reinterpret_cast<uintptr_t>(d.law) & 3u) || (reinterpret_cast<uintptr_t>(tx_pkts) & 3u) ||
+        (reinterpret_cast<uintptr_t>(tx_rtp12) & 3u))
+        return cudaErrorInvalidValue;
+    return (d.flags & IGD_F_SIGNED_CHAR) ? launch_fused_w<4, true, 24, true, true>(c, q) : launch_fused_w<4, false, 24, true, true>(c, q);
 }

@@ -34,6 +34,9 @@ cudaError_t igd_k_mix(const igd_launch_cfg &c, const int16_t *pcm, const uint16_
                       size_t nframes, size_t nbridges, int legs, int16_t *mix);
 cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d);
 cudaError_t igd_k_fused_packets(const igd_launch_cfg &c, const igd_packets_desc &d);
+cudaError_t igd_k_fused_gateway(const igd_launch_cfg &c, const igd_packets_desc &d, const igd_tx_plan_rec *plan,
+                                const uint8_t *tx_rtp12, uint8_t *tx_pkts, uint32_t *tx_sizes);
+cudaError_t igd_k_ed137_plan(const igd_launch_cfg &c, const igd_ed137_pack_desc &d, igd_tx_plan_rec *plan, int32_t *last_src);
 cudaError_t igd_k_event_summary(const igd_launch_cfg &c, const igd_meter_rec *meter,
                                 const uint16_t *gain, size_t F, size_t C, igd_summary_rec *out,
                                 igd_summary_db *db);

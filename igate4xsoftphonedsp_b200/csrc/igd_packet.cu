@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
     // The walk is sequential, its inputs are not: the fields of the NEXT run of 8 frames are in flight
     // while this run is walked (with a few thousand channels there is one warp per SM and nothing
     // else to hide the latency behind).
-    constexpr int kAhead = 8;
+    constexpr int kAhead = 16;
     uint4 raw[kAhead], nraw[kAhead];
     uint8_t pres[kAhead], npres[kAhead];
     auto fetch = [&](int f0, uint4 (&r)[kAhead], uint8_t (&p)[kAhead]) {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
             if (f < d.F) {
                 const size_t i = (size_t)f * d.C + c;
                 r[u] = __ldg(reinterpret_cast<const uint4 *>(d.fields + i));
-                p[u] = d.present ? d.present[i] : (uint8_t)1;
+                p[u] = d.present ? d.present[i] : d.sizes ? (uint8_t)(d.sizes[i] != 0u) : (uint8_t)1;
             }
         }
     };
@@ -289,6 +289,14 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
         act_mask = 0;
         for (int g = 0; g < G; g++) act_mask |= (act[g] != 0 ? 1u : 0u) << g;
     }
+    // steady-state skip (see the walk below): the words of the last full pass and whether it moved the state
+    uint32_t prevw[kG > 0 ? kG : 1];
+    uint64_t snap[kG > 0 ? kG : 1];
+    // runtime leg count: snapshots [bpb][G] u64 and last words [bpb][G] u32 follow the leg state in shared memory
+    uint64_t *snap_s = reinterpret_cast<uint64_t *>(legs_s + (size_t)bpb * G) + (owner ? threadIdx.x : 0) * G;
+    uint32_t *prev_s = reinterpret_cast<uint32_t *>(reinterpret_cast<uint64_t *>(legs_s + (size_t)bpb * G) + (size_t)bpb * G) +
+                       (owner ? threadIdx.x : 0) * G;
+    bool have_prev = false, steady = false, counting = false;
     for (int f0 = 0; f0 < d.F; f0 += T) {
         const int nt = min(T, d.F - f0);
         __syncthreads();
@@ -304,15 +312,62 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
                 auto word = [&](int g) { return wt[g]; };
                 auto active = [&](int g) { return ((act_mask >> g) & 1u) != 0u; };
                 uint16_t *gt = gain_s + t * row + threadIdx.x * G;
+                // Steady-state skip.  checkEvents() is a deterministic function of (state, words): when a pass
+                // left the state unchanged, every further pass over the SAME words leaves it unchanged too, so
+                // the gains simply repeat (PTT / squelch states last for hundreds of ticks; the hold-off
+                // counters settle within six).  SERVER mode has one more steady form: while a selection is in
+                // force (sqlStatusOn) a pass only counts sqlStatusCount up (roip_ed137.cpp:6028) and nothing
+                // reads the count again (:6029 needs !sqlStatusOn).  The full pass runs whenever the words
+                // change or the last full pass still moved the state -- bit-exact by construction.
+                bool same = have_prev;
                 if (kG > 0) {
-                    const igd_const_int<(kG > 0 ? kG : 1)> Gc;
-                    if (d.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, Gc, word, active);
-                    else igd_arb_server_best_tick(br, legs, Gc, word, active);
+#pragma unroll
+                    for (int g = 0; g < (kG > 0 ? kG : 1); g++) same = same && wt[g] == prevw[g];
+                } else {
+                    for (int g = 0; g < G && same; g++) same = wt[g] == prev_s[g];
+                }
+                if (same && steady) {
+                    if (counting) br.sqlStatusCount++;
+                } else {
+                    // snapshot -> full pass -> did anything move?
+                    uint64_t snap_fold = 0;
+                    const int32_t c0 = br.sqlStatusCount, l0 = br.ptt_level;
+                    const uint8_t o0 = br.sqlStatusOn;
+                    if (kG > 0) {
+#pragma unroll
+                        for (int g = 0; g < (kG > 0 ? kG : 1); g++) snap[g] = *reinterpret_cast<const uint64_t *>(&legs[g]);
+                    } else {
+                        for (int g = 0; g < G; g++) snap_s[g] = *reinterpret_cast<const uint64_t *>(&legs[g]);
+                    }
+                    if (kG > 0) {
+                        const igd_const_int<(kG > 0 ? kG : 1)> Gc;
+                        if (d.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, Gc, word, active);
+                        else igd_arb_server_best_tick(br, legs, Gc, word, active);
+                    } else {
+                        if (d.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, G, word, active);
+                        else igd_arb_server_best_tick(br, legs, G, word, active);
+                    }
+                    if (kG > 0) {
+#pragma unroll
+                        for (int g = 0; g < (kG > 0 ? kG : 1); g++) {
+                            snap_fold |= snap[g] ^ *reinterpret_cast<const uint64_t *>(&legs[g]);
+                            prevw[g] = wt[g];
+                        }
+                    } else {
+                        for (int g = 0; g < G; g++) {
+                            snap_fold |= snap_s[g] ^ *reinterpret_cast<const uint64_t *>(&legs[g]);
+                            prev_s[g] = wt[g];
+                        }
+                    }
+                    const bool legs_same = snap_fold == 0 && br.ptt_level == l0 && br.sqlStatusOn == o0;
+                    counting = legs_same && br.sqlStatusOn != 0 && br.sqlStatusCount == c0 + 1;
+                    steady = legs_same && (br.sqlStatusCount == c0 || counting);
+                    have_prev = true;
+                }
+                if (kG > 0) {
 #pragma unroll
                     for (int g = 0; g < (kG > 0 ? kG : 1); g++) gt[g] = legs[g].gain_q7;
                 } else {
-                    if (d.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, G, word, active);
-                    else igd_arb_server_best_tick(br, legs, G, word, active);
                     for (int g = 0; g < G; g++) gt[g] = legs[g].gain_q7;
                 }
             }
@@ -351,7 +406,11 @@ __global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d,
     if (c >= d.C) return;
     igd_ed137_state s = d.state[c];
     int32_t src = -1;
-    const bool stuck = 12u + d.payload_len > 60u;
+    const bool stuck = d.payload != nullptr && 12u + d.payload_len > 60u;   // gateway form: the payload does not exist yet
+    igd_tx_plan last;                    // steady-state skip: result of the last full step
+    last.word = 0; last.size = 0; last.pt123 = 0; last.marker = 0; last.copy_payload = 0;
+    uint64_t last_ctl = 0;
+    bool have_last = false, steady = false;
     constexpr int kAhead = 8;            // the walk is sequential, its inputs are not: fetch 8 frames ahead
     for (int f0 = 0; f0 < d.F; f0 += kAhead) {
         igd_ed137_ctl kk[kAhead];
@@ -373,15 +432,52 @@ __global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d,
             const int f = f0 + u;
             if (f >= d.F) break;
             const size_t i = (size_t)f * d.C + c;
+            bool ctl_same = have_last;
             if (d.ctl) {                                                     // the setters, :135-213
                 const igd_ed137_ctl k = kk[u];
+                const uint64_t kbits = *reinterpret_cast<const uint64_t *>(&k);
+                ctl_same = ctl_same && kbits == last_ctl;
+                last_ctl = kbits;
                 s.pttstatus = k.pttstatus; s.pttpriority = k.pttpriority; s.callRecorder = k.callRecorder;
                 s.sqlstatus = k.sqlstatus; s.ed137_bssi = k.ed137_bssi; s.pttid = k.pttid;
             }
             if (s.radiostatus && stuck) {                                    // stuck-audio detector :657-673
                 if (a40[u] == a50[u] && a40[u] == a60[u] && a40[u] == 0xd5) s.rtpFalse += 1; else s.rtpFalse = 0;
             }
-            const igd_tx_plan t = igd_ed137_tx_step(s, d.payload_len, d.now_ms0 + (long long)f * d.tick_ms);
+            const long long now = d.now_ms0 + (long long)f * d.tick_ms;
+            // Steady-state skip.  transport_send_rtp is a deterministic function of (state, setter values, clock)
+            // and the clock only enters through the keep-alive throttle (:685-706).  Once a call has left the
+            // state as it found it (the 30-packet start burst and the 5-packet slave-enable latch are over),
+            // every further call with the SAME setter values gives the same header; what is left per tick is
+            // the throttle.  The full step runs whenever the setter values change, the last full step still
+            // moved the state, or no sent header is cached for this situation -- bit-exact by construction.
+            igd_tx_plan t;
+            bool fast = false;
+            if (ctl_same && steady) {
+                if (last.copy_payload) {                                     // gated audio: goes out on every tick
+                    t = last; fast = true;
+                } else {
+                    const unsigned long long since = (unsigned long long)now - (unsigned long long)s.r2sSendtime;
+                    const unsigned long long ka = (unsigned long long)(long long)s.keepAlivePeroid;
+                    if (since < ka) {                                        // throttled (firstR2SPacket is over when steady)
+                        t.word = 0; t.size = 0; t.pt123 = 0; t.marker = 0; t.copy_payload = 0; fast = true;
+                    } else if (last.size != 0) {                             // keep-alive due: the cached header again
+                        s.r2sSendtime = now;
+                        t = last; fast = true;
+                    }
+                }
+            }
+            if (!fast) {
+                if ((s.calltype_flags & 1u) && s.callIn) { s.sqlstatus = 0; s.pttstatus = 0; }   // :675-679, before the snapshot
+                igd_ed137_state before = s;
+                t = igd_ed137_tx_step(s, d.payload_len, now);
+                before.r2sSendtime = s.r2sSendtime;                          // the throttle clock is not part of "steady"
+                const uint64_t *pa = reinterpret_cast<const uint64_t *>(&before), *pb = reinterpret_cast<const uint64_t *>(&s);
+                steady = pa[0] == pb[0] && pa[1] == pb[1] && pa[2] == pb[2] && pa[3] == pb[3] && pa[4] == pb[4] &&
+                         !s.firstR2SPacket;
+                last = t;            // cached header = the one built by THIS step (a throttled step caches size 0, so the
+                have_last = true;    // next keep-alive that is due takes the full step again, now in the settled state)
+            }
             if (t.copy_payload) src = f;
             igd_tx_plan_rec r;
             r.word = t.word;
@@ -724,8 +820,13 @@ cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d)
     case 1: k_gate_arbitrate<1><<<blocks, kArbThreads, stage, c.stream>>>(d, bpb); break;
     case 2: k_gate_arbitrate<2><<<blocks, kArbThreads, stage, c.stream>>>(d, bpb); break;
     case 4: k_gate_arbitrate<4><<<blocks, kArbThreads, stage, c.stream>>>(d, bpb); break;
-    default:   // runtime leg count: leg state in shared memory (<= 64 * 32 * 8 B = 16 KB, 40 KB in all)
-        k_gate_arbitrate<0><<<blocks, kArbThreads, stage + (size_t)kArbThreads * d.G * sizeof(igd_arb_leg), c.stream>>>(d, bpb);
+    default:   // runtime leg count: leg state + snapshots + last words in shared memory (<= 64 * 32 * 20 B = 40 KB, 64 KB in all)
+        {
+            const size_t smem = stage + (size_t)bpb * d.G * (sizeof(igd_arb_leg) + 8 + 4);
+            cudaError_t e = cudaFuncSetAttribute(k_gate_arbitrate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            k_gate_arbitrate<0><<<blocks, kArbThreads, smem, c.stream>>>(d, bpb);
+        }
     }
     return cudaGetLastError();
 }
@@ -756,6 +857,13 @@ cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc 
     e = cudaGetLastError();
     if (e != cudaSuccess || !d.stale_payload) return e;
     k_ed137_stale_update<<<grid_for(c, (size_t)d.C * 32, 256, 8), 256, 0, c.stream>>>(d, last_src);
+    return cudaGetLastError();
+}
+
+// the sender walk alone (gateway form: the fused kernel assembles the packets)
+cudaError_t igd_k_ed137_plan(const igd_launch_cfg &c, const igd_ed137_pack_desc &d, igd_tx_plan_rec *plan, int32_t *last_src)
+{
+    k_ed137_plan<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d, plan, last_src);
     return cudaGetLastError();
 }
 

@@ -428,7 +428,7 @@ class VoicePath:
             events = np.empty((F, Cn), dtype=N.RX_EVENT_DT)
         d = N.RxTrackDesc(C.sizeof(N.RxTrackDesc), mem, F, Cn, int(tick_ms), int(r2s_period_ms), int(wd_ticks),
                           int(frame0), int(now_ms0), self._ptr(fields), self._ptr(present), self._ptr(state),
-                          self._ptr(events))
+                          self._ptr(events), None)
         self._chk(self._lib.igd_rx_track(self._h, C.byref(d)))
         return events
 
@@ -457,6 +457,55 @@ class VoicePath:
                       self._ptr(active), self._ptr(legs), self._ptr(bridges), self._ptr(gain))
         self._chk(self._lib.igd_gate_arbitrate(self._h, C.byref(d)))
         return gain
+
+    # ------------------------------------------------------------ gateway: packets in, packets out
+    def gateway_process(self, rx_pkts, law, out_law, rx_state, arb_legs, arb_bridges, tx_rtp12, tx_state, rx_sizes=None,
+                        tx_ctl=None, active=None, mode=N.ARB_CLIENT_PTT, now_ms0=0, tick_ms=20, r2s_period_ms=200,
+                        wd_ticks=2, frame0=0, flags=0, want=("meter", "bmeter"), out=None):
+        """The whole per-tick voice path in one call (igd_gateway_process): received ED-137 packets of every leg
+        in, finished ED-137 packets of every bridge out.  rx_pkts u8 [F][B*4][180]; rx_sizes u32 [F][B*4] or None;
+        tx_rtp12 u8 [F][B][12]; states (rx_state RX_STATE_DT [B*4], arb_legs ARB_LEG_DT [B*4], arb_bridges
+        ARB_BRIDGE_DT [B], tx_state STATE_DT [B]) are updated in place.  Returns dict(tx_pkts [F][B][180],
+        tx_sizes [F][B]) plus the optional outputs named in `want` (rx_events, gain_q7, meter, bmeter, mix, enc)."""
+        mem = self._mode(rx_pkts, law, out_law, rx_state, arb_legs, arb_bridges, tx_rtp12, tx_state, rx_sizes, tx_ctl, active)
+        F, Cn, n = rx_pkts.shape
+        if n != N.PKT_MAX or Cn % 4:
+            raise IgdError("rx_pkts must be [F][B*4][180]")
+        B = Cn // 4
+        if out is not None:
+            o = out
+        elif mem == N.MEM_DEVICE:
+            dev = rx_pkts.device
+            mk = {"tx_pkts": lambda: torch.empty((F, B, N.PKT_MAX), dtype=torch.uint8, device=dev),
+                  "tx_sizes": lambda: torch.empty((F, B), dtype=torch.int32, device=dev),
+                  "rx_events": lambda: torch.empty((F, Cn, 2), dtype=torch.int32, device=dev),
+                  "gain_q7": lambda: torch.empty((F, Cn), dtype=torch.int16, device=dev),
+                  "meter": lambda: torch.empty((F, Cn, 4), dtype=torch.int32, device=dev),
+                  "bmeter": lambda: torch.empty((F, B), dtype=torch.int32, device=dev),
+                  "mix": lambda: torch.empty((F, B, N.FRAME), dtype=torch.int16, device=dev),
+                  "enc": lambda: torch.empty((F, B, N.FRAME), dtype=torch.uint8, device=dev)}
+            o = {k: mk[k]() for k in ("tx_pkts", "tx_sizes") + tuple(want)}
+        else:
+            rx_pkts = np.ascontiguousarray(rx_pkts, dtype=np.uint8)
+            if rx_sizes is not None:
+                rx_sizes = np.ascontiguousarray(rx_sizes, dtype=np.uint32)
+            law = np.ascontiguousarray(law, dtype=np.uint8)
+            out_law = np.ascontiguousarray(out_law, dtype=np.uint8)
+            tx_rtp12 = np.ascontiguousarray(tx_rtp12, dtype=np.uint8)
+            mk = {"tx_pkts": lambda: np.empty((F, B, N.PKT_MAX), np.uint8), "tx_sizes": lambda: np.empty((F, B), np.uint32),
+                  "rx_events": lambda: np.empty((F, Cn), N.RX_EVENT_DT), "gain_q7": lambda: np.empty((F, Cn), np.uint16),
+                  "meter": lambda: np.empty((F, Cn), N.METER_DT), "bmeter": lambda: np.empty((F, B), N.BRIDGE_DT),
+                  "mix": lambda: np.empty((F, B, N.FRAME), np.int16), "enc": lambda: np.empty((F, B, N.FRAME), np.uint8)}
+            o = {k: mk[k]() for k in ("tx_pkts", "tx_sizes") + tuple(want)}
+        d = N.GatewayDesc(C.sizeof(N.GatewayDesc), mem, F, B, 4, int(flags), int(mode), int(tick_ms), int(r2s_period_ms),
+                          int(wd_ticks), int(frame0), 0, int(now_ms0),
+                          self._ptr(rx_pkts), self._ptr(rx_sizes), self._ptr(law), self._ptr(active), self._ptr(rx_state),
+                          self._ptr(arb_legs), self._ptr(arb_bridges), self._ptr(out_law), self._ptr(tx_rtp12),
+                          self._ptr(tx_ctl), self._ptr(tx_state), self._ptr(o["tx_pkts"]), self._ptr(o["tx_sizes"]),
+                          self._ptr(o.get("rx_events")), self._ptr(o.get("gain_q7")), self._ptr(o.get("meter")),
+                          self._ptr(o.get("bmeter")), self._ptr(o.get("mix")), self._ptr(o.get("enc")))
+        self._chk(self._lib.igd_gateway_process(self._h, C.byref(d)))
+        return o
 
     # ------------------------------------------------------------ recorder
     def wav_image(self, payload, rate=8000, law=N.LAW_ULAW, ref_quirks=False):

@@ -33,7 +33,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
 #endif
 
-#define IGD_ABI_VERSION 1
+#define IGD_ABI_VERSION 2
 #define IGD_FRAME 160            /* 20 ms @ 8 kHz: roip_ed137.h:112-115           */
 #define IGD_PKT_HDR 20           /* sizeof(custom_rtp_hdr): ed137_rtp.h:22-47     */
 #define IGD_PKT_MAX 180          /* 20 + 160: TransportAdapter.cpp:814,844        */
@@ -384,9 +384,10 @@ typedef struct {
 #define IGD_RXE_DROPPED 0x08u    /* oversized / truncated packet (:286-291)        */
 #define IGD_RXE_LATE 0x10u       /* watchdog: now - r2sPacket > 3*r2s_period       */
 #define IGD_RXE_HANGUP 0x20u     /* watchdog: sixth late tick in a row, hang up    */
-#define IGD_RXE_FRAME 0x40u      /* a whole G.711 audio frame arrived: forwarded (pt 0 / 8) with
-                                    160 payload bytes -- what the fused path may decode; without
-                                    it the leg is silent on this tick (IGD_GAIN_NO_AUDIO)          */
+#define IGD_RXE_FRAME 0x40u      /* a whole G.711 audio frame arrived: forwarded (pt 0 / 8) with at
+                                    least 160 payload bytes (fields.payload_len == 160) -- what the
+                                    fused path may decode; without it the leg is silent on this
+                                    tick (IGD_GAIN_NO_AUDIO)                                       */
 typedef struct {
     uint32_t struct_size;
     int32_t mem;
@@ -401,6 +402,8 @@ typedef struct {
     const uint8_t *present;      /* [F][C] 0 = no packet on that tick; NULL = all  */
     igd_rx_state *state;         /* [C], updated in place                          */
     igd_rx_event *events;        /* [F][C] out                                     */
+    const uint32_t *sizes;       /* [F][C] optional, used when present == NULL: a packet arrived
+                                    iff sizes[f][c] != 0 (the sizes igd_ed137_parse was given)   */
 } igd_rx_track_desc;
 int igd_rx_track(igd_ctx *ctx, const igd_rx_track_desc *d);
 
@@ -452,6 +455,59 @@ typedef struct {
     uint16_t *gain_q7;           /* [F][B*G] out                                  */
 } igd_arb_desc;
 int igd_gate_arbitrate(igd_ctx *ctx, const igd_arb_desc *d);
+
+/* ------------------------------------------------- gateway: packets in, packets out
+ * One call = the whole per-tick voice path of a RoIP gateway for F ticks of B bridges x 4 legs,
+ * everything on the device: the receive callback's header work on every leg's packet
+ * (transport_rtp_cb, TransportAdapter.cpp:240-316 -> igd_ed137_parse fields only), the liveness /
+ * edge walk (igd_rx_track), checkEvents()'s gate decisions with silent no-audio ticks
+ * (igd_gate_arbitrate + IGD_ARB_F_SILENCE), the sender walk of the call each bridge's output leaves
+ * on (transport_send_rtp, :635-874) and the fused decode -> meter -> mix -> encode kernel, which
+ * reads the codes straight out of the received packets and writes FINISHED 180-byte ED-137 packets
+ * (header from the sender walk + the PJSIP RTP header, payload = this tick's encoded mix; the bytes of
+ * a slot past tx_sizes are zero) -- the bytes igd_ed137_pack produces without IGD_F_REF_QUIRKS.
+ * Five kernel launches; no payload, code or plan array crosses the API.  (tx_state.rtpFalse, the
+ * reference's never-read stuck-audio diagnostic counter, is not maintained here: the payload it
+ * looks at is produced after the sender walk.)
+ * Algorithmic bytes per bridge-frame (SURVEY 8d "with RTP"): 4*180 in + 180 + 320 (optional mix) + 4*16
+ * = 1284.  rx_events / gain_q7 / meter / bmeter / mix / enc are optional outputs (NULL = not wanted;
+ * rx_events and gain_q7 then live in the context's scratch).  G must be 4.                            */
+typedef struct {
+    uint32_t struct_size;        /* = sizeof(igd_gateway_desc)                    */
+    int32_t mem;                 /* IGD_MEM_DEVICE or IGD_MEM_HOST (all pointers) */
+    int32_t F, B, G;
+    uint32_t flags;              /* IGD_F_SIGNED_CHAR                             */
+    int32_t arb_mode;            /* IGD_ARB_*                                     */
+    int32_t tick_ms;             /* 20                                            */
+    int32_t r2s_period_ms;       /* 200                                           */
+    int32_t wd_ticks;            /* watchdog every wd_ticks ticks, 0 = never      */
+    int32_t frame0;
+    int32_t reserved;
+    int64_t now_ms0;
+    /* receive side */
+    const uint8_t *rx_pkts;      /* [F][B*G][180] as received (zero padded)       */
+    const uint32_t *rx_sizes;    /* [F][B*G] received sizes, 0 = nothing arrived; NULL = all 180 */
+    const uint8_t *law;          /* [B*G]                                         */
+    const uint8_t *active;       /* [B*G] or NULL                                 */
+    igd_rx_state *rx_state;      /* [B*G] in/out                                  */
+    igd_arb_leg *arb_legs;       /* [B*G] in/out                                  */
+    igd_arb_bridge *arb_bridges; /* [B] in/out                                    */
+    /* send side: the call each bridge's output goes out on */
+    const uint8_t *out_law;      /* [B]                                           */
+    const uint8_t *tx_rtp12;     /* [F][B][12] PJSIP-built RTP headers            */
+    const igd_ed137_ctl *tx_ctl; /* [F][B] setter values per tick, or NULL        */
+    igd_ed137_state *tx_state;   /* [B] in/out                                    */
+    /* outputs */
+    uint8_t *tx_pkts;            /* [F][B][180]                                   */
+    uint32_t *tx_sizes;          /* [F][B] 0 = suppressed, 20 = keep-alive, 180   */
+    igd_rx_event *rx_events;     /* [F][B*G] optional                             */
+    uint16_t *gain_q7;           /* [F][B*G] optional                             */
+    igd_meter_rec *meter;        /* [F][B*G] optional                             */
+    igd_bridge_rec *bmeter;      /* [F][B] optional (bytemean_out = the level of the outgoing payload) */
+    int16_t *mix;                /* [F][B][160] optional                          */
+    uint8_t *enc;                /* [F][B][160] optional                          */
+} igd_gateway_desc;
+int igd_gateway_process(igd_ctx *ctx, const igd_gateway_desc *d);
 
 /* ------------------------------------------------------------ recorder sink
  * replaces: WavWriter::start/wav_write/stop (WavWriter.cpp:63-156).

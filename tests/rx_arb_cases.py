@@ -48,9 +48,9 @@ def make_rx_stream(F, Cn, seed=0):
 
 
 def frame_flag(pkt, size):
-    """IGD_RXE_FRAME: a forwarded packet that is a whole G.711 audio frame (pt 0 / 8, 160 payload bytes) -- the
-    build's own notion (include/igate_dsp.h), derived from what the reference forwards to the stream"""
-    return N.RXE_FRAME if (int(pkt[1]) & 0x7F) in (0, 8) and size == 180 else 0
+    """IGD_RXE_FRAME: a forwarded packet that carries a whole G.711 audio frame (pt 0 / 8, at least 160 payload
+    bytes) -- the build's own notion (include/igate_dsp.h), derived from what the reference forwards to the stream"""
+    return N.RXE_FRAME if (int(pkt[1]) & 0x7F) in (0, 8) and 180 <= size < 1044 else 0
 
 
 def ref_comparable_sizes(sizes):

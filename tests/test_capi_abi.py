@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_record_sizes():
     lib = ig.load()
-    assert lib.igd_abi_version() == 1
+    assert lib.igd_abi_version() == 2
     assert C.sizeof(N.BatchDesc) == 24 + 8 * 8 and C.sizeof(N.PackDesc) == 40 + 8 * 8
     assert N.METER_DT.itemsize == 16 and N.STATE_DT.itemsize == 40 and N.FIELDS_DT.itemsize == 16
 

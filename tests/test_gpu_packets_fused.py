@@ -33,9 +33,11 @@ def make(F, B, seed, ragged, gains=(0, 0, 256)):
 
 
 def no_audio(pk, sizes):
-    """a packet that is not a whole G.711 audio frame: the leg is silent on that tick (IGD_GAIN_NO_AUDIO rule)"""
+    """a packet that is not a whole G.711 audio frame: the leg is silent on that tick (IGD_GAIN_NO_AUDIO rule:
+    pt 0 / 8 and at least 160 payload bytes -- igd_ed137_parse reports payload_len = min(size - 20, 160) -- and not
+    dropped, i.e. size - 20 < 1024)"""
     pt = pk[..., 1] & 0x7F
-    return ~(((pt == 0) | (pt == 8)) & (sizes == 180))
+    return ~(((pt == 0) | (pt == 8)) & (sizes >= 180) & (sizes < 1044))
 
 
 def want_of(vp, pk, sizes, law, gain, out_law, signed=0):
