@@ -215,6 +215,148 @@ def run_reference(args):
     }))
 
 
+def run_chain(args):
+    """--chain: SURVEY 8(d) "with RTP" accounting -- raw 180-byte ED-137 packets of every leg in, finished ED-137
+    packets of every bridge out, through igd_gateway_process (five launches: header fields, liveness walk, gate
+    arbitration, sender walk, fused decode -> meter -> mix -> encode -> packet kernel), device resident.
+    1284 algorithmic bytes per bridge-frame (4 x 180 in, 180 + 320 + 4 x 16 out)."""
+    import numpy as np
+    import torch
+    import igate4xsoftphonedsp_b200 as ig
+    from igate4xsoftphonedsp_b200 import _native as N
+    from igate4xsoftphonedsp_b200 import synth
+    args.warmup = max(args.warmup, 3)
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    vp = ig.VoicePath(dev.index)
+    vp.use_torch_stream()
+    Bc = args.chain_bridges
+    Fc = args.chain_frames
+    Cc = Bc * G
+    law_np, out_law_np = synth.laws(Cc), synth.out_laws(Bc)
+    law = torch.from_numpy(law_np).to(dev)
+    out_law = torch.from_numpy(out_law_np).to(dev)
+    codes = vp.g711_encode(synth.pcm_noise_tone_torch(Fc, Cc, dev), law)
+    gate = torch.from_numpy(synth.gates(Fc, Bc, G).reshape(Fc, Cc).astype(np.uint8)).to(dev)
+    pk = torch.zeros((Fc, Cc, 180), dtype=torch.uint8, device=dev)
+    pk[..., 0] = 0x90
+    pk[..., 1] = torch.where(law == 0, 8, 0).to(torch.uint8).view(1, Cc)            # PT 8 = PCMA, 0 = PCMU
+    f_idx = torch.arange(Fc, device=dev).view(Fc, 1)
+    pk[..., 2] = ((f_idx >> 8) & 255).to(torch.uint8)
+    pk[..., 3] = (f_idx & 255).to(torch.uint8)
+    pk[..., 12], pk[..., 13], pk[..., 15] = 0x01, 0x67, 0x01
+    prio = (1 + torch.arange(Cc, device=dev) % G % 4).view(1, Cc)                   # PTT type = 1 + g % 4 while the gate is open
+    pk[..., 16] = (gate.to(torch.int64) * (prio << 5)).to(torch.uint8)              # bits 31-29 of the big-endian word
+    pk[..., 20:] = codes
+    del codes
+    rtp12_np = synth.rtp12(Fc, Bc, np.where(out_law_np == 0, 8, 0).astype(np.uint8))
+    rtp12 = torch.from_numpy(rtp12_np).to(dev)
+    ctl_np = np.zeros((Fc, Bc), dtype=N.CTL_DT)
+    ctl_np["pttstatus"] = 1
+    ctl_np["pttpriority"] = 1
+    ctl = torch.from_numpy(ctl_np.view(np.int32).reshape(Fc, Bc, 2)).to(dev)
+    now0 = 1_000_000
+    tx0 = ig.make_state(Bc, now_ms=now0)
+
+    def fresh():
+        return (torch.zeros((Cc, 4), dtype=torch.int32, device=dev), torch.zeros((Cc, 2), dtype=torch.int32, device=dev),
+                torch.zeros((Bc, 4), dtype=torch.int32, device=dev),
+                torch.from_numpy(tx0.copy().view(np.int32).reshape(Bc, 10)).to(dev))
+
+    outs = None
+
+    def step(st, now):
+        nonlocal outs
+        outs = vp.gateway_process(pk, law, out_law, st[0], st[1], st[2], rtp12, st[3], tx_ctl=ctl, mode=N.ARB_CLIENT_PTT,
+                                  now_ms0=now, want=("meter", "bmeter", "mix"), out=outs)
+
+    # ---- parity: a fresh run, two bridges recomputed by the oracle from the raw packets (outside the timed region)
+    st = fresh()
+    outs = None
+    step(st, now0)
+    torch.cuda.synchronize()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import rx_arb_cases as R
+    import tx_scenarios as T
+    O = oracle_lib()
+    ok = True
+    for b in (0, Bc - 1):
+        chs = slice(b * G, b * G + G)
+        pkb = pk[:, chs].cpu().numpy()
+        szb = np.full((Fc, G), 180, np.uint32)
+        ev, _ = R.oracle_rx_walk(pkb, szb, np.ones((Fc, G), np.uint8), now0=now0)
+        g, _, _ = R.oracle_arb_walk(np.ascontiguousarray(ev["word"]), G, N.ARB_CLIENT_PTT)
+        g = np.where((ev["flags"] & N.RXE_FRAME) == 0, g | N.GAIN_NO_AUDIO, g).astype(np.uint16)
+        mix, enc, _, _ = O.process_batch(np.ascontiguousarray(pkb[:, :, 20:]), law_np[chs], g, out_law_np[b:b + 1], G)
+        s_ = dict(name="chain", legs=[dict(radiocall=1, callIn=0, calltype="TRx", keepalive=200, slave=None)], F=Fc,
+                  ctl=ctl_np[:, b:b + 1], tick_ms=20, now0=now0, payload=enc, rtp12=rtp12_np[:, b:b + 1])
+        wpk, wsz, _, _ = T.run_oracle(s_)
+        wpk, _ = T.clean_expectation(s_, wpk, wsz)
+        ok = ok and np.array_equal(outs["mix"][:, b].cpu().numpy(), mix[:, 0])
+        ok = ok and np.array_equal(outs["tx_pkts"][:, b].cpu().numpy(), wpk[:, 0])
+        ok = ok and np.array_equal(outs["tx_sizes"][:, b].cpu().numpy().view(np.uint32), wsz[:, 0])
+    parity = bool(ok)
+
+    for i in range(args.warmup):
+        step(st, now0 + (i + 1) * Fc * 20)
+    torch.cuda.synchronize()
+    l0 = vp.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(st, now0 + (args.warmup + i + 1) * Fc * 20)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = vp.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    t_end = time.perf_counter() + 1.5
+    k = 0
+    while time.perf_counter() < t_end:
+        for _ in range(20):
+            k += 1
+            step(st, now0 + (args.warmup + args.steps + k) * Fc * 20)
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
+    # ---- stage breakdown through the separate entry points (same kernels; the two-kernel pack instead of the fused packet output)
+    fields, _ = vp.ed137_parse(pk.view(Fc * Cc, 180), want_payload=False)
+    dummy_enc = torch.zeros((Fc, Bc, FRAME), dtype=torch.uint8, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    s2 = fresh()
+    for rep in range(3):
+        ev[0].record()
+        fields, _ = vp.ed137_parse(pk.view(Fc * Cc, 180), want_payload=False)
+        ev[1].record()
+        events = vp.rx_track(fields.view(Fc, Cc, 4), s2[0], now_ms0=now0 + rep * Fc * 20)
+        ev[2].record()
+        gain = vp.gate_arbitrate(events, s2[1], s2[2], G, N.ARB_CLIENT_PTT, silence=True)
+        ev[3].record()
+        vp.ed137_pack(rtp12, dummy_enc, s2[3], ctl, now_ms0=now0 + rep * Fc * 20)
+        ev[4].record()
+        torch.cuda.synchronize()
+    stage = {"fields": ev[0].elapsed_time(ev[1]), "rx_track": ev[1].elapsed_time(ev[2]), "gate_arbitrate": ev[2].elapsed_time(ev[3]),
+             "plan+assemble (separate call; the gateway runs the plan walk only)": ev[3].elapsed_time(ev[4])}
+    alg = 1284 * Bc * Fc
+    peak, peak_src = peaks()
+    value = Cc * Fc * FRAME / (ms * 1e-3)
+    print(json.dumps({
+        "metric": METRIC + " (packets in -> packets out)", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int16", "data": "synthetic",
+        "config": {"workload": f"chain: {Cc} channels ({Bc} bridges x {G} legs) x {Fc} ticks, raw 180-byte ED-137 packets of every leg in, "
+                               f"one finished ED-137 packet per bridge and tick out (igd_gateway_process, CLIENT arbitration, silence marking)",
+                   "l2": "inputs larger than L2" if Cc * Fc * 180 > (256 << 20) else "inputs may be L2 resident"},
+        "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
+                     "traffic": None, "kernel": "igd_gateway_process: k_ed137_fields + k_rx_track + k_gate_arbitrate + k_ed137_plan + "
+                                                  "k_fused_w<4, packets in, packets out>", "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": alg, "bytes_per_bridge_frame": 1284, "stage_ms": stage},
+        "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+        "parity_vs_oracle_on_two_bridges": parity,
+    }))
+    vp.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,7 +374,13 @@ def main():
                     help="BASELINE config 5: one mixed-codec batch of 65536 channels (16384 bridges x 4 legs, A-law / u-law "
                          "alternating) x 100 frames, bridges split over the ranks (strong scaling), per-channel dBFS "
                          "summaries gathered to rank 0 over NCCL and checked against the oracle; device-resident legs only")
+    ap.add_argument("--chain", action="store_true", help="packets in -> packets out (SURVEY 8d 'with RTP' accounting, 1284 B per "
+                    "bridge-frame) through igd_gateway_process, device resident, 1 GPU")
+    ap.add_argument("--chain-bridges", type=int, default=B)
+    ap.add_argument("--chain-frames", type=int, default=F)
     args = ap.parse_args()
+    if args.chain:
+        return run_chain(args)
     if args.cfg5:
         world_ = int(os.environ.get("WORLD_SIZE", "1"))
         if 16384 % world_:

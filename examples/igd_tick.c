@@ -34,7 +34,7 @@ int main(void)
     igd_rx_state rxs[C];
     igd_rx_event ev[C];
     memset(rxs, 0, sizeof rxs);
-    igd_rx_track_desc rx = {sizeof rx, IGD_MEM_HOST, F, C, 20, 200, 2, 0, 0, fields, NULL, rxs, ev};
+    igd_rx_track_desc rx = {sizeof rx, IGD_MEM_HOST, F, C, 20, 200, 2, 0, 0, fields, NULL, rxs, ev, NULL};
     if (rc == IGD_OK) rc = igd_rx_track(ctx, &rx);
 
     igd_arb_leg legs[C];

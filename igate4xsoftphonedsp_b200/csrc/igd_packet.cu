@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
     // The walk is sequential, its inputs are not: the fields of the NEXT run of 8 frames are in flight
     // while this run is walked (with a few thousand channels there is one warp per SM and nothing
     // else to hide the latency behind).
-    constexpr int kAhead = 16;
+    constexpr int kAhead = 8;
     uint4 raw[kAhead], nraw[kAhead];
     uint8_t pres[kAhead], npres[kAhead];
     auto fetch = [&](int f0, uint4 (&r)[kAhead], uint8_t (&p)[kAhead]) {
@@ -249,7 +249,8 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
 // SMs several times: the walk over F is sequential per bridge, so few bridges x many
 // frames must not sit on a handful of SMs); all 64 threads stage the words / gains of
 // a run of ticks through shared memory with coalesced rows.
-constexpr int kArbThreads = 64;
+constexpr int kArbThreads = 256;         // staging threads per block; the first bpb (<= kArbMaxBpb) of them walk a bridge each
+constexpr int kArbMaxBpb = 64;
 constexpr int kArbStageWords = 4096;     // words (and gains) of a run of ticks staged per block
 template <int kG> struct arb_legs {      // compile-time leg count: the leg state lives in registers
     igd_arb_leg v[kG > 0 ? kG : 1];
@@ -300,10 +301,24 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
     for (int f0 = 0; f0 < d.F; f0 += T) {
         const int nt = min(T, d.F - f0);
         __syncthreads();
-        for (int k = threadIdx.x; k < nt * row; k += kArbThreads) {      // coalesced: a tick's words are contiguous
-            const int t = k / row, j = k - t * row;
-            const uint8_t *wrow = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)(f0 + t) * Cn + (size_t)b0 * G) * d.word_stride;
-            words_s[k] = *reinterpret_cast<const uint32_t *>(wrow + (size_t)j * d.word_stride);
+        // coalesced (a tick's words are contiguous), eight independent loads in flight per thread: the walk
+        // below is short once the steady-state skip engages, so the staging latency is what is left
+        for (int k0 = threadIdx.x; k0 < nt * row; k0 += kArbThreads * 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = k0 + u * kArbThreads;
+                if (k < nt * row) {
+                    const int t = k / row, j = k - t * row;
+                    const uint8_t *wrow = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)(f0 + t) * Cn + (size_t)b0 * G) * d.word_stride;
+                    v[u] = __ldg(reinterpret_cast<const uint32_t *>(wrow + (size_t)j * d.word_stride));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = k0 + u * kArbThreads;
+                if (k < nt * row) words_s[k] = v[u];
+            }
         }
         __syncthreads();
         if (owner) {
@@ -374,14 +389,28 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
         }
         __syncthreads();
         const bool mark = (d.flags & IGD_ARB_F_SILENCE) != 0u && d.word_stride >= 8u;
-        for (int k = threadIdx.x; k < nt * row; k += kArbThreads) {
-            const int t = k / row, j = k - t * row;
-            uint16_t gv = gain_s[k];
-            if (mark) {      // words are igd_rx_event records: no whole audio frame on this tick -> the leg is silent
-                const uint8_t *ev = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)(f0 + t) * Cn + (size_t)b0 * G + j) * d.word_stride;
-                if (!(ev[4] & IGD_RXE_FRAME)) gv |= (uint16_t)IGD_GAIN_NO_AUDIO;
+        for (int k0 = threadIdx.x; k0 < nt * row; k0 += kArbThreads * 8) {
+            uint32_t fl[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {      // words are igd_rx_event records: the flags byte follows the word
+                const int k = k0 + u * kArbThreads;
+                fl[u] = IGD_RXE_FRAME;
+                if (mark && k < nt * row) {
+                    const int t = k / row, j = k - t * row;
+                    const uint8_t *ev = reinterpret_cast<const uint8_t *>(d.words) + ((size_t)(f0 + t) * Cn + (size_t)b0 * G + j) * d.word_stride;
+                    fl[u] = __ldg(ev + 4);
+                }
             }
-            d.gain_q7[(size_t)(f0 + t) * Cn + (size_t)b0 * G + j] = gv;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int k = k0 + u * kArbThreads;
+                if (k < nt * row) {
+                    const int t = k / row, j = k - t * row;
+                    uint16_t gv = gain_s[k];
+                    if (!(fl[u] & IGD_RXE_FRAME)) gv |= (uint16_t)IGD_GAIN_NO_AUDIO;   // no whole audio frame on this tick: silent
+                    d.gain_q7[(size_t)(f0 + t) * Cn + (size_t)b0 * G + j] = gv;
+                }
+            }
         }
     }
     __syncthreads();
@@ -441,6 +470,8 @@ __global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d,
                 s.pttstatus = k.pttstatus; s.pttpriority = k.pttpriority; s.callRecorder = k.callRecorder;
                 s.sqlstatus = k.sqlstatus; s.ed137_bssi = k.ed137_bssi; s.pttid = k.pttid;
             }
+            // :675-679 -- on every call, also the ones the steady-state skip answers (the step itself repeats it)
+            if (s.radiostatus && (s.calltype_flags & 1u) && s.callIn) { s.sqlstatus = 0; s.pttstatus = 0; }
             if (s.radiostatus && stuck) {                                    // stuck-audio detector :657-673
                 if (a40[u] == a50[u] && a40[u] == a60[u] && a40[u] == 0xd5) s.rtpFalse += 1; else s.rtpFalse = 0;
             }
@@ -468,7 +499,6 @@ __global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d,
                 }
             }
             if (!fast) {
-                if ((s.calltype_flags & 1u) && s.callIn) { s.sqlstatus = 0; s.pttstatus = 0; }   // :675-679, before the snapshot
                 igd_ed137_state before = s;
                 t = igd_ed137_tx_step(s, d.payload_len, now);
                 before.r2sSendtime = s.r2sSendtime;                          // the throttle clock is not part of "steady"
@@ -813,7 +843,7 @@ cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d)
     // bridges per block: 64, or fewer so that the grid is ~4 blocks per SM (the walk over F is sequential)
     const int want_blocks = 4 * (c.sm_count > 0 ? c.sm_count : 148);
     int bpb = (d.B + want_blocks - 1) / want_blocks;
-    bpb = bpb < 1 ? 1 : bpb > kArbThreads ? kArbThreads : bpb;
+    bpb = bpb < 1 ? 1 : bpb > kArbMaxBpb ? kArbMaxBpb : bpb;
     const unsigned blocks = (unsigned)((d.B + bpb - 1) / bpb);
     const size_t stage = (size_t)kArbStageWords * 6;
     switch (d.G) {

@@ -1,11 +1,9 @@
-# igate_dsp.pri -- include from iGate4xSoftphoneDSP.pro (next to its LIBS block, :64-92):
-#     include(/opt/igate_dsp/host/igate_dsp.pri)
-# Links the B200 voice path (libigate_dsp.so, CUDA runtime linked statically: the host build needs no
-# CUDA toolkit) and compiles the two host files with the project's own g++.
+# igate_dsp.pri -- include from iGate4xSoftphoneDSP.pro (next to :64-92); see INTEGRATION.md section 1
 IGD_ROOT = /opt/igate_dsp                       # include/ + lib/ + host/
 INCLUDEPATH += $$IGD_ROOT/include $$IGD_ROOT/host
 LIBS        += -L$$IGD_ROOT/lib -ligate_dsp -Wl,-rpath,$$IGD_ROOT/lib
-HEADERS     += $$IGD_ROOT/host/igate_shim.h $$IGD_ROOT/host/igate_eventlog.h
+HEADERS     += $$IGD_ROOT/host/igate_shim.h $$IGD_ROOT/host/igate_pj_compat.h $$IGD_ROOT/host/igate_eventlog.h
 SOURCES     += $$IGD_ROOT/host/igate_shim.cpp $$IGD_ROOT/host/igate_eventlog.cpp
-SOURCES     -= TransportAdapter.cpp             # its signatures are provided by igate_shim.cpp
-DEFINES     += IGATE_DSP_GPU=1
+SOURCES     -= TransportAdapter.cpp             # (:20-36) replaced as a whole by igate_shim.cpp
+HEADERS     -= TransportAdapter.h               # its declarations come from igate_shim.h
+DEFINES     += IGATE_DSP_GPU=1 IGD_HAVE_PJSIP=1 # igate_shim.cpp then includes the project's real <pjsua.h>

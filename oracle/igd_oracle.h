@@ -11,31 +11,26 @@
  * does per packet / per 20 ms frame, so that the CUDA path can be checked
  * bit-for-bit on the same inputs.
  *
- * Parity pinning status (see DESIGN.md "Oracle"):
- *   - ED-137 RTP header pack / parse : PINNED.  The header layout is checked
- *     against the reference's own `struct custom_rtp_hdr` (ed137_rtp.h:22-47)
- *     compiled from /root/reference by oracle/Makefile -> oracle/_ref/ and
- *     against golden packets generated through that struct
- *     (tests/golden/ed137_ref_headers.json).  The state machine is restated
- *     from TransportAdapter.cpp:635-874 (send), :422-633 (keep-alive) and
- *     :240-316 (receive); field parsers from Functions.cpp:1001-1179.
- *   - WavWriter RIFF sink            : PINNED against the reference's own
- *     WavWriter.cpp compiled verbatim into oracle/_ref/
- *     (tests/golden/wavwriter_ref.bin).
- *   - byte-mean meter, percent scale, event summary : restated from
- *     roip_ed137.cpp:6500-6587, audiometer.cpp:30-31, Functions.cpp:2126-2230
- *     (those files need Qt + PJSIP and cannot be compiled here) -- formula
- *     level restatement, pinned by hand-computed known answers.
- *   - G.711 and the conference-bridge mix : PARITY UNPINNED.  The arithmetic
- *     lives in pjproject (pjmedia/src/pjmedia/alaw_ulaw.c, g711.c,
- *     conference.c), which the reference links but does not vendor and does
- *     not version-pin (iGate4xSoftphoneDSP.pro:66-82; "pjsip 2.6 only",
- *     TransportAdapter.cpp:245).  The oracle restates the published ITU-T
- *     G.711 / Sun g711.c algorithm and the pjmedia
- *     rx_adj_level + saturating-sum semantics (Appendix D); it is pinned by
- *     the SHA-256 table hashes of Appendix B, by Python's independent
- *     `audioop` decoder (all 256 codes) and encoder (all non-negative inputs),
- *     and by the ITU known-answer codes.
+ * Parity pinning status:
+ *   - PINNED to the reference's own code compiled from /root/reference by oracle/Makefile into
+ *     oracle/_ref/ (TransportAdapter.cpp whole, ed137_rtp.h, WavWriter.cpp, and line-range extracts
+ *     of roip_ed137.cpp / Functions.cpp, under the stand-in Qt/PJSIP headers of oracle/ref_shim/):
+ *     the ED-137 header layout; the sender state machine transport_send_rtp (:635-874) with
+ *     setOutgoingRTP; sendR2SStatus (:422-633); the receive callback transport_rtp_cb (:240-316) with
+ *     setIncomingRTP, get_ed137_value, getR2SStatus; the field getters and by-call-id setters
+ *     (Functions.cpp:909-1179); checkEvents() gate arbitration (roip_ed137.cpp:5609-6348) with
+ *     setvolume / setSlotVolume; keeplogAudioLevel / createPTTEventDataLogger (Functions.cpp:2126-2230);
+ *     the WavWriter bytes.  tests/test_ref_pins.py compares oracle and reference on every shared
+ *     seeded case; tests/golden/ref_pins.json holds the digests of the REFERENCE run.
+ *   - restatement only: the percent scale (audiometer.cpp:30-31, one formula).
+ *   - G.711 and the conference-bridge mix : PARITY UNPINNED.  The arithmetic lives in pjproject
+ *     (pjmedia/src/pjmedia/alaw_ulaw.c, g711.c, conference.c), which the reference links but does not
+ *     vendor and does not version-pin (iGate4xSoftphoneDSP.pro:66-82; "pjsip 2.6 only",
+ *     TransportAdapter.cpp:245).  The oracle restates the published ITU-T G.711 / Sun g711.c
+ *     algorithm and the pjmedia rx_adj_level + saturating-sum semantics
+ *     (Appendix D); it is pinned by the SHA-256 table hashes of Appendix B, by Python's independent
+ *     `audioop` decoder (all 256 codes) and encoder (all non-negative inputs), and by the ITU
+ *     known-answer codes.
  */
 #ifndef IGD_ORACLE_H
 #define IGD_ORACLE_H

@@ -21,7 +21,8 @@ BIN = os.path.join(ROOT, "tests", "host_cpp", "shim_driver")
 
 
 def build_driver():
-    srcs = [DRIVER, SHIM_SRC, os.path.join(PKG, "host", "igate_shim.h")]
+    srcs = [DRIVER, SHIM_SRC, os.path.join(PKG, "host", "igate_shim.h"), os.path.join(PKG, "host", "igate_pj_compat.h"),
+            os.path.join(ROOT, "include", "igate_dsp.h"), os.path.join(PKG, "libigate_dsp.so")]
     if not os.path.exists(BIN) or os.path.getmtime(BIN) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", BIN, DRIVER, SHIM_SRC, "-L" + PKG, "-ligate_dsp",
                                "-Wl,-rpath," + PKG])
