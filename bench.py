@@ -217,7 +217,7 @@ def run_reference(args):
 
 def run_chain(args):
     """--chain: SURVEY 8(d) "with RTP" accounting -- raw 180-byte ED-137 packets of every leg in, finished ED-137
-    packets of every bridge out, through igd_gateway_process (five launches: header fields, liveness walk, gate
+    packets of every bridge out, through igd_gateway_process (four launches: header view + liveness walk, gate
     arbitration, sender walk, fused decode -> meter -> mix -> encode -> packet kernel), device resident.
     1284 algorithmic bytes per bridge-frame (4 x 180 in, 180 + 320 + 4 x 16 out)."""
     import numpy as np
@@ -348,7 +348,7 @@ def run_chain(args):
                                f"one finished ED-137 packet per bridge and tick out (igd_gateway_process, CLIENT arbitration, silence marking)",
                    "l2": "inputs larger than L2" if Cc * Fc * 180 > (256 << 20) else "inputs may be L2 resident"},
         "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
-                     "traffic": None, "kernel": "igd_gateway_process: k_ed137_fields + k_rx_track + k_gate_arbitrate + k_ed137_plan + "
+                     "traffic": None, "kernel": "igd_gateway_process: k_rx_track<packets> + k_gate_arbitrate + k_ed137_plan (side stream) + "
                                                   "k_fused_w<4, packets in, packets out>", "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg, "bytes_per_bridge_frame": 1284, "stage_ms": stage},
         "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,

@@ -275,7 +275,8 @@ __device__ __forceinline__ uint2 leg_chunk_u(uint32_t lane_base, uint4 w, uint32
 // kTx: the bridge output leaves as finished 180-byte ED-137 packets -- header from the sender plan (k_ed137_plan)
 // and the PJSIP RTP header, payload = this tick's encoded mix, every byte of a slot past the packet's size zero
 // (the bytes k_ed137_assemble_tile writes without IGD_F_REF_QUIRKS): no enc[] round trip, no assembly kernel.
-template <int G, bool kSigned, int kWarps, bool kPkt = false, bool kTx = false>
+// kOpt: some of mix / enc / meter / bmeter may be NULL (checked per store); false = all four are there, no checks.
+template <int G, bool kSigned, int kWarps, bool kPkt = false, bool kTx = false, bool kOpt = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
 {
     static_assert(kBfPerItem * G + kBfPerItem <= 32, "finish needs one lane per record");
@@ -367,13 +368,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         if (kTx) lwq |= (uint32_t)(__ldg(&q.plan[item * kBfPerItem + bfl].size) > IGD_PKT_HDR) << 9;   // bit 9: the packet carries the payload
     }
 
-    const bool want_mix = q.mix != nullptr, want_enc = q.enc != nullptr, want_meter = q.meter != nullptr,
-               want_bmeter = q.bmeter != nullptr;
+    const bool want_mix = !kOpt || q.mix != nullptr, want_enc = !kOpt || q.enc != nullptr,
+               want_meter = !kOpt || q.meter != nullptr, want_bmeter = !kOpt || q.bmeter != nullptr;
     for (uint32_t it = 0; item < items; item += nw, it++) {
         const uint32_t bf = item * kBfPerItem + bfl;
         const uint32_t next = item + nw;
         mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
-        uint2 gcur = gq;
+        const uint2 gcur = gq;
         const uint32_t lcur = lwq;
         const bool valid = worker && bf < total_bf;
         {
@@ -392,21 +393,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
         // warp-wide OR of the gains (REDUX): anything but 0 / 256 anywhere in the warp -> general
         // path; bit g of open_mask: some lane of the warp has leg g open
-        uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
-        // IGD_GAIN_NO_AUDIO anywhere in the warp (rare: keep-alive / lost-packet ticks): clear those legs' gains
-        // -- they then walk the shut path -- and remember them for the records.  Warp-uniform branch.
-        uint32_t silent = 0u;                                 // bit g: leg g of this lane's bridge-frame has no audio
-        const bool any_silent = ((orx | ory) & 0x80008000u) != 0u;
-        if (any_silent) {
-            gcur = split_no_audio(gcur, silent);
-            orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x); ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
-        }
+        // IGD_GAIN_NO_AUDIO (bit 15 of a gain) anywhere in the warp makes `general` true: the rare multiply path
+        // below treats a flagged leg as gain 0 and the finish writes its record as digital silence.  The common
+        // path (gains 0 / 2.0 only) is untouched by the flag handling.
+        const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
         const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
         const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
                                    ((ory >> 16) ? 8u : 0u);
         // open legs of this lane's bridge-frame, pre-shifted into the high half of the bridge partial
         // (every one of the ten partials carries it; the finish divides the sum by ten)
-        const uint32_t n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y))) << 16;
+        uint32_t n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y))) << 16;
+        if (general)             // legs without audio do not count as open (their halves are non-zero: the flag)
+            n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x & ~(((gcur.x & 0x80008000u) >> 15) * 0xFFFFu))) +
+                                  __popc(nonzero_halves(gcur.y & ~(((gcur.y & 0x80008000u) >> 15) * 0xFFFFu)))) << 16;
 #pragma unroll 1
         for (int h = 0; h < 2; h++) {
             const uint32_t ch = h == 0 ? c0 : (c0 >= (uint32_t)kC32 ? c0 - kC32 : c0 + kC32);   // this pass's chunk
@@ -450,7 +449,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
 #pragma unroll
                 for (int g = 0; g < G; g++) {
                     const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
-                    const uint2 ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (int)adj_of(g), acc);
+                    const uint32_t a = adj_of(g);
+                    const uint2 ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (a & IGD_GAIN_NO_AUDIO) ? 0 : (int)a, acc);
                     if (valid) mypart[g * kP] = ph;
                 }
             }
@@ -498,7 +498,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
             // the record of leg (lane / G, lane % G): the lanes of that bridge-frame hold its no-audio flags
             uint32_t sil_rec = 0u;
-            if (any_silent) sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / G) * kC32) & 31) >> (lane % G)) & 1u;
+            if (general) {       // rare: the record of leg (lane / G, lane % G) is silent when its gain carries the flag
+                uint32_t silent;
+                (void)split_no_audio(gcur, silent);
+                sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / G) * kC32) & 31) >> (lane % G)) & 1u;
+            }
             if (lane < kBfPerItem * G + kBfPerItem && !(lane < kBfPerItem * G && sil_rec)) {
 #pragma unroll
                 for (int i = 0; i < kChunks; i++) {
@@ -700,21 +704,18 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
             fence_proxy_async();
             if (it_n < items) fetch(it_n, grp_n, n + 1);
             mbar_wait(bar_s + (n & 1u) * 8, (n >> 1) & 1u);
-            uint2 gcur = gq;
+            const uint2 gcur = gq;
             const uint32_t lcur = lwq;
             load_unit(it_n, grp_n, last ? b_next : b, gq, lwq);          // next unit's gains / laws ride in registers
-            uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
-            uint32_t silent = 0u;                                        // bit g: leg g of this group has no audio on this lane's bridge-frame
-            const bool any_silent = ((orx | ory) & 0x80008000u) != 0u;   // warp-uniform, rare
-            if (any_silent) {
-                gcur = split_no_audio(gcur, silent);
-                orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x); ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
-            }
+            const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = __reduce_or_sync(0xFFFFFFFFu, gcur.y);
             const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;
             const uint32_t open_mask = ((orx & 0xFFFFu) ? 1u : 0u) | ((orx >> 16) ? 2u : 0u) | ((ory & 0xFFFFu) ? 4u : 0u) |
                                        ((ory >> 16) ? 8u : 0u);
             auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
-            n_open += (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y)));
+            if (!general) n_open += (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y)));
+            else          // IGD_GAIN_NO_AUDIO makes `general` true: flagged legs do not count as open
+                n_open += (uint32_t)(__popc(nonzero_halves(gcur.x & ~(((gcur.x & 0x80008000u) >> 15) * 0xFFFFu))) +
+                                     __popc(nonzero_halves(gcur.y & ~(((gcur.y & 0x80008000u) >> 15) * 0xFFFFu))));
             const uint32_t src = slot_s + (n & 1u) * kGSlotBytes + src_off;
             uint4 wh[kGLegs];
 #pragma unroll
@@ -727,7 +728,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
                 if ((uint32_t)g < legs) {                                 // warp-uniform
                     const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
                     uint2 ph;
-                    if (general) ph = leg_chunk_u<kSigned, 2, true>(lb, wh[g], 0u, (int)adj_of(g), acc);
+                    if (general) ph = leg_chunk_u<kSigned, 2, true>(lb, wh[g], 0u, (adj_of(g) & IGD_GAIN_NO_AUDIO) ? 0 : (int)adj_of(g), acc);
                     else if ((open_mask >> g) & 1u) ph = leg_chunk_u<kSigned, 1, true>(lb, wh[g], adj_of(g), 0, acc);
                     else ph = leg_chunk_shut<kSigned>(mlut, 4u * lane + (((lcur >> g) & 1u) << 7), wh[g]);
                     if (valid) part[(bfl * kGLegs + g) * kPst + c] = ph;
@@ -736,7 +737,11 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_g(const FusedParams q)
             __syncwarp();
             // the record of leg (lane / 4, lane % 4): the lanes of that bridge-frame hold its no-audio flags
             uint32_t sil_rec = 0u;
-            if (any_silent) sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / kGLegs) * kChunks) & 31) >> (lane % kGLegs)) & 1u;
+            if (general) {
+                uint32_t silent;
+                (void)split_no_audio(gcur, silent);
+                sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / kGLegs) * kChunks) & 31) >> (lane % kGLegs)) & 1u;
+            }
             if (lane < kGBf * kGLegs) {                                  // this group's leg records
                 const uint32_t fb = lane / kGLegs, g = lane - fb * kGLegs;
                 if (g < legs && item * kGBf + fb < total_bf && q.meter != nullptr) {
@@ -863,7 +868,8 @@ namespace {
 template <int G, bool kSigned, int kWarps, bool kPkt = false, bool kTx = false>
 cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
 {
-    auto kern = k_fused_w<G, kSigned, kWarps, kPkt, kTx>;
+    const bool all_out = q.mix && q.enc && q.meter && q.bmeter;
+    auto kern = all_out ? k_fused_w<G, kSigned, kWarps, kPkt, kTx, false> : k_fused_w<G, kSigned, kWarps, kPkt, kTx, true>;
     constexpr int kP = kPkt ? kChunks : kPst;
     const size_t smem = kLutBytes + (size_t)kWarps * slot_geom<G, kPkt>::kSlotBytes +
                         (size_t)kWarps * (kBfPerItem * G * kP + kBfPerItem * kP) * 8;

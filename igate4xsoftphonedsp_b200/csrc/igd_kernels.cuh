@@ -47,7 +47,8 @@ cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc 
                              igd_tx_plan_rec *plan, int32_t *last_src);
 cudaError_t igd_k_ed137_keepalive(const igd_launch_cfg &c, uint8_t *hdr20, igd_ed137_state *state, size_t C,
                                   long long now, uint32_t *sizes);
-cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d);
+// pkts != NULL: the walk reads the header words straight out of the packets [F][C][180] (d.fields unused)
+cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d, const uint8_t *pkts = nullptr);
 cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d);
 cudaError_t igd_k_wav_images(const igd_launch_cfg &c, const uint8_t *codes, size_t F, size_t C, const uint32_t *chans,
                              size_t nchan, const uint8_t *law_ch, int rate, int ref_quirks, uint8_t *out,

@@ -101,18 +101,9 @@ __global__ void __launch_bounds__(256) k_ed137_parse_tile(const uint8_t *__restr
     }
 }
 
-// Fields only (no payload wanted, e.g. the RX front-end feeding k_rx_track): one thread per packet
-// reads the three header words it needs -- 1-2 DRAM sectors per packet instead of the whole packet.
-__global__ void __launch_bounds__(256) k_ed137_fields(const uint8_t *__restrict__ pkts,
-                                                      const uint32_t *__restrict__ sizes, size_t npkts,
-                                                      size_t stride, igd_ed137_fields *__restrict__ fields)
+// transport_rtp_cb's view of a packet header (TransportAdapter.cpp:248-292) from its words 0, 3, 4 and its size
+__device__ __forceinline__ igd_ed137_fields fields_of_header(uint32_t w0, uint32_t w3, uint32_t w4, uint32_t size)
 {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npkts) return;
-    const uint32_t *pw = reinterpret_cast<const uint32_t *>(pkts + i * stride);
-    const uint32_t size = sizes ? sizes[i] : (uint32_t)stride;
-    const uint32_t navail = min(size, (uint32_t)stride) / 4;
-    const uint32_t w0 = navail > 0 ? __ldg(pw) : 0u, w3 = navail > 3 ? __ldg(pw + 3) : 0u, w4 = navail > 4 ? __ldg(pw + 4) : 0u;
     const uint32_t pt = (w0 >> 8) & 0x7Fu;
     const bool too_short = size < IGD_PKT_HDR;
     const uint32_t plen_raw = size - IGD_PKT_HDR;
@@ -132,6 +123,22 @@ __global__ void __launch_bounds__(256) k_ed137_fields(const uint8_t *__restrict_
     f.squelch = (uint8_t)e.squelch;
     f.bss = (uint8_t)e.bss;
     f.flags = (uint8_t)(e.flags | (dropped ? IGD_EDF_DROPPED : 0u));
+    return f;
+}
+
+// Fields only (no payload wanted, e.g. the RX front-end feeding k_rx_track): one thread per packet
+// reads the three header words it needs -- 1-2 DRAM sectors per packet instead of the whole packet.
+__global__ void __launch_bounds__(256) k_ed137_fields(const uint8_t *__restrict__ pkts,
+                                                      const uint32_t *__restrict__ sizes, size_t npkts,
+                                                      size_t stride, igd_ed137_fields *__restrict__ fields)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npkts) return;
+    const uint32_t *pw = reinterpret_cast<const uint32_t *>(pkts + i * stride);
+    const uint32_t size = sizes ? sizes[i] : (uint32_t)stride;
+    const uint32_t navail = min(size, (uint32_t)stride) / 4;
+    const uint32_t w0 = navail > 0 ? __ldg(pw) : 0u, w3 = navail > 3 ? __ldg(pw + 3) : 0u, w4 = navail > 4 ? __ldg(pw + 4) : 0u;
+    const igd_ed137_fields f = fields_of_header(w0, w3, w4, size);
     *reinterpret_cast<uint4 *>(fields + i) = *reinterpret_cast<const uint4 *>(&f);
 }
 
@@ -195,7 +202,12 @@ __global__ void __launch_bounds__(256) k_ed137_parse(const uint8_t *__restrict__
 // transport_rtp_cb (TransportAdapter.cpp:240-316) and the R2S watchdog
 // (roip_ed137.cpp:1767-1780).  Consecutive threads read consecutive 16-byte field
 // records and write consecutive 8-byte events: coalesced, latency-bound.
-__global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
+// kPres: 0 = a packet on every tick, 1 = d.present[], 2 = d.sizes[] != 0 (resolved at launch: a per-element
+// choice between the three inside the prefetch loop cost 2.6x on the walk)
+//        3 = gateway form: d.fields is NULL, the header words are read straight out of the received packets
+//            (pkts [F][C][180], sizes optional) -- no field array between the header pass and the walk
+template <int kPres>
+__global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d, const uint8_t *__restrict__ pkts = nullptr)
 {
     const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= d.C) return;
@@ -203,7 +215,10 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
     // The walk is sequential, its inputs are not: the fields of the NEXT run of 8 frames are in flight
     // while this run is walked (with a few thousand channels there is one warp per SM and nothing
     // else to hide the latency behind).
-    constexpr int kAhead = 8;
+#ifndef IGD_RX_AHEAD
+#define IGD_RX_AHEAD 8
+#endif
+    constexpr int kAhead = IGD_RX_AHEAD;
     uint4 raw[kAhead], nraw[kAhead];
     uint8_t pres[kAhead], npres[kAhead];
     auto fetch = [&](int f0, uint4 (&r)[kAhead], uint8_t (&p)[kAhead]) {
@@ -212,8 +227,17 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
             const int f = f0 + u;
             if (f < d.F) {
                 const size_t i = (size_t)f * d.C + c;
-                r[u] = __ldg(reinterpret_cast<const uint4 *>(d.fields + i));
-                p[u] = d.present ? d.present[i] : d.sizes ? (uint8_t)(d.sizes[i] != 0u) : (uint8_t)1;
+                if (kPres == 3) {
+                    const uint32_t size = d.sizes ? __ldg(d.sizes + i) : (uint32_t)IGD_PKT_MAX;
+                    const uint32_t navail = min(size, (uint32_t)IGD_PKT_MAX) / 4;
+                    const uint32_t *pw = reinterpret_cast<const uint32_t *>(pkts + i * IGD_PKT_MAX);
+                    // raw header words now, the field record when the tick is walked (keeps the loads in flight)
+                    r[u] = make_uint4(navail > 0 ? __ldg(pw) : 0u, navail > 3 ? __ldg(pw + 3) : 0u, navail > 4 ? __ldg(pw + 4) : 0u, size);
+                    p[u] = (uint8_t)(size != 0u);
+                } else {
+                    r[u] = __ldg(reinterpret_cast<const uint4 *>(d.fields + i));
+                    p[u] = kPres == 1 ? d.present[i] : kPres == 2 ? (uint8_t)(__ldg(d.sizes + i) != 0u) : (uint8_t)1;
+                }
             }
         }
     };
@@ -227,7 +251,8 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
             const int f = f0 + u;
             if (f >= d.F) break;
             const size_t i = (size_t)f * d.C + c;
-            const igd_ed137_fields fl = *reinterpret_cast<const igd_ed137_fields *>(&raw[u]);
+            const igd_ed137_fields fl = kPres == 3 ? fields_of_header(raw[u].x, raw[u].y, raw[u].z, raw[u].w)
+                                                   : *reinterpret_cast<const igd_ed137_fields *>(&raw[u]);
             const bool wd = d.wd_ticks > 0 && ((d.frame0 + f) % d.wd_ticks) == d.wd_ticks - 1;
             const uint32_t ev = igd_rx_step(s, fl, pres[u] != 0, wd, d.now_ms0 + (long long)f * d.tick_ms, d.r2s_period_ms);
             igd_rx_event e;
@@ -249,7 +274,17 @@ __global__ void __launch_bounds__(128) k_rx_track(const igd_rx_track_desc d)
 // SMs several times: the walk over F is sequential per bridge, so few bridges x many
 // frames must not sit on a handful of SMs); all 64 threads stage the words / gains of
 // a run of ticks through shared memory with coalesced rows.
-constexpr int kArbThreads = 256;         // staging threads per block; the first bpb (<= kArbMaxBpb) of them walk a bridge each
+// the leg state as one integer, built from the fields (taking the struct's address would push the
+// register-resident leg array of the compile-time-G kernels into local memory)
+__device__ __forceinline__ uint64_t arb_leg_bits(const igd_arb_leg &l)
+{
+    return (uint64_t)l.last | ((uint64_t)l.msec << 8) | ((uint64_t)l.on << 16) | ((uint64_t)(uint8_t)l.rssi << 24) |
+           ((uint64_t)l.gain_q7 << 32);
+}
+#ifndef IGD_ARB_THREADS
+#define IGD_ARB_THREADS 128
+#endif
+constexpr int kArbThreads = IGD_ARB_THREADS;   // staging threads per block; the first bpb (<= kArbMaxBpb) of them walk a bridge each
 constexpr int kArbMaxBpb = 64;
 constexpr int kArbStageWords = 4096;     // words (and gains) of a run of ticks staged per block
 template <int kG> struct arb_legs {      // compile-time leg count: the leg state lives in registers
@@ -323,6 +358,24 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
         __syncthreads();
         if (owner) {
             for (int t = 0; t < nt; t++) {
+                if (kG == 4 && have_prev && steady) {
+                    // tight scan over the ticks whose four words repeat the last full pass's: one 16-byte load,
+                    // one compare, one 8-byte store of the (unchanged) gains per tick
+                    const uint2 gpk = make_uint2((uint32_t)legs[0].gain_q7 | ((uint32_t)legs[1].gain_q7 << 16),
+                                                 (uint32_t)legs[2 % (kG > 0 ? kG : 1)].gain_q7 | ((uint32_t)legs[3 % (kG > 0 ? kG : 1)].gain_q7 << 16));
+                    int t2 = t;
+#pragma unroll 4
+                    for (; t2 < nt; t2++) {
+                        const uint4 w = *reinterpret_cast<const uint4 *>(words_s + t2 * row + threadIdx.x * 4);
+                        if ((w.x ^ prevw[0]) | (w.y ^ prevw[1 % (kG > 0 ? kG : 1)]) | (w.z ^ prevw[2 % (kG > 0 ? kG : 1)]) |
+                            (w.w ^ prevw[3 % (kG > 0 ? kG : 1)]))
+                            break;
+                        *reinterpret_cast<uint2 *>(gain_s + t2 * row + threadIdx.x * 4) = gpk;
+                    }
+                    if (counting) br.sqlStatusCount += t2 - t;
+                    t = t2;
+                    if (t >= nt) break;
+                }
                 const uint32_t *wt = words_s + t * row + threadIdx.x * G;
                 auto word = [&](int g) { return wt[g]; };
                 auto active = [&](int g) { return ((act_mask >> g) & 1u) != 0u; };
@@ -341,6 +394,9 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
                 } else {
                     for (int g = 0; g < G && same; g++) same = wt[g] == prev_s[g];
                 }
+#ifdef IGD_X_ARB_NOSKIP
+                same = false;
+#endif
                 if (same && steady) {
                     if (counting) br.sqlStatusCount++;
                 } else {
@@ -350,9 +406,9 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
                     const uint8_t o0 = br.sqlStatusOn;
                     if (kG > 0) {
 #pragma unroll
-                        for (int g = 0; g < (kG > 0 ? kG : 1); g++) snap[g] = *reinterpret_cast<const uint64_t *>(&legs[g]);
+                        for (int g = 0; g < (kG > 0 ? kG : 1); g++) snap[g] = arb_leg_bits(legs[g]);
                     } else {
-                        for (int g = 0; g < G; g++) snap_s[g] = *reinterpret_cast<const uint64_t *>(&legs[g]);
+                        for (int g = 0; g < G; g++) snap_s[g] = arb_leg_bits(legs[g]);
                     }
                     if (kG > 0) {
                         const igd_const_int<(kG > 0 ? kG : 1)> Gc;
@@ -365,12 +421,12 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
                     if (kG > 0) {
 #pragma unroll
                         for (int g = 0; g < (kG > 0 ? kG : 1); g++) {
-                            snap_fold |= snap[g] ^ *reinterpret_cast<const uint64_t *>(&legs[g]);
+                            snap_fold |= snap[g] ^ arb_leg_bits(legs[g]);
                             prevw[g] = wt[g];
                         }
                     } else {
                         for (int g = 0; g < G; g++) {
-                            snap_fold |= snap_s[g] ^ *reinterpret_cast<const uint64_t *>(&legs[g]);
+                            snap_fold |= snap_s[g] ^ arb_leg_bits(legs[g]);
                             prev_s[g] = wt[g];
                         }
                     }
@@ -484,6 +540,9 @@ __global__ void __launch_bounds__(128) k_ed137_plan(const igd_ed137_pack_desc d,
             // moved the state, or no sent header is cached for this situation -- bit-exact by construction.
             igd_tx_plan t;
             bool fast = false;
+#ifdef IGD_X_PLAN_NOSKIP
+            ctl_same = false;
+#endif
             if (ctl_same && steady) {
                 if (last.copy_payload) {                                     // gated audio: goes out on every tick
                     t = last; fast = true;
@@ -832,9 +891,13 @@ cudaError_t igd_k_ed137_parse(const igd_launch_cfg &c, const uint8_t *pkts, cons
     return cudaGetLastError();
 }
 
-cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d)
+cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d, const uint8_t *pkts)
 {
-    k_rx_track<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d);
+    const unsigned blocks = (unsigned)((d.C + 127) / 128);
+    if (pkts) k_rx_track<3><<<blocks, 128, 0, c.stream>>>(d, pkts);
+    else if (d.present) k_rx_track<1><<<blocks, 128, 0, c.stream>>>(d);
+    else if (d.sizes) k_rx_track<2><<<blocks, 128, 0, c.stream>>>(d);
+    else k_rx_track<0><<<blocks, 128, 0, c.stream>>>(d);
     return cudaGetLastError();
 }
 

@@ -459,14 +459,16 @@ int igd_gate_arbitrate(igd_ctx *ctx, const igd_arb_desc *d);
 /* ------------------------------------------------- gateway: packets in, packets out
  * One call = the whole per-tick voice path of a RoIP gateway for F ticks of B bridges x 4 legs,
  * everything on the device: the receive callback's header work on every leg's packet
- * (transport_rtp_cb, TransportAdapter.cpp:240-316 -> igd_ed137_parse fields only), the liveness /
- * edge walk (igd_rx_track), checkEvents()'s gate decisions with silent no-audio ticks
+ * (transport_rtp_cb, TransportAdapter.cpp:240-316) and the liveness / edge walk (igd_rx_track, reading the
+ * header words straight out of the packets), checkEvents()'s gate decisions with silent no-audio ticks
  * (igd_gate_arbitrate + IGD_ARB_F_SILENCE), the sender walk of the call each bridge's output leaves
  * on (transport_send_rtp, :635-874) and the fused decode -> meter -> mix -> encode kernel, which
  * reads the codes straight out of the received packets and writes FINISHED 180-byte ED-137 packets
  * (header from the sender walk + the PJSIP RTP header, payload = this tick's encoded mix; the bytes of
  * a slot past tx_sizes are zero) -- the bytes igd_ed137_pack produces without IGD_F_REF_QUIRKS.
- * Five kernel launches; no payload, code or plan array crosses the API.  (tx_state.rtpFalse, the
+ * Four or five kernel launches (header view + liveness walk -- one kernel from 32 768 channels up, two below --
+ * arbitration, sender walk on a side stream, fused kernel); no payload, code or plan array exists between
+ * them, nothing but packets and state crosses the API.  (tx_state.rtpFalse, the
  * reference's never-read stuck-audio diagnostic counter, is not maintained here: the payload it
  * looks at is produced after the sender walk.)
  * Algorithmic bytes per bridge-frame (SURVEY 8d "with RTP"): 4*180 in + 180 + 320 (optional mix) + 4*16

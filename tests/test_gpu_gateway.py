@@ -1,5 +1,5 @@
 """igd_gateway_process: received ED-137 packets of every leg in -> finished ED-137 packets of every bridge out,
-five kernel launches, nothing but packets and state across the API.  Checked (1) against the composition of the
+four kernel launches, nothing but packets and state across the API.  Checked (1) against the composition of the
 separately verified entry points (parse -> rx_track -> gate_arbitrate(silence) -> process_packets -> ed137_pack)
 and (2) directly against the oracle / the reference: the receive walk (transport_rtp_cb), checkEvents, the
 decode -> mix -> encode arithmetic and the sender (transport_send_rtp, clean mode = no Q2/Q3 quirks)."""
