@@ -137,6 +137,8 @@ __device__ __forceinline__ uint32_t add_16x2(uint32_t a, uint32_t b)
 {
     uint32_t r; asm("add.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r;
 }
+// -x per 16-bit half (two's complement, 0x8000 stays 0x8000 = 32768 unsigned): ~x + 1
+__device__ __forceinline__ uint32_t neg_16x2(uint32_t x) { return add_16x2(~x, 0x00010001u); }
 
 // ------------------------------------------------------------------ partials
 // 8-byte per-chunk meter partial: lo = sum((x/4)^2) over the 16 samples (< 2^31);
@@ -198,11 +200,7 @@ __device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t 
     const uint32_t sgn = prmt_full<0xBB99>(pk, 0u);                 // sign of each half, replicated
     uint32_t t = pk ^ sgn;                                          // |x| or |x|-1
     t = min_u16x2(t, E.hi_pos ^ (sgn & E.hi_x));                    // u-law clip
-#ifdef IGD_X_ZERO2
     const uint32_t p = max_s16x2(add_16x2(t, E.bias_pos ^ (sgn & E.bias_x)), E.zero2);
-#else
-    const uint32_t p = max_s16x2(add_16x2(t, E.bias_pos ^ (sgn & E.bias_x)), 0u);
-#endif
     const uint32_t P = add_16x2(p, max_u16x2(p, E.thr));            // leading one -> segment
     // 8388608.0f + P per half, built on the FMA pipe (IDP.2A picks the half and adds the magic;
     // the compressor is ALU-bound, a PRMT here measured 4 % slower)

@@ -106,12 +106,14 @@ __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_p
     u_np = __dp4a(e_np.z, 0x01010101u, u_np); u_np = __dp4a(e_np.w, 0x01010101u, u_np);
     return make_uint2(u_np, 0u);
 #endif
-    uint32_t mx = max_s16x2(max_s16x2(pk[0], pk[1]), pk[2]), mn = min_s16x2(min_s16x2(pk[0], pk[1]), pk[2]);
-    mx = max_s16x2(max_s16x2(mx, pk[3]), pk[4]); mn = min_s16x2(min_s16x2(mn, pk[3]), pk[4]);
-    mx = max_s16x2(max_s16x2(mx, pk[5]), pk[6]); mn = min_s16x2(min_s16x2(mn, pk[5]), pk[6]);
-    mx = max_s16x2(mx, pk[7]); mn = min_s16x2(mn, pk[7]);
-    const int hi = max((int)(short)(mx & 0xFFFFu), (int)mx >> 16);
-    const int lo = min((int)(short)(mn & 0xFFFFu), (int)mn >> 16);
+    // max|v| of the 16 saturated samples: packed running max / min that start at zero (a free third input of the
+    // 3-input min/max), so max >= 0 >= min and |.| is max_u16(max, 0 - min) per half -- 32768 for -32768 included
+    uint32_t mx = max_s16x2(max_s16x2(E.zero2, pk[0]), pk[1]), mn = min_s16x2(min_s16x2(E.zero2, pk[0]), pk[1]);
+    mx = max_s16x2(max_s16x2(mx, pk[2]), pk[3]); mn = min_s16x2(min_s16x2(mn, pk[2]), pk[3]);
+    mx = max_s16x2(max_s16x2(mx, pk[4]), pk[5]); mn = min_s16x2(min_s16x2(mn, pk[4]), pk[5]);
+    mx = max_s16x2(max_s16x2(mx, pk[6]), pk[7]); mn = min_s16x2(min_s16x2(mn, pk[6]), pk[7]);
+    const uint32_t pk2 = max_u16x2(mx, neg_16x2(mn));
+    const uint32_t peak = max(pk2 & 0xFFFFu, pk2 >> 16);
     const uint4 e = encode16_packed(pk, E);
     if (st_enc) st16_stream(enc_dst, e);
     if (enc_out) *enc_out = e;
@@ -124,7 +126,7 @@ __device__ __forceinline__ uint2 mix_out_chunk(const int (&acc)[16], const enc_p
         u = __dp4a(e.z, 0x01010101u, u); u = __dp4a(e.w, 0x01010101u, u);
         esum = (int)u;
     }
-    return make_uint2((uint32_t)esum, (uint32_t)max(hi, -lo));
+    return make_uint2((uint32_t)esum, peak);
 }
 
 // raw gain bits of one bridge-frame (G u16 values) in two registers
@@ -471,11 +473,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                 const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
                 const uint2 e1 = *reinterpret_cast<const uint2 *>(et + 4);
                 E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y;
-#ifdef IGD_X_ZERO2
-                E.zero2 = et[6];
-#else
-                E.zero2 = 0u;
-#endif
+                E.zero2 = et[6];      // a zero the compiler cannot fold (see enc_pk)
             }
             const uint32_t o16 = bf * kChunks + ch;     // 16-sample chunk index of the outputs
             uint4 ev;
