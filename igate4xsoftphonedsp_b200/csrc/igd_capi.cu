@@ -12,6 +12,7 @@
 #include <new>
 
 #include "igd_kernels.cuh"
+#include "igd_math.cuh"
 
 namespace {
 constexpr int kSlots = 13;
@@ -539,23 +540,76 @@ int igd_process_batch(igd_ctx *c, const igd_batch_desc *d)
     return fused_job_host(c, j);
 }
 
+// packets form for leg counts other than 4: the payloads are extracted into the context's scratch (k_ed137_parse
+// writes codes = payload bytes, zero past payload_len), legs whose packet is not a whole audio frame get
+// IGD_GAIN_NO_AUDIO, and the codes-form kernels (k_fused_w for G <= 4, k_fused_g up to 32 legs) run on that.
+// Same results as the G = 4 packet kernel's rule; one extra pass over the packets.
+__global__ void __launch_bounds__(256) k_mark_no_audio(const igd_ed137_fields *__restrict__ fields, const uint16_t *__restrict__ gain,
+                                                       uint16_t *__restrict__ out, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t *fw = reinterpret_cast<const uint32_t *>(fields + i);
+    uint16_t g = gain[i];
+    if (igd_fields_no_audio(__ldg(fw + 1), __ldg(fw + 2), __ldg(fw + 3))) g |= (uint16_t)IGD_GAIN_NO_AUDIO;
+    out[i] = g;
+}
+
+static int process_packets_any_g(igd_ctx *c, const igd_packets_desc *d)
+{
+    const size_t F = d->F, B = d->B, G = d->G, C = B * G, n = F * C;
+    const int mem = d->mem;
+    int rc;
+    const uint8_t *dpk, *dlaw, *dol; const igd_ed137_fields *dfl; const uint16_t *dg;
+    if ((rc = in_arg(c, mem, 0, d->pkts, n * IGD_PKT_MAX, &dpk))) return rc;
+    if ((rc = in_arg(c, mem, 1, d->fields, n, &dfl))) return rc;
+    if ((rc = in_arg(c, mem, 2, d->law, C, &dlaw))) return rc;
+    if ((rc = in_arg(c, mem, 3, d->gain_q7, n, &dg))) return rc;
+    if ((rc = in_arg(c, mem, 4, d->out_law, B, &dol))) return rc;
+    void *dcodes, *dgain2, *dfl2;
+    if ((rc = scratch(c, 9, n * IGD_FRAME, &dcodes))) return rc;
+    if ((rc = scratch(c, 10, n * sizeof(uint16_t), &dgain2))) return rc;
+    if ((rc = scratch(c, 11, n * sizeof(igd_ed137_fields), &dfl2))) return rc;
+    // the extraction copies bytes 20..179 of every slot; slots that do not hold a whole audio frame are flagged
+    // IGD_GAIN_NO_AUDIO below (from the caller's field records), so what was copied for them is never interpreted
+    igd_batch_desc k;
+    memset(&k, 0, sizeof k);
+    k.struct_size = sizeof k; k.mem = IGD_MEM_DEVICE; k.F = d->F; k.B = d->B; k.G = d->G; k.flags = d->flags;
+    k.codes = static_cast<const uint8_t *>(dcodes); k.law = dlaw; k.gain_q7 = static_cast<const uint16_t *>(dgain2); k.out_law = dol;
+    if ((rc = out_arg(c, mem, 5, d->mix, d->mix ? F * B * IGD_FRAME : 0, &k.mix))) return rc;
+    if ((rc = out_arg(c, mem, 6, d->enc, d->enc ? F * B * IGD_FRAME : 0, &k.enc))) return rc;
+    if ((rc = out_arg(c, mem, 7, d->meter, d->meter ? n : 0, &k.meter))) return rc;
+    if ((rc = out_arg(c, mem, 8, d->bmeter, d->bmeter ? F * B : 0, &k.bmeter))) return rc;
+    if (mem == IGD_MEM_HOST) { if (!d->mix) k.mix = nullptr; if (!d->enc) k.enc = nullptr; if (!d->meter) k.meter = nullptr; if (!d->bmeter) k.bmeter = nullptr; }
+    IGD_CUDA(c, igd_k_ed137_parse(cfg_of(c), dpk, nullptr, n, IGD_PKT_MAX, static_cast<igd_ed137_fields *>(dfl2), static_cast<uint8_t *>(dcodes)));
+    k_mark_no_audio<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(dfl, dg, static_cast<uint16_t *>(dgain2), n);
+    IGD_CUDA(c, cudaGetLastError());
+    IGD_CUDA(c, igd_k_fused(cfg_of(c), k));
+    c->launches += 3;
+    if (d->mix && (rc = out_done(c, mem, d->mix, k.mix, F * B * IGD_FRAME))) return rc;
+    if (d->enc && (rc = out_done(c, mem, d->enc, k.enc, F * B * IGD_FRAME))) return rc;
+    if (d->meter && (rc = out_done(c, mem, d->meter, k.meter, n))) return rc;
+    if (d->bmeter && (rc = out_done(c, mem, d->bmeter, k.bmeter, F * B))) return rc;
+    return finish(c, mem);
+}
+
 int igd_process_packets(igd_ctx *c, const igd_packets_desc *d)
 {
     if (!c || !d || d->struct_size != sizeof(igd_packets_desc))
         return fail(c, IGD_EINVAL, "igd_process_packets: bad descriptor");
-    if (d->F < 0 || d->B < 0) return fail(c, IGD_EINVAL, "igd_process_packets: bad shape");
-    if (d->G != 4)
-        return fail(c, IGD_EINVAL, "igd_process_packets: G must be 4 (use igd_ed137_parse + igd_process_batch)");
+    if (d->F < 0 || d->B < 0 || d->G < 1 || d->G > IGD_MAX_LEGS) return fail(c, IGD_EINVAL, "igd_process_packets: bad shape");
     if (d->F == 0 || d->B == 0) return IGD_OK;
     if (!d->pkts || !d->fields || !d->law || !d->gain_q7 || !d->out_law)
         return fail(c, IGD_EINVAL, "igd_process_packets: null input buffer");
     if (!d->mix && !d->enc && !d->meter && !d->bmeter)
         return fail(c, IGD_EINVAL, "igd_process_packets: no output requested (mix, enc, meter, bmeter are all NULL)");
     IGD_BIND(c);
+    if (d->mem == IGD_MEM_DEVICE &&
+        (!aligned(d->pkts, 16) || !aligned(d->fields, 16) || !aligned(d->mix, 32) || !aligned(d->enc, 16) ||
+         !aligned(d->meter, 16) || !aligned(d->gain_q7, d->G == 4 ? 8 : 2) || !aligned(d->law, d->G == 4 ? 4 : 1) || !aligned(d->bmeter, 4)))
+        return fail(c, IGD_EINVAL, "igd_process_packets: misaligned device pointer");
+    if (d->G != 4) return process_packets_any_g(c, d);
     if (d->mem == IGD_MEM_DEVICE) {
-        if (!aligned(d->pkts, 16) || !aligned(d->fields, 16) || !aligned(d->mix, 32) || !aligned(d->enc, 16) ||
-            !aligned(d->meter, 16) || !aligned(d->gain_q7, 8) || !aligned(d->law, 4) || !aligned(d->bmeter, 4))
-            return fail(c, IGD_EINVAL, "igd_process_packets: misaligned device pointer");
         IGD_CUDA(c, igd_k_fused_packets(cfg_of(c), *d));
         c->launches++;
         return IGD_OK;

@@ -333,7 +333,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
 
     const bool worker = lane < kBfPerItem * kC32;
     const uint32_t bfl = worker ? lane / kC32 : 0u;
-    const uint32_t c0 = worker ? (lane - bfl * kC32 + chunk_rotation(bfl)) % kChunks : 0u;   // first chunk; second = +-5
+    // first chunk; second = +-5.  The per-bridge-frame rotation is the conflict minimum for the 640-byte bridge-frames of
+    // the codes form; the 720-byte bridge-frames of the packet form (45 sixteen-byte units, odd) are best left unrotated
+    // (brute force over all rotations: 10 instead of 20 LDS.128 wavefronts per pair of passes)
+    const uint32_t c0 = worker ? (lane - bfl * kC32 + (kPkt ? 0u : chunk_rotation(bfl))) % kChunks : 0u;
     const uint32_t src = slot_s + bfl * geom::kBfBytes;
     const uint32_t lane4 = lut_bytes + 4u * lane;
     const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kBfPerItem) % (uint32_t)q.B);

@@ -310,7 +310,8 @@ class VoicePath:
         pkts u8 [F][B*legs][180] as received; fields [F][B*legs] from ed137_parse; the rest as
         process_batch.  A leg-frame whose packet is not a whole G.711 audio frame (keep-alive,
         truncated, dropped, absent) is silent (GAIN_NO_AUDIO); otherwise identical results to
-        ed137_parse(...)[1] fed to process_batch; legs must be 4.
+        ed137_parse(...)[1] fed to process_batch.  legs = 4 runs one kernel; other leg counts
+        extract the payloads inside the library first.
         """
         mem = self._mode(pkts, fields, law, gain_q7, out_law)
         F, Cn, n = pkts.shape

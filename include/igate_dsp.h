@@ -336,9 +336,12 @@ int igd_ed137_keepalive(igd_ctx *ctx, uint8_t *hdr20, igd_ed137_state *state, si
  * never gives such a packet's bytes to the decoder.  Otherwise the results are
  * identical to igd_ed137_parse(payload_out) followed by igd_process_batch on that
  * payload with those gains; the payload array is never materialised.
- * G must be 4 (the reference's four radios per softphone, roip_ed137.cpp:130-139);
- * other leg counts take the two-call form (IGD_EINVAL here).  Device pointers:
- * pkts 16-byte aligned, the rest as for igd_process_batch.                       */
+ * G = 4 (the reference's four radios per softphone, roip_ed137.cpp:130-139) runs ONE
+ * kernel that reads the codes out of the packets; any other leg count (e.g. the 32
+ * inbound call slots of a CLIENT-mode softphone, :141-150) extracts the payloads into
+ * the context's scratch first and runs the codes-form kernels -- same results, one
+ * more pass over the packets.  Device pointers: pkts 16-byte aligned, the rest as for
+ * igd_process_batch.                                                             */
 typedef struct {
     uint32_t struct_size;        /* = sizeof(igd_packets_desc)                    */
     int32_t mem;

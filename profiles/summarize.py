@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Turns the artefacts of profiles/capture.sh (gpurun_out/launches.csv, gpurun_out/prof_fused.ncu-rep)
 into the committed summaries under profiles/.  Run here (ncu CLI, no GPU needed):
-    python profiles/summarize.py r01
+    python profiles/summarize.py r01                       (artefacts in gpurun_out/)
+    python profiles/summarize.py r02 gpurun_out/r02        (artefacts of profiles/capture_r02.sh)
 """
 import collections
 import csv
@@ -13,8 +14,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
-GP = os.path.join(ROOT, "gpurun_out")
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+GP = os.path.join(ROOT, sys.argv[2]) if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out")
 
 # ---- launch list: per-kernel share of the step
 rows = [r for r in csv.reader(l for l in open(os.path.join(GP, "launches.csv")) if not l.startswith("=="))]

@@ -79,8 +79,25 @@ def test_packets_in_device_pointers_repeated_launches(vp):
         check(got, want)
 
 
-def test_packets_in_rejects_other_leg_counts(vp):
-    pk = np.zeros((1, 6, 180), np.uint8)
-    with pytest.raises(ig.IgdError):
-        vp.process_packets(pk, np.zeros((1, 6), N.FIELDS_DT), np.zeros(6, np.uint8), np.zeros((1, 6), np.uint16),
-                           np.zeros(2, np.uint8), legs=3)
+@pytest.mark.parametrize("legs,B,F", [(2, 9, 7), (3, 5, 6), (8, 6, 5), (32, 2, 4), (1, 11, 3)])
+def test_packets_in_any_leg_count(vp, legs, B, F):
+    """leg counts other than 4 (e.g. the 32 inbound call slots of a CLIENT softphone, roip_ed137.cpp:141-150):
+    same rule, payload extracted inside the library"""
+    rng = np.random.default_rng(legs * 100 + B)
+    Cn = B * legs
+    pk = rng.integers(0, 256, (F, Cn, 180), dtype=np.uint8)
+    pk[..., 0] = 0x90
+    pk[..., 1] = rng.choice(np.array([8, 0, 8, 0, 123, 96], np.uint8), (F, Cn))
+    sizes = rng.choice(np.array([180, 180, 180, 20, 100, 0, 200], np.uint32), (F, Cn))
+    law = rng.integers(0, 2, Cn).astype(np.uint8)
+    out_law = rng.integers(0, 2, B).astype(np.uint8)
+    gain = rng.choice(np.array([0, 256, 256, 64], np.uint16), (F, Cn))
+    fields, payload = vp.ed137_parse(pk.reshape(F * Cn, 180), sizes.reshape(-1))
+    g = np.where(no_audio(pk, sizes), gain | N.GAIN_NO_AUDIO, gain).astype(np.uint16)
+    want = O.process_batch(payload.reshape(F, Cn, 160), law, g, out_law, legs)
+    check(vp.process_packets(pk, fields.reshape(F, Cn), law, gain, out_law, legs=legs), want)
+    dev = "cuda:0"
+    d = [torch.from_numpy(a).to(dev) for a in (pk, fields.view(np.int32).reshape(F, Cn, 4), law, gain.view(np.int16), out_law)]
+    r = vp.process_packets(*d, legs=legs, want=("mix", "enc"))
+    torch.cuda.synchronize()
+    assert np.array_equal(r["mix"].cpu().numpy(), want[0]) and np.array_equal(r["enc"].cpu().numpy(), want[1])
