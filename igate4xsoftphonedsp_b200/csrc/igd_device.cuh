@@ -207,22 +207,25 @@ __device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t 
     g0 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, 0x0001u, 0x4B000000u)), 0.0078125f, -65536.0f));
     g1 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, 0x0100u, 0x4B000000u)), 0.0078125f, -65536.0f));
 }
+// 2 packed words (4 samples) -> 4 code bytes
+__device__ __forceinline__ uint32_t encode4_packed(uint32_t pa, uint32_t pb, const enc_pk &E)
+{
+    uint32_t g0, g1, g2, g3;
+    enc_pair(pa, E, g0, g1);
+    enc_pair(pb, E, g2, g3);
+    // upper halves of the floats hold the code at bits [10:3]: pack two per word, one shift
+    // moves both into bytes 1 and 3, one PRMT gathers the four codes
+    const uint32_t h01 = __byte_perm(g0, g1, 0x7632) << 5, h23 = __byte_perm(g2, g3, 0x7632) << 5;
+    const uint32_t codes = __byte_perm(h01, h23, 0x7531);
+    const uint32_t sg = __byte_perm(pa, pb, 0x7531);   // sign bit of each sample in bit 7
+    return codes ^ ((sg & 0x80808080u) ^ E.mask4);
+}
 // 8 packed words (16 samples) -> 16 code bytes
 __device__ __forceinline__ uint4 encode16_packed(const uint32_t (&pk)[8], const enc_pk &E)
 {
     uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        uint32_t g0, g1, g2, g3;
-        enc_pair(pk[2 * j], E, g0, g1);
-        enc_pair(pk[2 * j + 1], E, g2, g3);
-        // upper halves of the floats hold the code at bits [10:3]: pack two per word, one shift
-        // moves both into bytes 1 and 3, one PRMT gathers the four codes
-        const uint32_t h01 = __byte_perm(g0, g1, 0x7632) << 5, h23 = __byte_perm(g2, g3, 0x7632) << 5;
-        const uint32_t codes = __byte_perm(h01, h23, 0x7531);
-        const uint32_t sg = __byte_perm(pk[2 * j], pk[2 * j + 1], 0x7531);   // sign bit of each sample in bit 7
-        w[j] = codes ^ ((sg & 0x80808080u) ^ E.mask4);
-    }
+    for (int j = 0; j < 4; j++) w[j] = encode4_packed(pk[2 * j], pk[2 * j + 1], E);
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 

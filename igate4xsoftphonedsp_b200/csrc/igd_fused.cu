@@ -547,6 +547,287 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
 }
 
 // ------------------------------------------------------------------------------------
+// Quarter-frame lanes (codes form, G in {1,2,3,4}): the same warp-autonomous design as k_fused_w with ALL 32 lanes
+// at work.  An item is 8 consecutive bridge-frames (8*G*160 contiguous code bytes, one bulk copy); lane = (bridge-frame
+// bfl = lane / 4, quarter qd = lane % 4) and owns the five 8-sample chunks qd, qd + 4, ... qd + 16 of that bridge-frame,
+// all G legs: per pass the four lanes of a bridge-frame read 32 contiguous code bytes per leg and write 64 contiguous
+// bytes of mix and 32 of codes.  What this buys over 5 lanes per bridge-frame (k_fused_w):
+//   * 32 of 32 lanes busy instead of 30, the per-item setup paid once per 8 bridge-frames instead of 6;
+//   * a lane's chunks belong to ONE bridge-frame, so the per-leg meter sums run in registers across the five passes:
+//     4 partials per record instead of 10, written once per item; the finish gives every lane one leg record (G = 4)
+//     instead of running a 24-lane leg branch and a 6-lane bridge branch one after the other.
+// The pass order is rotated per bridge-frame (G = 4: by bfl % 4, the brute-forced conflict minimum of the LDS.64 slot
+// reads: 8 instead of 20 wavefronts per five passes and half-warp; an 8-byte read cannot be conflict-free here).
+constexpr int kQBf = 8;        // bridge-frames per item
+constexpr int kQLanes = 4;     // lanes per bridge-frame
+constexpr int kQPass = 5;      // 8-sample chunks per lane
+
+// decode + meter + gain/accumulate one 8-sample chunk of one leg; the leg's meter sums run in the caller's registers
+// selector constants of the lookups and the byte sum, held in registers the compiler cannot rematerialise (it otherwise
+// rebuilds them with a UMOV / IMAD.MOV in every leg block of every pass: 7 of 220 warp-instructions per bridge-frame)
+struct q_consts { uint32_t k0, k1, k2, k3, ones; };
+__device__ __forceinline__ uint32_t lut_lookup_r(uint32_t lane_base, uint32_t word, uint32_t ksel)
+{
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(__dp4a(word, ksel, lane_base)));
+    return v;
+}
+__device__ __forceinline__ void sq_acc(uint32_t &sq, uint32_t x)      // sq += x * x as ONE dependent IMAD (no IADD tree)
+{
+    asm("mad.lo.u32 %0, %1, %1, %0;" : "+r"(sq) : "r"(x));
+}
+template <bool kSigned, int kMode>
+__device__ __forceinline__ void leg_chunk8(uint32_t lane_base, uint2 w, uint32_t sel, int adj, int (&acc)[8], uint32_t &sq,
+                                           uint32_t &mx, int &bsum, const q_consts &K)
+{
+    const uint32_t wd[2] = {w.x, w.y};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+        const uint32_t e0 = lut_lookup_r(lane_base, wd[j], K.k0), e1 = lut_lookup_r(lane_base, wd[j], K.k1);
+        const uint32_t e2 = lut_lookup_r(lane_base, wd[j], K.k2), e3 = lut_lookup_r(lane_base, wd[j], K.k3);
+        const uint32_t x0 = e0 & 0xFFFFu, x1 = e1 & 0xFFFFu, x2 = e2 & 0xFFFFu, x3 = e3 & 0xFFFFu;
+        sq_acc(sq, x0); sq_acc(sq, x1); sq_acc(sq, x2); sq_acc(sq, x3);       // 40 samples * 8064^2 < 2^32
+        mx = max_u16x2(max_u16x2(mx, e0), e1); mx = max_u16x2(max_u16x2(mx, e2), e3);
+        bsum = kSigned ? __dp4a((int)wd[j], (int)K.ones, bsum) : (int)__dp4a(wd[j], K.ones, (uint32_t)bsum);
+        if (kMode == 1) {
+            acc[4 * j + 0] = dp2a_lo(e0, sel, acc[4 * j + 0]);
+            acc[4 * j + 1] = dp2a_lo(e1, sel, acc[4 * j + 1]);
+            acc[4 * j + 2] = dp2a_lo(e2, sel, acc[4 * j + 2]);
+            acc[4 * j + 3] = dp2a_lo(e3, sel, acc[4 * j + 3]);
+        } else if (kMode == 2) {
+            const int s0 = (int)e0 < 0 ? -(int)x0 : (int)x0, s1 = (int)e1 < 0 ? -(int)x1 : (int)x1;
+            const int s2 = (int)e2 < 0 ? -(int)x2 : (int)x2, s3 = (int)e3 < 0 ? -(int)x3 : (int)x3;
+            acc[4 * j + 0] += clamp16((4 * s0 * adj) >> 7);
+            acc[4 * j + 1] += clamp16((4 * s1 * adj) >> 7);
+            acc[4 * j + 2] += clamp16((4 * s2 * adj) >> 7);
+            acc[4 * j + 3] += clamp16((4 * s3 * adj) >> 7);
+        }
+    }
+}
+
+template <int G, bool kSigned, int kWarps, bool kOpt>
+__global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
+{
+    constexpr int kBfBytes = G * IGD_FRAME, kSlotBytes = kQBf * kBfBytes;
+    constexpr int kLegRecs = kQBf * G;             // leg records per item (<= 32)
+    constexpr int kLegStride = kLegRecs + 1;       // partial layout [quarter][record], odd stride: conflict-free both ways
+    constexpr int kBrStride = kQBf + 1;
+    constexpr int kParts = kQLanes * kLegStride + kQLanes * kBrStride;
+    __shared__ uint64_t bars[kWarps];
+    __shared__ __align__(16) uint32_t enc_tab[2][8];
+    __shared__ __align__(16) uint32_t k_tab[8];
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t lut_bytes = shared_addr(smem);
+
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, (uint32_t)t >> 5, 0);
+    const uint32_t slot_s = shared_addr(smem + kLutBytes) + warp * kSlotBytes;
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes + (size_t)kWarps * kSlotBytes) + (size_t)warp * kParts;
+    uint2 *bpart = part + kQLanes * kLegStride;
+    const uint32_t bar_s = shared_addr(bars) + warp * 8;
+
+    build_decode_lut_abs(lut, (int)warp, (int)lane, kWarps);
+    if (t < 2) {
+        const enc_pk e = enc_pk_make(t);
+        enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
+        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4; enc_tab[t][6] = 0u; enc_tab[t][7] = 0u;
+    }
+    if (t < 5) k_tab[t] = t < 4 ? 0x80u << (8 * t) : 0x01010101u;
+    if (lane == 0) {
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t total_bf = (uint32_t)q.total_bf;
+    const uint32_t items = (total_bf + kQBf - 1) / kQBf;
+    const uint32_t nw = gridDim.x * kWarps;
+    uint32_t item = warp * gridDim.x + blockIdx.x;
+    auto fetch = [&](uint32_t it_idx) {
+        const uint32_t bf0 = it_idx * kQBf;
+        const uint32_t left = total_bf - bf0;
+        const uint32_t bytes = (left < (uint32_t)kQBf ? left : (uint32_t)kQBf) * kBfBytes;
+        if (lane == 0) {
+            mbar_expect_tx(bar_s, bytes);
+            bulk_g2s(slot_s, q.codes + (size_t)bf0 * kBfBytes, bytes, bar_s);
+        }
+    };
+    if (item < items) fetch(item);
+
+    const uint32_t bfl = lane >> 2, qd = lane & 3u;
+    // first pass of this lane: the four bridge-frames of a half-warp must start in four different 8-bank groups;
+    // slot word address = bfl * 40 G + 8 pass + 2 qd, so the group is (5 G bfl + pass) % 4 -- distinct by itself for odd G
+    const uint32_t rot = G == 4 ? (bfl & 3u) : G == 2 ? ((bfl >> 1) & 1u) : 0u;
+    const uint32_t src = slot_s + bfl * kBfBytes + qd * 8;             // + g * 160 + pass * 32
+    const uint32_t lane4 = lut_bytes + 4u * lane;
+    const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kQBf) % (uint32_t)q.B);
+    uint32_t b = (item * kQBf + bfl) % (uint32_t)q.B;
+    auto load_laws = [&](uint32_t bb) -> uint32_t {
+        uint32_t r = 0;
+        if (G == 4) {
+            const uint32_t lw = __ldg(reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4));
+            r = (lw & 1u) | ((lw >> 7) & 2u) | ((lw >> 14) & 4u) | ((lw >> 21) & 8u);
+        } else {
+#pragma unroll
+            for (int g = 0; g < G; g++) r |= (uint32_t)(__ldg(q.law + (size_t)bb * G + g) & 1u) << g;
+        }
+        return r | ((uint32_t)(__ldg(q.out_law + bb) & 1u) << 8);
+    };
+    uint2 gq = make_uint2(0u, 0u);
+    uint32_t lwq = 0u;
+    if (item < items && item * kQBf + bfl < total_bf) {
+        gq = load_gains<G>(q.gain + (size_t)(item * kQBf + bfl) * G);
+        lwq = load_laws(b);
+    }
+    const bool want_mix = !kOpt || q.mix != nullptr, want_enc = !kOpt || q.enc != nullptr,
+               want_meter = !kOpt || q.meter != nullptr, want_bmeter = !kOpt || q.bmeter != nullptr;
+    q_consts K;      // read back from shared memory: ptxas folds a constant it can see, however it is written
+    {
+        const volatile uint32_t *kt = k_tab;
+        K.k0 = kt[0]; K.k1 = kt[1]; K.k2 = kt[2]; K.k3 = kt[3]; K.ones = kt[4];
+    }
+
+    for (uint32_t it = 0; item < items; item += nw, it++) {
+        const uint32_t bf = item * kQBf + bfl;
+        const uint32_t next = item + nw;
+        mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
+        const uint2 gcur = gq;
+        const uint32_t lcur = lwq;
+        const bool valid = bf < total_bf;
+        {
+            b += b_step;
+            if (b >= (uint32_t)q.B) b -= (uint32_t)q.B;
+            const uint32_t bfn = bf + nw * kQBf;
+            if (next < items && bfn < total_bf) {                // next item's gains and laws ride in three registers
+                gq = load_gains<G>(q.gain + (size_t)bfn * G);
+                lwq = load_laws(b);
+            }
+        }
+        auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
+        const uint32_t orx = __reduce_or_sync(0xFFFFFFFFu, gcur.x), ory = G > 2 ? __reduce_or_sync(0xFFFFFFFFu, gcur.y) : 0u;
+        const bool general = ((orx | ory) & 0xFEFFFEFFu) != 0u;      // also when IGD_GAIN_NO_AUDIO is set anywhere in the warp
+        // one warp-uniform flag per leg (a packed mask costs an extract + compare per leg and pass)
+        const bool open_leg[4] = {__any_sync(0xFFFFFFFFu, (gcur.x & 0xFFFFu) != 0u) != 0, (orx >> 16) != 0u,
+                                  G > 2 && __any_sync(0xFFFFFFFFu, (gcur.y & 0xFFFFu) != 0u) != 0, (ory >> 16) != 0u};
+        uint32_t n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x)) + __popc(nonzero_halves(gcur.y))) << 16;
+        if (general)
+            n_open16 = (uint32_t)(__popc(nonzero_halves(gcur.x & ~(((gcur.x & 0x80008000u) >> 15) * 0xFFFFu))) +
+                                  __popc(nonzero_halves(gcur.y & ~(((gcur.y & 0x80008000u) >> 15) * 0xFFFFu)))) << 16;
+        const uint32_t o8_0 = bf * (IGD_FRAME / 8) + qd;
+        // the G legs' meter sums of this lane's quarter, and the bridge's
+        uint32_t msq[G], mmx[G];
+        int mbs[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) { msq[g] = 0u; mmx[g] = 0u; mbs[g] = 0; }
+        uint32_t bmx = 0u, bmn = 0u;
+        int esum = 0;
+        enc_pk E;
+        {
+            const uint32_t *et = enc_tab[(lcur >> 8) & 1u];
+            const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
+            const uint4 e1 = *reinterpret_cast<const uint4 *>(et + 4);
+            E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y; E.zero2 = e1.z;
+        }
+        uint32_t pp = rot;                                           // chunk qd + 4 * pp of the bridge-frame
+#ifdef IGD_X_QUNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+        for (int p = 0; p < kQPass; p++) {
+            uint2 wh[G];
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wh[g].x), "=r"(wh[g].y) : "r"(src + g * IGD_FRAME + pp * 32));
+            int acc[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = 0;
+            if (!general) {
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
+                    if (open_leg[g]) leg_chunk8<kSigned, 1>(lb, wh[g], adj_of(g), 0, acc, msq[g], mmx[g], mbs[g], K);
+                    else leg_chunk8<kSigned, 0>(lb, wh[g], 0u, 0, acc, msq[g], mmx[g], mbs[g], K);
+                }
+            } else {
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    const uint32_t lb = lane4 + (((lcur >> g) & 1u) << 15);
+                    const uint32_t a = adj_of(g);
+                    leg_chunk8<kSigned, 2>(lb, wh[g], 0u, (a & IGD_GAIN_NO_AUDIO) ? 0 : (int)a, acc, msq[g], mmx[g], mbs[g], K);
+                }
+            }
+            if (p == kQPass - 1) {
+                // every lane has consumed the last of its codes: refill the slot (generic reads ordered before the
+                // async-proxy writes of the bulk copy, see k_fused_w)
+                fence_proxy_async();
+                __syncwarp();
+                if (next < items) fetch(next);
+            }
+            // bridge output of this 8-sample chunk
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
+            const uint32_t o8 = o8_0 + 4u * pp;          // 8-sample chunk index of the outputs
+            if (valid && want_mix) st16_stream(q.mix + (size_t)o8 * 8, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            bmx = max_s16x2(max_s16x2(bmx, pk[0]), pk[1]); bmx = max_s16x2(max_s16x2(bmx, pk[2]), pk[3]);
+            bmn = min_s16x2(min_s16x2(bmn, pk[0]), pk[1]); bmn = min_s16x2(min_s16x2(bmn, pk[2]), pk[3]);
+            const uint32_t c0 = encode4_packed(pk[0], pk[1], E), c1 = encode4_packed(pk[2], pk[3], E);
+            if (valid && want_enc) __stcs(reinterpret_cast<uint2 *>(q.enc + (size_t)o8 * 8), make_uint2(c0, c1));
+            if (kSigned) { esum = __dp4a((int)c0, (int)K.ones, esum); esum = __dp4a((int)c1, (int)K.ones, esum); }
+            else esum = (int)__dp4a(c1, K.ones, __dp4a(c0, K.ones, (uint32_t)esum));
+            pp = pp == (uint32_t)kQPass - 1 ? 0u : pp + 1;
+        }
+        // ---- partials of this lane's quarter: {sum (x/4)^2, peak/4 | bytesum << 16} per leg, {codesum, peak | open << 16}
+#pragma unroll
+        for (int g = 0; g < G; g++) part[qd * kLegStride + bfl * G + g] = make_uint2(msq[g], __byte_perm(mmx[g], (uint32_t)mbs[g], 0x5410));
+        {
+            const uint32_t pk2 = max_u16x2(bmx, neg_16x2(bmn));
+            bpart[qd * kBrStride + bfl] = make_uint2((uint32_t)esum, max(pk2 & 0xFFFFu, pk2 >> 16) | n_open16);
+        }
+        __syncwarp();
+        // ---- finish: one leg record per lane (all 32 at G = 4), then one bridge record per lane 0..7
+        {
+            const uint32_t bf0 = item * kQBf;
+            uint32_t sil_rec = 0u;
+            if (general) {
+                uint32_t silent;
+                (void)split_no_audio(gcur, silent);
+                sil_rec = (__shfl_sync(0xFFFFFFFFu, silent, (int)((lane / G) * kQLanes) & 31) >> (lane % G)) & 1u;
+            }
+            if (lane < (uint32_t)kLegRecs && bf0 + lane / G < total_bf && want_meter) {
+                unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
+                if (!sil_rec) {
+#pragma unroll
+                    for (int j = 0; j < kQLanes; j++) {
+                        const uint2 v = part[j * kLegStride + lane];
+                        sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
+                    }
+                }
+                const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
+                st16_stream(q.meter + ((size_t)bf0 * G + lane), *reinterpret_cast<const uint4 *>(&r));
+            }
+            if (lane < (uint32_t)kQBf && bf0 + lane < total_bf && want_bmeter) {
+                int es = 0, hi = 0; uint32_t pk = 0;
+#pragma unroll
+                for (int j = 0; j < kQLanes; j++) {
+                    const uint2 v = bpart[j * kBrStride + lane];
+                    es += (int)v.x; pk = max_u16x2(pk, v.y); hi = dp2a_lo(v.y, 0x0100u, hi);
+                }
+                igd_bridge_rec r;
+                r.bytemean_out = (uint8_t)igd_bytemean_from_sum(es, IGD_FRAME);
+                r.n_open = (uint8_t)((uint32_t)hi / kQLanes);
+                r.mix_peak = (uint16_t)(pk & 0xFFFFu);
+                q.bmeter[bf0 + lane] = r;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // Warp-autonomous fused kernel for ANY leg count (1..IGD_MAX_LEGS), e.g. the 32 inbound calls of a
 // CLIENT-mode softphone (roip_ed137.cpp:141-150).  Same building blocks as k_fused_w; what changes:
 //   * a warp's item is 3 consecutive bridge-frames, lane = ONE 16-sample chunk (10 lanes per
@@ -883,6 +1164,22 @@ cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
     return cudaGetLastError();
 }
 
+template <int G, bool kSigned, int kWarps>
+cudaError_t launch_fused_q(const igd_launch_cfg &c, const FusedParams &q)
+{
+    const bool all_out = q.mix && q.enc && q.meter && q.bmeter;
+    auto kern = all_out ? k_fused_q<G, kSigned, kWarps, false> : k_fused_q<G, kSigned, kWarps, true>;
+    const size_t smem = kLutBytes + (size_t)kWarps * kQBf * G * IGD_FRAME +
+                        (size_t)kWarps * (kQLanes * (kQBf * G + 1) + kQLanes * (kQBf + 1)) * 8;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (q.total_bf + kQBf - 1) / kQBf;
+    long long grid = c.sm_count;
+    if (grid > items) grid = items;
+    kern<<<(int)grid, kWarps * 32, smem, c.stream>>>(q);
+    return cudaGetLastError();
+}
+
 template <bool kSigned, int kWarps>
 cudaError_t launch_fused_g(const igd_launch_cfg &c, const FusedParams &q)
 {
@@ -934,6 +1231,12 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     const bool fits32 = q.total_bf < (1ll << 28) &&          // 16-sample chunk indices (10 per bridge-frame) stay below 2^32
                         (reinterpret_cast<uintptr_t>(d.gain_q7) & (size_t)(2 * d.G - 1) & 7u) == 0 &&
                         (d.G != 4 || (reinterpret_cast<uintptr_t>(d.law) & 3u) == 0);
+    if (fits32 && (d.flags & IGD_F_KERNEL_Q) && (reinterpret_cast<uintptr_t>(d.mix) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d.enc) & 7u) == 0) {
+        if (d.G == 4) return sc ? launch_fused_q<4, true, 24>(c, q) : launch_fused_q<4, false, 24>(c, q);
+        if (d.G == 3) return sc ? launch_fused_q<3, true, 24>(c, q) : launch_fused_q<3, false, 24>(c, q);
+        if (d.G == 2) return sc ? launch_fused_q<2, true, 24>(c, q) : launch_fused_q<2, false, 24>(c, q);
+        if (d.G == 1) return sc ? launch_fused_q<1, true, 24>(c, q) : launch_fused_q<1, false, 24>(c, q);
+    }
     if (fits32 && d.G == 4) return sc ? launch_fused_w<4, true, 24>(c, q) : launch_fused_w<4, false, 24>(c, q);
     if (fits32 && d.G == 2) return sc ? launch_fused_w<2, true, 24>(c, q) : launch_fused_w<2, false, 24>(c, q);
     if (fits32 && d.G == 1) return sc ? launch_fused_w<1, true, 24>(c, q) : launch_fused_w<1, false, 24>(c, q);
