@@ -180,6 +180,11 @@ struct enc_pk {
     uint32_t mask4;              // output XOR mask for x>=0, replicated per byte
     uint32_t zero2;              // packed (0, 0) in a register the compiler cannot fold: max.s16x2(x, 0) with a
                                  // literal makes it rebuild the constant (PRMT RZ) for every packed pair
+    // the law-independent constants of enc_pair; enc_pk_make leaves them literal (folded into the instructions),
+    // a kernel that reads them back from shared memory keeps them in (uniform) registers instead of rebuilding
+    // them in every loop trip
+    uint32_t sel_lo = 0x0001u, sel_hi = 0x0100u, f_magic = 0x4B000000u;
+    float f_scale = 0.0078125f;
 };
 __device__ __forceinline__ enc_pk enc_pk_make(int law)
 {
@@ -204,8 +209,8 @@ __device__ __forceinline__ void enc_pair(uint32_t pk, const enc_pk &E, uint32_t 
     const uint32_t P = add_16x2(p, max_u16x2(p, E.thr));            // leading one -> segment
     // 8388608.0f + P per half, built on the FMA pipe (IDP.2A picks the half and adds the magic;
     // the compressor is ALU-bound, a PRMT here measured 4 % slower)
-    g0 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, 0x0001u, 0x4B000000u)), 0.0078125f, -65536.0f));
-    g1 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, 0x0100u, 0x4B000000u)), 0.0078125f, -65536.0f));
+    g0 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, E.sel_lo, E.f_magic)), E.f_scale, -65536.0f));
+    g1 = __float_as_uint(fmaf(__uint_as_float(dp2a_lo_u(P, E.sel_hi, E.f_magic)), E.f_scale, -65536.0f));
 }
 // 2 packed words (4 samples) -> 4 code bytes
 __device__ __forceinline__ uint32_t encode4_packed(uint32_t pa, uint32_t pb, const enc_pk &E)

@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
     constexpr int kParts = kQLanes * kLegStride + kQLanes * kBrStride;
     __shared__ uint64_t bars[kWarps];
     __shared__ __align__(16) uint32_t enc_tab[2][8];
-    __shared__ __align__(16) uint32_t k_tab[8];
+    __shared__ __align__(16) uint32_t k_tab[12];
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
     const uint32_t lut_bytes = shared_addr(smem);
@@ -634,7 +634,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
         enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
         enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4; enc_tab[t][6] = 0u; enc_tab[t][7] = 0u;
     }
-    if (t < 5) k_tab[t] = t < 4 ? 0x80u << (8 * t) : 0x01010101u;
+    if (t < 9) k_tab[t] = t < 4 ? 0x80u << (8 * t) : t == 4 ? 0x01010101u : t == 5 ? 0x0001u : t == 6 ? 0x0100u : t == 7 ? 0x4B000000u
+                                                                                                                  : 0x3C000000u;
     if (lane == 0) {
         mbar_init(bar_s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -664,22 +665,23 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
     const uint32_t lane4 = lut_bytes + 4u * lane;
     const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kQBf) % (uint32_t)q.B);
     uint32_t b = (item * kQBf + bfl) % (uint32_t)q.B;
-    auto load_laws = [&](uint32_t bb) -> uint32_t {
+    // laws of bridge bb as loaded (G = 4: one word; else one byte per leg in a word) and the bridge's output law; the
+    // bits are picked out when the item is worked on, so that the prefetch below does not wait for its own loads
+    auto load_laws = [&](uint32_t bb, uint32_t &olaw) -> uint32_t {
         uint32_t r = 0;
-        if (G == 4) {
-            const uint32_t lw = __ldg(reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4));
-            r = (lw & 1u) | ((lw >> 7) & 2u) | ((lw >> 14) & 4u) | ((lw >> 21) & 8u);
-        } else {
+        if (G == 4) r = __ldg(reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4));
+        else {
 #pragma unroll
-            for (int g = 0; g < G; g++) r |= (uint32_t)(__ldg(q.law + (size_t)bb * G + g) & 1u) << g;
+            for (int g = 0; g < G; g++) r |= (uint32_t)__ldg(q.law + (size_t)bb * G + g) << (8 * g);
         }
-        return r | ((uint32_t)(__ldg(q.out_law + bb) & 1u) << 8);
+        olaw = __ldg(q.out_law + bb);
+        return r;
     };
     uint2 gq = make_uint2(0u, 0u);
-    uint32_t lwq = 0u;
+    uint32_t lwq = 0u, owq = 0u;
     if (item < items && item * kQBf + bfl < total_bf) {
         gq = load_gains<G>(q.gain + (size_t)(item * kQBf + bfl) * G);
-        lwq = load_laws(b);
+        lwq = load_laws(b, owq);
     }
     const bool want_mix = !kOpt || q.mix != nullptr, want_enc = !kOpt || q.enc != nullptr,
                want_meter = !kOpt || q.meter != nullptr, want_bmeter = !kOpt || q.bmeter != nullptr;
@@ -688,13 +690,19 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
         const volatile uint32_t *kt = k_tab;
         K.k0 = kt[0]; K.k1 = kt[1]; K.k2 = kt[2]; K.k3 = kt[3]; K.ones = kt[4];
     }
+    // this lane's pass order as byte offsets into the bridge-frame's codes (32 * chunk row), one byte per pass
+    uint32_t seq_lo = (32u * (rot % 5u)) | (32u * ((rot + 1u) % 5u)) << 8 | (32u * ((rot + 2u) % 5u)) << 16 |
+                            (32u * ((rot + 3u) % 5u)) << 24,
+             seq_hi = 32u * ((rot + 4u) % 5u);
+    asm volatile("" : "+r"(seq_lo), "+r"(seq_hi));      // computed here, once: not sunk into the pass loop
 
     for (uint32_t it = 0; item < items; item += nw, it++) {
         const uint32_t bf = item * kQBf + bfl;
         const uint32_t next = item + nw;
         mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
         const uint2 gcur = gq;
-        const uint32_t lcur = lwq;
+        // bit g = law of leg g, bit 8 = output law
+        const uint32_t lcur = (lwq & 1u) | ((lwq >> 7) & 2u) | ((lwq >> 14) & 4u) | ((lwq >> 21) & 8u) | ((owq & 1u) << 8);
         const bool valid = bf < total_bf;
         {
             b += b_step;
@@ -702,7 +710,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
             const uint32_t bfn = bf + nw * kQBf;
             if (next < items && bfn < total_bf) {                // next item's gains and laws ride in three registers
                 gq = load_gains<G>(q.gain + (size_t)bfn * G);
-                lwq = load_laws(b);
+                lwq = load_laws(b, owq);
             }
         }
         auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
@@ -729,18 +737,31 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
             const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
             const uint4 e1 = *reinterpret_cast<const uint4 *>(et + 4);
             E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y; E.zero2 = e1.z;
+            const volatile uint32_t *kt = k_tab;
+            E.sel_lo = kt[5]; E.sel_hi = kt[6]; E.f_magic = kt[7]; E.f_scale = __uint_as_float(kt[8]);
         }
-        uint32_t pp = rot;                                           // chunk qd + 4 * pp of the bridge-frame
+        uint8_t *mixp = reinterpret_cast<uint8_t *>(q.mix) + (size_t)o8_0 * 16;
+        uint8_t *encp = q.enc + (size_t)o8_0 * 8;
+        asm volatile("" : "+l"(mixp), "+l"(encp));          // per item, not per pass
 #ifdef IGD_X_QUNROLL
 #pragma unroll
 #else
 #pragma unroll 1
 #endif
         for (int p = 0; p < kQPass; p++) {
+            const uint32_t pp32 = __byte_perm(seq_lo, seq_hi, 0x7650u + (uint32_t)p);     // byte p, upper bytes zero
             uint2 wh[G];
 #pragma unroll
             for (int g = 0; g < G; g++)
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wh[g].x), "=r"(wh[g].y) : "r"(src + g * IGD_FRAME + pp * 32));
+                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wh[g].x), "=r"(wh[g].y) : "r"(src + pp32 + g * IGD_FRAME));
+            if (p == kQPass - 1) {
+                // every lane has read the last of its codes: refill the slot now, a whole pass of work ahead of the
+                // next item (the fence completes the reads above and orders them before the bulk copy's
+                // async-proxy writes, see k_fused_w)
+                fence_proxy_async();
+                __syncwarp();
+                if (next < items) fetch(next);
+            }
             int acc[8];
 #pragma unroll
             for (int i = 0; i < 8; i++) acc[i] = 0;
@@ -759,26 +780,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
                     leg_chunk8<kSigned, 2>(lb, wh[g], 0u, (a & IGD_GAIN_NO_AUDIO) ? 0 : (int)a, acc, msq[g], mmx[g], mbs[g], K);
                 }
             }
-            if (p == kQPass - 1) {
-                // every lane has consumed the last of its codes: refill the slot (generic reads ordered before the
-                // async-proxy writes of the bulk copy, see k_fused_w)
-                fence_proxy_async();
-                __syncwarp();
-                if (next < items) fetch(next);
-            }
             // bridge output of this 8-sample chunk
             uint32_t pk[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) pk[i] = pack_sat16(acc[2 * i + 1], acc[2 * i]);
-            const uint32_t o8 = o8_0 + 4u * pp;          // 8-sample chunk index of the outputs
-            if (valid && want_mix) st16_stream(q.mix + (size_t)o8 * 8, make_uint4(pk[0], pk[1], pk[2], pk[3]));
+            if (valid && want_mix) st16_stream(mixp + 2u * pp32, make_uint4(pk[0], pk[1], pk[2], pk[3]));
             bmx = max_s16x2(max_s16x2(bmx, pk[0]), pk[1]); bmx = max_s16x2(max_s16x2(bmx, pk[2]), pk[3]);
             bmn = min_s16x2(min_s16x2(bmn, pk[0]), pk[1]); bmn = min_s16x2(min_s16x2(bmn, pk[2]), pk[3]);
             const uint32_t c0 = encode4_packed(pk[0], pk[1], E), c1 = encode4_packed(pk[2], pk[3], E);
-            if (valid && want_enc) __stcs(reinterpret_cast<uint2 *>(q.enc + (size_t)o8 * 8), make_uint2(c0, c1));
+            if (valid && want_enc) __stcs(reinterpret_cast<uint2 *>(encp + pp32), make_uint2(c0, c1));
             if (kSigned) { esum = __dp4a((int)c0, (int)K.ones, esum); esum = __dp4a((int)c1, (int)K.ones, esum); }
             else esum = (int)__dp4a(c1, K.ones, __dp4a(c0, K.ones, (uint32_t)esum));
-            pp = pp == (uint32_t)kQPass - 1 ? 0u : pp + 1;
         }
         // ---- partials of this lane's quarter: {sum (x/4)^2, peak/4 | bytesum << 16} per leg, {codesum, peak | open << 16}
 #pragma unroll
