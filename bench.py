@@ -484,7 +484,7 @@ def main():
     avg_launch_s = (total_ms / args.steps) * 1e-3
     achieved = BYTES_PER_BF * B * F / avg_launch_s / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(BYTES_PER_BF * B * F), "kernel": "k_fused_w<G=4, 24 autonomous warps/SM, per-warp TMA slot>", "peak_source": peak_src,
+                "traffic": ncu_traffic(BYTES_PER_BF * B * F), "kernel": "k_fused_q<G=4, 24 autonomous warps/SM, 8 bridge-frames per per-warp TMA slot, 4 lanes per bridge-frame>", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": BYTES_PER_BF * B * F,
                 "launch_ms": {"avg": total_ms / args.steps, "min": per_launch_ms[0], "max": per_launch_ms[-1]}}
 

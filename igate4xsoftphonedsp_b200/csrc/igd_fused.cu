@@ -341,16 +341,17 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
     const uint32_t lane4 = lut_bytes + 4u * lane;
     const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kBfPerItem) % (uint32_t)q.B);
     uint32_t b = (item * kBfPerItem + bfl) % (uint32_t)q.B;
-    auto load_laws = [&](uint32_t bb) -> uint32_t {      // the G leg laws (1 bit each) and the output law (bit 8)
+    // the G leg laws and the output law of bridge bb as loaded (the bits are picked out when the item is worked on:
+    // unpacking them here would make the prefetch wait for its own loads)
+    auto load_laws = [&](uint32_t bb, uint32_t &olaw) -> uint32_t {
         uint32_t r = 0;
-        if (G == 4) {
-            const uint32_t lw = __ldg(reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4));
-            r = (lw & 1u) | ((lw >> 7) & 2u) | ((lw >> 14) & 4u) | ((lw >> 21) & 8u);
-        } else {
+        if (G == 4) r = __ldg(reinterpret_cast<const uint32_t *>(q.law + (size_t)bb * 4));
+        else {
 #pragma unroll
-            for (int g = 0; g < G; g++) r |= (uint32_t)(__ldg(q.law + (size_t)bb * G + g) & 1u) << g;
+            for (int g = 0; g < G; g++) r |= (uint32_t)__ldg(q.law + (size_t)bb * G + g) << (8 * g);
         }
-        return r | ((uint32_t)(__ldg(q.out_law + bb) & 1u) << 8);
+        olaw = __ldg(q.out_law + bb);
+        return r;
     };
     // packet form: a leg whose packet is not a whole audio frame (keep-alive, truncated, dropped, absent) is
     // silent -- its gain gets IGD_GAIN_NO_AUDIO, the bytes of its slot are never interpreted
@@ -365,12 +366,12 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         return g;
     };
     uint2 gq = make_uint2(0u, 0u);
-    uint32_t lwq = 0u;
+    uint32_t lwq = 0u, owq = 0u, pszq = 0u;
     if (worker && item < items && item * kBfPerItem + bfl < total_bf) {
         gq = load_gains<G>(q.gain + (size_t)(item * kBfPerItem + bfl) * G);
-        lwq = load_laws(b);
+        lwq = load_laws(b, owq);
         if (kPkt && q.fields) gq = mark_no_audio(gq, item * kBfPerItem + bfl);
-        if (kTx) lwq |= (uint32_t)(__ldg(&q.plan[item * kBfPerItem + bfl].size) > IGD_PKT_HDR) << 9;   // bit 9: the packet carries the payload
+        if (kTx) pszq = __ldg(&q.plan[item * kBfPerItem + bfl].size);
     }
 
     const bool want_mix = !kOpt || q.mix != nullptr, want_enc = !kOpt || q.enc != nullptr,
@@ -380,7 +381,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
         const uint32_t next = item + nw;
         mbar_wait(bar_s, it & 1u);                           // this item's codes have landed
         const uint2 gcur = gq;
-        const uint32_t lcur = lwq;
+        // bit g = law of leg g, bit 8 = output law, bit 9 (kTx) = the outgoing packet carries the payload
+        const uint32_t lcur = (lwq & 1u) | ((lwq >> 7) & 2u) | ((lwq >> 14) & 4u) | ((lwq >> 21) & 8u) | ((owq & 1u) << 8) |
+                              (kTx ? (uint32_t)(pszq > IGD_PKT_HDR) << 9 : 0u);
         const bool valid = worker && bf < total_bf;
         {
             b += b_step;
@@ -388,9 +391,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
             const uint32_t bfn = bf + nw * kBfPerItem;
             if (worker && next < items && bfn < total_bf) {      // next item's gains and laws ride in three registers
                 gq = load_gains<G>(q.gain + (size_t)bfn * G);
-                lwq = load_laws(b);
+                lwq = load_laws(b, owq);
                 if (kPkt && q.fields) gq = mark_no_audio(gq, bfn);
-                if (kTx) lwq |= (uint32_t)(__ldg(&q.plan[bfn].size) > IGD_PKT_HDR) << 9;
+                if (kTx) pszq = __ldg(&q.plan[bfn].size);
             }
         }
         // every lane runs the same instruction stream (idle / tail lanes on stale bytes with all
@@ -438,6 +441,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                     wh[g] = make_uint4(v[kOff], v[kOff + 1], v[kOff + 2], v[kOff + 3]);
                 }
             }
+            if (h == 1) {
+                // Every lane has read the rest of its codes: refill the slot now, a whole pass of work ahead of the
+                // next item.  The fence completes the slot reads above (generic proxy) and orders them before the
+                // bulk copy's writes (async proxy).  (Issuing the copy right behind the LDS UNFENCED lost the race at
+                // G = 1: a 960-byte copy that hits L2 overtook loads still queued behind the other warps' table
+                // lookups -- profiles/tools/determinism_soak.py.)
+                fence_proxy_async();
+                __syncwarp();
+                if (next < items) fetch(next);
+            }
             uint2 *mypart = part + bfl * (G * kP) + ch;
             int acc[16];
 #pragma unroll
@@ -458,17 +471,6 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_w(const FusedParams q)
                     const uint2 ph = leg_chunk_u<kSigned, 2>(lb, wh[g], 0u, (a & IGD_GAIN_NO_AUDIO) ? 0 : (int)a, acc);
                     if (valid) mypart[g * kP] = ph;
                 }
-            }
-            if (h == 1) {
-                // Every lane has consumed the rest of its codes: refill the slot.  The fence orders the
-                // slot reads (generic proxy) before the bulk copy's writes (async proxy); placed here,
-                // after the lookups that depend on those reads, it has nothing left to wait for.
-                // (Issuing the copy right behind the LDS, unfenced, lost the race at G = 1: a 960-byte
-                // copy that hits L2 overtook loads still queued behind the other warps' table lookups
-                // -- profiles/tools/determinism_soak.py.)
-                fence_proxy_async();
-                __syncwarp();
-                if (next < items) fetch(next);
             }
             enc_pk E;
             {
@@ -1243,7 +1245,7 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     const bool fits32 = q.total_bf < (1ll << 28) &&          // 16-sample chunk indices (10 per bridge-frame) stay below 2^32
                         (reinterpret_cast<uintptr_t>(d.gain_q7) & (size_t)(2 * d.G - 1) & 7u) == 0 &&
                         (d.G != 4 || (reinterpret_cast<uintptr_t>(d.law) & 3u) == 0);
-    if (fits32 && (d.flags & IGD_F_KERNEL_Q) && (reinterpret_cast<uintptr_t>(d.mix) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d.enc) & 7u) == 0) {
+    if (fits32 && !(d.flags & IGD_F_KERNEL_W) && (reinterpret_cast<uintptr_t>(d.mix) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d.enc) & 7u) == 0) {
         if (d.G == 4) return sc ? launch_fused_q<4, true, 24>(c, q) : launch_fused_q<4, false, 24>(c, q);
         if (d.G == 3) return sc ? launch_fused_q<3, true, 24>(c, q) : launch_fused_q<3, false, 24>(c, q);
         if (d.G == 2) return sc ? launch_fused_q<2, true, 24>(c, q) : launch_fused_q<2, false, 24>(c, q);

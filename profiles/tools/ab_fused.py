@@ -43,12 +43,12 @@ def timed(flags, reps=20):
 
 
 res = {"lib": os.environ.get("IGD_LIB_PATH", "default"), "shape": f"{B} bridges x {G} legs x {F} frames"}
-ref = {k: v.clone() for k, v in vp.process_batch(codes, law, gain, out_law, G, flags=0, out=out).items()}
-for name, fl in (("default", 0), ("kernel_q", N.F_KERNEL_Q), ("default_again", 0), ("kernel_q_again", N.F_KERNEL_Q)):
+ref = {k: v.clone() for k, v in vp.process_batch(codes, law, gain, out_law, G, flags=N.F_KERNEL_W, out=out).items()}
+for name, fl in (("kernel_w", N.F_KERNEL_W), ("kernel_q", 0), ("kernel_w_again", N.F_KERNEL_W), ("kernel_q_again", 0)):
     res[name + "_ms (median, min)"] = timed(fl)
-got = vp.process_batch(codes, law, gain, out_law, G, flags=N.F_KERNEL_Q, out=out)
-res["q_equals_default"] = all(torch.equal(ref[k].view(torch.uint8), got[k].view(torch.uint8)) for k in ref)
-bytes_per_bf = G * 160 + 320 + 160 + G * 16 + 4 + G * 2
+got = vp.process_batch(codes, law, gain, out_law, G, flags=0, out=out)
+res["q_equals_w"] = all(torch.equal(ref[k].view(torch.uint8), got[k].view(torch.uint8)) for k in ref)
+bytes_per_bf = G * 160 + 320 + 160 + G * 16      # bench.py BYTES_PER_BF (1184 at G = 4)
 res["GBps_q"] = F * B * bytes_per_bf / (res["kernel_q_ms (median, min)"][0] * 1e-3) / 1e9
-res["GBps_default"] = F * B * bytes_per_bf / (res["default_ms (median, min)"][0] * 1e-3) / 1e9
+res["GBps_w"] = F * B * bytes_per_bf / (res["kernel_w_ms (median, min)"][0] * 1e-3) / 1e9
 print(json.dumps(res))

@@ -1,6 +1,7 @@
-"""The quarter-frame-lane fused kernel (k_fused_q, IGD_F_KERNEL_Q) against the oracle: the same cases as the default
-kernel -- every leg count it is built for, ragged item tails, both char signs, arbitrary and NO_AUDIO gains,
-optional outputs -- and byte-for-byte against the default kernel at a size that fills the grid."""
+"""The two fused kernels for G <= 4 -- k_fused_q (quarter-frame lanes, the default of igd_process_batch) and k_fused_w
+(five lanes per bridge-frame, IGD_F_KERNEL_W; the packet forms run it) -- against the oracle on the same cases: every
+leg count, ragged item tails, both char signs, arbitrary and NO_AUDIO gains, optional outputs; and byte-for-byte
+against each other at a size that fills the grid."""
 import numpy as np
 import pytest
 
@@ -11,13 +12,14 @@ from igate4xsoftphonedsp_b200 import synth
 from test_gpu_fused import check, make
 
 pytestmark = pytest.mark.gpu
-Q = N.F_KERNEL_Q
+KERNELS = [0, N.F_KERNEL_W]
 
 
 @pytest.mark.parametrize("G,B,F", [(4, 37, 9), (4, 32, 1), (4, 1, 1), (4, 3, 3), (2, 45, 7), (1, 100, 3), (3, 21, 5),
                                    (1, 1, 1), (2, 1, 9), (3, 1, 7), (4, 1024, 5)])
 @pytest.mark.parametrize("signed", [0, 1])
-def test_q_random_codes(vp, G, B, F, signed):
+@pytest.mark.parametrize("Q", KERNELS)
+def test_q_random_codes(vp, G, B, F, signed, Q):
     codes, law, _, out_law = make(F, B, G, random_codes=True, seed=G * 100 + B)
     rng = np.random.default_rng(7 + signed)
     gain = rng.choice(np.array([0, 0, 13, 64, 128, 256, 300], np.uint16), (F, B * G))
@@ -27,7 +29,8 @@ def test_q_random_codes(vp, G, B, F, signed):
 
 
 @pytest.mark.parametrize("G", [1, 2, 3, 4])
-def test_q_gates_only_fast_path(vp, G):
+@pytest.mark.parametrize("Q", KERNELS)
+def test_q_gates_only_fast_path(vp, G, Q):
     """gains 0 / 256 only (the PTT gates of the bench workload): the selector path, no multiply"""
     F, B = 11, 29
     codes, law, gain, out_law = make(F, B, G, random_codes=True, seed=G)
@@ -36,7 +39,8 @@ def test_q_gates_only_fast_path(vp, G):
 
 
 @pytest.mark.parametrize("G", [1, 2, 3, 4])
-def test_q_no_audio_legs(vp, G):
+@pytest.mark.parametrize("Q", KERNELS)
+def test_q_no_audio_legs(vp, G, Q):
     F, B = 6, 19
     codes, law, gain, out_law = make(F, B, G, random_codes=True, seed=40 + G)
     rng = np.random.default_rng(G)
@@ -45,7 +49,8 @@ def test_q_no_audio_legs(vp, G):
 
 
 @pytest.mark.parametrize("want", [("enc",), ("mix", "bmeter"), ("meter",), ("enc", "meter", "bmeter")])
-def test_q_optional_outputs(vp, want):
+@pytest.mark.parametrize("Q", KERNELS)
+def test_q_optional_outputs(vp, want, Q):
     F, B, G = 5, 23, 4
     codes, law, gain, out_law = make(F, B, G, random_codes=True, seed=5)
     ref = dict(zip(("mix", "enc", "meter", "bmeter"), O.process_batch(codes, law, gain, out_law, G)))
@@ -59,11 +64,11 @@ def test_q_optional_outputs(vp, want):
 
 
 @pytest.mark.parametrize("G", [1, 2, 3, 4])
-def test_q_equals_default_kernel_full_grid(vp, G):
+def test_q_equals_w_full_grid(vp, G):
     """more items than warps in the grid (148 x 24 x 8 bridge-frames), ragged tail: several trips through every slot"""
     B, F = 1021, 131
     codes, law, gain, out_law = make(F, B, G, random_codes=True, seed=77)
     a = vp.process_batch(codes, law, gain, out_law, G)
-    b = vp.process_batch(codes, law, gain, out_law, G, flags=Q)
+    b = vp.process_batch(codes, law, gain, out_law, G, flags=N.F_KERNEL_W)
     for k in ("mix", "enc", "meter", "bmeter"):
         assert a[k].tobytes() == b[k].tobytes(), k
