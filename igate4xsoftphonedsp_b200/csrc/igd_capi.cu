@@ -962,7 +962,7 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     // 5. decode -> meter -> mix -> encode -> packets
     igd_packets_desc fp;
     memset(&fp, 0, sizeof fp);
-    fp.struct_size = sizeof fp; fp.mem = IGD_MEM_DEVICE; fp.F = d->F; fp.B = d->B; fp.G = 4; fp.flags = d->flags & IGD_F_SIGNED_CHAR;
+    fp.struct_size = sizeof fp; fp.mem = IGD_MEM_DEVICE; fp.F = d->F; fp.B = d->B; fp.G = 4; fp.flags = d->flags & (IGD_F_SIGNED_CHAR | IGD_F_KERNEL_W);
     fp.pkts = dpk; fp.fields = nullptr; fp.law = dlaw; fp.gain_q7 = dgain; fp.out_law = dol;
     fp.mix = dmix; fp.enc = denc; fp.meter = dmt; fp.bmeter = dbm;
     IGD_CUDA(c, igd_k_fused_gateway(k, fp, static_cast<igd_tx_plan_rec *>(dplan), drtp, dtp, dts));

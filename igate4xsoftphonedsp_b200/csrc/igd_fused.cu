@@ -607,10 +607,14 @@ __device__ __forceinline__ void leg_chunk8(uint32_t lane_base, uint2 w, uint32_t
     }
 }
 
-template <int G, bool kSigned, int kWarps, bool kOpt>
+// kPkt / kTx as in k_fused_w: the codes are read straight out of the raw 180-byte packets (G = 4: an item is 8 * 720
+// contiguous bytes, still ONE bulk copy; 23 warps fit the shared memory), the bridge output leaves as finished packets.
+template <int G, bool kSigned, int kWarps, bool kOpt, bool kPkt = false, bool kTx = false>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
 {
-    constexpr int kBfBytes = G * IGD_FRAME, kSlotBytes = kQBf * kBfBytes;
+    constexpr int kLegBytes = kPkt ? IGD_PKT_MAX : IGD_FRAME, kLegOff = kPkt ? IGD_PKT_HDR : 0;
+    constexpr int kBfBytes = G * kLegBytes, kSlotBytes = kQBf * kBfBytes;
+    static_assert(!kPkt || (kBfBytes % 16) == 0, "packet form: a ragged last item must still be a multiple of 16 bytes");
     constexpr int kLegRecs = kQBf * G;             // leg records per item (<= 32)
     constexpr int kLegStride = kLegRecs + 1;       // partial layout [quarter][record], odd stride: conflict-free both ways
     constexpr int kBrStride = kQBf + 1;
@@ -662,8 +666,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
     const uint32_t bfl = lane >> 2, qd = lane & 3u;
     // first pass of this lane: the four bridge-frames of a half-warp must start in four different 8-bank groups;
     // slot word address = bfl * 40 G + 8 pass + 2 qd, so the group is (5 G bfl + pass) % 4 -- distinct by itself for odd G
-    const uint32_t rot = G == 4 ? (bfl & 3u) : G == 2 ? ((bfl >> 1) & 1u) : 0u;
-    const uint32_t src = slot_s + bfl * kBfBytes + qd * 8;             // + g * 160 + pass * 32
+    // (packet form, 720-byte bridge-frames: brute force finds nothing better than no rotation)
+    const uint32_t rot = kPkt ? 0u : G == 4 ? (bfl & 3u) : G == 2 ? ((bfl >> 1) & 1u) : 0u;
+    const uint32_t src = slot_s + bfl * kBfBytes + kLegOff + qd * 8;   // + g * leg bytes + pass * 32
     const uint32_t lane4 = lut_bytes + 4u * lane;
     const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kQBf) % (uint32_t)q.B);
     uint32_t b = (item * kQBf + bfl) % (uint32_t)q.B;
@@ -679,11 +684,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
         olaw = __ldg(q.out_law + bb);
         return r;
     };
+    // packet form: a leg whose packet is not a whole audio frame is silent (see k_fused_w)
+    auto mark_no_audio = [&](uint2 g, uint32_t bfi) -> uint2 {
+        const uint32_t *fw = reinterpret_cast<const uint32_t *>(q.fields + (size_t)bfi * G);
+#pragma unroll
+        for (int l = 0; l < G; l++) {
+            if (igd_fields_no_audio(__ldg(fw + 4 * l + 1), __ldg(fw + 4 * l + 2), __ldg(fw + 4 * l + 3))) {
+                if (l < 2) g.x |= 0x8000u << (16 * l); else g.y |= 0x8000u << (16 * (l - 2));
+            }
+        }
+        return g;
+    };
     uint2 gq = make_uint2(0u, 0u);
-    uint32_t lwq = 0u, owq = 0u;
+    uint32_t lwq = 0u, owq = 0u, pszq = 0u;
     if (item < items && item * kQBf + bfl < total_bf) {
         gq = load_gains<G>(q.gain + (size_t)(item * kQBf + bfl) * G);
         lwq = load_laws(b, owq);
+        if (kPkt && q.fields) gq = mark_no_audio(gq, item * kQBf + bfl);
+        if (kTx) pszq = __ldg(&q.plan[item * kQBf + bfl].size);
     }
     const bool want_mix = !kOpt || q.mix != nullptr, want_enc = !kOpt || q.enc != nullptr,
                want_meter = !kOpt || q.meter != nullptr, want_bmeter = !kOpt || q.bmeter != nullptr;
@@ -705,6 +723,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
         const uint2 gcur = gq;
         // bit g = law of leg g, bit 8 = output law
         const uint32_t lcur = (lwq & 1u) | ((lwq >> 7) & 2u) | ((lwq >> 14) & 4u) | ((lwq >> 21) & 8u) | ((owq & 1u) << 8);
+        const bool pay = kTx && pszq > IGD_PKT_HDR;               // the outgoing packet carries this tick's payload
         const bool valid = bf < total_bf;
         {
             b += b_step;
@@ -713,6 +732,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
             if (next < items && bfn < total_bf) {                // next item's gains and laws ride in three registers
                 gq = load_gains<G>(q.gain + (size_t)bfn * G);
                 lwq = load_laws(b, owq);
+                if (kPkt && q.fields) gq = mark_no_audio(gq, bfn);
+                if (kTx) pszq = __ldg(&q.plan[bfn].size);
             }
         }
         auto adj_of = [&](int g) -> uint32_t { return g == 0 ? (gcur.x & 0xFFFFu) : g == 1 ? (gcur.x >> 16) : g == 2 ? (gcur.y & 0xFFFFu) : (gcur.y >> 16); };
@@ -744,7 +765,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
         }
         uint8_t *mixp = reinterpret_cast<uint8_t *>(q.mix) + (size_t)o8_0 * 16;
         uint8_t *encp = q.enc + (size_t)o8_0 * 8;
-        asm volatile("" : "+l"(mixp), "+l"(encp));          // per item, not per pass
+        uint8_t *txp = kTx ? q.tx_pkts + (size_t)bf * IGD_PKT_MAX + IGD_PKT_HDR + qd * 8 : nullptr;   // 4-byte aligned
+        asm volatile("" : "+l"(mixp), "+l"(encp), "+l"(txp));          // per item, not per pass
 #ifdef IGD_X_QUNROLL
 #pragma unroll
 #else
@@ -754,8 +776,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
             const uint32_t pp32 = __byte_perm(seq_lo, seq_hi, 0x7650u + (uint32_t)p);     // byte p, upper bytes zero
             uint2 wh[G];
 #pragma unroll
-            for (int g = 0; g < G; g++)
-                asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wh[g].x), "=r"(wh[g].y) : "r"(src + pp32 + g * IGD_FRAME));
+            for (int g = 0; g < G; g++) {
+                // packet form: payload at byte 20 of a 180-byte packet -- 8-byte aligned for odd g only
+                if ((kBfBytes % 8) == 0 && ((g * kLegBytes + kLegOff) % 8) == 0)
+                    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(wh[g].x), "=r"(wh[g].y) : "r"(src + pp32 + g * kLegBytes));
+                else {
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wh[g].x) : "r"(src + pp32 + g * kLegBytes));
+                    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(wh[g].y) : "r"(src + pp32 + g * kLegBytes));
+                }
+            }
             if (p == kQPass - 1) {
                 // every lane has read the last of its codes: refill the slot now, a whole pass of work ahead of the
                 // next item (the fence completes the reads above and orders them before the bulk copy's
@@ -791,6 +820,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
             bmn = min_s16x2(min_s16x2(bmn, pk[0]), pk[1]); bmn = min_s16x2(min_s16x2(bmn, pk[2]), pk[3]);
             const uint32_t c0 = encode4_packed(pk[0], pk[1], E), c1 = encode4_packed(pk[2], pk[3], E);
             if (valid && want_enc) __stcs(reinterpret_cast<uint2 *>(encp + pp32), make_uint2(c0, c1));
+            if (kTx && valid) {      // payload bytes of the outgoing packet: the codes, or zeros (see k_fused_w)
+                uint32_t *tp = reinterpret_cast<uint32_t *>(txp + pp32);
+                __stcs(tp, pay ? c0 : 0u); __stcs(tp + 1, pay ? c1 : 0u);
+            }
             if (kSigned) { esum = __dp4a((int)c0, (int)K.ones, esum); esum = __dp4a((int)c1, (int)K.ones, esum); }
             else esum = (int)__dp4a(c1, K.ones, __dp4a(c0, K.ones, (uint32_t)esum));
         }
@@ -822,6 +855,23 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
                 }
                 const igd_meter_rec r = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
                 st16_stream(q.meter + ((size_t)bf0 * G + lane), *reinterpret_cast<const uint4 *>(&r));
+            }
+            if (kTx && lane < (uint32_t)kQBf && bf0 + lane < total_bf) {
+                // the packet's 20-byte header (TransportAdapter.cpp:715-800) and its size, as in k_fused_w
+                const uint32_t j = lane;
+                const uint32_t *pr = reinterpret_cast<const uint32_t *>(q.plan + (bf0 + j));
+                const uint32_t pw = __ldg(pr), psf = __ldg(pr + 1);      // word; size | flags << 16
+                const uint32_t psize = psf & 0xFFFFu, pfl = psf >> 16;
+                const uint32_t *hdr = reinterpret_cast<const uint32_t *>(q.rtp12 + (size_t)(bf0 + j) * 12);
+                uint32_t v0 = __ldg(hdr) | 0x10u;                                          // x = 1 (:725)
+                v0 = (v0 & ~0x8000u) | ((pfl & 2u) ? 0x8000u : 0u);                        // m (:715-723)
+                if (pfl & 1u) v0 = (v0 & ~0x7F00u) | (123u << 8);                          // pt = 123
+                uint32_t *tp = reinterpret_cast<uint32_t *>(q.tx_pkts + (size_t)(bf0 + j) * IGD_PKT_MAX);
+                const bool any = psize != 0u;
+                tp[0] = any ? v0 : 0u; tp[1] = any ? __ldg(hdr + 1) : 0u; tp[2] = any ? __ldg(hdr + 2) : 0u;
+                tp[3] = any ? 0x01006701u : 0u;                                            // 0x0167, 0x0001 big-endian
+                tp[4] = any ? __byte_perm(pw, 0u, 0x0123) : 0u;                            // htonl (:800)
+                q.tx_sizes[bf0 + j] = psize;
             }
             if (lane < (uint32_t)kQBf && bf0 + lane < total_bf && want_bmeter) {
                 int es = 0, hi = 0; uint32_t pk = 0;
@@ -1178,12 +1228,12 @@ cudaError_t launch_fused_w(const igd_launch_cfg &c, const FusedParams &q)
     return cudaGetLastError();
 }
 
-template <int G, bool kSigned, int kWarps>
+template <int G, bool kSigned, int kWarps, bool kPkt = false, bool kTx = false>
 cudaError_t launch_fused_q(const igd_launch_cfg &c, const FusedParams &q)
 {
     const bool all_out = q.mix && q.enc && q.meter && q.bmeter;
-    auto kern = all_out ? k_fused_q<G, kSigned, kWarps, false> : k_fused_q<G, kSigned, kWarps, true>;
-    const size_t smem = kLutBytes + (size_t)kWarps * kQBf * G * IGD_FRAME +
+    auto kern = all_out ? k_fused_q<G, kSigned, kWarps, false, kPkt, kTx> : k_fused_q<G, kSigned, kWarps, true, kPkt, kTx>;
+    const size_t smem = kLutBytes + (size_t)kWarps * kQBf * G * (kPkt ? IGD_PKT_MAX : IGD_FRAME) +
                         (size_t)kWarps * (kQLanes * (kQBf * G + 1) + kQLanes * (kQBf + 1)) * 8;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -1275,7 +1325,11 @@ cudaError_t igd_k_fused_packets(const igd_launch_cfg &c, const igd_packets_desc 
     if (d.G != 4 || q.total_bf >= (1ll << 28) || (reinterpret_cast<uintptr_t>(d.gain_q7) & 7u) ||
         (reinterpret_cast<uintptr_t>(d.law) & 3u))
         return cudaErrorInvalidValue;
-    return (d.flags & IGD_F_SIGNED_CHAR) ? launch_fused_w<4, true, 24, true>(c, q) : launch_fused_w<4, false, 24, true>(c, q);
+    const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
+    // quarter-lane kernel (23 warps: 8 x 720-byte bridge-frames per slot) unless asked for the older one
+    if (!(d.flags & IGD_F_KERNEL_W) && (reinterpret_cast<uintptr_t>(d.mix) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d.enc) & 7u) == 0)
+        return sc ? launch_fused_q<4, true, 23, true>(c, q) : launch_fused_q<4, false, 23, true>(c, q);
+    return sc ? launch_fused_w<4, true, 24, true>(c, q) : launch_fused_w<4, false, 24, true>(c, q);
 }
 
 // gateway form: packets in (gains carry IGD_GAIN_NO_AUDIO, no field records needed) -> packets out
@@ -1293,5 +1347,8 @@ cudaError_t igd_k_fused_gateway(const igd_launch_cfg &c, const igd_packets_desc 
         (reinterpret_cast<uintptr_t>(d.law) & 3u) || (reinterpret_cast<uintptr_t>(tx_pkts) & 3u) ||
         (reinterpret_cast<uintptr_t>(tx_rtp12) & 3u))
         return cudaErrorInvalidValue;
-    return (d.flags & IGD_F_SIGNED_CHAR) ? launch_fused_w<4, true, 24, true, true>(c, q) : launch_fused_w<4, false, 24, true, true>(c, q);
+    const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
+    if (!(d.flags & IGD_F_KERNEL_W) && (reinterpret_cast<uintptr_t>(d.mix) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d.enc) & 7u) == 0)
+        return sc ? launch_fused_q<4, true, 23, true, true>(c, q) : launch_fused_q<4, false, 23, true, true>(c, q);
+    return sc ? launch_fused_w<4, true, 24, true, true>(c, q) : launch_fused_w<4, false, 24, true, true>(c, q);
 }

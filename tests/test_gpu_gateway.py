@@ -61,14 +61,15 @@ def composed(vp, case, mode, F, B):
 
 @pytest.mark.parametrize("F,B,mode,seed", [(60, 9, N.ARB_CLIENT_PTT, 1), (33, 50, N.ARB_SERVER_BEST, 2), (7, 1, N.ARB_CLIENT_PTT, 3),
                                            (120, 130, N.ARB_CLIENT_PTT, 4)])
-def test_gateway_equals_composition_of_verified_calls(vp, F, B, mode, seed):
+@pytest.mark.parametrize("kern", [0, N.F_KERNEL_W])      # quarter-lane fused kernel (default) and its predecessor
+def test_gateway_equals_composition_of_verified_calls(vp, F, B, mode, seed, kern):
     case = make_case(F, B, seed, mode)
     want = composed(vp, case, mode, F, B)
     Cn = B * G
     rx_state, legs, bridges = np.zeros(Cn, N.RX_STATE_DT), np.zeros(Cn, N.ARB_LEG_DT), np.zeros(B, N.ARB_BRIDGE_DT)
     tx_state = tx_state_of(case)
     got = vp.gateway_process(case["pk"], case["law"], case["out_law"], rx_state, legs, bridges, case["rtp12"], tx_state,
-                             rx_sizes=case["sizes"], tx_ctl=case["ctl"], mode=mode, now_ms0=case["now0"],
+                             rx_sizes=case["sizes"], tx_ctl=case["ctl"], mode=mode, now_ms0=case["now0"], flags=kern,
                              want=("rx_events", "gain_q7", "meter", "bmeter", "mix", "enc"))
     assert got["rx_events"].tobytes() == want["ev"].tobytes()
     assert np.array_equal(got["gain_q7"], want["gain"])

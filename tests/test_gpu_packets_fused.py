@@ -50,19 +50,22 @@ def want_of(vp, pk, sizes, law, gain, out_law, signed=0):
 
 @pytest.mark.parametrize("F,B,ragged", [(7, 5, True), (3, 1, True), (1, 1, False), (40, 64, False), (50, 333, True),
                                         (77, 250, False)])
-def test_packets_in_equals_parse_then_process_batch(vp, F, B, ragged):
+@pytest.mark.parametrize("kern", [0, N.F_KERNEL_W])      # quarter-lane kernel (default) and its predecessor
+def test_packets_in_equals_parse_then_process_batch(vp, F, B, ragged, kern):
     pk, sizes, law, gain, out_law = make(F, B, 100 * F + B, ragged)
     fields, want = want_of(vp, pk, sizes, law, gain, out_law)
-    check(vp.process_packets(pk, fields, law, gain, out_law), want)
+    check(vp.process_packets(pk, fields, law, gain, out_law, flags=kern), want)
 
 
-def test_packets_in_general_gains_and_signed_char(vp):
+@pytest.mark.parametrize("kern", [0, N.F_KERNEL_W])
+def test_packets_in_general_gains_and_signed_char(vp, kern):
     pk, sizes, law, gain, out_law = make(9, 13, 5, True, gains=(0, 13, 64, 128, 256, 300))
     fields, want = want_of(vp, pk, sizes, law, gain, out_law, signed=1)
-    check(vp.process_packets(pk, fields, law, gain, out_law, flags=ig.F_SIGNED_CHAR), want)
+    check(vp.process_packets(pk, fields, law, gain, out_law, flags=ig.F_SIGNED_CHAR | kern), want)
 
 
-def test_packets_in_device_pointers_repeated_launches(vp):
+@pytest.mark.parametrize("kern", [0, N.F_KERNEL_W])
+def test_packets_in_device_pointers_repeated_launches(vp, kern):
     """many items per warp, L2-resident packets, device buffers: every launch equals the oracle."""
     F, B = 60, 400
     pk, sizes, law, gain, out_law = make(F, B, 77, True)
@@ -71,7 +74,7 @@ def test_packets_in_device_pointers_repeated_launches(vp):
     d = [torch.from_numpy(a).to(dev) for a in (pk, fields.view(np.int32).reshape(F, B * G, 4), law,
                                                gain.view(np.int16), out_law)]
     for rep in range(4):
-        r = vp.process_packets(*d)
+        r = vp.process_packets(*d, flags=kern)
         torch.cuda.synchronize()
         got = {"mix": r["mix"].cpu().numpy(), "enc": r["enc"].cpu().numpy(),
                "meter": r["meter"].cpu().numpy().view(ig.METER_DT).reshape(F, B * G),
