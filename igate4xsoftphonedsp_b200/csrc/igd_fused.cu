@@ -710,6 +710,8 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
         const volatile uint32_t *kt = k_tab;
         K.k0 = kt[0]; K.k1 = kt[1]; K.k2 = kt[2]; K.k3 = kt[3]; K.ones = kt[4];
     }
+    const uint32_t ksel_lo = *(const volatile uint32_t *)(k_tab + 5), ksel_hi = *(const volatile uint32_t *)(k_tab + 6),
+                   kf_magic = *(const volatile uint32_t *)(k_tab + 7), kf_scale = *(const volatile uint32_t *)(k_tab + 8);
     // this lane's pass order as byte offsets into the bridge-frame's codes (32 * chunk row), one byte per pass
     uint32_t seq_lo = (32u * (rot % 5u)) | (32u * ((rot + 1u) % 5u)) << 8 | (32u * ((rot + 2u) % 5u)) << 16 |
                             (32u * ((rot + 3u) % 5u)) << 24,
@@ -760,8 +762,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
             const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
             const uint4 e1 = *reinterpret_cast<const uint4 *>(et + 4);
             E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y; E.zero2 = e1.z;
-            const volatile uint32_t *kt = k_tab;
-            E.sel_lo = kt[5]; E.sel_hi = kt[6]; E.f_magic = kt[7]; E.f_scale = __uint_as_float(kt[8]);
+            E.sel_lo = ksel_lo; E.sel_hi = ksel_hi; E.f_magic = kf_magic; E.f_scale = __uint_as_float(kf_scale);
         }
         uint8_t *mixp = reinterpret_cast<uint8_t *>(q.mix) + (size_t)o8_0 * 16;
         uint8_t *encp = q.enc + (size_t)o8_0 * 8;
@@ -889,6 +890,304 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
         }
         __syncwarp();
     }
+}
+
+// ------------------------------------------------------------------------------------
+// Eight legs (k_fused_h): the quarter-lane idea turned sideways.  An item is 4 bridge-frames with all 8 legs (8 * 160
+// contiguous code bytes per bridge-frame, one 5120-byte bulk copy); the 8 lanes of a bridge-frame are its 8 sample
+// columns: a lane walks five 4-sample chunks (column + 8 * pass) of ALL 8 legs, so a leg's meter sums run in three
+// registers across the passes like in k_fused_q, the mix of a chunk never leaves the lane, and every lane finishes
+// exactly one leg record per item (8 partials, one per column).  20 warps (96 registers: 24 of them the meters).
+// Measured at 512 bridges x 8 legs x 1640 frames: 0.417 ms against k_fused_g's 0.468 (58 % / 52 % of the HBM peak).
+// The template keeps the leg-group generalisation (GP = 16 / 32: lanes = leg group x column, the chunk's mix summed
+// over the leg groups by shuffle-adds) but only GP = 8 is instantiated: with more than one leg group the saturate /
+// compress / store of a chunk is done by a quarter or half of the lanes at the whole warp's issue cost, and the
+// variant measured no faster than k_fused_g.
+constexpr int kHLegs = 8;      // legs per lane
+constexpr int kHCols = 8;      // sample columns per bridge-frame
+constexpr int kHPass = 5;      // 4-sample chunks per lane and leg
+constexpr int kHLegStride = 33;   // partial layout [column][record], odd stride
+
+template <bool kSigned, int kMode>
+__device__ __forceinline__ void leg_chunk4(uint32_t lane_base, uint32_t w, uint32_t sel, int adj, int (&acc)[4], uint32_t &sq,
+                                           uint32_t &mx, int &bsum, const q_consts &K)
+{
+    const uint32_t e0 = lut_lookup_r(lane_base, w, K.k0), e1 = lut_lookup_r(lane_base, w, K.k1);
+    const uint32_t e2 = lut_lookup_r(lane_base, w, K.k2), e3 = lut_lookup_r(lane_base, w, K.k3);
+    const uint32_t x0 = e0 & 0xFFFFu, x1 = e1 & 0xFFFFu, x2 = e2 & 0xFFFFu, x3 = e3 & 0xFFFFu;
+    sq_acc(sq, x0); sq_acc(sq, x1); sq_acc(sq, x2); sq_acc(sq, x3);       // 20 samples * 8064^2 < 2^32
+    mx = max_u16x2(max_u16x2(mx, e0), e1); mx = max_u16x2(max_u16x2(mx, e2), e3);
+    bsum = kSigned ? __dp4a((int)w, (int)K.ones, bsum) : (int)__dp4a(w, K.ones, (uint32_t)bsum);
+    if (kMode == 1) {
+        acc[0] = dp2a_lo(e0, sel, acc[0]); acc[1] = dp2a_lo(e1, sel, acc[1]);
+        acc[2] = dp2a_lo(e2, sel, acc[2]); acc[3] = dp2a_lo(e3, sel, acc[3]);
+    } else if (kMode == 2) {
+        const int s0 = (int)e0 < 0 ? -(int)x0 : (int)x0, s1 = (int)e1 < 0 ? -(int)x1 : (int)x1;
+        const int s2 = (int)e2 < 0 ? -(int)x2 : (int)x2, s3 = (int)e3 < 0 ? -(int)x3 : (int)x3;
+        acc[0] += clamp16((4 * s0 * adj) >> 7); acc[1] += clamp16((4 * s1 * adj) >> 7);
+        acc[2] += clamp16((4 * s2 * adj) >> 7); acc[3] += clamp16((4 * s3 * adj) >> 7);
+    }
+}
+
+template <int GP, bool kSigned, int kWarps, bool kOpt>
+__global__ void __launch_bounds__(kWarps * 32, 1) k_fused_h(const FusedParams q)
+{
+    static_assert(GP == 8, "leg groups (GP = 16 / 32) need the pass order shared by the lanes that are summed: not finished");
+    constexpr int kBf = 32 / GP;                        // bridge-frames per item
+    constexpr int kLG = GP / kHLegs;                    // leg groups = lanes that share a sample column
+    constexpr int kSlotBytes = kBf * GP * IGD_FRAME;    // 5120
+    constexpr int kParts = kHCols * kHLegStride;
+    __shared__ uint64_t bars[kWarps];
+    __shared__ __align__(16) uint32_t enc_tab[2][8];
+    __shared__ __align__(16) uint32_t k_tab[12];
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t *lut = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t lut_bytes = shared_addr(smem);
+
+    const int t = threadIdx.x;
+    const uint32_t lane = t & 31;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, (uint32_t)t >> 5, 0);
+    const uint32_t slot_s = shared_addr(smem + kLutBytes) + warp * kSlotBytes;
+    uint2 *part = reinterpret_cast<uint2 *>(smem + kLutBytes + (size_t)kWarps * kSlotBytes) + (size_t)warp * kParts;
+    const uint32_t bar_s = shared_addr(bars) + warp * 8;
+
+    build_decode_lut_abs(lut, (int)warp, (int)lane, kWarps);
+    if (t < 2) {
+        const enc_pk e = enc_pk_make(t);
+        enc_tab[t][0] = e.bias_pos; enc_tab[t][1] = e.bias_x; enc_tab[t][2] = e.hi_pos; enc_tab[t][3] = e.hi_x;
+        enc_tab[t][4] = e.thr; enc_tab[t][5] = e.mask4; enc_tab[t][6] = 0u; enc_tab[t][7] = 0u;
+    }
+    if (t < 9) k_tab[t] = t < 4 ? 0x80u << (8 * t) : t == 4 ? 0x01010101u : t == 5 ? 0x0001u : t == 6 ? 0x0100u : t == 7 ? 0x4B000000u
+                                                                                                                  : 0x3C000000u;
+    if (lane == 0) {
+        mbar_init(bar_s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const uint32_t G = (uint32_t)q.G;                   // a multiple of 8, <= GP
+    const uint32_t bf_bytes = G * IGD_FRAME;
+    const uint32_t total_bf = (uint32_t)q.total_bf;
+    const uint32_t items = (total_bf + kBf - 1) / kBf;
+    const uint32_t nw = gridDim.x * kWarps;
+    uint32_t item = warp * gridDim.x + blockIdx.x;
+    auto fetch = [&](uint32_t it_idx) {
+        const uint32_t bf0 = it_idx * kBf;
+        const uint32_t left = total_bf - bf0;
+        const uint32_t bytes = (left < (uint32_t)kBf ? left : (uint32_t)kBf) * bf_bytes;
+        if (lane == 0) {
+            mbar_expect_tx(bar_s, bytes);
+            bulk_g2s(slot_s, q.codes + (size_t)bf0 * bf_bytes, bytes, bar_s);
+        }
+    };
+    if (item < items) fetch(item);
+
+    const uint32_t bfl = lane / GP, r = lane % GP, sc = r & 7u, lg = r >> 3;
+    const bool active = lg * kHLegs < G;               // G = 24 under GP = 32: the lanes of leg group 3 idle
+    // pass order rotated per group of 8 lanes: the groups of a warp read 8 consecutive words each, all at a multiple of
+    // 32 words from each other -- four different rows of the slot keep them on different banks
+    const uint32_t rot = (lane >> 3) & 3u;
+    uint32_t seq_lo = (32u * (rot % 5u)) | (32u * ((rot + 1u) % 5u)) << 8 | (32u * ((rot + 2u) % 5u)) << 16 |
+                      (32u * ((rot + 3u) % 5u)) << 24,
+             seq_hi = 32u * ((rot + 4u) % 5u);
+    asm volatile("" : "+r"(seq_lo), "+r"(seq_hi));
+    const uint32_t src = slot_s + bfl * bf_bytes + lg * (kHLegs * IGD_FRAME) + sc * 4;    // + leg * 160 + pass * 32
+    const uint32_t lane4 = lut_bytes + 4u * lane;
+    const uint32_t b_step = (uint32_t)(((unsigned long long)nw * kBf) % (uint32_t)q.B);
+    uint32_t b = (item * kBf + bfl) % (uint32_t)q.B;
+    // record of this lane in the finish: (bridge-frame, leg) = (lane / G, lane % G); its partials come from the lanes
+    // of that bridge-frame's leg group, its no-audio flag from any of them
+    const uint32_t rec_bf = lane / G, rec_leg = lane - rec_bf * G;
+    const uint32_t rec_src = rec_bf * GP + (rec_leg >> 3) * 8u;
+
+    uint4 gq = make_uint4(0u, 0u, 0u, 0u);
+    uint2 lwq = make_uint2(0u, 0u);
+    uint32_t owq = 0u;
+    auto prefetch = [&](uint32_t bfi, uint32_t bb) {
+        gq = __ldg(reinterpret_cast<const uint4 *>(q.gain + (size_t)bfi * G + lg * kHLegs));
+        lwq = __ldg(reinterpret_cast<const uint2 *>(q.law + (size_t)bb * G + lg * kHLegs));
+        owq = __ldg(q.out_law + bb);
+    };
+    if (active && item < items && item * kBf + bfl < total_bf) prefetch(item * kBf + bfl, b);
+
+    const bool want_mix = !kOpt || q.mix != nullptr, want_enc = !kOpt || q.enc != nullptr,
+               want_meter = !kOpt || q.meter != nullptr, want_bmeter = !kOpt || q.bmeter != nullptr;
+    q_consts K;
+    {
+        const volatile uint32_t *kt = k_tab;
+        K.k0 = kt[0]; K.k1 = kt[1]; K.k2 = kt[2]; K.k3 = kt[3]; K.ones = kt[4];
+    }
+    const uint32_t ksel_lo = *(const volatile uint32_t *)(k_tab + 5), ksel_hi = *(const volatile uint32_t *)(k_tab + 6),
+                   kf_magic = *(const volatile uint32_t *)(k_tab + 7), kf_scale = *(const volatile uint32_t *)(k_tab + 8);
+
+    for (uint32_t it = 0; item < items; item += nw, it++) {
+        const uint32_t bf = item * kBf + bfl;
+        const uint32_t next = item + nw;
+        mbar_wait(bar_s, it & 1u);
+        const uint4 gcur = gq;
+        const uint32_t gw[4] = {gcur.x, gcur.y, gcur.z, gcur.w};
+        // bit j = law of this lane's leg j
+        const uint32_t lbits = (lwq.x & 1u) | ((lwq.x >> 7) & 2u) | ((lwq.x >> 14) & 4u) | ((lwq.x >> 21) & 8u) |
+                               ((lwq.y & 1u) << 4) | ((lwq.y >> 3) & 0x20u) | ((lwq.y >> 10) & 0x40u) | ((lwq.y >> 17) & 0x80u);
+        const uint32_t olaw = owq & 1u;
+        const bool valid = bf < total_bf;
+        {
+            b += b_step;
+            if (b >= (uint32_t)q.B) b -= (uint32_t)q.B;
+            const uint32_t bfn = bf + nw * kBf;
+            gq = make_uint4(0u, 0u, 0u, 0u);
+            if (active && next < items && bfn < total_bf) prefetch(bfn, b);
+        }
+        auto adj_of = [&](int j) -> uint32_t { return (j & 1) ? (gw[j >> 1] >> 16) : (gw[j >> 1] & 0xFFFFu); };
+        uint32_t orw[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) orw[k] = __reduce_or_sync(0xFFFFFFFFu, gw[k]);
+        const bool general = ((orw[0] | orw[1] | orw[2] | orw[3]) & 0xFEFFFEFFu) != 0u;
+        bool open_leg[kHLegs];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            open_leg[2 * k] = __any_sync(0xFFFFFFFFu, (gw[k] & 0xFFFFu) != 0u) != 0;
+            open_leg[2 * k + 1] = (orw[k] >> 16) != 0u;
+        }
+        // open legs among this lane's eight; one lane per leg group (column 0) carries the count into the bridge record
+        uint32_t n_open = 0, silent8 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t w = gw[k];
+            if (general) {
+                const uint32_t f = w & 0x80008000u;
+                silent8 |= (((f >> 15) & 1u) | ((f >> 30) & 2u)) << (2 * k);
+                w &= ~((f >> 15) * 0xFFFFu);
+            }
+            n_open += (uint32_t)__popc(nonzero_halves(w));
+        }
+        if (sc != 0u) n_open = 0u;
+
+        uint32_t msq[kHLegs], mmx[kHLegs];
+        int mbs[kHLegs];
+#pragma unroll
+        for (int j = 0; j < kHLegs; j++) { msq[j] = 0u; mmx[j] = 0u; mbs[j] = 0; }
+        uint32_t bmx = 0u, bmn = 0u;
+        int esum = 0;
+        enc_pk E;
+        {
+            const uint32_t *et = enc_tab[olaw];
+            const uint4 e0 = *reinterpret_cast<const uint4 *>(et);
+            const uint4 e1 = *reinterpret_cast<const uint4 *>(et + 4);
+            E.bias_pos = e0.x; E.bias_x = e0.y; E.hi_pos = e0.z; E.hi_x = e0.w; E.thr = e1.x; E.mask4 = e1.y; E.zero2 = e1.z;
+            E.sel_lo = ksel_lo; E.sel_hi = ksel_hi; E.f_magic = kf_magic; E.f_scale = __uint_as_float(kf_scale);
+        }
+        uint8_t *mixp = reinterpret_cast<uint8_t *>(q.mix) + ((size_t)bf * IGD_FRAME + sc * 4) * 2;
+        uint8_t *encp = q.enc + (size_t)bf * IGD_FRAME + sc * 4;
+        asm volatile("" : "+l"(mixp), "+l"(encp));
+#pragma unroll 1
+        for (int p = 0; p < kHPass; p++) {
+            const uint32_t pp32 = __byte_perm(seq_lo, seq_hi, 0x7650u + (uint32_t)p);
+            uint32_t wh[kHLegs];
+#pragma unroll
+            for (int j = 0; j < kHLegs; j++)
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(wh[j]) : "r"(src + pp32 + j * IGD_FRAME));
+            if (p == kHPass - 1) {      // refill right behind the last reads (see k_fused_q)
+                fence_proxy_async();
+                __syncwarp();
+                if (next < items) fetch(next);
+            }
+            int acc[4] = {0, 0, 0, 0};
+            if (!general) {
+#pragma unroll
+                for (int j = 0; j < kHLegs; j++) {
+                    const uint32_t lb = lane4 + (((lbits >> j) & 1u) << 15);
+                    if (open_leg[j]) leg_chunk4<kSigned, 1>(lb, wh[j], adj_of(j), 0, acc, msq[j], mmx[j], mbs[j], K);
+                    else leg_chunk4<kSigned, 0>(lb, wh[j], 0u, 0, acc, msq[j], mmx[j], mbs[j], K);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < kHLegs; j++) {
+                    const uint32_t lb = lane4 + (((lbits >> j) & 1u) << 15);
+                    const uint32_t a = adj_of(j);
+                    leg_chunk4<kSigned, 2>(lb, wh[j], 0u, (a & IGD_GAIN_NO_AUDIO) ? 0 : (int)a, acc, msq[j], mmx[j], mbs[j], K);
+                }
+            }
+            // the chunk's mix is the sum over the leg groups of this bridge-frame
+            if (kLG >= 2) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[i] += __shfl_xor_sync(0xFFFFFFFFu, acc[i], 8);
+            }
+            if (kLG >= 4) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) acc[i] += __shfl_xor_sync(0xFFFFFFFFu, acc[i], 16);
+            }
+            if (kLG == 1 || lg == 0u) {
+                const uint32_t pk0 = pack_sat16(acc[1], acc[0]), pk1 = pack_sat16(acc[3], acc[2]);
+                if (valid && want_mix) __stcs(reinterpret_cast<uint2 *>(mixp + 2u * pp32), make_uint2(pk0, pk1));
+                bmx = max_s16x2(max_s16x2(bmx, pk0), pk1);
+                bmn = min_s16x2(min_s16x2(bmn, pk0), pk1);
+                const uint32_t c0 = encode4_packed(pk0, pk1, E);
+                if (valid && want_enc) __stcs(reinterpret_cast<uint32_t *>(encp + pp32), c0);
+                esum = kSigned ? __dp4a((int)c0, (int)K.ones, esum) : (int)__dp4a(c0, K.ones, (uint32_t)esum);
+            }
+        }
+        // ---- partials of this lane's column, one per leg
+        if (active) {
+#pragma unroll
+            for (int j = 0; j < kHLegs; j++)
+                part[sc * kHLegStride + bfl * G + lg * kHLegs + j] = make_uint2(msq[j], __byte_perm(mmx[j], (uint32_t)mbs[j], 0x5410));
+        }
+        // ---- bridge record: code sum and open count (packed: |code sum| < 2^19), peak -- reduced over the bridge-frame's lanes
+        {
+            const uint32_t pk2 = max_u16x2(bmx, neg_16x2(bmn));
+            uint32_t peak = max(pk2 & 0xFFFFu, pk2 >> 16);
+            int es = esum + (int)(n_open << 20);
+#pragma unroll
+            for (int m = 1; m < GP; m <<= 1) {
+                es += __shfl_xor_sync(0xFFFFFFFFu, es, m);
+                peak = max(peak, __shfl_xor_sync(0xFFFFFFFFu, peak, m));
+            }
+            if (r == 0u && valid && want_bmeter) {
+                const int n = (es + (1 << 19)) >> 20;
+                igd_bridge_rec br;
+                br.bytemean_out = (uint8_t)igd_bytemean_from_sum(es - (n << 20), IGD_FRAME);
+                br.n_open = (uint8_t)n;
+                br.mix_peak = (uint16_t)peak;
+                q.bmeter[bf] = br;
+            }
+        }
+        __syncwarp();
+        // ---- finish: one leg record per lane
+        {
+            const uint32_t bf0 = item * kBf;
+            uint32_t sil_rec = 0u;
+            if (general) sil_rec = (__shfl_sync(0xFFFFFFFFu, silent8, (int)(rec_src & 31u)) >> (rec_leg & 7u)) & 1u;
+            if (lane < (uint32_t)kBf * G && bf0 + rec_bf < total_bf && want_meter) {
+                unsigned long long sq = 0; uint32_t pk = 0; int bsum = 0;
+                if (!sil_rec) {
+#pragma unroll
+                    for (int j = 0; j < kHCols; j++) {
+                        const uint2 v = part[j * kHLegStride + lane];
+                        sq += v.x; pk = max_u16x2(pk, v.y); bsum = dp2a_lo(v.y, 0x0100u, bsum);
+                    }
+                }
+                const igd_meter_rec rr = meter_finish(sq << 4, (pk & 0xFFFFu) << 2, bsum, true);
+                st16_stream(q.meter + ((size_t)bf0 * G + lane), *reinterpret_cast<const uint4 *>(&rr));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int GP, bool kSigned, int kWarps>
+cudaError_t launch_fused_h(const igd_launch_cfg &c, const FusedParams &q)
+{
+    const bool all_out = q.mix && q.enc && q.meter && q.bmeter;
+    auto kern = all_out ? k_fused_h<GP, kSigned, kWarps, false> : k_fused_h<GP, kSigned, kWarps, true>;
+    const size_t smem = kLutBytes + (size_t)kWarps * (32 * IGD_FRAME + kHCols * kHLegStride * 8);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const long long items = (q.total_bf + (32 / GP) - 1) / (32 / GP);
+    long long grid = c.sm_count;
+    if (grid > items) grid = items;
+    kern<<<(int)grid, kWarps * 32, smem, c.stream>>>(q);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------
@@ -1305,6 +1604,11 @@ cudaError_t igd_k_fused(const igd_launch_cfg &c, const igd_batch_desc &d)
     if (fits32 && d.G == 2) return sc ? launch_fused_w<2, true, 24>(c, q) : launch_fused_w<2, false, 24>(c, q);
     if (fits32 && d.G == 1) return sc ? launch_fused_w<1, true, 24>(c, q) : launch_fused_w<1, false, 24>(c, q);
     if (q.total_bf < (1ll << 28) && d.G == 3) return sc ? launch_fused_w<3, true, 24>(c, q) : launch_fused_w<3, false, 24>(c, q);
+    // eight legs: a lane walks all 8 legs of one sample column (k_fused_h)
+    if (!(d.flags & IGD_F_KERNEL_W) && d.G == 8 && q.total_bf < (1ll << 26) &&
+        ((reinterpret_cast<uintptr_t>(d.gain_q7) & 15u) | (reinterpret_cast<uintptr_t>(d.law) & 7u) |
+         (reinterpret_cast<uintptr_t>(d.mix) & 7u) | (reinterpret_cast<uintptr_t>(d.enc) & 3u)) == 0)
+        return sc ? launch_fused_h<8, true, 20>(c, q) : launch_fused_h<8, false, 20>(c, q);
     // any other leg count: the warp-autonomous group walk (needs 16-byte aligned codes, which the C ABI
     // checks, and 32-bit bridge-frame indices); the block-cooperative kernel is the last resort
     if (q.total_bf < (1ll << 28) && (long long)q.total_bf * d.G < (1ll << 32))
