@@ -60,7 +60,10 @@ def composed(vp, case, mode, F, B):
 
 
 @pytest.mark.parametrize("F,B,mode,seed", [(60, 9, N.ARB_CLIENT_PTT, 1), (33, 50, N.ARB_SERVER_BEST, 2), (7, 1, N.ARB_CLIENT_PTT, 3),
-                                           (120, 130, N.ARB_CLIENT_PTT, 4)])
+                                           (120, 130, N.ARB_CLIENT_PTT, 4),
+                                           # >= 32 768 channels: the packet-fed liveness walk, and the batch walked in
+                                           # L2-sized slices of ticks (state carried from slice to slice)
+                                           (23, 8192, N.ARB_CLIENT_PTT, 5), (9, 8200, N.ARB_SERVER_BEST, 6)])
 @pytest.mark.parametrize("kern", [0, N.F_KERNEL_W])      # quarter-lane fused kernel (default) and its predecessor
 def test_gateway_equals_composition_of_verified_calls(vp, F, B, mode, seed, kern):
     case = make_case(F, B, seed, mode)
