@@ -58,8 +58,9 @@ enum {
 #define IGD_F_REF_QUIRKS 0x2u    /* quirks Q2/Q3 of SURVEY.md Appendix A in the
                                     packet path (stale payload; outgoing byte-mean
                                     over header+payload)                          */
-#define IGD_F_KERNEL_W 0x8u       /* diagnostics: igd_process_batch with G <= 4 runs the five-lanes-per-bridge-frame
-                                     kernel (k_fused_w, the one the packet forms use) instead of k_fused_q */
+#define IGD_F_KERNEL_W 0x8u       /* diagnostics (A/B runs, tests): the previous generation of the fused kernel -- k_fused_w
+                                     instead of k_fused_q (G <= 4, codes and packet forms), k_fused_g instead of
+                                     k_fused_h (G = 8).  Same results, bit for bit. */
 #define IGD_F_GENERIC_KERNEL 0x4u /* diagnostic (igd_process_batch): run the block-cooperative kernel that
                                     serves batches beyond 32-bit indices instead of the warp-autonomous
                                     ones; same results, slower                                       */
