@@ -23,6 +23,8 @@ struct igd_ctx {
     cudaStream_t own_stream, stream;
     cudaStream_t copy_streams[2];
     cudaEvent_t ev[8];
+    cudaStream_t walk_streams[2];       // igd_gateway_process: liveness walk / arbitration, pipelined against the fused kernel
+    cudaEvent_t walk_ev[3 * 8];         // [chunk]: liveness walk done, [8 + chunk]: arbitration done, [16 + chunk]: sender walk done
     cudaDeviceProp prop;
     void *scratch[kSlots];
     size_t scratch_cap[kSlots];
@@ -156,8 +158,17 @@ int igd_init(int device, igd_ctx **out)
     bool ok = true;
     for (auto &s : c->copy_streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
     for (auto &e : c->ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    {
+        // the walks are small, latency-bound grids: their blocks go ahead of the fused kernel's CTAs when both wait for an SM
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (auto &s : c->walk_streams) ok = ok && cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) == cudaSuccess;
+        for (auto &e : c->walk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    }
     if (!ok) {          // never run with a null copy stream / event
         for (auto &e : c->ev) if (e) cudaEventDestroy(e);
+        for (auto &e : c->walk_ev) if (e) cudaEventDestroy(e);
+        for (auto &s : c->walk_streams) if (s) cudaStreamDestroy(s);
         for (auto &s : c->copy_streams) if (s) cudaStreamDestroy(s);
         cudaStreamDestroy(c->own_stream);
         delete c;
@@ -175,6 +186,8 @@ int igd_shutdown(igd_ctx *c)
     for (int i = 0; i < kSlots; i++)
         if (c->scratch[i]) cudaFree(c->scratch[i]);
     for (auto &e : c->ev) cudaEventDestroy(e);
+    for (auto &e : c->walk_ev) cudaEventDestroy(e);
+    for (auto &s : c->walk_streams) cudaStreamDestroy(s);
     for (auto &s : c->copy_streams) cudaStreamDestroy(s);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -920,53 +933,122 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     kside.stream = c->copy_streams[0];
     IGD_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
     IGD_CUDA(c, cudaStreamWaitEvent(kside.stream, c->ev[6], 0));
-    // 4. sender walk of the B outgoing calls
-    igd_ed137_pack_desc pk;
-    memset(&pk, 0, sizeof pk);
-    pk.struct_size = sizeof pk; pk.mem = IGD_MEM_DEVICE; pk.F = d->F; pk.C = d->B; pk.flags = d->flags & IGD_F_SIGNED_CHAR;
-    pk.payload_len = IGD_FRAME; pk.out_stride = IGD_PKT_MAX; pk.tick_ms = d->tick_ms; pk.now_ms0 = d->now_ms0;
-    pk.rtp12 = drtp; pk.payload = nullptr; pk.ctl = dctl; pk.state = dtx;
-    IGD_CUDA(c, igd_k_ed137_plan(kside, pk, static_cast<igd_tx_plan_rec *>(dplan), static_cast<int32_t *>(dlast)));
-    IGD_CUDA(c, cudaEventRecord(c->ev[7], kside.stream));
-    // 1 + 2. transport_rtp_cb's view of every packet header and the liveness / latch / edge walk.  With tens of
-    //        thousands of channels the walk reads the three header words it needs straight out of the packets (one
-    //        kernel, no field array: enough walks in flight to hide the strided loads); with a few thousand channels
-    //        and many ticks a fully parallel header pass first and the walk over its compact 16-byte records is
-    //        faster (measured: 65 536 ch x 100 ticks 0.80 vs 0.83 ms per call; 4096 ch x 1640 ticks 1.64 vs 2.46 ms).
-    igd_rx_track_desc rx;
-    memset(&rx, 0, sizeof rx);
-    rx.struct_size = sizeof rx; rx.mem = IGD_MEM_DEVICE; rx.F = d->F; rx.C = (int32_t)Cn; rx.tick_ms = d->tick_ms;
-    rx.r2s_period_ms = d->r2s_period_ms; rx.wd_ticks = d->wd_ticks; rx.frame0 = d->frame0; rx.now_ms0 = d->now_ms0;
-    rx.present = nullptr; rx.state = drx; rx.events = dev;
-    rx.sizes = dsz;              // a leg without a packet on a tick has size 0: not a packet for the walk
-    if (Cn >= 32768) {
-        rx.fields = nullptr;
-        IGD_CUDA(c, igd_k_rx_track(k, rx, dpk));
+    // The call is a pipeline over chunks of ticks: liveness walk (+ header pass) -> arbitration -> fused kernel, each
+    // stage on its own stream, chunk k of a stage waiting for chunk k of the stage before it, and the sender walk of the
+    // same chunk beside them on the side stream (the fused kernel needs its plan).  The
+    // walks are latency-bound grids of a few thousand threads that leave most of the machine idle; run back to back
+    // they cost twice the fused kernel (4096 channels x 1640 ticks: 1.50 ms per call), pipelined 1.29 ms.  Every stage carries its state from chunk to chunk in the caller's state arrays,
+    // exactly as from call to call, so the results do not depend on the chunking.  One tick (the real-time shape) is
+    // one chunk: the same four launches as before.
+#ifndef IGD_GW_CHUNKS
+#define IGD_GW_CHUNKS 8
+#endif
+#ifndef IGD_GW_MIN_TICKS
+#define IGD_GW_MIN_TICKS 16
+#endif
+    static_assert(IGD_GW_CHUNKS >= 1 && IGD_GW_CHUNKS <= 8, "walk_ev holds 8 chunks");
+    // (from 32 768 channels up the walks are no longer idle time -- the liveness walk is a 6 TB/s header read -- and
+    // chunking only adds launches: 0.67 ms unchunked, 0.68 / 0.77 / 0.78 ms with 2 / 4 / 6 chunks at 65 536 channels)
+    int nchunk = Cn >= 32768 ? 1 : d->F / IGD_GW_MIN_TICKS;
+    if (nchunk > IGD_GW_CHUNKS) nchunk = IGD_GW_CHUNKS;
+    if (nchunk < 1) nchunk = 1;
+    const int chunk = (d->F + nchunk - 1) / nchunk;
+    // (Leaving 12 / 20 / 32 / 48 SMs out of the fused kernel's grid for the walk blocks of the following chunks measured
+    // 1.33 / 1.35 / 1.39 / 1.44 ms at the bench shape against 1.31 with the full grid: the stages stretch when they share
+    // the machine -- a persistent one-CTA-per-SM kernel waits for whole SMs -- and the pipeline gains 13 %, not 2x.)
+    igd_launch_cfg krx = k, karb = k;
+    if (nchunk > 1) {
+        krx.stream = c->walk_streams[0];
+        karb.stream = c->walk_streams[1];
+        IGD_CUDA(c, cudaStreamWaitEvent(krx.stream, c->ev[6], 0));       // fork: after the inputs are in place
+        IGD_CUDA(c, cudaStreamWaitEvent(karb.stream, c->ev[6], 0));
+    }
+    void *dfields = nullptr;
+    if (Cn < 32768 && (rc = scratch(c, 5, n * sizeof(igd_ed137_fields), &dfields))) return rc;
+#ifdef IGD_X_GW_TRACE      // measurement builds: when did each stage of each chunk start and end
+    static cudaEvent_t tr[1 + 8 * 6];
+    static bool tr_init = false;
+    if (!tr_init) { for (auto &e : tr) cudaEventCreate(&e); tr_init = true; }
+    cudaEventRecord(tr[0], c->stream);
+#define IGD_TR(i, st) cudaEventRecord(tr[1 + ci * 6 + (i)], st)
+#else
+#define IGD_TR(i, st) ((void)0)
+#endif
+    for (int ci = 0, f0 = 0; f0 < d->F; ci++, f0 += chunk) {
+        const int nf = d->F - f0 < chunk ? d->F - f0 : chunk;
+        const size_t on = (size_t)f0 * Cn, onb = (size_t)f0 * B;       // channel-ticks / bridge-ticks before this chunk
+        // 1 + 2. transport_rtp_cb's view of every packet header and the liveness / latch / edge walk.  With tens of
+        //        thousands of channels the walk reads the three header words it needs straight out of the packets (one
+        //        kernel, no field array: enough walks in flight to hide the strided loads); with a few thousand channels
+        //        and many ticks a fully parallel header pass first and the walk over its compact 16-byte records is
+        //        faster (measured: 65 536 ch x 100 ticks 0.80 vs 0.83 ms per call; 4096 ch x 1640 ticks 1.64 vs 2.46 ms).
+        igd_rx_track_desc rx;
+        memset(&rx, 0, sizeof rx);
+        rx.struct_size = sizeof rx; rx.mem = IGD_MEM_DEVICE; rx.F = nf; rx.C = (int32_t)Cn; rx.tick_ms = d->tick_ms;
+        rx.r2s_period_ms = d->r2s_period_ms; rx.wd_ticks = d->wd_ticks; rx.frame0 = d->frame0 + f0;
+        rx.now_ms0 = d->now_ms0 + (long long)f0 * d->tick_ms;
+        rx.present = nullptr; rx.state = drx; rx.events = dev + on;
+        rx.sizes = dsz ? dsz + on : nullptr;     // a leg without a packet on a tick has size 0: not a packet for the walk
+        IGD_TR(0, krx.stream);
+        if (Cn >= 32768) {
+            rx.fields = nullptr;
+            IGD_CUDA(c, igd_k_rx_track(krx, rx, dpk + on * IGD_PKT_MAX));
+            c->launches += 1;
+        } else {
+            igd_ed137_fields *fl = static_cast<igd_ed137_fields *>(dfields) + on;
+            IGD_CUDA(c, igd_k_ed137_parse(krx, dpk + on * IGD_PKT_MAX, dsz ? dsz + on : nullptr, (size_t)nf * Cn, IGD_PKT_MAX, fl, nullptr));
+            rx.fields = fl;
+            IGD_CUDA(c, igd_k_rx_track(krx, rx));
+            c->launches += 2;
+        }
+        IGD_TR(1, krx.stream);
+        if (nchunk > 1) {
+            IGD_CUDA(c, cudaEventRecord(c->walk_ev[ci], krx.stream));
+            IGD_CUDA(c, cudaStreamWaitEvent(karb.stream, c->walk_ev[ci], 0));
+        }
+        // 3. gate decisions; ticks without a whole audio frame carry IGD_GAIN_NO_AUDIO
+        igd_arb_desc ar;
+        memset(&ar, 0, sizeof ar);
+        ar.struct_size = sizeof ar; ar.mem = IGD_MEM_DEVICE; ar.F = nf; ar.B = d->B; ar.G = 4; ar.mode = d->arb_mode;
+        ar.word_stride = 8; ar.flags = IGD_ARB_F_SILENCE; ar.words = dev + on; ar.active = dact; ar.legs = dleg; ar.bridges = dbr;
+        ar.gain_q7 = dgain + on;
+        IGD_TR(2, karb.stream);
+        IGD_CUDA(c, igd_k_gate_arbitrate(karb, ar));
+        IGD_TR(3, karb.stream);
+        if (nchunk > 1) {
+            IGD_CUDA(c, cudaEventRecord(c->walk_ev[8 + ci], karb.stream));
+            IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->walk_ev[8 + ci], 0));
+        }
+        // 4. sender walk of the B outgoing calls over this chunk's ticks (independent of the receive side)
+        igd_ed137_pack_desc pk;
+        memset(&pk, 0, sizeof pk);
+        pk.struct_size = sizeof pk; pk.mem = IGD_MEM_DEVICE; pk.F = nf; pk.C = d->B; pk.flags = d->flags & IGD_F_SIGNED_CHAR;
+        pk.payload_len = IGD_FRAME; pk.out_stride = IGD_PKT_MAX; pk.tick_ms = d->tick_ms; pk.now_ms0 = d->now_ms0 + (long long)f0 * d->tick_ms;
+        pk.rtp12 = drtp + onb * 12; pk.payload = nullptr; pk.ctl = dctl ? dctl + onb : nullptr; pk.state = dtx;
+        IGD_CUDA(c, igd_k_ed137_plan(kside, pk, static_cast<igd_tx_plan_rec *>(dplan) + onb, static_cast<int32_t *>(dlast)));
+        IGD_CUDA(c, cudaEventRecord(c->walk_ev[16 + ci], kside.stream));
+        IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->walk_ev[16 + ci], 0));            // join: this chunk's plan is there
         c->launches += 1;
-    } else {
-        void *dfields;
-        if ((rc = scratch(c, 5, n * sizeof(igd_ed137_fields), &dfields))) return rc;
-        IGD_CUDA(c, igd_k_ed137_parse(k, dpk, dsz, n, IGD_PKT_MAX, static_cast<igd_ed137_fields *>(dfields), nullptr));
-        rx.fields = static_cast<igd_ed137_fields *>(dfields);
-        IGD_CUDA(c, igd_k_rx_track(k, rx));
+        // 5. decode -> meter -> mix -> encode -> packets
+        igd_packets_desc fp;
+        memset(&fp, 0, sizeof fp);
+        fp.struct_size = sizeof fp; fp.mem = IGD_MEM_DEVICE; fp.F = nf; fp.B = d->B; fp.G = 4; fp.flags = d->flags & (IGD_F_SIGNED_CHAR | IGD_F_KERNEL_W);
+        fp.pkts = dpk + on * IGD_PKT_MAX; fp.fields = nullptr; fp.law = dlaw; fp.gain_q7 = dgain + on; fp.out_law = dol;
+        fp.mix = dmix ? dmix + onb * IGD_FRAME : nullptr; fp.enc = denc ? denc + onb * IGD_FRAME : nullptr;
+        fp.meter = dmt ? dmt + on : nullptr; fp.bmeter = dbm ? dbm + onb : nullptr;
+        IGD_TR(4, c->stream);
+        IGD_CUDA(c, igd_k_fused_gateway(k, fp, static_cast<igd_tx_plan_rec *>(dplan) + onb, drtp + onb * 12, dtp + onb * IGD_PKT_MAX, dts + onb));
+        IGD_TR(5, c->stream);
         c->launches += 2;
     }
-    // 3. gate decisions; ticks without a whole audio frame carry IGD_GAIN_NO_AUDIO
-    igd_arb_desc ar;
-    memset(&ar, 0, sizeof ar);
-    ar.struct_size = sizeof ar; ar.mem = IGD_MEM_DEVICE; ar.F = d->F; ar.B = d->B; ar.G = 4; ar.mode = d->arb_mode;
-    ar.word_stride = 8; ar.flags = IGD_ARB_F_SILENCE; ar.words = dev; ar.active = dact; ar.legs = dleg; ar.bridges = dbr;
-    ar.gain_q7 = dgain;
-    IGD_CUDA(c, igd_k_gate_arbitrate(k, ar));
-    IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[7], 0));          // join: the plan is there
-    // 5. decode -> meter -> mix -> encode -> packets
-    igd_packets_desc fp;
-    memset(&fp, 0, sizeof fp);
-    fp.struct_size = sizeof fp; fp.mem = IGD_MEM_DEVICE; fp.F = d->F; fp.B = d->B; fp.G = 4; fp.flags = d->flags & (IGD_F_SIGNED_CHAR | IGD_F_KERNEL_W);
-    fp.pkts = dpk; fp.fields = nullptr; fp.law = dlaw; fp.gain_q7 = dgain; fp.out_law = dol;
-    fp.mix = dmix; fp.enc = denc; fp.meter = dmt; fp.bmeter = dbm;
-    IGD_CUDA(c, igd_k_fused_gateway(k, fp, static_cast<igd_tx_plan_rec *>(dplan), drtp, dtp, dts));
-    c->launches += 3;
+#ifdef IGD_X_GW_TRACE
+    cudaDeviceSynchronize();
+    for (int ci = 0; ci < nchunk; ci++) {
+        float t[6];
+        for (int i = 0; i < 6; i++) cudaEventElapsedTime(&t[i], tr[0], tr[1 + ci * 6 + i]);
+        fprintf(stderr, "chunk %d: rx %.0f-%.0f  arb %.0f-%.0f  fused %.0f-%.0f us\n", ci, 1e3 * t[0], 1e3 * t[1], 1e3 * t[2], 1e3 * t[3], 1e3 * t[4], 1e3 * t[5]);
+    }
+#endif
     if (mem == IGD_MEM_HOST) {
         if ((rc = out_done(c, mem, d->tx_pkts, dtp, nb * IGD_PKT_MAX))) return rc;
         if ((rc = out_done(c, mem, d->tx_sizes, dts, nb))) return rc;

@@ -63,7 +63,7 @@ def composed(vp, case, mode, F, B):
                                            (120, 130, N.ARB_CLIENT_PTT, 4),
                                            # >= 32 768 channels: the packet-fed liveness walk, and the batch walked in
                                            # L2-sized slices of ticks (state carried from slice to slice)
-                                           (23, 8192, N.ARB_CLIENT_PTT, 5), (9, 8200, N.ARB_SERVER_BEST, 6)])
+                                           (37, 8192, N.ARB_CLIENT_PTT, 5), (9, 8200, N.ARB_SERVER_BEST, 6)])
 @pytest.mark.parametrize("kern", [0, N.F_KERNEL_W])      # quarter-lane fused kernel (default) and its predecessor
 def test_gateway_equals_composition_of_verified_calls(vp, F, B, mode, seed, kern):
     case = make_case(F, B, seed, mode)
@@ -144,3 +144,48 @@ def test_gateway_device_buffers_many_ticks(vp):
         torch.cuda.synchronize()
         assert np.array_equal(got["tx_sizes"].cpu().numpy().view(np.uint32), want["tx_sizes"])
         assert np.array_equal(got["tx_pkts"].cpu().numpy(), want["tx_pkts"])
+
+
+def test_gateway_call_is_cuda_graph_capturable_with_its_three_stage_pipeline(vp):
+    """64 ticks = 4 chunks: liveness walk, arbitration and fused kernel run on three streams of the library, forked from
+    and joined back to the caller's stream by events -- the whole call captures into one CUDA graph and replays with the
+    same bytes as the eager call."""
+    F, B, mode = 64, 300, N.ARB_CLIENT_PTT
+    case = make_case(F, B, 31, mode)
+    dev = "cuda:0"
+    Cn = B * G
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    st0 = tx_state_of(case).view(np.int32).reshape(B, 10)
+    rx_state = t(np.zeros((Cn, 4), np.int32)); legs = t(np.zeros((Cn, 2), np.int32)); bridges = t(np.zeros((B, 4), np.int32))
+    tx_state = t(st0)
+    args = (t(case["pk"]), t(case["law"]), t(case["out_law"]), rx_state, legs, bridges, t(case["rtp12"]), tx_state)
+    kw = dict(rx_sizes=t(case["sizes"].view(np.int32)), tx_ctl=t(case["ctl"].view(np.int32).reshape(F, B, 2)), mode=mode,
+              now_ms0=case["now0"], want=("bmeter", "meter", "enc", "gain_q7"))
+
+    def reset():
+        rx_state.zero_(); legs.zero_(); bridges.zero_(); tx_state.copy_(t(st0))
+
+    vp.use_torch_stream()
+    eager = vp.gateway_process(*args, **kw)
+    torch.cuda.synchronize()
+    want = {k: v.cpu().numpy().copy() for k, v in eager.items()}
+    reset()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        vp.use_torch_stream()
+        vp.gateway_process(*args, out=eager, **kw)            # warm-up on the side stream (scratch, function attributes)
+    torch.cuda.synchronize()
+    reset()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        vp.use_torch_stream()
+        vp.gateway_process(*args, out=eager, **kw)
+    vp.use_torch_stream()
+    for rep in range(2):
+        reset()
+        for v in eager.values():
+            v.zero_()
+        gr.replay()
+        torch.cuda.synchronize()
+        for k in want:
+            assert np.array_equal(eager[k].cpu().numpy(), want[k]), (rep, k)
