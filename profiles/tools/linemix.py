@@ -1,8 +1,9 @@
 """per-source-line executed warp-instructions of one kernel: ncu report x nvdisasm -g line table (run here, no GPU).
-usage: linemix.py report.ncu-rep libigate_dsp.so kernel_substr [nbf]"""
+usage: linemix.py report.ncu-rep libigate_dsp.so kernel_substr [nbf] [launch index in the report, default 0]"""
 import csv, io, re, subprocess, sys, collections, os, tempfile
 rep, so, ksub = sys.argv[1:4]
 nbf = float(sys.argv[4]) if len(sys.argv) > 4 else 1024 * 1640
+which = int(sys.argv[5]) if len(sys.argv) > 5 else 0
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=tmp, capture_output=True)
 dis = []                          # every embedded cubin (one per translation unit)
@@ -25,16 +26,17 @@ for l in dis:
         ins.append((int(m.group(1), 16), cur, m.group(2).strip()))
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hd, body = None, []
-for r in rows:                       # first captured launch only
+hd, body, seen = None, [], -1
+for r in rows:                       # one captured launch only
     if r and r[0] == "Kernel Name":
-        if hd is not None:
-            break
         continue
     if r and r[0] == "Address":
-        hd = r
+        seen += 1
+        if seen > which:
+            break
+        hd, body = r, []
         continue
-    if hd:
+    if hd and seen == which:
         body.append(r)
 ia = hd.index("Instructions Executed"); isrc = hd.index("Source")
 assert len(body) == len(ins), (len(body), len(ins))
