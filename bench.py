@@ -337,6 +337,53 @@ def run_chain(args):
         torch.cuda.synchronize()
     stage = {"fields": ev[0].elapsed_time(ev[1]), "rx_track": ev[1].elapsed_time(ev[2]), "gate_arbitrate": ev[2].elapsed_time(ev[3]),
              "plan+assemble (separate call; the gateway runs the plan walk only)": ev[3].elapsed_time(ev[4])}
+    # ---- end to end: the same call with pinned HOST buffers -- packets, RTP headers and setter values copied in, the
+    # finished packets, their sizes and the meter records copied out, the four state arrays round-tripped, every step
+    e2e = None
+    if not args.no_e2e:
+        affinity0 = os.sched_getaffinity(0)
+        numa = pin_to_gpu_numa_node(dev.index)
+
+        def pinned(t):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t)
+            return h
+
+        h_pk, h_rtp, h_ctl = pinned(pk), pinned(rtp12), pinned(ctl)
+        h_out_t = {"tx_pkts": torch.empty((Fc, Bc, 180), dtype=torch.uint8, pin_memory=True),
+                   "tx_sizes": torch.empty((Fc, Bc), dtype=torch.int32, pin_memory=True),
+                   "meter": torch.empty((Fc, Cc, 4), dtype=torch.int32, pin_memory=True),
+                   "bmeter": torch.empty((Fc, Bc), dtype=torch.int32, pin_memory=True)}
+        for t in h_out_t.values():
+            t.zero_()
+        os.sched_setaffinity(0, affinity0)
+        h_out = {"tx_pkts": h_out_t["tx_pkts"].numpy(), "tx_sizes": h_out_t["tx_sizes"].numpy().view(np.uint32),
+                 "meter": h_out_t["meter"].numpy().view(ig.METER_DT).reshape(Fc, Cc),
+                 "bmeter": h_out_t["bmeter"].numpy().view(ig.BRIDGE_DT).reshape(Fc, Bc)}
+        h_state = (np.zeros(Cc, N.RX_STATE_DT), np.zeros(Cc, N.ARB_LEG_DT), np.zeros(Bc, N.ARB_BRIDGE_DT), tx0.copy())
+        h_ctl_np = h_ctl.numpy().view(N.CTL_DT).reshape(Fc, Bc)
+
+        def host_step(now):
+            vp.gateway_process(h_pk.numpy(), law_np, out_law_np, h_state[0], h_state[1], h_state[2], h_rtp.numpy(), h_state[3],
+                               tx_ctl=h_ctl_np, mode=N.ARB_CLIENT_PTT, now_ms0=now, want=("meter", "bmeter"), out=h_out)
+
+        host_step(now0)                         # a fresh run from the same start state as the device-resident parity run
+        st_d = fresh()
+        outs = None
+        step(st_d, now0)
+        torch.cuda.synchronize()
+        ok_e2e = bool(torch.equal(h_out_t["tx_pkts"], outs["tx_pkts"].cpu()) and torch.equal(h_out_t["bmeter"], outs["bmeter"].cpu()))
+        esteps = max(2, min(args.steps, 5))
+        host_step(now0 + Fc * 20)
+        t0 = time.perf_counter()
+        for i in range(esteps):
+            host_step(now0 + (i + 2) * Fc * 20)
+        dt = time.perf_counter() - t0
+        h2d = h_pk.numel() + h_rtp.numel() + h_ctl.numel() * 4 + law_np.nbytes + out_law_np.nbytes + sum(a.nbytes for a in h_state)
+        d2h = sum(v.nbytes for v in h_out.values()) + sum(a.nbytes for a in h_state)
+        e2e = {"value": Cc * Fc * FRAME * esteps / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": esteps, "outputs": ["tx_pkts", "tx_sizes", "meter", "bmeter", "state arrays"], "matches_device_path": ok_e2e,
+               "host_buffers": numa, "note": "PCIe-bound on the packets in (h2d_bytes_per_step)"}
     alg = 1284 * Bc * Fc
     peak, peak_src = peaks()
     value = Cc * Fc * FRAME / (ms * 1e-3)
@@ -349,9 +396,9 @@ def run_chain(args):
                    "l2": "inputs larger than L2" if Cc * Fc * 180 > (256 << 20) else "inputs may be L2 resident"},
         "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
                      "traffic": None, "kernel": "igd_gateway_process: k_rx_track<packets> + k_gate_arbitrate + k_ed137_plan (side stream) + "
-                                                  "k_fused_w<4, packets in, packets out>", "peak_source": peak_src,
+                                                  "k_fused_q<4, packets in, packets out>", "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg, "bytes_per_bridge_frame": 1284, "stage_ms": stage},
-        "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+        "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "parity_vs_oracle_on_two_bridges": parity,
     }))
     vp.close()

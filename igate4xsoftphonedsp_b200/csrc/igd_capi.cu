@@ -24,7 +24,9 @@ struct igd_ctx {
     cudaStream_t copy_streams[2];
     cudaEvent_t ev[8];
     cudaStream_t walk_streams[2];       // igd_gateway_process: liveness walk / arbitration, pipelined against the fused kernel
-    cudaEvent_t walk_ev[3 * 8];         // [chunk]: liveness walk done, [8 + chunk]: arbitration done, [16 + chunk]: sender walk done
+    cudaEvent_t walk_ev[5 * 8];         // [chunk]: liveness walk done, [8 + chunk]: arbitration done, [16 + chunk]: sender walk done,
+                                        // host form: [24 + chunk]: the chunk's inputs are on the device, [32 + chunk]: its outputs are ready
+    cudaStream_t io_streams[2];         // igd_gateway_process, host form: chunk-wise H2D / D2H beside the kernels
     cudaDeviceProp prop;
     void *scratch[kSlots];
     size_t scratch_cap[kSlots];
@@ -42,6 +44,10 @@ int fail(igd_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
         else
             snprintf(c->err, sizeof(c->err), "%s", what);
     }
+    // a CUDA call failed in the middle of a call: nothing of this library may still be copying to or from the
+    // caller's host buffers (or the shared scratch) when the error is returned -- drain whatever was queued on the
+    // side streams (a sticky error makes this return at once; under stream capture it is refused, harmlessly)
+    if (e != cudaSuccess) cudaDeviceSynchronize();
     return code;
 }
 
@@ -164,11 +170,13 @@ int igd_init(int device, igd_ctx **out)
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         for (auto &s : c->walk_streams) ok = ok && cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, hi) == cudaSuccess;
         for (auto &e : c->walk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+        for (auto &s : c->io_streams) ok = ok && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess;
     }
     if (!ok) {          // never run with a null copy stream / event
         for (auto &e : c->ev) if (e) cudaEventDestroy(e);
         for (auto &e : c->walk_ev) if (e) cudaEventDestroy(e);
         for (auto &s : c->walk_streams) if (s) cudaStreamDestroy(s);
+        for (auto &s : c->io_streams) if (s) cudaStreamDestroy(s);
         for (auto &s : c->copy_streams) if (s) cudaStreamDestroy(s);
         cudaStreamDestroy(c->own_stream);
         delete c;
@@ -188,6 +196,7 @@ int igd_shutdown(igd_ctx *c)
     for (auto &e : c->ev) cudaEventDestroy(e);
     for (auto &e : c->walk_ev) cudaEventDestroy(e);
     for (auto &s : c->walk_streams) cudaStreamDestroy(s);
+    for (auto &s : c->io_streams) cudaStreamDestroy(s);
     for (auto &s : c->copy_streams) cudaStreamDestroy(s);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -872,8 +881,16 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     int rc;
     // ---- inputs (host form: staged; slots 0..5 in, 6..11 scratch / out)
     const uint8_t *dpk, *dlaw, *dact = nullptr, *dol, *drtp; const uint32_t *dsz = nullptr; const igd_ed137_ctl *dctl = nullptr;
-    if ((rc = in_arg(c, mem, 0, d->rx_pkts, n * IGD_PKT_MAX, &dpk))) return rc;
-    if (d->rx_sizes && (rc = in_arg(c, mem, 1, d->rx_sizes, n, &dsz))) return rc;
+    // (host form: the four per-tick input arrays are only given room here; they come over chunk by chunk, beside the
+    //  kernels of the chunk before -- see the pipeline below)
+    const bool host = mem == IGD_MEM_HOST;
+    if (!host) { dpk = d->rx_pkts; dsz = d->rx_sizes; }
+    else {
+        void *p0 = nullptr, *p1 = nullptr;
+        if ((rc = scratch(c, 0, n * IGD_PKT_MAX, &p0))) return rc;
+        if (d->rx_sizes && (rc = scratch(c, 1, n * sizeof(uint32_t), &p1))) return rc;
+        dpk = static_cast<const uint8_t *>(p0); dsz = static_cast<const uint32_t *>(p1);
+    }
     void *small = nullptr;       // law, active, out_law, states in one staged block (host form)
     igd_rx_state *drx; igd_arb_leg *dleg; igd_arb_bridge *dbr; igd_ed137_state *dtx;
     if (mem == IGD_MEM_DEVICE) {
@@ -897,8 +914,13 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
         drx = reinterpret_cast<igd_rx_state *>(sb + o_rx); dleg = reinterpret_cast<igd_arb_leg *>(sb + o_leg);
         dbr = reinterpret_cast<igd_arb_bridge *>(sb + o_br); dtx = reinterpret_cast<igd_ed137_state *>(sb + o_tx);
     }
-    if ((rc = in_arg(c, mem, 3, d->tx_rtp12, nb * 12, &drtp))) return rc;
-    if (d->tx_ctl && (rc = in_arg(c, mem, 4, d->tx_ctl, nb, &dctl))) return rc;
+    if (!host) { drtp = d->tx_rtp12; dctl = d->tx_ctl; }
+    else {
+        void *p3 = nullptr, *p4 = nullptr;
+        if ((rc = scratch(c, 3, nb * 12, &p3))) return rc;
+        if (d->tx_ctl && (rc = scratch(c, 4, nb * sizeof(igd_ed137_ctl), &p4))) return rc;
+        drtp = static_cast<const uint8_t *>(p3); dctl = static_cast<const igd_ed137_ctl *>(p4);
+    }
     // ---- intermediates that never cross the API: field records, events, gains, sender plan
     void *dplan, *dlast, *dev_s = nullptr, *dgain_s = nullptr;
     if ((rc = scratch(c, 6, nb * sizeof(igd_tx_plan_rec) + B * sizeof(int32_t), &dplan))) return rc;
@@ -950,7 +972,11 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     // (from 32 768 channels up the walks are no longer idle time -- the liveness walk is a 6 TB/s header read -- and
     // chunking only adds launches: 0.67 ms unchunked, 0.68 / 0.77 / 0.78 ms with 2 / 4 / 6 chunks at 65 536 channels)
     int nchunk = Cn >= 32768 ? 1 : d->F / IGD_GW_MIN_TICKS;
+    // host form: the chunks are what the copies overlap with -- the call is bound by the packets coming in over PCIe,
+    // so the chunk count follows the bytes (about 64 MiB of packets each), whatever the channel count
+    if (host) nchunk = (int)((n * IGD_PKT_MAX + (48u << 20)) >> 26);
     if (nchunk > IGD_GW_CHUNKS) nchunk = IGD_GW_CHUNKS;
+    if (nchunk > d->F) nchunk = d->F;
     if (nchunk < 1) nchunk = 1;
     const int chunk = (d->F + nchunk - 1) / nchunk;
     // (Leaving 12 / 20 / 32 / 48 SMs out of the fused kernel's grid for the walk blocks of the following chunks measured
@@ -977,6 +1003,19 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     for (int ci = 0, f0 = 0; f0 < d->F; ci++, f0 += chunk) {
         const int nf = d->F - f0 < chunk ? d->F - f0 : chunk;
         const size_t on = (size_t)f0 * Cn, onb = (size_t)f0 * B;       // channel-ticks / bridge-ticks before this chunk
+        const size_t cn = (size_t)nf * Cn, cnb = (size_t)nf * B;        // ... and in it
+        if (host) {      // this chunk's inputs, on the copy-in stream; every stage that reads them waits for the event
+            cudaStream_t sin = c->io_streams[0];
+            if (ci == 0) IGD_CUDA(c, cudaStreamWaitEvent(sin, c->ev[6], 0));
+            IGD_CUDA(c, cudaMemcpyAsync(const_cast<uint8_t *>(dpk) + on * IGD_PKT_MAX, d->rx_pkts + on * IGD_PKT_MAX, cn * IGD_PKT_MAX, cudaMemcpyHostToDevice, sin));
+            if (dsz) IGD_CUDA(c, cudaMemcpyAsync(const_cast<uint32_t *>(dsz) + on, d->rx_sizes + on, cn * sizeof(uint32_t), cudaMemcpyHostToDevice, sin));
+            IGD_CUDA(c, cudaMemcpyAsync(const_cast<uint8_t *>(drtp) + onb * 12, d->tx_rtp12 + onb * 12, cnb * 12, cudaMemcpyHostToDevice, sin));
+            if (dctl) IGD_CUDA(c, cudaMemcpyAsync(const_cast<igd_ed137_ctl *>(dctl) + onb, d->tx_ctl + onb, cnb * sizeof(igd_ed137_ctl), cudaMemcpyHostToDevice, sin));
+            IGD_CUDA(c, cudaEventRecord(c->walk_ev[24 + ci], sin));
+            IGD_CUDA(c, cudaStreamWaitEvent(krx.stream, c->walk_ev[24 + ci], 0));
+            IGD_CUDA(c, cudaStreamWaitEvent(kside.stream, c->walk_ev[24 + ci], 0));
+            if (krx.stream != c->stream) IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->walk_ev[24 + ci], 0));
+        }
         // 1 + 2. transport_rtp_cb's view of every packet header and the liveness / latch / edge walk.  With tens of
         //        thousands of channels the walk reads the three header words it needs straight out of the packets (one
         //        kernel, no field array: enough walks in flight to hide the strided loads); with a few thousand channels
@@ -1040,6 +1079,19 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
         IGD_CUDA(c, igd_k_fused_gateway(k, fp, static_cast<igd_tx_plan_rec *>(dplan) + onb, drtp + onb * 12, dtp + onb * IGD_PKT_MAX, dts + onb));
         IGD_TR(5, c->stream);
         c->launches += 2;
+        if (host) {      // this chunk's outputs, on the copy-out stream, beside the kernels of the next chunk
+            cudaStream_t sout = c->io_streams[1];
+            IGD_CUDA(c, cudaEventRecord(c->walk_ev[32 + ci], c->stream));
+            IGD_CUDA(c, cudaStreamWaitEvent(sout, c->walk_ev[32 + ci], 0));
+            IGD_CUDA(c, cudaMemcpyAsync(d->tx_pkts + onb * IGD_PKT_MAX, dtp + onb * IGD_PKT_MAX, cnb * IGD_PKT_MAX, cudaMemcpyDeviceToHost, sout));
+            IGD_CUDA(c, cudaMemcpyAsync(d->tx_sizes + onb, dts + onb, cnb * sizeof(uint32_t), cudaMemcpyDeviceToHost, sout));
+            if (d->rx_events) IGD_CUDA(c, cudaMemcpyAsync(d->rx_events + on, dev + on, cn * sizeof(igd_rx_event), cudaMemcpyDeviceToHost, sout));
+            if (d->gain_q7) IGD_CUDA(c, cudaMemcpyAsync(d->gain_q7 + on, dgain + on, cn * sizeof(uint16_t), cudaMemcpyDeviceToHost, sout));
+            if (d->meter) IGD_CUDA(c, cudaMemcpyAsync(d->meter + on, dmt + on, cn * sizeof(igd_meter_rec), cudaMemcpyDeviceToHost, sout));
+            if (d->bmeter) IGD_CUDA(c, cudaMemcpyAsync(d->bmeter + onb, dbm + onb, cnb * sizeof(igd_bridge_rec), cudaMemcpyDeviceToHost, sout));
+            if (d->mix) IGD_CUDA(c, cudaMemcpyAsync(d->mix + onb * IGD_FRAME, dmix + onb * IGD_FRAME, cnb * IGD_FRAME * sizeof(int16_t), cudaMemcpyDeviceToHost, sout));
+            if (d->enc) IGD_CUDA(c, cudaMemcpyAsync(d->enc + onb * IGD_FRAME, denc + onb * IGD_FRAME, cnb * IGD_FRAME, cudaMemcpyDeviceToHost, sout));
+        }
     }
 #ifdef IGD_X_GW_TRACE
     cudaDeviceSynchronize();
@@ -1050,14 +1102,10 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     }
 #endif
     if (mem == IGD_MEM_HOST) {
-        if ((rc = out_done(c, mem, d->tx_pkts, dtp, nb * IGD_PKT_MAX))) return rc;
-        if ((rc = out_done(c, mem, d->tx_sizes, dts, nb))) return rc;
-        if (d->rx_events && (rc = out_done(c, mem, d->rx_events, dev, n))) return rc;
-        if (d->gain_q7 && (rc = out_done(c, mem, d->gain_q7, dgain, n))) return rc;
-        if (d->meter && (rc = out_done(c, mem, d->meter, dmt, n))) return rc;
-        if (d->bmeter && (rc = out_done(c, mem, d->bmeter, dbm, nb))) return rc;
-        if (d->mix && (rc = out_done(c, mem, d->mix, dmix, nb * IGD_FRAME))) return rc;
-        if (d->enc && (rc = out_done(c, mem, d->enc, denc, nb * IGD_FRAME))) return rc;
+        // the per-tick outputs went out chunk by chunk; the state arrays follow, and the caller's stream waits for the
+        // copy-out stream before the call returns
+        IGD_CUDA(c, cudaEventRecord(c->ev[7], c->io_streams[1]));
+        IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev[7], 0));
         if ((rc = out_done(c, mem, d->rx_state, drx, Cn))) return rc;
         if ((rc = out_done(c, mem, d->arb_legs, dleg, Cn))) return rc;
         if ((rc = out_done(c, mem, d->arb_bridges, dbr, B))) return rc;
