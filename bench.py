@@ -264,11 +264,12 @@ def run_chain(args):
                 torch.from_numpy(tx0.copy().view(np.int32).reshape(Bc, 10)).to(dev))
 
     outs = None
+    walk_flags = N.F_WALK_SERIAL if args.serial_walks else 0      # A/B: the thread-per-channel walks
 
     def step(st, now):
         nonlocal outs
         outs = vp.gateway_process(pk, law, out_law, st[0], st[1], st[2], rtp12, st[3], tx_ctl=ctl, mode=N.ARB_CLIENT_PTT,
-                                  now_ms0=now, want=("meter", "bmeter", "mix"), out=outs)
+                                  now_ms0=now, want=("meter", "bmeter", "mix"), out=outs, flags=walk_flags)
 
     # ---- parity: a fresh run, two bridges recomputed by the oracle from the raw packets (outside the timed region)
     st = fresh()
@@ -365,7 +366,7 @@ def run_chain(args):
 
         def host_step(now):
             vp.gateway_process(h_pk.numpy(), law_np, out_law_np, h_state[0], h_state[1], h_state[2], h_rtp.numpy(), h_state[3],
-                               tx_ctl=h_ctl_np, mode=N.ARB_CLIENT_PTT, now_ms0=now, want=("meter", "bmeter"), out=h_out)
+                               tx_ctl=h_ctl_np, mode=N.ARB_CLIENT_PTT, now_ms0=now, want=("meter", "bmeter"), out=h_out, flags=walk_flags)
 
         host_step(now0)                         # a fresh run from the same start state as the device-resident parity run
         st_d = fresh()
@@ -395,8 +396,9 @@ def run_chain(args):
                                f"one finished ED-137 packet per bridge and tick out (igd_gateway_process, CLIENT arbitration, silence marking)",
                    "l2": "inputs larger than L2" if Cc * Fc * 180 > (256 << 20) else "inputs may be L2 resident"},
         "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
-                     "traffic": None, "kernel": "igd_gateway_process: k_rx_track<packets> + k_gate_arbitrate + k_ed137_plan (side stream) + "
-                                                  "k_fused_q<4, packets in, packets out>", "peak_source": peak_src,
+                     "traffic": None, "kernel": ("igd_gateway_process: k_rx_track<packets> + k_gate_arbitrate + k_ed137_plan (side stream) + "
+                                if args.serial_walks else "igd_gateway_process: k_rxarb_walk (liveness walk + arbitration, warp per bridge, "
+                                "ticks across the lanes) + k_plan_walk (side stream) + ") + "k_fused_q<4, packets in, packets out>", "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg, "bytes_per_bridge_frame": 1284, "stage_ms": stage},
         "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "parity_vs_oracle_on_two_bridges": parity,
@@ -423,6 +425,7 @@ def main():
                          "summaries gathered to rank 0 over NCCL and checked against the oracle; device-resident legs only")
     ap.add_argument("--chain", action="store_true", help="packets in -> packets out (SURVEY 8d 'with RTP' accounting, 1284 B per "
                     "bridge-frame) through igd_gateway_process, device resident, 1 GPU")
+    ap.add_argument("--serial-walks", action="store_true", help="--chain: IGD_F_WALK_SERIAL, the thread-per-channel walks (A/B)")
     ap.add_argument("--chain-bridges", type=int, default=B)
     ap.add_argument("--chain-frames", type=int, default=F)
     args = ap.parse_args()

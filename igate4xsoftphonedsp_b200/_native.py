@@ -18,7 +18,7 @@ PKT_HDR = 20
 PKT_MAX = 180
 LAW_ALAW, LAW_ULAW = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-F_SIGNED_CHAR, F_REF_QUIRKS, F_GENERIC_KERNEL, F_KERNEL_W = 0x1, 0x2, 0x4, 0x8
+F_SIGNED_CHAR, F_REF_QUIRKS, F_GENERIC_KERNEL, F_KERNEL_W, F_WALK_SERIAL = 0x1, 0x2, 0x4, 0x8, 0x10
 CT_IDLE, CT_RXONLY, CT_TXISH = 0x1, 0x2, 0x4
 EDF_ACTIVE, EDF_RRC, EDF_MAIN_TX, EDF_MAIN_RX, EDF_DROPPED = 0x01, 0x02, 0x04, 0x08, 0x10
 

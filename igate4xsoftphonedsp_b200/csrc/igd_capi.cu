@@ -12,6 +12,7 @@
 #include <new>
 
 #include "igd_kernels.cuh"
+#include "igd_walks.cuh"      // igd_rxarb_args
 #include "igd_math.cuh"
 
 namespace {
@@ -925,9 +926,16 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     void *dplan, *dlast, *dev_s = nullptr, *dgain_s = nullptr;
     if ((rc = scratch(c, 6, nb * sizeof(igd_tx_plan_rec) + B * sizeof(int32_t), &dplan))) return rc;
     dlast = static_cast<uint8_t *>(dplan) + nb * sizeof(igd_tx_plan_rec);
-    igd_rx_event *dev; uint16_t *dgain;
+    // The walks: from IGD_WALK_MIN_TICKS ticks per call up, one warp per bridge / sender with the tick axis across its
+    // lanes (igd_walks.cuh: k_rxarb_walk = liveness walk + arbitration straight from the packets, k_plan_walk); below
+    // that -- the real-time shape, one tick per call -- and under IGD_F_WALK_SERIAL the thread-per-channel kernels.
+    const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS;
+    igd_rx_event *dev = nullptr; uint16_t *dgain;
     if (mem == IGD_MEM_DEVICE && d->rx_events) dev = d->rx_events;
-    else { if ((rc = scratch(c, 7, n * sizeof(igd_rx_event), &dev_s))) return rc; dev = static_cast<igd_rx_event *>(dev_s); }
+    else if (!lanes || d->rx_events) {      // the lane walk hands the words to the arbitration in registers: no event array unless wanted
+        if ((rc = scratch(c, 7, n * sizeof(igd_rx_event), &dev_s))) return rc;
+        dev = static_cast<igd_rx_event *>(dev_s);
+    }
     if (mem == IGD_MEM_DEVICE && d->gain_q7) dgain = d->gain_q7;
     else { if ((rc = scratch(c, 8, n * sizeof(uint16_t), &dgain_s))) return rc; dgain = static_cast<uint16_t *>(dgain_s); }
     // ---- outputs
@@ -990,7 +998,7 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
         IGD_CUDA(c, cudaStreamWaitEvent(karb.stream, c->ev[6], 0));
     }
     void *dfields = nullptr;
-    if (Cn < 32768 && (rc = scratch(c, 5, n * sizeof(igd_ed137_fields), &dfields))) return rc;
+    if (!lanes && Cn < 32768 && (rc = scratch(c, 5, n * sizeof(igd_ed137_fields), &dfields))) return rc;
 #ifdef IGD_X_GW_TRACE      // measurement builds: when did each stage of each chunk start and end
     static cudaEvent_t tr[1 + 8 * 6];
     static bool tr_init = false;
@@ -1021,6 +1029,21 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
         //        kernel, no field array: enough walks in flight to hide the strided loads); with a few thousand channels
         //        and many ticks a fully parallel header pass first and the walk over its compact 16-byte records is
         //        faster (measured: 65 536 ch x 100 ticks 0.80 vs 0.83 ms per call; 4096 ch x 1640 ticks 1.64 vs 2.46 ms).
+        if (lanes) {
+            igd_rxarb_args ra;
+            ra.F = nf; ra.B = d->B; ra.mode = d->arb_mode; ra.tick_ms = d->tick_ms; ra.r2s_period_ms = d->r2s_period_ms;
+            ra.wd_ticks = d->wd_ticks; ra.frame0 = d->frame0 + f0; ra.now_ms0 = d->now_ms0 + (long long)f0 * d->tick_ms;
+            ra.pkts = dpk + on * IGD_PKT_MAX; ra.sizes = dsz ? dsz + on : nullptr; ra.active = dact;
+            ra.rx_state = drx; ra.legs = dleg; ra.bridges = dbr; ra.events = dev ? dev + on : nullptr; ra.gain_q7 = dgain + on;
+            IGD_TR(0, krx.stream);
+            IGD_CUDA(c, igd_k_rxarb_walk(krx, ra));
+            IGD_TR(3, krx.stream);
+            c->launches += 1;
+            if (nchunk > 1) {
+                IGD_CUDA(c, cudaEventRecord(c->walk_ev[8 + ci], krx.stream));
+                IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->walk_ev[8 + ci], 0));
+            }
+        } else {
         igd_rx_track_desc rx;
         memset(&rx, 0, sizeof rx);
         rx.struct_size = sizeof rx; rx.mem = IGD_MEM_DEVICE; rx.F = nf; rx.C = (int32_t)Cn; rx.tick_ms = d->tick_ms;
@@ -1058,10 +1081,11 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
             IGD_CUDA(c, cudaEventRecord(c->walk_ev[8 + ci], karb.stream));
             IGD_CUDA(c, cudaStreamWaitEvent(c->stream, c->walk_ev[8 + ci], 0));
         }
+        }
         // 4. sender walk of the B outgoing calls over this chunk's ticks (independent of the receive side)
         igd_ed137_pack_desc pk;
         memset(&pk, 0, sizeof pk);
-        pk.struct_size = sizeof pk; pk.mem = IGD_MEM_DEVICE; pk.F = nf; pk.C = d->B; pk.flags = d->flags & IGD_F_SIGNED_CHAR;
+        pk.struct_size = sizeof pk; pk.mem = IGD_MEM_DEVICE; pk.F = nf; pk.C = d->B; pk.flags = d->flags & (IGD_F_SIGNED_CHAR | IGD_F_WALK_SERIAL);
         pk.payload_len = IGD_FRAME; pk.out_stride = IGD_PKT_MAX; pk.tick_ms = d->tick_ms; pk.now_ms0 = d->now_ms0 + (long long)f0 * d->tick_ms;
         pk.rtp12 = drtp + onb * 12; pk.payload = nullptr; pk.ctl = dctl ? dctl + onb : nullptr; pk.state = dtx;
         IGD_CUDA(c, igd_k_ed137_plan(kside, pk, static_cast<igd_tx_plan_rec *>(dplan) + onb, static_cast<int32_t *>(dlast)));

@@ -5,21 +5,13 @@
 #include <stdint.h>
 
 #include "../../include/igate_dsp.h"
+#include "igd_math.cuh"      // igd_tx_plan_rec
 
 struct igd_launch_cfg {
     int sm_count;
     cudaStream_t stream;
 };
 
-// Plan of one outgoing packet, produced by the per-channel sender walk and
-// consumed by the packet assembly kernel.
-struct igd_tx_plan_rec {
-    uint32_t word;        // host-order ED-137 word
-    uint16_t size;        // 0 = suppressed
-    uint8_t flags;        // bit0 pt123, bit1 marker, bit2 copy_payload
-    uint8_t reserved;
-    int32_t src_frame;    // frame whose payload the packet carries (-1: none yet)
-};
 
 cudaError_t igd_k_g711_decode(const igd_launch_cfg &c, const uint8_t *codes, const uint8_t *law_ch,
                               int law, int16_t *pcm, size_t n, size_t nch);
@@ -47,6 +39,11 @@ cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc 
                              igd_tx_plan_rec *plan, int32_t *last_src);
 cudaError_t igd_k_ed137_keepalive(const igd_launch_cfg &c, uint8_t *hdr20, igd_ed137_state *state, size_t C,
                                   long long now, uint32_t *sizes);
+// the walks with the tick axis across the lanes of a warp (igd_walks.cuh / igd_walks.cu)
+#define IGD_WALK_MIN_TICKS 8       // below this many ticks per call the thread-per-channel kernels run
+struct igd_rxarb_args;
+cudaError_t igd_k_rxarb_walk(const igd_launch_cfg &c, const igd_rxarb_args &a);
+cudaError_t igd_k_plan_walk(const igd_launch_cfg &c, const igd_ed137_pack_desc &d, igd_tx_plan_rec *plan, int32_t *last_src);
 // pkts != NULL: the walk reads the header words straight out of the packets [F][C][180] (d.fields unused)
 cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d, const uint8_t *pkts = nullptr);
 cudaError_t igd_k_gate_arbitrate(const igd_launch_cfg &c, const igd_arb_desc &d);

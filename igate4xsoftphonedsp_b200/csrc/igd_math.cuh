@@ -207,6 +207,16 @@ IGD_HD igd_tx_plan igd_ed137_tx_step(S &a, uint32_t payload_len, long long now)
     return r;
 }
 
+// Plan of one outgoing packet, produced by the per-channel sender walk and
+// consumed by the packet assembly kernel.
+struct igd_tx_plan_rec {
+    uint32_t word;        // host-order ED-137 word
+    uint16_t size;        // 0 = suppressed
+    uint8_t flags;        // bit0 pt123, bit1 marker, bit2 copy_payload
+    uint8_t reserved;
+    int32_t src_frame;    // frame whose payload the packet carries (-1: none yet)
+};
+
 // Timer-driven keep-alive: sendR2SStatus (TransportAdapter.cpp:422-633), the twin of the step above.
 // It differs where the reference differs: no payload, the slave-enable "changed" values are NOT latched
 // (:513-516 vs :744-745), an extra Idle&&callIn branch (:585-589), and a packet only leaves when the PT

@@ -985,8 +985,7 @@ int igd_k_launches_ed137_pack() { return 3; }
 cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc &d,
                              igd_tx_plan_rec *plan, int32_t *last_src)
 {
-    k_ed137_plan<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d, plan, last_src);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = igd_k_ed137_plan(c, d, plan, last_src);
     if (e != cudaSuccess) return e;
     const bool al16 = ((reinterpret_cast<uintptr_t>(d.payload) | reinterpret_cast<uintptr_t>(d.stale_payload)) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(d.pkts) & 3) == 0;
@@ -1005,6 +1004,8 @@ cudaError_t igd_k_ed137_pack(const igd_launch_cfg &c, const igd_ed137_pack_desc 
 // the sender walk alone (gateway form: the fused kernel assembles the packets)
 cudaError_t igd_k_ed137_plan(const igd_launch_cfg &c, const igd_ed137_pack_desc &d, igd_tx_plan_rec *plan, int32_t *last_src)
 {
+    // a call of several ticks: one warp per sender, tick axis across the lanes (k_plan_walk, igd_walks.cu)
+    if (!(d.flags & IGD_F_WALK_SERIAL) && d.F >= IGD_WALK_MIN_TICKS) return igd_k_plan_walk(c, d, plan, last_src);
     k_ed137_plan<<<(d.C + 127) / 128, 128, 0, c.stream>>>(d, plan, last_src);
     return cudaGetLastError();
 }

@@ -61,6 +61,11 @@ enum {
 #define IGD_F_KERNEL_W 0x8u       /* diagnostics (A/B runs, tests): the previous generation of the fused kernel -- k_fused_w
                                      instead of k_fused_q (G <= 4, codes and packet forms), k_fused_g instead of
                                      k_fused_h (G = 8).  Same results, bit for bit. */
+#define IGD_F_WALK_SERIAL 0x10u    /* diagnostics (A/B runs, tests; igd_gateway_process, igd_ed137_pack): walk the per-call
+                                     state machines with one thread per channel / bridge / sender (k_rx_track,
+                                     k_gate_arbitrate, k_ed137_plan) instead of one warp per bridge / sender with the
+                                     tick axis across its lanes (k_rxarb_walk, k_plan_walk; calls of >= 8 ticks).
+                                     Same results, bit for bit. */
 #define IGD_F_GENERIC_KERNEL 0x4u /* diagnostic (igd_process_batch): run the block-cooperative kernel that
                                     serves batches beyond 32-bit indices instead of the warp-autonomous
                                     ones; same results, slower                                       */
