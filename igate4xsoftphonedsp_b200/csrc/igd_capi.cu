@@ -929,7 +929,10 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     // The walks: from IGD_WALK_MIN_TICKS ticks per call up, one warp per bridge / sender with the tick axis across its
     // lanes (igd_walks.cuh: k_rxarb_walk = liveness walk + arbitration straight from the packets, k_plan_walk); below
     // that -- the real-time shape, one tick per call -- and under IGD_F_WALK_SERIAL the thread-per-channel kernels.
-    const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS;
+#ifndef IGD_GW_LANE_MAX_CH
+#define IGD_GW_LANE_MAX_CH 32768       // measured: 65 536 channels x 100 ticks 0.69 ms with the lane walk, 0.66 with the thread-per-channel walks
+#endif
+    const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS && Cn < (size_t)IGD_GW_LANE_MAX_CH;
     igd_rx_event *dev = nullptr; uint16_t *dgain;
     if (mem == IGD_MEM_DEVICE && d->rx_events) dev = d->rx_events;
     else if (!lanes || d->rx_events) {      // the lane walk hands the words to the arbitration in registers: no event array unless wanted
@@ -980,6 +983,12 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     // (from 32 768 channels up the walks are no longer idle time -- the liveness walk is a 6 TB/s header read -- and
     // chunking only adds launches: 0.67 ms unchunked, 0.68 / 0.77 / 0.78 ms with 2 / 4 / 6 chunks at 65 536 channels)
     int nchunk = Cn >= 32768 ? 1 : d->F / IGD_GW_MIN_TICKS;
+    // the lane walks: a single launch of the receive-side walk, then the fused kernel (the persistent fused CTA leaves
+    // no registers on its SM for a walk block, so chunks of the two do not overlap -- they only add launches)
+#ifndef IGD_GW_LANE_CHUNKS
+#define IGD_GW_LANE_CHUNKS 1
+#endif
+    if (lanes && nchunk > IGD_GW_LANE_CHUNKS) nchunk = IGD_GW_LANE_CHUNKS;
     // host form: the chunks are what the copies overlap with -- the call is bound by the packets coming in over PCIe,
     // so the chunk count follows the bytes (about 64 MiB of packets each), whatever the channel count
     if (host) nchunk = (int)((n * IGD_PKT_MAX + (48u << 20)) >> 26);

@@ -429,17 +429,23 @@ IGD_HD void igd_arb_server_best_tick(BR &b, L *legs, GI G, W word, A active)
     for (int i = 0; i < G; i++)
                 if (legs[i].last > 0) legs[i].gain_q7 = 0;
             b.sqlStatusOn = 1;
+            // the first radio nobody beats (:6060-6121); found first, applied after, so that every leg index below is
+            // a compile-time constant once the loops unroll (a `break` out of the search made the compiler keep the
+            // leg array in local memory behind a run-time index)
+            int best_i = -1;
             IGD_UNROLL
-    for (int i = 0; i < G; i++) {
+            for (int i = 0; i < G; i++) {
                 bool best = legs[i].last != 0;
                 IGD_UNROLL
                 for (int j = 0; j < G; j++)
                     if (best && j != i && legs[i].rssi < legs[j].rssi) best = false;
-                if (best) {
-                    IGD_UNROLL
-                    for (int j = 0; j < G; j++) legs[j].on = (uint8_t)(j == i);
-                    if (active(i)) legs[i].gain_q7 = 256;
-                    break;
+                if (best && best_i < 0) best_i = i;
+            }
+            if (best_i >= 0) {
+                IGD_UNROLL
+                for (int j = 0; j < G; j++) {
+                    legs[j].on = (uint8_t)(j == best_i);
+                    if (j == best_i && active(j)) legs[j].gain_q7 = 256;
                 }
             }
         }

@@ -8,7 +8,10 @@
 
 namespace {
 
-constexpr int kWalkWarps = 4;        // warps (= bridges / senders) per block
+#ifndef IGD_WALK_WARPS
+#define IGD_WALK_WARPS 4
+#endif
+constexpr int kWalkWarps = IGD_WALK_WARPS;        // warps (= bridges / senders) per block
 
 __global__ void __launch_bounds__(kWalkWarps * 32) k_rxarb_walk(const igd_rxarb_args a)
 {

@@ -64,22 +64,71 @@ struct igd_rxarb_args {
 };
 
 struct igd_w_raw { uint32_t w0, w3, w4, size; };
+// igd_arb_leg with its fields in full registers (the byte-wide fields of the API struct cost a PRMT per update).
+// msec keeps its 8 bits: `++lastTxmsec < 6` must wrap where the reference's uint8_t wraps; the tick functions narrow
+// what they store into the other fields themselves.
+struct igd_w_leg { uint32_t last; uint8_t msec; uint32_t on; int32_t rssi; uint32_t gain_q7, reserved; };
 
-// the header words of (tick t, channel ch), as k_rx_track<3> reads them
-IGD_HD igd_w_raw igd_w_fetch_hdr(const igd_rxarb_args &a, int t, size_t ch, size_t Cn)
+// the header words of the four legs of one bridge on tick t.  Every load is unconditional and independent of the
+// others (a slot of the [F][C][180] buffer always exists, whatever the received size says): thirteen loads in flight
+// per lane.  What transport_rtp_cb may not look at -- words beyond the received size -- is masked when the tick is
+// walked (igd_w_hdr_mask), as k_rx_track<packets> does by not loading it.
+IGD_HD void igd_w_fetch_hdr4(const igd_rxarb_args &a, int t, size_t ch0, size_t Cn, igd_w_raw (&r)[4])
 {
-    igd_w_raw r;
-    r.w0 = r.w3 = r.w4 = 0u; r.size = 0u;
+    IGD_UNROLL
+    for (int g = 0; g < 4; g++) { r[g].w0 = r[g].w3 = r[g].w4 = 0u; r[g].size = 0u; }
     if (t < a.F) {
-        const size_t i = (size_t)t * Cn + ch;
-        r.size = a.sizes ? IGD_W_LDG(a.sizes + i) : (uint32_t)IGD_PKT_MAX;
-        const uint32_t navail = (r.size < (uint32_t)IGD_PKT_MAX ? r.size : (uint32_t)IGD_PKT_MAX) / 4;
+        const size_t i = (size_t)t * Cn + ch0;
         const uint32_t *pw = reinterpret_cast<const uint32_t *>(a.pkts + i * IGD_PKT_MAX);
-        if (navail > 0) r.w0 = IGD_W_LDG(pw);
-        if (navail > 3) r.w3 = IGD_W_LDG(pw + 3);
-        if (navail > 4) r.w4 = IGD_W_LDG(pw + 4);
+        IGD_UNROLL
+        for (int g = 0; g < 4; g++) {
+            r[g].w0 = IGD_W_LDG(pw + g * (IGD_PKT_MAX / 4));
+            r[g].w3 = IGD_W_LDG(pw + g * (IGD_PKT_MAX / 4) + 3);
+            r[g].w4 = IGD_W_LDG(pw + g * (IGD_PKT_MAX / 4) + 4);
+            r[g].size = (uint32_t)IGD_PKT_MAX;
+        }
+        if (a.sizes) {
+            IGD_UNROLL
+            for (int g = 0; g < 4; g++) r[g].size = IGD_W_LDG(a.sizes + i + g);
+        }
     }
+}
+IGD_HD igd_w_raw igd_w_hdr_mask(igd_w_raw r)
+{
+    const uint32_t navail = (r.size < (uint32_t)IGD_PKT_MAX ? r.size : (uint32_t)IGD_PKT_MAX) / 4;
+    r.w0 = navail > 0 ? r.w0 : 0u; r.w3 = navail > 3 ? r.w3 : 0u; r.w4 = navail > 4 ? r.w4 : 0u;
     return r;
+}
+
+// igd_arb_client_tick (igd_math.cuh; roip_ed137.cpp:6124-6231) for the four register-resident legs of the walk, written
+// as selects: the branchy form is a chain of short data-dependent branches per leg, and a full pass is the one
+// strictly sequential piece of this kernel (ncu: half of its stall samples were branch resolution and the fixed
+// latency behind it).  Same order of updates, leg after leg; held to the oracle by tests/test_walks_host.py.
+IGD_HD void igd_w_client_tick4(igd_arb_bridge &b, igd_w_leg (&legs)[4], const uint32_t (&w)[4], const uint32_t act_mask)
+{
+    int level = b.ptt_level;
+    IGD_UNROLL
+    for (int i = 0; i < 4; i++) {
+        const bool act = ((act_mask >> i) & 1u) != 0u;
+        int ptt = (int)(w[i] >> 29);
+        const bool ne = (uint32_t)ptt != legs[i].last, rel = ne && ptt == 0;          // :6136-6153
+        const uint8_t m1 = (uint8_t)(legs[i].msec + 1);
+        const uint8_t msec = rel ? m1 : ne ? legs[i].msec : (uint8_t)0;
+        ptt = rel && m1 < 6 ? 1 : ptt;                                                 // released: held for five more ticks
+        const bool win = act && ptt != 0 && ptt > level;                               // :6155-6175
+        level = win ? ptt : level;
+        IGD_UNROLL
+        for (int j = 0; j < 4; j++)
+            if (j != i) legs[j].gain_q7 = win && legs[j].on != 0u ? 0u : legs[j].gain_q7;
+        const bool on_i = legs[i].on != 0u;
+        const bool press = act && ptt > 0 && !on_i, release = act && ptt == 0 && on_i; // :6177-6231
+        legs[i].gain_q7 = release ? 0u : win ? 256u : legs[i].gain_q7;
+        legs[i].on = press ? 1u : release ? 0u : legs[i].on;
+        level = release ? 0 : level;
+        legs[i].msec = act ? msec : legs[i].msec;
+        legs[i].last = act ? (uint32_t)ptt : legs[i].last;
+    }
+    b.ptt_level = level;
 }
 
 // `b` = bridge of this warp (warp-uniform); every lane of the warp calls this together
@@ -91,15 +140,15 @@ IGD_HD void igd_rxarb_walk(const igd_rxarb_args &a, const int b)
     // ---- state, warp-uniform in registers
     long long r2sPacket[G];
     uint32_t value[G], paysz[G], rtpAudio[G], r2sCount[G];
-    igd_arb_leg legs[G];
+    igd_w_leg legs[G];
     IGD_UNROLL
     for (int g = 0; g < G; g++) {
         const igd_rx_state s = a.rx_state[ch0 + g];
         r2sPacket[g] = s.r2sPacket; value[g] = s.ed137_value; paysz[g] = s.payloadsize; rtpAudio[g] = s.rtpAudio; r2sCount[g] = s.r2sCount;
         const uint32_t *lp = reinterpret_cast<const uint32_t *>(a.legs + ch0 + g);     // field by field: the array stays in registers
         const uint32_t l0 = lp[0], l1 = lp[1];
-        legs[g].last = (uint8_t)l0; legs[g].msec = (uint8_t)(l0 >> 8); legs[g].on = (uint8_t)(l0 >> 16); legs[g].rssi = (int8_t)(l0 >> 24);
-        legs[g].gain_q7 = (uint16_t)l1; legs[g].reserved = (uint16_t)(l1 >> 16);
+        legs[g].last = l0 & 0xFFu; legs[g].msec = (uint8_t)(l0 >> 8); legs[g].on = (l0 >> 16) & 0xFFu; legs[g].rssi = (int32_t)(int8_t)(l0 >> 24);
+        legs[g].gain_q7 = l1 & 0xFFFFu; legs[g].reserved = l1 >> 16;
     }
     igd_arb_bridge br = a.bridges[b];
     uint32_t act_mask = 0xFu;
@@ -109,13 +158,14 @@ IGD_HD void igd_rxarb_walk(const igd_rxarb_args &a, const int b)
         for (int g = 0; g < G; g++) act_mask |= (a.active[ch0 + g] != 0 ? 1u : 0u) << g;
     }
     uint32_t prevw[G] = {0u, 0u, 0u, 0u};      // words of the tick before the current step's first
-    bool have_prev = false, steady = false, counting = false;
+    bool have_prev = false, steady = false, counting = false, hold = false;
+    uint32_t hold_legs = 0u;
+    int hold_k = 0;
     const int wd_p0 = a.wd_ticks > 0 ? (int)(a.frame0 % a.wd_ticks) : 0;
     const long long late_after = (long long)a.r2s_period_ms * 3;
 
     igd_w_raw nraw[G];
-    IGD_UNROLL
-    for (int g = 0; g < G; g++) nraw[g] = igd_w_fetch_hdr(a, lane, ch0 + g, Cn);
+    igd_w_fetch_hdr4(a, lane, ch0, Cn, nraw);
     for (int t0 = 0; t0 < a.F; t0 += 32) {
         const int nt = a.F - t0 < 32 ? a.F - t0 : 32;
         const int t = t0 + lane;
@@ -123,9 +173,8 @@ IGD_HD void igd_rxarb_walk(const igd_rxarb_args &a, const int b)
         const long long now = a.now_ms0 + (long long)t * a.tick_ms;
         igd_w_raw raw[G];
         IGD_UNROLL
-        for (int g = 0; g < G; g++) raw[g] = nraw[g];
-        IGD_UNROLL
-        for (int g = 0; g < G; g++) nraw[g] = igd_w_fetch_hdr(a, t + 32, ch0 + g, Cn);   // the next step's headers are in flight
+        for (int g = 0; g < G; g++) raw[g] = igd_w_hdr_mask(nraw[g]);
+        igd_w_fetch_hdr4(a, t + 32, ch0, Cn, nraw);                  // the next step's headers are in flight
         bool wd = false;
         if (a.wd_ticks > 0) {
             const int q = t + wd_p0 + 1;
@@ -204,45 +253,60 @@ IGD_HD void igd_rxarb_walk(const igd_rxarb_args &a, const int b)
         uint32_t g01 = 0u, g23 = 0u;        // this lane's tick: the four gains
         int tl = 0;
         while (tl < nt) {
-            if (steady) {
+            if (steady || hold) {
                 const uint32_t m = chg & ~igd_w_lt(tl);
-                const int nxt = m ? igd_w_ffs(m) - 1 : nt;
+                int nxt = m ? igd_w_ffs(m) - 1 : nt;
+                // CLIENT hold-off (roip_ed137.cpp:6140-6147): the last pass only counted lastTxmsec up on released legs.
+                // msec enters a pass through `++msec < 6` alone, so the passes repeat while that stays true: hold_k more
+                if (hold && nxt - tl > hold_k) nxt = tl + hold_k;
                 if (lane >= tl && lane < nxt) {
-                    g01 = (uint32_t)legs[0].gain_q7 | ((uint32_t)legs[1].gain_q7 << 16);
-                    g23 = (uint32_t)legs[2].gain_q7 | ((uint32_t)legs[3].gain_q7 << 16);
+                    g01 = legs[0].gain_q7 | (legs[1].gain_q7 << 16);
+                    g23 = legs[2].gain_q7 | (legs[3].gain_q7 << 16);
                 }
                 if (counting) br.sqlStatusCount += nxt - tl;
+                if (hold) {
+                    IGD_UNROLL
+                    for (int g = 0; g < G; g++) legs[g].msec = (uint8_t)(legs[g].msec + (((hold_legs >> g) & 1u) ? nxt - tl : 0));
+                    hold = false;           // the next tick takes the full pass (it releases, or re-arms the hold)
+                }
                 tl = nxt;
                 if (tl >= nt) break;
             }
             uint32_t w[G];
             IGD_UNROLL
             for (int g = 0; g < G; g++) w[g] = igd_w_shfl(W[g], tl);
-            uint64_t snap[G];
+            igd_w_leg was[G];
             IGD_UNROLL
-            for (int g = 0; g < G; g++)
-                snap[g] = (uint64_t)legs[g].last | ((uint64_t)legs[g].msec << 8) | ((uint64_t)legs[g].on << 16) |
-                          ((uint64_t)(uint8_t)legs[g].rssi << 24) | ((uint64_t)legs[g].gain_q7 << 32);
+            for (int g = 0; g < G; g++) was[g] = legs[g];
             const int32_t c0 = br.sqlStatusCount, l0 = br.ptt_level;
-            const uint8_t o0 = br.sqlStatusOn;
+            const uint32_t o0 = br.sqlStatusOn;
             auto word = [&](int g) { return w[g]; };
             auto active = [&](int g) { return ((act_mask >> g) & 1u) != 0u; };
             const igd_const_int<G> Gc;
-            if (a.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, Gc, word, active);
+            if (a.mode == IGD_ARB_CLIENT_PTT) igd_w_client_tick4(br, legs, w, act_mask);
             else igd_arb_server_best_tick(br, legs, Gc, word, active);
-            uint64_t fold = 0;
+            uint32_t moved = 0u, ticked = 0u, mrest = 0u;      // fields that moved; legs whose msec went up by one; other msec moves
+            int room = 5;
             IGD_UNROLL
-            for (int g = 0; g < G; g++)
-                fold |= snap[g] ^ ((uint64_t)legs[g].last | ((uint64_t)legs[g].msec << 8) | ((uint64_t)legs[g].on << 16) |
-                                   ((uint64_t)(uint8_t)legs[g].rssi << 24) | ((uint64_t)legs[g].gain_q7 << 32));
-            const bool legs_same = fold == 0 && br.ptt_level == l0 && br.sqlStatusOn == o0;
+            for (int g = 0; g < G; g++) {
+                moved |= (was[g].last ^ legs[g].last) | (was[g].on ^ legs[g].on) | (uint32_t)(was[g].rssi ^ legs[g].rssi) |
+                         (was[g].gain_q7 ^ legs[g].gain_q7);
+                const bool up1 = (uint32_t)legs[g].msec == (uint32_t)was[g].msec + 1u;
+                ticked |= up1 ? 1u << g : 0u;
+                mrest |= up1 ? 0u : (uint32_t)(was[g].msec ^ legs[g].msec);
+                if (up1) room = room < 5 - (int)legs[g].msec ? room : 5 - (int)legs[g].msec;
+            }
+            const bool rest_same = moved == 0u && br.ptt_level == l0 && br.sqlStatusOn == o0;
+            const bool legs_same = rest_same && ticked == 0u && mrest == 0u;
             // SERVER mode's second steady form: while a selection is in force a pass only counts sqlStatusCount up
             // (roip_ed137.cpp:6028) and nothing reads the count again (:6029 needs !sqlStatusOn)
             counting = legs_same && br.sqlStatusOn != 0 && br.sqlStatusCount == c0 + 1;
             steady = legs_same && (br.sqlStatusCount == c0 || counting);
+            hold = a.mode == IGD_ARB_CLIENT_PTT && rest_same && mrest == 0u && ticked != 0u && br.sqlStatusCount == c0 && room > 0;
+            hold_legs = ticked; hold_k = room;
             if (lane == tl) {
-                g01 = (uint32_t)legs[0].gain_q7 | ((uint32_t)legs[1].gain_q7 << 16);
-                g23 = (uint32_t)legs[2].gain_q7 | ((uint32_t)legs[3].gain_q7 << 16);
+                g01 = legs[0].gain_q7 | (legs[1].gain_q7 << 16);
+                g23 = legs[2].gain_q7 | (legs[3].gain_q7 << 16);
             }
             tl++;
         }
@@ -267,8 +331,8 @@ IGD_HD void igd_rxarb_walk(const igd_rxarb_args &a, const int b)
                 s.rtpAudio = (uint8_t)rtpAudio[g]; s.r2sCount = (uint8_t)r2sCount[g];
                 a.rx_state[ch0 + g] = s;
                 uint32_t *lp = reinterpret_cast<uint32_t *>(a.legs + ch0 + g);
-                lp[0] = (uint32_t)legs[g].last | ((uint32_t)legs[g].msec << 8) | ((uint32_t)legs[g].on << 16) | ((uint32_t)(uint8_t)legs[g].rssi << 24);
-                lp[1] = (uint32_t)legs[g].gain_q7 | ((uint32_t)legs[g].reserved << 16);
+                lp[0] = (legs[g].last & 0xFFu) | ((uint32_t)legs[g].msec << 8) | ((legs[g].on & 0xFFu) << 16) | ((uint32_t)legs[g].rssi << 24);
+                lp[1] = (legs[g].gain_q7 & 0xFFFFu) | (legs[g].reserved << 16);
             }
         }
     }

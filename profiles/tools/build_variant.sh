@@ -7,7 +7,7 @@ HERE=$(cd "$(dirname "$0")" && pwd); ROOT=$(cd "$HERE/../.." && pwd)
 NAME=$1; shift
 OUT=$HERE/variants; mkdir -p $OUT/obj_$NAME
 SRC=$ROOT/igate4xsoftphonedsp_b200/csrc
-for u in igd_fused igd_codec igd_packet igd_capi; do
+for u in igd_fused igd_codec igd_packet igd_walks igd_capi; do
   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -cudart static "$@" -c -o $OUT/obj_$NAME/$u.o $SRC/$u.cu &
 done
 wait

@@ -167,3 +167,37 @@ def test_rxarb_walk_watchdog_strikes_saturate_at_255():
     st = (np.zeros(B * G, N.RX_STATE_DT), np.zeros(B * G, N.ARB_LEG_DT), np.zeros(B, N.ARB_BRIDGE_DT))
     ev, _ = run_rxarb(pk, sizes, mode, st, 777, wd_ticks=1)
     assert ev.tobytes() == ev_w.tobytes() and st[0].tobytes() == st_w.tobytes()
+
+
+@pytest.mark.parametrize("mode,seed", [(N.ARB_CLIENT_PTT, 61), (N.ARB_SERVER_BEST, 62), (N.ARB_CLIENT_PTT, 63), (N.ARB_SERVER_BEST, 64)])
+def test_rxarb_walk_from_arbitrary_start_states(mode, seed):
+    """whatever the state arrays hold (counters mid-way, a uint8 lastTxmsec about to wrap, a level nobody holds): the
+    walk continues exactly as the reference's per-tick code would"""
+    F, B = 90, 16
+    Cn = B * G
+    rng = np.random.default_rng(seed)
+    pk, sizes = rx_case(F, B, seed, mode)
+    present = (sizes != 0).astype(np.uint8)
+    rx0 = np.zeros(Cn, N.RX_STATE_DT)
+    rx0["r2sPacket"] = 1_000_000 - rng.integers(0, 2000, Cn)
+    rx0["ed137_value"] = rng.integers(0, 1 << 32, Cn, dtype=np.uint64).astype(np.uint32)
+    rx0["payloadsize"] = rng.integers(0, 1 << 16, Cn)
+    rx0["rtpAudio"] = rng.integers(0, 2, Cn)
+    rx0["r2sCount"] = rng.choice([0, 1, 4, 5, 6, 200, 254, 255], Cn)
+    lg0 = np.zeros(Cn, N.ARB_LEG_DT)
+    lg0["last"] = rng.integers(0, 8 if mode == N.ARB_CLIENT_PTT else 2, Cn)
+    lg0["msec"] = rng.choice([0, 1, 2, 4, 5, 6, 7, 200, 254, 255], Cn)
+    lg0["on"] = rng.integers(0, 2, Cn)
+    lg0["rssi"] = rng.integers(-1, 32, Cn)
+    lg0["gain_q7"] = rng.choice([0, 256, 13], Cn)
+    br0 = np.zeros(B, N.ARB_BRIDGE_DT)
+    br0["ptt_level"] = rng.integers(0, 8, B)
+    br0["sqlStatusCount"] = rng.choice([0, 1, 3, 4, 5, 9, 2_000_000_000], B)
+    br0["sqlStatusOn"] = rng.integers(0, 2, B)
+    ev_w, st_w = R.oracle_rx_walk(pk, sizes, present, now0=1_000_000, wd_ticks=2, state=rx0)
+    g_w, lg_w, br_w = R.oracle_arb_walk(np.ascontiguousarray(ev_w["word"]), G, mode, legs=lg0, bridges=br0)
+    g_w = np.where((ev_w["flags"] & N.RXE_FRAME) == 0, g_w | N.GAIN_NO_AUDIO, g_w).astype(np.uint16)
+    st = (rx0.copy(), lg0.copy(), br0.copy())
+    ev, gain = run_rxarb(pk, sizes, mode, st, 1_000_000)
+    assert ev.tobytes() == ev_w.tobytes() and np.array_equal(gain, g_w)
+    assert st[0].tobytes() == st_w.tobytes() and st[1].tobytes() == lg_w.tobytes() and st[2].tobytes() == br_w.tobytes()
