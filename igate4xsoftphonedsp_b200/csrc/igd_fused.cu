@@ -610,7 +610,7 @@ __device__ __forceinline__ void leg_chunk8(uint32_t lane_base, uint2 w, uint32_t
 // kPkt / kTx as in k_fused_w: the codes are read straight out of the raw 180-byte packets (G = 4: an item is 8 * 720
 // contiguous bytes, still ONE bulk copy; 23 warps fit the shared memory), the bridge output leaves as finished packets.
 template <int G, bool kSigned, int kWarps, bool kOpt, bool kPkt = false, bool kTx = false>
-__global__ void __launch_bounds__(kWarps * 32, 1) k_fused_q(const FusedParams q)
+__global__ void __launch_bounds__((kWarps > 23 ? kWarps : 23) * 32, 1) k_fused_q(const FusedParams q)   // (fewer warps keep the 80-register budget)
 {
     constexpr int kLegBytes = kPkt ? IGD_PKT_MAX : IGD_FRAME, kLegOff = kPkt ? IGD_PKT_HDR : 0;
     constexpr int kBfBytes = G * kLegBytes, kSlotBytes = kQBf * kBfBytes;
@@ -1636,6 +1636,9 @@ cudaError_t igd_k_fused_packets(const igd_launch_cfg &c, const igd_packets_desc 
     return sc ? launch_fused_w<4, true, 24, true>(c, q) : launch_fused_w<4, false, 24, true>(c, q);
 }
 
+#ifndef IGD_GW_FUSED_WARPS
+#define IGD_GW_FUSED_WARPS 23
+#endif
 // gateway form: packets in (gains carry IGD_GAIN_NO_AUDIO, no field records needed) -> packets out
 cudaError_t igd_k_fused_gateway(const igd_launch_cfg &c, const igd_packets_desc &d, const igd_tx_plan_rec *plan,
                                 const uint8_t *tx_rtp12, uint8_t *tx_pkts, uint32_t *tx_sizes)
@@ -1653,6 +1656,6 @@ cudaError_t igd_k_fused_gateway(const igd_launch_cfg &c, const igd_packets_desc 
         return cudaErrorInvalidValue;
     const bool sc = (d.flags & IGD_F_SIGNED_CHAR) != 0;
     if (!(d.flags & IGD_F_KERNEL_W) && (reinterpret_cast<uintptr_t>(d.mix) & 15u) == 0 && (reinterpret_cast<uintptr_t>(d.enc) & 7u) == 0)
-        return sc ? launch_fused_q<4, true, 23, true, true>(c, q) : launch_fused_q<4, false, 23, true, true>(c, q);
+        return sc ? launch_fused_q<4, true, IGD_GW_FUSED_WARPS, true, true>(c, q) : launch_fused_q<4, false, IGD_GW_FUSED_WARPS, true, true>(c, q);
     return sc ? launch_fused_w<4, true, 24, true, true>(c, q) : launch_fused_w<4, false, 24, true, true>(c, q);
 }

@@ -104,31 +104,48 @@ IGD_HD igd_w_raw igd_w_hdr_mask(igd_w_raw r)
 // as selects: the branchy form is a chain of short data-dependent branches per leg, and a full pass is the one
 // strictly sequential piece of this kernel (ncu: half of its stall samples were branch resolution and the fixed
 // latency behind it).  Same order of updates, leg after leg; held to the oracle by tests/test_walks_host.py.
-IGD_HD void igd_w_client_tick4(igd_arb_bridge &b, igd_w_leg (&legs)[4], const uint32_t (&w)[4], const uint32_t act_mask)
+// Also says what the pass did to the state: `moved` != 0 when anything but a hold-off count changed, `ticked` = the
+// legs whose lastTxmsec went up by one (:6141), `room` = how many more passes may do just that before the first
+// of them releases (msec enters a pass through `++msec < 6` alone).
+IGD_HD void igd_w_client_tick4(igd_arb_bridge &b, igd_w_leg (&legs)[4], const uint32_t (&w)[4], const uint32_t act_mask,
+                               uint32_t &moved, uint32_t &ticked, int &room)
 {
-    int level = b.ptt_level;
+    const int level0 = b.ptt_level;
+    int level = level0;
+    const uint32_t g0 = legs[0].gain_q7, g1 = legs[1].gain_q7, g2 = legs[2].gain_q7, g3 = legs[3].gain_q7;
+    bool mv = false;
+    ticked = 0u; room = 5;
+    // (`&` / `|` on the predicates, not `&&` / `||`: the short-circuit forms come out as branches)
     IGD_UNROLL
     for (int i = 0; i < 4; i++) {
         const bool act = ((act_mask >> i) & 1u) != 0u;
-        int ptt = (int)(w[i] >> 29);
-        const bool ne = (uint32_t)ptt != legs[i].last, rel = ne && ptt == 0;          // :6136-6153
-        const uint8_t m1 = (uint8_t)(legs[i].msec + 1);
-        const uint8_t msec = rel ? m1 : ne ? legs[i].msec : (uint8_t)0;
-        ptt = rel && m1 < 6 ? 1 : ptt;                                                 // released: held for five more ticks
-        const bool win = act && ptt != 0 && ptt > level;                               // :6155-6175
+        const int ptt_w = (int)(w[i] >> 29);
+        const uint32_t last0 = legs[i].last;
+        const uint8_t msec0 = legs[i].msec, m1 = (uint8_t)(msec0 + 1);
+        const bool ne = (uint32_t)ptt_w != last0, rel = ne & (ptt_w == 0);            // :6136-6153
+        const uint8_t msec = rel ? m1 : ne ? msec0 : (uint8_t)0;
+        const int ptt = rel & (m1 < 6) ? 1 : ptt_w;                                    // released: held for five more ticks
+        const bool win = act & (ptt != 0) & (ptt > level);                             // :6155-6175
         level = win ? ptt : level;
         IGD_UNROLL
         for (int j = 0; j < 4; j++)
-            if (j != i) legs[j].gain_q7 = win && legs[j].on != 0u ? 0u : legs[j].gain_q7;
+            if (j != i) legs[j].gain_q7 = win & (legs[j].on != 0u) ? 0u : legs[j].gain_q7;
         const bool on_i = legs[i].on != 0u;
-        const bool press = act && ptt > 0 && !on_i, release = act && ptt == 0 && on_i; // :6177-6231
+        const bool press = act & (ptt > 0) & !on_i, release = act & (ptt == 0) & on_i; // :6177-6231
         legs[i].gain_q7 = release ? 0u : win ? 256u : legs[i].gain_q7;
         legs[i].on = press ? 1u : release ? 0u : legs[i].on;
         level = release ? 0 : level;
-        legs[i].msec = act ? msec : legs[i].msec;
-        legs[i].last = act ? (uint32_t)ptt : legs[i].last;
+        mv = mv | press | release | (act & (((uint32_t)ptt != last0) | (!ne & (msec0 != 0))));
+        const bool tick1 = act & rel;
+        const int r = 5 - (int)m1;
+        ticked |= tick1 ? 1u << i : 0u;
+        room = tick1 & (r < room) ? r : room;
+        legs[i].msec = act ? msec : msec0;
+        legs[i].last = act ? (uint32_t)ptt : last0;
     }
     b.ptt_level = level;
+    moved = (mv | (level != level0) ? 1u : 0u) | (g0 ^ legs[0].gain_q7) | (g1 ^ legs[1].gain_q7) | (g2 ^ legs[2].gain_q7) |
+            (g3 ^ legs[3].gain_q7);
 }
 
 // `b` = bridge of this warp (warp-uniform); every lane of the warp calls this together
@@ -275,35 +292,36 @@ IGD_HD void igd_rxarb_walk(const igd_rxarb_args &a, const int b)
             uint32_t w[G];
             IGD_UNROLL
             for (int g = 0; g < G; g++) w[g] = igd_w_shfl(W[g], tl);
-            igd_w_leg was[G];
-            IGD_UNROLL
-            for (int g = 0; g < G; g++) was[g] = legs[g];
-            const int32_t c0 = br.sqlStatusCount, l0 = br.ptt_level;
-            const uint32_t o0 = br.sqlStatusOn;
-            auto word = [&](int g) { return w[g]; };
-            auto active = [&](int g) { return ((act_mask >> g) & 1u) != 0u; };
-            const igd_const_int<G> Gc;
-            if (a.mode == IGD_ARB_CLIENT_PTT) igd_w_client_tick4(br, legs, w, act_mask);
-            else igd_arb_server_best_tick(br, legs, Gc, word, active);
-            uint32_t moved = 0u, ticked = 0u, mrest = 0u;      // fields that moved; legs whose msec went up by one; other msec moves
-            int room = 5;
-            IGD_UNROLL
-            for (int g = 0; g < G; g++) {
-                moved |= (was[g].last ^ legs[g].last) | (was[g].on ^ legs[g].on) | (uint32_t)(was[g].rssi ^ legs[g].rssi) |
-                         (was[g].gain_q7 ^ legs[g].gain_q7);
-                const bool up1 = (uint32_t)legs[g].msec == (uint32_t)was[g].msec + 1u;
-                ticked |= up1 ? 1u << g : 0u;
-                mrest |= up1 ? 0u : (uint32_t)(was[g].msec ^ legs[g].msec);
-                if (up1) room = room < 5 - (int)legs[g].msec ? room : 5 - (int)legs[g].msec;
+            if (a.mode == IGD_ARB_CLIENT_PTT) {
+                uint32_t moved, ticked;
+                int room;
+                igd_w_client_tick4(br, legs, w, act_mask, moved, ticked, room);
+                steady = moved == 0u && ticked == 0u;
+                hold = moved == 0u && ticked != 0u && room > 0;
+                hold_legs = ticked; hold_k = room;
+                counting = false;
+            } else {
+                igd_w_leg was[G];
+                IGD_UNROLL
+                for (int g = 0; g < G; g++) was[g] = legs[g];
+                const int32_t c0 = br.sqlStatusCount, l0 = br.ptt_level;
+                const uint32_t o0 = br.sqlStatusOn;
+                auto word = [&](int g) { return w[g]; };
+                auto active = [&](int g) { return ((act_mask >> g) & 1u) != 0u; };
+                const igd_const_int<G> Gc;
+                igd_arb_server_best_tick(br, legs, Gc, word, active);
+                uint32_t moved = 0u;
+                IGD_UNROLL
+                for (int g = 0; g < G; g++)
+                    moved |= (was[g].last ^ legs[g].last) | (was[g].on ^ legs[g].on) | (uint32_t)(was[g].rssi ^ legs[g].rssi) |
+                             (was[g].gain_q7 ^ legs[g].gain_q7) | (uint32_t)(was[g].msec ^ legs[g].msec);
+                const bool legs_same = moved == 0u && br.ptt_level == l0 && br.sqlStatusOn == o0;
+                // SERVER mode's second steady form: while a selection is in force a pass only counts sqlStatusCount up
+                // (roip_ed137.cpp:6028) and nothing reads the count again (:6029 needs !sqlStatusOn)
+                counting = legs_same && br.sqlStatusOn != 0 && br.sqlStatusCount == c0 + 1;
+                steady = legs_same && (br.sqlStatusCount == c0 || counting);
+                hold = false;
             }
-            const bool rest_same = moved == 0u && br.ptt_level == l0 && br.sqlStatusOn == o0;
-            const bool legs_same = rest_same && ticked == 0u && mrest == 0u;
-            // SERVER mode's second steady form: while a selection is in force a pass only counts sqlStatusCount up
-            // (roip_ed137.cpp:6028) and nothing reads the count again (:6029 needs !sqlStatusOn)
-            counting = legs_same && br.sqlStatusOn != 0 && br.sqlStatusCount == c0 + 1;
-            steady = legs_same && (br.sqlStatusCount == c0 || counting);
-            hold = a.mode == IGD_ARB_CLIENT_PTT && rest_same && mrest == 0u && ticked != 0u && br.sqlStatusCount == c0 && room > 0;
-            hold_legs = ticked; hold_k = room;
             if (lane == tl) {
                 g01 = legs[0].gain_q7 | (legs[1].gain_q7 << 16);
                 g23 = legs[2].gain_q7 | (legs[3].gain_q7 << 16);
