@@ -216,7 +216,11 @@ def run_reference(args):
 
 
 def run_chain(args):
-    """--chain: SURVEY 8(d) "with RTP" accounting -- raw 180-byte ED-137 packets of every leg in, finished ED-137
+    print(json.dumps(measure_chain(args)))
+
+
+def measure_chain(args, vp=None):
+    """--chain (and the "chain" object of the default line): SURVEY 8(d) "with RTP" accounting -- raw 180-byte ED-137 packets of every leg in, finished ED-137
     packets of every bridge out, through igd_gateway_process (four launches: header view + liveness walk, gate
     arbitration, sender walk, fused decode -> meter -> mix -> encode -> packet kernel), device resident.
     1284 algorithmic bytes per bridge-frame (4 x 180 in, 180 + 320 + 4 x 16 out)."""
@@ -228,7 +232,9 @@ def run_chain(args):
     args.warmup = max(args.warmup, 3)
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
-    vp = ig.VoicePath(dev.index)
+    own_vp = vp is None
+    if own_vp:
+        vp = ig.VoicePath(dev.index)
     vp.use_torch_stream()
     Bc = args.chain_bridges
     Fc = args.chain_frames
@@ -388,7 +394,9 @@ def run_chain(args):
     alg = 1284 * Bc * Fc
     peak, peak_src = peaks()
     value = Cc * Fc * FRAME / (ms * 1e-3)
-    print(json.dumps({
+    if own_vp:
+        vp.close()
+    return ({
         "metric": METRIC + " (packets in -> packets out)", "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int16", "data": "synthetic",
@@ -402,8 +410,7 @@ def run_chain(args):
                      "algorithmic_bytes_per_step": alg, "bytes_per_bridge_frame": 1284, "stage_ms": stage},
         "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "parity_vs_oracle_on_two_bridges": parity,
-    }))
-    vp.close()
+    })
 
 
 def main():
@@ -425,6 +432,7 @@ def main():
                          "summaries gathered to rank 0 over NCCL and checked against the oracle; device-resident legs only")
     ap.add_argument("--chain", action="store_true", help="packets in -> packets out (SURVEY 8d 'with RTP' accounting, 1284 B per "
                     "bridge-frame) through igd_gateway_process, device resident, 1 GPU")
+    ap.add_argument("--no-chain", action="store_true", help="skip the packets-in -> packets-out measurement of the default line")
     ap.add_argument("--serial-walks", action="store_true", help="--chain: IGD_F_WALK_SERIAL, the thread-per-channel walks (A/B)")
     ap.add_argument("--chain-bridges", type=int, default=B)
     ap.add_argument("--chain-frames", type=int, default=F)
@@ -641,6 +649,23 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
                "outputs_equal_gpu": equal, "single_thread": {"value": v1, "sample": desc1}}
 
+    # ---- the same hot path with its callers on either side (SURVEY 8d "with RTP"): packets in -> packets out through
+    # igd_gateway_process at the bench shape, device resident -- a compact copy of what `--chain` prints in full
+    chain = None
+    if rank == 0 and world == 1 and not (args.cfg4 or args.cfg5 or args.no_chain) and args.frames == 1640:
+        import copy
+        a2 = copy.copy(args)
+        a2.no_e2e, a2.steps, a2.warmup, a2.serial_walks, a2.chain_bridges, a2.chain_frames = True, 10, 3, False, B, F
+        try:
+            full = measure_chain(a2, vp=vp)
+            chain = {"workload": full["config"]["workload"], "value": full["value"], "unit": full["unit"],
+                     "ms_per_step": full["ms_per_step"], "vs_fused_kernel_ms": full["ms_per_step"] / (total_ms / args.steps),
+                     "roofline": {k: full["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "bytes_per_bridge_frame", "kernel")},
+                     "gpu_launches_per_step": full["gpu_launches"] // a2.steps,
+                     "parity_vs_oracle_on_two_bridges": full["parity_vs_oracle_on_two_bridges"]}
+        except Exception as e:      # the headline line must not depend on the extra measurement
+            chain = {"error": f"{type(e).__name__}: {e}"}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -651,7 +676,7 @@ def main():
                        "summaries_gathered_to_rank0": n_summaries, "summaries_parity_vs_oracle": summaries_parity,
                        "parity_frames_checked": parity_frames},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "parity_vs_oracle_on_timed_output": parity,
+            "clocks": clocks, "parity_vs_oracle_on_timed_output": parity, "chain": chain,
         }))
     if world > 1:
         dist.barrier()
