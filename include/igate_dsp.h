@@ -477,8 +477,11 @@ int igd_gate_arbitrate(igd_ctx *ctx, const igd_arb_desc *d);
  * reads the codes straight out of the received packets and writes FINISHED 180-byte ED-137 packets
  * (header from the sender walk + the PJSIP RTP header, payload = this tick's encoded mix; the bytes of
  * a slot past tx_sizes are zero) -- the bytes igd_ed137_pack produces without IGD_F_REF_QUIRKS.
- * Four or five kernel launches (header view + liveness walk -- one kernel from 32 768 channels up, two below --
- * arbitration, sender walk on a side stream, fused kernel); no payload, code or plan array exists between
+ * Calls of >= 8 ticks below 32 768 channels: three kernels -- the receive-side walk (liveness + arbitration of one
+ * bridge per warp, the tick axis across its lanes, header words straight out of the packets), the sender walk (one
+ * warp per outgoing call, on a side stream) and the fused kernel.  Otherwise (one tick per call, or tens of
+ * thousands of channels, or IGD_F_WALK_SERIAL) the thread-per-channel walks: header view + liveness walk,
+ * arbitration, sender walk on a side stream, fused kernel.  No payload, code or plan array exists between
  * them, nothing but packets and state crosses the API.  (tx_state.rtpFalse, the
  * reference's never-read stuck-audio diagnostic counter, is not maintained here: the payload it
  * looks at is produced after the sender walk.)
@@ -489,7 +492,7 @@ typedef struct {
     uint32_t struct_size;        /* = sizeof(igd_gateway_desc)                    */
     int32_t mem;                 /* IGD_MEM_DEVICE or IGD_MEM_HOST (all pointers) */
     int32_t F, B, G;
-    uint32_t flags;              /* IGD_F_SIGNED_CHAR                             */
+    uint32_t flags;              /* IGD_F_SIGNED_CHAR, IGD_F_KERNEL_W, IGD_F_WALK_SERIAL */
     int32_t arb_mode;            /* IGD_ARB_*                                     */
     int32_t tick_ms;             /* 20                                            */
     int32_t r2s_period_ms;       /* 200                                           */
