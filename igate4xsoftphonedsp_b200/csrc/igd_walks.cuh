@@ -198,41 +198,79 @@ IGD_HD void igd_rxarb_walk(const igd_rxarb_args &a, const int b)
             wd = valid && q >= a.wd_ticks && q % a.wd_ticks == 0;
         }
         uint32_t W[G], noaud = 0u;
+        // ---- transport_rtp_cb's view of every header (TransportAdapter.cpp:248-292)
+        uint32_t pt[G], word[G], len_raw[G];
+        bool present[G], dropped[G], accepted[G], frame[G];
+        uint32_t kinds = 0u;                 // bit g: leg g's packet on this tick is forwarded audio (pt != 123)
+        bool plain = true;                   // all four legs: a packet, accepted, not dropped
         IGD_UNROLL
         for (int g = 0; g < G; g++) {
-            // ---- transport_rtp_cb's view of the header (TransportAdapter.cpp:248-292)
-            const uint32_t size = raw[g].size, pt = (raw[g].w0 >> 8) & 0x7Fu;
-            const bool present = valid && size != 0u;
+            const uint32_t size = raw[g].size;
+            pt[g] = (raw[g].w0 >> 8) & 0x7Fu;
+            present[g] = valid && size != 0u;
             const bool too_short = size < (uint32_t)IGD_PKT_HDR;
             const uint32_t plen_raw = size - (uint32_t)IGD_PKT_HDR;
-            const bool dropped = too_short || plen_raw >= 1024u;
-            const bool accepted = !too_short && (pt == 8u || pt == 0u || pt == 18u || pt == 123u);
-            const uint32_t word = accepted ? igd_w_bswap(raw[g].w4) : 0u;
-            const uint32_t len_raw = accepted ? raw[g].w3 >> 16 : 0u;
-            const uint32_t plen = dropped ? 0u : (plen_raw < (uint32_t)IGD_FRAME ? plen_raw : (uint32_t)IGD_FRAME);
+            dropped[g] = too_short || plen_raw >= 1024u;
+            accepted[g] = !too_short && (pt[g] == 8u || pt[g] == 0u || pt[g] == 18u || pt[g] == 123u);
+            word[g] = accepted[g] ? igd_w_bswap(raw[g].w4) : 0u;
+            len_raw[g] = accepted[g] ? raw[g].w3 >> 16 : 0u;
+            const uint32_t plen = dropped[g] ? 0u : (plen_raw < (uint32_t)IGD_FRAME ? plen_raw : (uint32_t)IGD_FRAME);
+            frame[g] = (pt[g] == 0u || pt[g] == 8u) && plen == 160u;
+            plain = plain & present[g] & accepted[g] & !dropped[g];
+            kinds |= (pt[g] != 123u ? 1u : 0u) << g;
+        }
+        // A step in which every tick of every leg brings an accepted, undropped packet of one kind per leg (a radio
+        // that keeps sending audio, or keeps sending keep-alives -- the usual 640 ms): the forward fills are the
+        // identity, an edge can only sit on the step's first tick, and no watchdog tick is late (now - r2sPacket = 0).
+        const uint32_t kinds0 = igd_w_shfl(kinds, 0);
+        const bool uniform = late_after >= 0 && igd_w_ballot(valid && !(plain && kinds == kinds0)) == 0u;
+        if (uniform) {
+            const uint32_t m_wd = igd_w_ballot(wd);
+            const bool wd_seen = (m_wd & igd_w_le(lane)) != 0u;
+            IGD_UNROLL
+            for (int g = 0; g < G; g++) {
+                const bool kind = ((kinds0 >> g) & 1u) != 0u;
+                const bool audio_before = lane > 0 ? kind : rtpAudio[g] != 0u;
+                const uint32_t ev = 0x01u | (kind ? 0x02u : 0u) | (kind && frame[g] ? 0x40u : 0u) | (kind != audio_before ? 0x04u : 0u);
+                const uint32_t after = wd_seen ? 0u : r2sCount[g];
+                W[g] = word[g];
+                if (!(ev & 0x40u)) noaud |= 1u << g;
+                if (a.events && valid) {
+                    uint32_t *ep = reinterpret_cast<uint32_t *>(a.events + (size_t)t * Cn + ch0 + g);   // {word, flags | r2sCount << 8}
+                    ep[0] = W[g]; ep[1] = ev | (after << 8);
+                }
+                value[g] = igd_w_shfl(word[g], nt - 1);
+                paysz[g] = igd_w_shfl(len_raw[g], nt - 1);
+                r2sPacket[g] = a.now_ms0 + (long long)(t0 + nt - 1) * a.tick_ms;
+                rtpAudio[g] = kind ? 1u : 0u;
+                r2sCount[g] = m_wd ? 0u : r2sCount[g];
+            }
+        } else {
+        IGD_UNROLL
+        for (int g = 0; g < G; g++) {
             // ---- latch :252-256: the word / length of the last accepted packet up to this tick
-            const uint32_t m_acc = igd_w_ballot(present && accepted);
+            const uint32_t m_acc = igd_w_ballot(present[g] && accepted[g]);
             const int s_acc = igd_w_top(m_acc & igd_w_le(lane));
-            const uint32_t wv = igd_w_shfl(word, s_acc < 0 ? 0 : s_acc), pv = igd_w_shfl(len_raw, s_acc < 0 ? 0 : s_acc);
+            const uint32_t wv = igd_w_shfl(word[g], s_acc < 0 ? 0 : s_acc), pv = igd_w_shfl(len_raw[g], s_acc < 0 ? 0 : s_acc);
             W[g] = s_acc >= 0 ? wv : value[g];
             const uint32_t P = s_acc >= 0 ? pv : paysz[g];
             // ---- r2sPacket :289,302,311: stamped by every packet
-            const uint32_t m_pres = igd_w_ballot(present);
+            const uint32_t m_pres = igd_w_ballot(present[g]);
             const int s_pres = igd_w_top(m_pres & igd_w_le(lane));
             const long long r2s = s_pres >= 0 ? a.now_ms0 + (long long)(t0 + s_pres) * a.tick_ms : r2sPacket[g];
             // ---- rtpAudio :298-315: set by the packets that are not dropped; an edge where it flips
-            const bool def = present && !dropped, aud = def && pt != 123u;
+            const bool def = present[g] && !dropped[g], aud = def && pt[g] != 123u;
             const uint32_t m_def = igd_w_ballot(def), m_aud = igd_w_ballot(aud);
             const int s_def = igd_w_top(m_def & igd_w_lt(lane));
             const bool audio_before = s_def >= 0 ? ((m_aud >> s_def) & 1u) != 0u : rtpAudio[g] != 0u;
             uint32_t ev = 0u;
-            if (present) ev |= 0x01u;
-            if (present && dropped) ev |= 0x08u;
+            if (present[g]) ev |= 0x01u;
+            if (present[g] && dropped[g]) ev |= 0x08u;
             if (aud) {
                 ev |= 0x02u;
-                if ((pt == 0u || pt == 8u) && plen == 160u) ev |= 0x40u;
+                if (frame[g]) ev |= 0x40u;
             }
-            if (def && (pt != 123u) != audio_before) ev |= 0x04u;
+            if (def && (pt[g] != 123u) != audio_before) ev |= 0x04u;
             // ---- watchdog roip_ed137.cpp:1767-1780: strikes = late watchdog ticks since the last one in time
             const bool late = wd && now - r2s > late_after, rst = wd && !late;
             const uint32_t m_late = igd_w_ballot(late), m_rst = igd_w_ballot(rst);
@@ -258,6 +296,7 @@ IGD_HD void igd_rxarb_walk(const igd_rxarb_args &a, const int b)
             if (m_pres) r2sPacket[g] = a.now_ms0 + (long long)(t0 + igd_w_top(m_pres)) * a.tick_ms;
             if (m_def) rtpAudio[g] = (m_aud >> igd_w_top(m_def)) & 1u;
             r2sCount[g] = igd_w_shfl(after, nt - 1);
+        }
         }
         // ---- gate arbitration over this step's ticks: full passes where the words change or the state still moves
         bool differs = false;

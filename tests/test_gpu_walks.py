@@ -58,3 +58,23 @@ def test_pack_lane_walk_equals_the_thread_per_sender_walk_on_every_tx_scenario(v
             got.append((pk, sz, bm, st))
         for a, b in zip(*got):
             assert a.tobytes() == b.tobytes(), s["name"]
+
+
+@pytest.mark.parametrize("mode,seed", [(N.ARB_CLIENT_PTT, 81), (N.ARB_SERVER_BEST, 82)])
+def test_gateway_lane_walk_on_long_uniform_stretches_against_the_oracle(vp, mode, seed):
+    """legs that keep sending one kind of packet for seconds: the walk's uniform-step path (and the general one around
+    the odd packets in between), events / gains / state against the oracle walks"""
+    import rx_arb_cases as R
+    from test_walks_host import steady_rx_case
+    F, B = 300, 40
+    Cn = B * G
+    pk, sizes = steady_rx_case(F, B, seed, mode)
+    case = make_case(F, B, seed, mode)
+    st = (np.zeros(Cn, N.RX_STATE_DT), np.zeros(Cn, N.ARB_LEG_DT), np.zeros(B, N.ARB_BRIDGE_DT), tx_state_of(case))
+    got = vp.gateway_process(pk, case["law"], case["out_law"], st[0], st[1], st[2], case["rtp12"], st[3], rx_sizes=sizes,
+                             tx_ctl=case["ctl"], mode=mode, now_ms0=case["now0"], wd_ticks=2, want=("rx_events", "gain_q7"))
+    ev_w, st_w = R.oracle_rx_walk(pk, sizes, (sizes != 0).astype(np.uint8), now0=case["now0"], wd_ticks=2)
+    g_w, lg_w, br_w = R.oracle_arb_walk(np.ascontiguousarray(ev_w["word"]), G, mode)
+    g_w = np.where((ev_w["flags"] & N.RXE_FRAME) == 0, g_w | N.GAIN_NO_AUDIO, g_w).astype(np.uint16)
+    assert got["rx_events"].tobytes() == ev_w.tobytes() and np.array_equal(got["gain_q7"], g_w)
+    assert st[0].tobytes() == st_w.tobytes() and st[1].tobytes() == lg_w.tobytes() and st[2].tobytes() == br_w.tobytes()

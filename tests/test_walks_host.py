@@ -201,3 +201,48 @@ def test_rxarb_walk_from_arbitrary_start_states(mode, seed):
     ev, gain = run_rxarb(pk, sizes, mode, st, 1_000_000)
     assert ev.tobytes() == ev_w.tobytes() and np.array_equal(gain, g_w)
     assert st[0].tobytes() == st_w.tobytes() and st[1].tobytes() == lg_w.tobytes() and st[2].tobytes() == br_w.tobytes()
+
+
+def steady_rx_case(F, B, seed, mode):
+    """long stretches of one packet kind per leg (a radio that keeps sending audio, or keep-alives), a few odd packets and
+    gaps in between: most 32-tick steps take the walk's uniform-step path, the rest the general one"""
+    rng = np.random.default_rng(seed)
+    Cn = B * G
+    L = R.O.lib()
+    pk = rng.integers(0, 256, (F, Cn, 180), dtype=np.uint8)
+    sizes = np.full((F, Cn), 180, np.uint32)
+    hdr = np.zeros(20, np.uint8)
+    w = R.make_arb_words(F, B, G, mode, seed=seed + 1)
+    for c in range(Cn):
+        f = 0
+        while f < F:
+            run = int(rng.integers(40, 160))
+            ka = rng.random() < 0.4
+            pt = 123 if ka else int(rng.choice([8, 0]))
+            for k in range(f, min(F, f + run)):
+                L.orc_hdr_write(hdr.ctypes.data, 2, 0, 1, 0, 0, pt, k & 0xFFFF, 160 * k, c, 0x0167, 1, int(w[k, c]))
+                pk[k, c, :20] = hdr
+                sizes[k, c] = 20 if ka else 180
+            f += run
+    odd = rng.random((F, Cn)) < 0.004
+    sizes[odd] = rng.choice([0, 12, 100, 1044], int(odd.sum()))
+    return pk, sizes
+
+
+@pytest.mark.parametrize("mode,seed,wd", [(N.ARB_CLIENT_PTT, 71, 2), (N.ARB_SERVER_BEST, 72, 3), (N.ARB_CLIENT_PTT, 73, 1)])
+def test_rxarb_walk_long_uniform_stretches(mode, seed, wd):
+    F, B = 330, 5
+    Cn = B * G
+    pk, sizes = steady_rx_case(F, B, seed, mode)
+    present = (sizes != 0).astype(np.uint8)
+    rx0 = np.zeros(Cn, N.RX_STATE_DT)
+    rx0["r2sCount"] = np.arange(Cn) % 7
+    rx0["rtpAudio"] = np.arange(Cn) % 2
+    rx0["r2sPacket"] = 1_000_000 - 5000
+    ev_w, st_w = R.oracle_rx_walk(pk, sizes, present, now0=1_000_000, wd_ticks=wd, state=rx0)
+    g_w, lg_w, br_w = R.oracle_arb_walk(np.ascontiguousarray(ev_w["word"]), G, mode)
+    g_w = np.where((ev_w["flags"] & N.RXE_FRAME) == 0, g_w | N.GAIN_NO_AUDIO, g_w).astype(np.uint16)
+    st = (rx0.copy(), np.zeros(Cn, N.ARB_LEG_DT), np.zeros(B, N.ARB_BRIDGE_DT))
+    ev, gain = run_rxarb(pk, sizes, mode, st, 1_000_000, wd_ticks=wd)
+    assert ev.tobytes() == ev_w.tobytes() and np.array_equal(gain, g_w)
+    assert st[0].tobytes() == st_w.tobytes() and st[1].tobytes() == lg_w.tobytes() and st[2].tobytes() == br_w.tobytes()
