@@ -929,10 +929,17 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     // The walks: from IGD_WALK_MIN_TICKS ticks per call up, one warp per bridge / sender with the tick axis across its
     // lanes (igd_walks.cuh: k_rxarb_walk = liveness walk + arbitration straight from the packets, k_plan_walk); below
     // that -- the real-time shape, one tick per call -- and under IGD_F_WALK_SERIAL the thread-per-channel kernels.
+    // Measured (bench.py --chain, lane / thread-per-channel walks): 4096 ch x 1640 ticks 0.65 / 1.26 ms, 16 384 x 400
+    // 0.63 / 0.96, 32 768 x 200 0.64 / 0.73, 65 536 x 100 0.668 / 0.663: tens of thousands of independent walks hide a
+    // thread-per-channel walk's latency as long as the call is short.
 #ifndef IGD_GW_LANE_MAX_CH
-#define IGD_GW_LANE_MAX_CH 32768       // measured: 65 536 channels x 100 ticks 0.69 ms with the lane walk, 0.66 with the thread-per-channel walks
+#define IGD_GW_LANE_MAX_CH 65536
 #endif
-    const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS && Cn < (size_t)IGD_GW_LANE_MAX_CH;
+#ifndef IGD_GW_LANE_LONG_CALL
+#define IGD_GW_LANE_LONG_CALL 200
+#endif
+    const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS &&
+                       (Cn < (size_t)IGD_GW_LANE_MAX_CH || d->F >= IGD_GW_LANE_LONG_CALL);
     igd_rx_event *dev = nullptr; uint16_t *dgain;
     if (mem == IGD_MEM_DEVICE && d->rx_events) dev = d->rx_events;
     else if (!lanes || d->rx_events) {      // the lane walk hands the words to the arbitration in registers: no event array unless wanted
