@@ -12,6 +12,8 @@ python bench.py --chain --steps 20 --serial-walks --no-e2e > $O/chain_bench_shap
 python bench.py --chain --steps 20 --chain-bridges 16384 --chain-frames 100 > $O/chain_65536ch.json 2>> $O/bench.err
 python bench.py --chain --steps 20 --no-e2e --chain-bridges 4096 --chain-frames 400 > $O/chain_16384ch_400ticks.json 2>> $O/bench.err
 python bench.py --chain --steps 20 --no-e2e --serial-walks --chain-bridges 4096 --chain-frames 400 > $O/chain_16384ch_400ticks_serial_walks.json 2>> $O/bench.err
+python bench.py --chain --steps 20 --no-e2e --chain-bridges 8192 --chain-frames 200 > $O/chain_32768ch_200ticks.json 2>> $O/bench.err
+python bench.py --chain --steps 20 --no-e2e --serial-walks --chain-bridges 8192 --chain-frames 200 > $O/chain_32768ch_200ticks_serial_walks.json 2>> $O/bench.err
 # 2) the gateway call: every launch with its device time (cold-cache, serialised: compare SHARES), lane walks and serial walks
 CH="python bench.py --chain --no-e2e --steps 2 --warmup 3"
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -c 80 --csv --log-file $O/chain_launches_bench_shape.csv $CH > /dev/null 2>&1
