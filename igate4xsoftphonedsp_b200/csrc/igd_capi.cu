@@ -940,9 +940,13 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
 #endif
     const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS &&
                        (Cn < (size_t)IGD_GW_LANE_MAX_CH || d->F >= IGD_GW_LANE_LONG_CALL);
+    // wide and short (tens of thousands of channels, fewer than 200 ticks): the thread-per-channel form, but the receive
+    // walk and the arbitration as ONE kernel with one thread per bridge (k_rxarb_bridge)
+    const bool bridge_walk = !lanes && !(d->flags & IGD_F_WALK_SERIAL) && Cn >= 32768;
+    const bool one_kernel = lanes || bridge_walk;      // receive walk + arbitration in one launch, words handed over in registers
     igd_rx_event *dev = nullptr; uint16_t *dgain;
     if (mem == IGD_MEM_DEVICE && d->rx_events) dev = d->rx_events;
-    else if (!lanes || d->rx_events) {      // the lane walk hands the words to the arbitration in registers: no event array unless wanted
+    else if (!one_kernel || d->rx_events) {      // no event array between the walk and the arbitration unless it is wanted
         if ((rc = scratch(c, 7, n * sizeof(igd_rx_event), &dev_s))) return rc;
         dev = static_cast<igd_rx_event *>(dev_s);
     }
@@ -1045,14 +1049,14 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
         //        kernel, no field array: enough walks in flight to hide the strided loads); with a few thousand channels
         //        and many ticks a fully parallel header pass first and the walk over its compact 16-byte records is
         //        faster (measured: 65 536 ch x 100 ticks 0.80 vs 0.83 ms per call; 4096 ch x 1640 ticks 1.64 vs 2.46 ms).
-        if (lanes) {
+        if (one_kernel) {
             igd_rxarb_args ra;
             ra.F = nf; ra.B = d->B; ra.mode = d->arb_mode; ra.tick_ms = d->tick_ms; ra.r2s_period_ms = d->r2s_period_ms;
             ra.wd_ticks = d->wd_ticks; ra.frame0 = d->frame0 + f0; ra.now_ms0 = d->now_ms0 + (long long)f0 * d->tick_ms;
             ra.pkts = dpk + on * IGD_PKT_MAX; ra.sizes = dsz ? dsz + on : nullptr; ra.active = dact;
             ra.rx_state = drx; ra.legs = dleg; ra.bridges = dbr; ra.events = dev ? dev + on : nullptr; ra.gain_q7 = dgain + on;
             IGD_TR(0, krx.stream);
-            IGD_CUDA(c, igd_k_rxarb_walk(krx, ra));
+            IGD_CUDA(c, lanes ? igd_k_rxarb_walk(krx, ra) : igd_k_rxarb_bridge(krx, ra));
             IGD_TR(3, krx.stream);
             c->launches += 1;
             if (nchunk > 1) {

@@ -43,6 +43,8 @@ cudaError_t igd_k_ed137_keepalive(const igd_launch_cfg &c, uint8_t *hdr20, igd_e
 #define IGD_WALK_MIN_TICKS 8       // below this many ticks per call the thread-per-channel kernels run
 struct igd_rxarb_args;
 cudaError_t igd_k_rxarb_walk(const igd_launch_cfg &c, const igd_rxarb_args &a);
+// the same receive side with one thread per bridge (wide, short calls; igd_packet.cu)
+cudaError_t igd_k_rxarb_bridge(const igd_launch_cfg &c, const igd_rxarb_args &a);
 cudaError_t igd_k_plan_walk(const igd_launch_cfg &c, const igd_ed137_pack_desc &d, igd_tx_plan_rec *plan, int32_t *last_src);
 // pkts != NULL: the walk reads the header words straight out of the packets [F][C][180] (d.fields unused)
 cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d, const uint8_t *pkts = nullptr);

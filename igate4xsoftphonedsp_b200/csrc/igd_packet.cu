@@ -1,6 +1,7 @@
 // igd_packet.cu -- ED-137 RTP parse / pack / keep-alive, RX liveness walk, gate arbitration, recorder sink
 // (hand-written sm_100a kernels of the iGate4x voice path; design notes in igd_fused.cu and DESIGN.md)
 #include "igd_device.cuh"
+#include "igd_walks.cuh"      // igd_rxarb_args
 
 namespace {
 
@@ -530,6 +531,113 @@ __global__ void __launch_bounds__(kArbThreads) k_gate_arbitrate(const igd_arb_de
     }
 }
 
+// ============================================================ receive side of a wide, short call: one thread per bridge
+// Tens of thousands of channels and a few ticks per call (65 536 x 100): enough independent walks to hide a
+// thread's latency, so the thread-per-channel form stays -- but as ONE kernel: a thread walks the four legs of its
+// bridge through transport_rtp_cb's state (igd_rx_step, header words straight out of the packets, as k_rx_track<3>)
+// and hands the four latched words to checkEvents() (the steady-state skip of k_gate_arbitrate) in registers.  No
+// event array between the two, one launch less, and the arbitration's own 100-tick latency chain (0.10 ms) rides on
+// the header reads, which bound this kernel (every 20-byte header costs the DRAM line(s) it lies in: 0.94 GB).
+constexpr int kRbAhead = 4;          // ticks whose header words are in flight per thread (4 legs x 4 words each)
+__global__ void __launch_bounds__(64) k_rxarb_bridge(const igd_rxarb_args a)
+{
+    constexpr int G = 4;
+    const int b = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (b >= a.B) return;
+    const size_t Cn = (size_t)a.B * G, ch0 = (size_t)b * G;
+    igd_rx_state s[G];
+    arb_legs<G> lr;
+#pragma unroll
+    for (int g = 0; g < G; g++) { s[g] = a.rx_state[ch0 + g]; lr.v[g] = a.legs[ch0 + g]; }
+    igd_arb_leg *legs = lr.v;
+    igd_arb_bridge br = a.bridges[b];
+    uint32_t act_mask = 0xFu;
+    if (a.active) {
+        act_mask = 0;
+#pragma unroll
+        for (int g = 0; g < G; g++) act_mask |= (a.active[ch0 + g] != 0 ? 1u : 0u) << g;
+    }
+    uint32_t prevw[G] = {0u, 0u, 0u, 0u};
+    uint64_t snap[G];
+    bool have_prev = false, steady = false, counting = false;
+    uint4 raw[kRbAhead][G];              // {word 0, word 3, word 4, received size} of the next kRbAhead ticks
+    auto fetch = [&](int f, uint4 (&r)[G]) {
+        if (f < a.F) {
+            const size_t i = (size_t)f * Cn + ch0;
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(a.pkts + i * IGD_PKT_MAX);
+#pragma unroll
+            for (int g = 0; g < G; g++)
+                r[g] = make_uint4(__ldg(pw + g * kPktWords), __ldg(pw + g * kPktWords + 3), __ldg(pw + g * kPktWords + 4),
+                                  a.sizes ? __ldg(a.sizes + i + g) : (uint32_t)IGD_PKT_MAX);
+        }
+    };
+#pragma unroll
+    for (int u = 0; u < kRbAhead; u++) fetch(u, raw[u]);
+    const int wd_ticks = a.wd_ticks;
+    int wd_phase = wd_ticks > 0 ? (int)(a.frame0 % wd_ticks) : 0;
+    long long now = a.now_ms0;
+    for (int f0 = 0; f0 < a.F; f0 += kRbAhead) {
+#pragma unroll
+        for (int u = 0; u < kRbAhead; u++) {
+            const int f = f0 + u;
+            if (f >= a.F) break;
+            const bool wd = wd_ticks > 0 && wd_phase == wd_ticks - 1;
+            wd_phase = wd_phase + 1 == wd_ticks ? 0 : wd_phase + 1;
+            uint32_t w[G], noaud = 0u;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const uint4 r = raw[u][g];
+                const uint32_t navail = min(r.w, (uint32_t)IGD_PKT_MAX) / 4;      // words transport_rtp_cb may look at
+                const igd_ed137_fields fl = fields_of_header(navail > 0 ? r.x : 0u, navail > 3 ? r.y : 0u, navail > 4 ? r.z : 0u, r.w);
+                const uint32_t ev = igd_rx_step(s[g], fl, r.w != 0u, wd, now, a.r2s_period_ms);
+                w[g] = s[g].ed137_value;
+                if (!(ev & IGD_RXE_FRAME)) noaud |= 1u << g;
+                if (a.events) {
+                    igd_rx_event e;
+                    e.word = s[g].ed137_value; e.flags = (uint8_t)ev; e.r2sCount = s[g].r2sCount; e.reserved = 0;
+                    *reinterpret_cast<uint2 *>(a.events + (size_t)f * Cn + ch0 + g) = *reinterpret_cast<const uint2 *>(&e);
+                }
+            }
+            fetch(f + kRbAhead, raw[u]);                              // this slot's next tick goes in flight
+            now += a.tick_ms;
+            // checkEvents() with the steady-state skip (see k_gate_arbitrate)
+            bool same = have_prev;
+#pragma unroll
+            for (int g = 0; g < G; g++) same = same && w[g] == prevw[g];
+            if (same && steady) {
+                if (counting) br.sqlStatusCount++;
+            } else {
+                uint64_t fold = 0;
+                const int32_t c0 = br.sqlStatusCount, l0 = br.ptt_level;
+                const uint8_t o0 = br.sqlStatusOn;
+#pragma unroll
+                for (int g = 0; g < G; g++) snap[g] = arb_leg_bits(legs[g]);
+                auto word = [&](int g) { return w[g]; };
+                auto active = [&](int g) { return ((act_mask >> g) & 1u) != 0u; };
+                const igd_const_int<G> Gc;
+                if (a.mode == IGD_ARB_CLIENT_PTT) igd_arb_client_tick(br, legs, Gc, word, active);
+                else igd_arb_server_best_tick(br, legs, Gc, word, active);
+#pragma unroll
+                for (int g = 0; g < G; g++) {
+                    fold |= snap[g] ^ arb_leg_bits(legs[g]);
+                    prevw[g] = w[g];
+                }
+                const bool legs_same = fold == 0 && br.ptt_level == l0 && br.sqlStatusOn == o0;
+                counting = legs_same && br.sqlStatusOn != 0 && br.sqlStatusCount == c0 + 1;
+                steady = legs_same && (br.sqlStatusCount == c0 || counting);
+                have_prev = true;
+            }
+            const uint32_t na = (uint32_t)IGD_GAIN_NO_AUDIO;       // a tick without a whole audio frame is silent (IGD_ARB_F_SILENCE)
+            const uint32_t g01 = (uint32_t)legs[0].gain_q7 | ((uint32_t)legs[1].gain_q7 << 16) | ((noaud & 1u) ? na : 0u) | ((noaud & 2u) ? na << 16 : 0u);
+            const uint32_t g23 = (uint32_t)legs[2].gain_q7 | ((uint32_t)legs[3].gain_q7 << 16) | ((noaud & 4u) ? na : 0u) | ((noaud & 8u) ? na << 16 : 0u);
+            *reinterpret_cast<uint2 *>(a.gain_q7 + (size_t)f * Cn + ch0) = make_uint2(g01, g23);
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < G; g++) { a.rx_state[ch0 + g] = s[g]; a.legs[ch0 + g] = lr.v[g]; }
+    a.bridges[b] = br;
+}
+
 // Phase 1: one thread per channel walks its frames through the sender state
 // machine (transport_send_rtp, TransportAdapter.cpp:635-874) and writes a plan
 // record per packet.  The state is tiny and strictly sequential per channel.
@@ -947,6 +1055,13 @@ cudaError_t igd_k_rx_track(const igd_launch_cfg &c, const igd_rx_track_desc &d, 
     else if (d.present) k_rx_track<1><<<blocks, 128, 0, c.stream>>>(d);
     else if (d.sizes) k_rx_track<2><<<blocks, 128, 0, c.stream>>>(d);
     else k_rx_track<0><<<blocks, 128, 0, c.stream>>>(d);
+    return cudaGetLastError();
+}
+
+cudaError_t igd_k_rxarb_bridge(const igd_launch_cfg &c, const igd_rxarb_args &a)
+{
+    if (a.B <= 0 || a.F <= 0) return cudaSuccess;
+    k_rxarb_bridge<<<(unsigned)((a.B + 63) / 64), 64, 0, c.stream>>>(a);
     return cudaGetLastError();
 }
 

@@ -1,4 +1,5 @@
-"""The walks with the tick axis across the lanes (k_rxarb_walk, k_plan_walk: calls of >= 8 ticks) against the
+"""The walks with the tick axis across the lanes (k_rxarb_walk, k_plan_walk: calls of >= 8 ticks) and the one-thread-per-bridge
+receive walk of wide, short calls (k_rxarb_bridge: from 65 536 channels, fewer than 200 ticks) against the
 thread-per-channel kernels they replace (IGD_F_WALK_SERIAL: k_rx_track, k_gate_arbitrate, k_ed137_plan), which
 test_gpu_rx_arb.py / test_gpu_ed137_summary_wav.py hold to the oracle.  The same code runs lane for lane on the
 host against the oracle in test_walks_host.py; test_gpu_gateway.py holds the gateway call (which runs the lane
@@ -16,7 +17,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("F,B,mode,seed,wd", [(8, 3, N.ARB_CLIENT_PTT, 1, 2), (100, 40, N.ARB_SERVER_BEST, 2, 2),
                                               (333, 70, N.ARB_CLIENT_PTT, 3, 3), (64, 9000, N.ARB_CLIENT_PTT, 4, 2),
-                                              (45, 8200, N.ARB_SERVER_BEST, 5, 1), (200, 5, N.ARB_SERVER_BEST, 6, 0)])
+                                              (45, 8200, N.ARB_SERVER_BEST, 5, 1), (200, 5, N.ARB_SERVER_BEST, 6, 0),
+                                              # wide and short: one thread per bridge walks liveness + arbitration (k_rxarb_bridge)
+                                              (24, 16400, N.ARB_CLIENT_PTT, 7, 2), (10, 16500, N.ARB_SERVER_BEST, 8, 3)])
 def test_gateway_lane_walks_equal_the_thread_per_channel_walks(vp, F, B, mode, seed, wd):
     case = make_case(F, B, seed, mode)
     Cn = B * G
