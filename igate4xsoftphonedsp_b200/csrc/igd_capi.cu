@@ -929,20 +929,20 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     // The walks: from IGD_WALK_MIN_TICKS ticks per call up, one warp per bridge / sender with the tick axis across its
     // lanes (igd_walks.cuh: k_rxarb_walk = liveness walk + arbitration straight from the packets, k_plan_walk); below
     // that -- the real-time shape, one tick per call -- and under IGD_F_WALK_SERIAL the thread-per-channel kernels.
-    // Measured (bench.py --chain, lane / thread-per-channel walks): 4096 ch x 1640 ticks 0.65 / 1.26 ms, 16 384 x 400
-    // 0.63 / 0.96, 32 768 x 200 0.64 / 0.73, 65 536 x 100 0.668 / 0.663: tens of thousands of independent walks hide a
-    // thread-per-channel walk's latency as long as the call is short.
+    // Measured (bench.py --chain; lane walk / thread-per-channel walks / one thread per bridge, ms per call):
+    // 4096 ch x 1640 ticks 0.65 / 1.26 / -, 16 384 x 400 0.63 / 0.96 / -, 32 768 x 200 0.64 / 0.73 / 0.66,
+    // 65 536 x 100 0.668 / 0.663 / 0.575, 65 536 x 200 1.31 / - / 1.14: from 65 536 channels up a thread per bridge has
+    // enough independent walks to be bound by the header reads alone, below that the lanes' parallelism wins.
 #ifndef IGD_GW_LANE_MAX_CH
 #define IGD_GW_LANE_MAX_CH 65536
 #endif
-#ifndef IGD_GW_LANE_LONG_CALL
-#define IGD_GW_LANE_LONG_CALL 200
+    const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS && Cn < (size_t)IGD_GW_LANE_MAX_CH;
+    // tens of thousands of channels (or the real-time shape of 32 768 channels and more): the thread-per-channel form, but
+    // the receive walk and the arbitration as ONE kernel with one thread per bridge (k_rxarb_bridge)
+#ifndef IGD_GW_BRIDGE_MIN_CH
+#define IGD_GW_BRIDGE_MIN_CH 32768
 #endif
-    const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS &&
-                       (Cn < (size_t)IGD_GW_LANE_MAX_CH || d->F >= IGD_GW_LANE_LONG_CALL);
-    // wide and short (tens of thousands of channels, fewer than 200 ticks): the thread-per-channel form, but the receive
-    // walk and the arbitration as ONE kernel with one thread per bridge (k_rxarb_bridge)
-    const bool bridge_walk = !lanes && !(d->flags & IGD_F_WALK_SERIAL) && Cn >= 32768;
+    const bool bridge_walk = !lanes && !(d->flags & IGD_F_WALK_SERIAL) && Cn >= (size_t)IGD_GW_BRIDGE_MIN_CH;
     const bool one_kernel = lanes || bridge_walk;      // receive walk + arbitration in one launch, words handed over in registers
     igd_rx_event *dev = nullptr; uint16_t *dgain;
     if (mem == IGD_MEM_DEVICE && d->rx_events) dev = d->rx_events;

@@ -63,7 +63,10 @@ def composed(vp, case, mode, F, B):
                                            (120, 130, N.ARB_CLIENT_PTT, 4),
                                            # >= 32 768 channels: the packet-fed liveness walk, and the batch walked in
                                            # L2-sized slices of ticks (state carried from slice to slice)
-                                           (37, 8192, N.ARB_CLIENT_PTT, 5), (9, 8200, N.ARB_SERVER_BEST, 6)])
+                                           (37, 8192, N.ARB_CLIENT_PTT, 5), (9, 8200, N.ARB_SERVER_BEST, 6),
+                                           # the real-time shape of a wide batch (a few ticks, >= 32 768 channels) and a wide
+                                           # call: one thread per bridge walks liveness + arbitration (k_rxarb_bridge)
+                                           (5, 8300, N.ARB_CLIENT_PTT, 7), (12, 16390, N.ARB_SERVER_BEST, 8)])
 @pytest.mark.parametrize("kern", [0, N.F_KERNEL_W])      # quarter-lane fused kernel (default) and its predecessor
 def test_gateway_equals_composition_of_verified_calls(vp, F, B, mode, seed, kern):
     case = make_case(F, B, seed, mode)
