@@ -942,7 +942,8 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
 #ifndef IGD_GW_BRIDGE_MIN_CH
 #define IGD_GW_BRIDGE_MIN_CH 32768
 #endif
-    const bool bridge_walk = !lanes && !(d->flags & IGD_F_WALK_SERIAL) && Cn >= (size_t)IGD_GW_BRIDGE_MIN_CH;
+    const bool bridge_walk = !lanes && !(d->flags & IGD_F_WALK_SERIAL) &&
+                             (Cn >= (size_t)IGD_GW_BRIDGE_MIN_CH || d->F < IGD_WALK_MIN_TICKS);      // ... and every call of a few ticks
     const bool one_kernel = lanes || bridge_walk;      // receive walk + arbitration in one launch, words handed over in registers
     igd_rx_event *dev = nullptr; uint16_t *dgain;
     if (mem == IGD_MEM_DEVICE && d->rx_events) dev = d->rx_events;
@@ -1018,7 +1019,7 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
         IGD_CUDA(c, cudaStreamWaitEvent(karb.stream, c->ev[6], 0));
     }
     void *dfields = nullptr;
-    if (!lanes && Cn < 32768 && (rc = scratch(c, 5, n * sizeof(igd_ed137_fields), &dfields))) return rc;
+    if (!one_kernel && Cn < 32768 && (rc = scratch(c, 5, n * sizeof(igd_ed137_fields), &dfields))) return rc;
 #ifdef IGD_X_GW_TRACE      // measurement builds: when did each stage of each chunk start and end
     static cudaEvent_t tr[1 + 8 * 6];
     static bool tr_init = false;
