@@ -62,9 +62,9 @@ enum {
                                      instead of k_fused_q (G <= 4, codes and packet forms), k_fused_g instead of
                                      k_fused_h (G = 8).  Same results, bit for bit. */
 #define IGD_F_WALK_SERIAL 0x10u    /* diagnostics (A/B runs, tests; igd_gateway_process, igd_ed137_pack): walk the per-call
-                                     state machines with one thread per channel / bridge / sender (k_rx_track,
-                                     k_gate_arbitrate, k_ed137_plan) instead of one warp per bridge / sender with the
-                                     tick axis across its lanes (k_rxarb_walk, k_plan_walk; calls of >= 8 ticks).
+                                     state machines with separate thread-per-channel / -bridge / -sender kernels
+                                     (k_rx_track, k_gate_arbitrate, k_ed137_plan) instead of k_rxarb_walk / k_plan_walk
+                                     (one warp per bridge / sender, tick axis across its lanes) or k_rxarb_bridge.
                                      Same results, bit for bit. */
 #define IGD_F_GENERIC_KERNEL 0x4u /* diagnostic (igd_process_batch): run the block-cooperative kernel that
                                     serves batches beyond 32-bit indices instead of the warp-autonomous
@@ -477,11 +477,10 @@ int igd_gate_arbitrate(igd_ctx *ctx, const igd_arb_desc *d);
  * reads the codes straight out of the received packets and writes FINISHED 180-byte ED-137 packets
  * (header from the sender walk + the PJSIP RTP header, payload = this tick's encoded mix; the bytes of
  * a slot past tx_sizes are zero) -- the bytes igd_ed137_pack produces without IGD_F_REF_QUIRKS.
- * Calls of >= 8 ticks below 32 768 channels: three kernels -- the receive-side walk (liveness + arbitration of one
- * bridge per warp, the tick axis across its lanes, header words straight out of the packets), the sender walk (one
- * warp per outgoing call, on a side stream) and the fused kernel.  Otherwise (one tick per call, or tens of
- * thousands of channels, or IGD_F_WALK_SERIAL) the thread-per-channel walks: header view + liveness walk,
- * arbitration, sender walk on a side stream, fused kernel.  No payload, code or plan array exists between
+ * Three kernels: the receive-side walk (liveness + arbitration in one launch, header words straight out of the
+ * packets: one bridge per warp with the tick axis across its lanes for calls of >= 8 ticks below 65 536 channels,
+ * one bridge per thread otherwise), the sender walk (on a side stream) and the fused kernel.  IGD_F_WALK_SERIAL:
+ * header view + liveness walk, arbitration and sender walk as separate thread-per-channel kernels.  No payload, code or plan array exists between
  * them, nothing but packets and state crosses the API.  (tx_state.rtpFalse, the
  * reference's never-read stuck-audio diagnostic counter, is not maintained here: the payload it
  * looks at is produced after the sender walk.)
