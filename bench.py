@@ -221,8 +221,8 @@ def run_chain(args):
 
 def measure_chain(args, vp=None):
     """--chain (and the "chain" object of the default line): SURVEY 8(d) "with RTP" accounting -- raw 180-byte ED-137 packets of every leg in, finished ED-137
-    packets of every bridge out, through igd_gateway_process (four launches: header view + liveness walk, gate
-    arbitration, sender walk, fused decode -> meter -> mix -> encode -> packet kernel), device resident.
+    packets of every bridge out, through igd_gateway_process (receive-side walk = liveness + gate arbitration, sender
+    walk on a side stream, fused decode -> meter -> mix -> encode -> packet kernel), device resident.
     1284 algorithmic bytes per bridge-frame (4 x 180 in, 180 + 320 + 4 x 16 out)."""
     import numpy as np
     import torch
@@ -406,7 +406,8 @@ def measure_chain(args, vp=None):
         "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": peak, "unit": "GB/s", "frac": alg / ms / 1e6 / peak,
                      "traffic": None, "kernel": ("igd_gateway_process: k_rx_track<packets> + k_gate_arbitrate + k_ed137_plan (side stream) + "
                                 if args.serial_walks else "igd_gateway_process: k_rxarb_walk (liveness walk + arbitration, warp per bridge, "
-                                "ticks across the lanes) + k_plan_walk (side stream) + ") + "k_fused_q<4, packets in, packets out>", "peak_source": peak_src,
+                                "ticks across the lanes) + k_plan_walk (side stream) + " if Cc < 65536 and Fc >= 8 else
+                                "igd_gateway_process: k_rxarb_bridge (liveness walk + arbitration, one thread per bridge) + sender walk (side stream) + ") + "k_fused_q<4, packets in, packets out>", "peak_source": peak_src,
                      "algorithmic_bytes_per_step": alg, "bytes_per_bridge_frame": 1284, "stage_ms": stage},
         "cpu_baseline": None, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "parity_vs_oracle_on_two_bridges": parity,
