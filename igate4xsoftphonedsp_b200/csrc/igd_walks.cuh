@@ -122,6 +122,11 @@ IGD_HD void igd_w_client_tick4(igd_arb_bridge &b, igd_w_leg (&legs)[4], const ui
         const int ptt_w = (int)(w[i] >> 29);
         const uint32_t last0 = legs[i].last;
         const uint8_t msec0 = legs[i].msec, m1 = (uint8_t)(msec0 + 1);
+        // A leg that is where its word says -- same PTT as last tick, no hold-off count, neither beating the level nor
+        // about to be switched on or off -- leaves this pass without a trace: most legs on most passes (the steady
+        // check finds four of them).  The branch is warp-uniform, one per leg, around ~50 instructions.
+        if (!act | (((uint32_t)ptt_w == last0) & (msec0 == 0) & !((ptt_w != 0) & (ptt_w > level)) & ((ptt_w > 0) == (legs[i].on != 0u))))
+            continue;
         const bool ne = (uint32_t)ptt_w != last0, rel = ne & (ptt_w == 0);            // :6136-6153
         const uint8_t msec = rel ? m1 : ne ? msec0 : (uint8_t)0;
         const int ptt = rel & (m1 < 6) ? 1 : ptt_w;                                    // released: held for five more ticks
