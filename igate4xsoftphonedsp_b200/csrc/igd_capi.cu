@@ -926,19 +926,21 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
     void *dplan, *dlast, *dev_s = nullptr, *dgain_s = nullptr;
     if ((rc = scratch(c, 6, nb * sizeof(igd_tx_plan_rec) + B * sizeof(int32_t), &dplan))) return rc;
     dlast = static_cast<uint8_t *>(dplan) + nb * sizeof(igd_tx_plan_rec);
-    // The walks: from IGD_WALK_MIN_TICKS ticks per call up, one warp per bridge / sender with the tick axis across its
-    // lanes (igd_walks.cuh: k_rxarb_walk = liveness walk + arbitration straight from the packets, k_plan_walk); below
-    // that -- the real-time shape, one tick per call -- and under IGD_F_WALK_SERIAL the thread-per-channel kernels.
-    // Measured (bench.py --chain; lane walk / thread-per-channel walks / one thread per bridge, ms per call):
-    // 4096 ch x 1640 ticks 0.65 / 1.26 / -, 16 384 x 400 0.63 / 0.96 / -, 32 768 x 200 0.64 / 0.73 / 0.66,
-    // 65 536 x 100 0.668 / 0.663 / 0.575, 65 536 x 200 1.31 / - / 1.14: from 65 536 channels up a thread per bridge has
-    // enough independent walks to be bound by the header reads alone, below that the lanes' parallelism wins.
+    // The receive side (liveness walk + gate arbitration) comes in three forms:
+    //   lanes        one warp per bridge, tick axis across its lanes (igd_walks.cuh: k_rxarb_walk), sender k_plan_walk:
+    //                calls of IGD_WALK_MIN_TICKS ticks and more below IGD_GW_LANE_MAX_CH channels;
+    //   bridge_walk  one thread per bridge, both state machines in one kernel (k_rxarb_bridge): from 65 536 channels up,
+    //                and every call of a few ticks (the real-time shape);
+    //   otherwise    (IGD_F_WALK_SERIAL) header view / liveness walk / arbitration as separate thread-per-channel kernels,
+    //                pipelined over chunks of ticks below 32 768 channels.
+    // Measured (bench.py --chain; lanes / separate kernels / bridge_walk, ms per call): 4096 ch x 1640 ticks 0.61 / 1.26 /
+    // 2.8, 16 384 x 400 0.61 / 0.96 / 1.5, 32 768 x 200 0.62 / 0.73 / 0.66, 65 536 x 100 0.668 / 0.663 / 0.575, 65 536 x 200
+    // 1.31 / - / 1.14: from 65 536 channels up a thread per bridge has enough independent walks to be bound by the header
+    // reads alone, below that the lanes' parallelism wins.
 #ifndef IGD_GW_LANE_MAX_CH
 #define IGD_GW_LANE_MAX_CH 65536
 #endif
     const bool lanes = !(d->flags & IGD_F_WALK_SERIAL) && d->F >= IGD_WALK_MIN_TICKS && Cn < (size_t)IGD_GW_LANE_MAX_CH;
-    // tens of thousands of channels (or the real-time shape of 32 768 channels and more): the thread-per-channel form, but
-    // the receive walk and the arbitration as ONE kernel with one thread per bridge (k_rxarb_bridge)
 #ifndef IGD_GW_BRIDGE_MIN_CH
 #define IGD_GW_BRIDGE_MIN_CH 32768
 #endif
@@ -971,20 +973,19 @@ int igd_gateway_process(igd_ctx *c, const igd_gateway_desc *d)
         if (d->enc) denc = o8 + o_en;
     }
     const igd_launch_cfg k = cfg_of(c);
-    // The sender walk does not depend on the receive side: it runs on a side stream, concurrently with
-    // fields -> liveness walk -> arbitration (all three walks are latency-bound grids of a few thousand threads).
-    // Fork / join through events, so the whole call stays capturable in a CUDA graph.
+    // The sender walk does not depend on the receive side: it runs on a side stream, concurrently with the receive-side
+    // walk(s).  Fork / join through events, so the whole call stays capturable in a CUDA graph.
     igd_launch_cfg kside = k;
     kside.stream = c->copy_streams[0];
     IGD_CUDA(c, cudaEventRecord(c->ev[6], c->stream));
     IGD_CUDA(c, cudaStreamWaitEvent(kside.stream, c->ev[6], 0));
-    // The call is a pipeline over chunks of ticks: liveness walk (+ header pass) -> arbitration -> fused kernel, each
-    // stage on its own stream, chunk k of a stage waiting for chunk k of the stage before it, and the sender walk of the
-    // same chunk beside them on the side stream (the fused kernel needs its plan).  The
-    // walks are latency-bound grids of a few thousand threads that leave most of the machine idle; run back to back
-    // they cost twice the fused kernel (4096 channels x 1640 ticks: 1.50 ms per call), pipelined 1.29 ms.  Every stage carries its state from chunk to chunk in the caller's state arrays,
-    // exactly as from call to call, so the results do not depend on the chunking.  One tick (the real-time shape) is
-    // one chunk: the same four launches as before.
+    // With the separate thread-per-channel kernels (IGD_F_WALK_SERIAL) the call is a pipeline over chunks of ticks: liveness
+    // walk (+ header pass) -> arbitration -> fused kernel, each stage on its own stream, chunk k of a stage waiting for
+    // chunk k of the stage before it, and the sender walk of the same chunk beside them on the side stream (the fused
+    // kernel needs its plan).  Those walks are latency-bound grids of a few thousand threads; back to back they cost twice
+    // the fused kernel (4096 channels x 1640 ticks: 1.50 ms per call), pipelined 1.26-1.3 ms.  Every stage carries its
+    // state from chunk to chunk in the caller's state arrays, exactly as from call to call, so the results do not depend
+    // on the chunking.  The host form uses the same chunks to overlap its copies, whatever the walk.
 #ifndef IGD_GW_CHUNKS
 #define IGD_GW_CHUNKS 8
 #endif
