@@ -246,3 +246,36 @@ def test_rxarb_walk_long_uniform_stretches(mode, seed, wd):
     ev, gain = run_rxarb(pk, sizes, mode, st, 1_000_000, wd_ticks=wd)
     assert ev.tobytes() == ev_w.tobytes() and np.array_equal(gain, g_w)
     assert st[0].tobytes() == st_w.tobytes() and st[1].tobytes() == lg_w.tobytes() and st[2].tobytes() == br_w.tobytes()
+
+
+@pytest.mark.parametrize("seed", range(100, 140))
+def test_rxarb_walk_random_shapes_modes_and_call_splits(seed):
+    """random tick counts (also fewer than one warp step and one past a step boundary), bridge counts, modes, watchdog
+    periods, active masks, streams (ragged or steady) and call boundaries: always the oracle's events, gains and state"""
+    rng = np.random.default_rng(seed)
+    F = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 97, 150]))
+    B = int(rng.integers(1, 5))
+    mode = int(rng.choice([N.ARB_CLIENT_PTT, N.ARB_SERVER_BEST]))
+    wd = int(rng.integers(0, 5))
+    Cn = B * G
+    pk, sizes = (steady_rx_case if rng.random() < 0.5 else rx_case)(F, B, seed, mode)
+    if rng.random() < 0.3:
+        sizes = None
+    active = None if rng.random() < 0.5 else (rng.random(Cn) < 0.75).astype(np.uint8)
+    now0 = int(rng.integers(0, 1 << 40))
+    sz = np.full((F, Cn), 180, np.uint32) if sizes is None else sizes
+    ev_w, st_w = R.oracle_rx_walk(pk, sz, (sz != 0).astype(np.uint8), now0=now0, wd_ticks=wd)
+    g_w, lg_w, br_w = R.oracle_arb_walk(np.ascontiguousarray(ev_w["word"]), G, mode, active=active)
+    g_w = np.where((ev_w["flags"] & N.RXE_FRAME) == 0, g_w | N.GAIN_NO_AUDIO, g_w).astype(np.uint16)
+    cuts = sorted({0, F} | {int(x) for x in rng.integers(0, F + 1, int(rng.integers(0, 4)))})
+    st = (np.zeros(Cn, N.RX_STATE_DT), np.zeros(Cn, N.ARB_LEG_DT), np.zeros(B, N.ARB_BRIDGE_DT))
+    evs, gains = [], []
+    for f0, f1 in zip(cuts[:-1], cuts[1:]):
+        if f1 > f0:
+            e, g = run_rxarb(np.ascontiguousarray(pk[f0:f1]), None if sizes is None else np.ascontiguousarray(sizes[f0:f1]), mode, st,
+                             now0 + 20 * f0, wd_ticks=wd, frame0=f0, active=active)
+            evs.append(e)
+            gains.append(g)
+    assert np.concatenate(evs).tobytes() == ev_w.tobytes()
+    assert np.array_equal(np.concatenate(gains), g_w)
+    assert st[0].tobytes() == st_w.tobytes() and st[1].tobytes() == lg_w.tobytes() and st[2].tobytes() == br_w.tobytes()
